@@ -1,0 +1,111 @@
+/*
+ * mqvs.h -- C ABI of libmqvs.so, the B200-native exact vector-search backend behind MediQuery-RAG's
+ * `vectorstore` object.
+ *
+ * The reference has NO native interface for this path: its three call sites go through
+ * langchain_chroma.Chroma (pure Python) into chromadb / chroma-hnswlib, which are un-vendored.  Each entry
+ * point below therefore cites the reference call (file:line under /root/reference) whose work it does; the
+ * Python class in mediquery-rag_b200/vectorstore.py binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every in/out buffer; the library owns the
+ * corpus in HBM, scratch, streams.  Every function returns MQVS_OK (0) or a negative code and never throws;
+ * mqvs_last_error() gives the thread-local message.  A handle is not re-entrant (one call at a time per
+ * handle, enforced by an internal mutex) but may be used from any host thread.
+ * "is_device" flags say whether a pointer is device memory on the store's first device (1) or host (0).
+ */
+#ifndef MQVS_H_
+#define MQVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQVS_VERSION 100
+
+#if defined(__GNUC__)
+#define MQVS_API __attribute__((visibility("default")))
+#else
+#define MQVS_API
+#endif
+
+enum { MQVS_OK = 0, MQVS_E_INVALID = -1, MQVS_E_CUDA = -2, MQVS_E_NCCL = -3, MQVS_E_OOM = -4, MQVS_E_IO = -5 };
+enum { MQVS_F32 = 0, MQVS_BF16 = 1 };
+
+/* widest embedding the kernels are built for; rows are zero-padded to MQVS_DIM_PAD elements in HBM
+ * (768 = width of shaw/dmeta-embedding-zh, src/medical_engine.py:43) */
+#define MQVS_DIM_PAD 768
+#define MQVS_MAX_K 1024
+
+typedef struct mqvs_store mqvs_t;
+
+typedef struct mqvs_stats {
+    uint64_t rows;               /* rows stored (all devices) */
+    uint64_t searches;           /* mqvs_search calls completed */
+    uint64_t queries;            /* sum of B over those calls */
+    uint64_t kernel_launches;    /* kernels launched by this handle since creation */
+    uint64_t scan_launches;      /* of those, corpus-scan (K2) launches */
+    uint64_t scan_bytes;         /* algorithmic corpus bytes streamed by the scans: rows * 768 * sizeof(elem) per pass */
+    double   scan_ms;            /* device time of the scan launches (CUDA events on the launch stream) */
+    double   last_search_ms;     /* device time of the last search, first kernel to last */
+    double   last_scan_ms;       /* device time of the last search's scan launches */
+    uint32_t last_scan_passes;   /* corpus passes the last search needed */
+    uint32_t last_path;          /* 0 = SIMT fp32 scan, 1 = tensor-core shortlist + fp32 rescoring */
+} mqvs_stats;
+
+MQVS_API int mqvs_version(void);
+MQVS_API const char* mqvs_last_error(void);
+MQVS_API int mqvs_device_count(int* out);
+
+/* Chroma(persist_directory=..., embedding_function=...) -- src/medical_engine.py:52 -- and the collection
+ * Chroma.from_documents creates -- src/ingest_medical.py:106-110.  dim <= MQVS_DIM_PAD. */
+MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out);
+MQVS_API void mqvs_destroy(mqvs_t* s);
+MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out);
+MQVS_API int mqvs_reserve(mqvs_t* s, uint64_t capacity_rows);
+
+/* collection.upsert(embeddings=...) under Chroma.from_documents / add_texts -- src/ingest_medical.py:106.
+ * x: [n, dim] row-major, x_dtype MQVS_F32 (bf16 input is not accepted).  Runs K1 (L2-normalise + pack).
+ * Rows with a non-finite norm are rejected: nothing is appended and MQVS_E_INVALID is returned. */
+MQVS_API int mqvs_add(mqvs_t* s, const void* x, int x_dtype, int x_is_device, uint64_t n, uint64_t* first_row_out);
+
+/* Bench/test utility (BASELINE.json configs 2-5 use synthetic 768-d unit vectors; 100M rows cannot be staged
+ * through the host): appends n rows v[r, c] = uniform[-1,1) from splitmix64(seed, (first_index + r) * dim + c),
+ * generated on the device and passed through the same K1. */
+MQVS_API int mqvs_add_synthetic(mqvs_t* s, uint64_t seed, uint64_t first_index, uint64_t n, uint64_t* first_row_out);
+
+/* vectorstore.similarity_search(query, k) -- src/agents/nodes.py:93 (k=5), src/medical_engine.py:70 (k=3) --
+ * after the embedder: q [B, dim] fp32 (normalised here), mask = optional allow-bitmask over rows (bit r&31 of
+ * word r>>5; ceil(rows/32) words; NULL = all rows), the Chroma `where` filter compiled by the host.
+ * Outputs [B, k] row-major: cosine similarity descending, ties -> lower row id; slots beyond the number of
+ * allowed rows hold (-inf, -1).  Blocks until the outputs are ready. */
+MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
+                float* out_scores, int64_t* out_ids, int out_is_device);
+
+/* Same, enqueued on `cuda_stream` (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) with all
+ * buffers on the device; returns after enqueueing.  id_base is added to every returned id (row-sharded
+ * stores: the rank's first global row). */
+MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
+                      float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
+
+/* Cross-shard merge after the all-gather of per-rank candidates: scores/ids
+ * [W, B, k] on `device` -> best k per query [B, k], same ordering rule; empty slots are id < 0. */
+MQVS_API int mqvs_merge_candidates(int device, const float* scores_dev, const int64_t* ids_dev, int W, int B, int k,
+                          float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
+
+/* collection.get(ids, include=["embeddings"]): stored (normalised) rows as fp32, [n, dim] to host. */
+MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float* out_host);
+
+/* persist_directory -- src/ingest_medical.py:109, src/medical_engine.py:32-37,52: raw row file + header. */
+MQVS_API int mqvs_save(mqvs_t* s, const char* path);
+MQVS_API int mqvs_load(mqvs_t* s, const char* path);
+
+MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);
+/* 0 = choose by batch size, 1 = force the SIMT fp32 scan, 2 = force the tensor-core path */
+MQVS_API int mqvs_set_path(mqvs_t* s, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQVS_H_ */

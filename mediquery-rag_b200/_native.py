@@ -1,0 +1,205 @@
+"""ctypes binding of libmqvs.so (include/mqvs.h).  There is NO fallback: if the library is missing or no
+B200 is visible, the calls raise -- the product never computes on the CPU."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmqvs.so")
+
+OK, E_INVALID, E_CUDA, E_NCCL, E_OOM, E_IO = 0, -1, -2, -3, -4, -5
+F32, BF16 = 0, 1
+DIM_PAD = 768
+MAX_K = 1024
+DTYPES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16}
+
+
+class MqvsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mqvs error {code}: {msg}")
+        self.code = code
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_uint64), ("searches", ctypes.c_uint64), ("queries", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint64), ("scan_launches", ctypes.c_uint64),
+                ("scan_bytes", ctypes.c_uint64), ("scan_ms", ctypes.c_double), ("last_search_ms", ctypes.c_double),
+                ("last_scan_ms", ctypes.c_double), ("last_scan_passes", ctypes.c_uint32),
+                ("last_path", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+# name -> (restype, argtypes); the loader test checks every symbol include/mqvs.h declares is here and exported
+_vp, _i, _u64, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64
+SIGNATURES = {
+    "mqvs_version": (_i, []),
+    "mqvs_last_error": (ctypes.c_char_p, []),
+    "mqvs_device_count": (_i, [ctypes.POINTER(_i)]),
+    "mqvs_create": (_i, [_i, ctypes.POINTER(_i), _i, _i, _u64, ctypes.POINTER(_vp)]),
+    "mqvs_destroy": (None, [_vp]),
+    "mqvs_count": (_i, [_vp, ctypes.POINTER(_u64)]),
+    "mqvs_reserve": (_i, [_vp, _u64]),
+    "mqvs_add": (_i, [_vp, _vp, _i, _i, _u64, ctypes.POINTER(_u64)]),
+    "mqvs_add_synthetic": (_i, [_vp, _u64, _u64, _u64, ctypes.POINTER(_u64)]),
+    "mqvs_search": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i]),
+    "mqvs_search_async": (_i, [_vp, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "mqvs_merge_candidates": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "mqvs_get_rows": (_i, [_vp, _vp, _u64, _vp]),
+    "mqvs_save": (_i, [_vp, ctypes.c_char_p]),
+    "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
+    "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
+    "mqvs_set_path": (_i, [_vp, _i]),
+}
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                              "(nvcc, sm_100a); there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise MqvsError(rc, load().mqvs_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = _i(0)
+    check(load().mqvs_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def _ptr(a) -> ctypes.c_void_p:
+    """numpy array -> host pointer; torch tensor -> data_ptr; None -> NULL."""
+    if a is None:
+        return ctypes.c_void_p(None)
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(a.data_ptr())
+
+
+def _is_torch(a) -> bool:
+    return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
+
+
+class Index:
+    """One row shard on one B200: thin owner of an mqvs_t handle."""
+
+    def __init__(self, dim: int, store_dtype: str = "fp32", device: int = 0, capacity_rows: int = 0):
+        self._h = _vp(None)
+        self.dim = int(dim)
+        self.store_dtype = store_dtype
+        self.device = int(device)
+        dev = (_i * 1)(self.device)
+        check(load().mqvs_create(1, dev, self.dim, DTYPES[store_dtype], int(capacity_rows), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load().mqvs_destroy(self._h)
+            self._h = _vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        n = _u64(0)
+        check(load().mqvs_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def reserve(self, rows: int) -> None:
+        check(load().mqvs_reserve(self._h, int(rows)))
+
+    def add(self, x) -> int:
+        """x: [n, dim] fp32 numpy array (host) or CUDA torch tensor on this index's device.  -> first row id."""
+        first = _u64(0)
+        if _is_torch(x):
+            if not x.is_cuda or x.dtype.itemsize != 4 or not x.is_contiguous() or x.shape[-1] != self.dim:
+                raise ValueError("device embeddings must be a contiguous fp32 CUDA tensor [n, dim]")
+            n, dev = (x.shape[0] if x.dim() == 2 else 1), 1
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            if x.ndim == 1:
+                x = x[None, :]
+            if x.ndim != 2 or x.shape[1] != self.dim:
+                raise ValueError(f"embeddings must be [n, {self.dim}], got {x.shape}")
+            n, dev = x.shape[0], 0
+        check(load().mqvs_add(self._h, _ptr(x), F32, dev, n, ctypes.byref(first)))
+        return first.value
+
+    def add_synthetic(self, seed: int, first_index: int, n: int) -> int:
+        first = _u64(0)
+        check(load().mqvs_add_synthetic(self._h, seed & 0xFFFFFFFFFFFFFFFF, int(first_index), int(n), ctypes.byref(first)))
+        return first.value
+
+    def search(self, q, k: int, mask=None):
+        """q [B, dim] fp32 host array -> (scores [B, k] float32, ids [B, k] int64) host arrays."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B, {self.dim}], got {q.shape}")
+        B = q.shape[0]
+        scores = np.empty((B, k), np.float32)
+        ids = np.empty((B, k), np.int64)
+        mask_dev = 0
+        if mask is not None:
+            if _is_torch(mask):
+                mask_dev = 1
+            else:
+                mask = np.ascontiguousarray(mask, dtype=np.uint32)
+                if mask.shape[0] < (len(self) + 31) // 32:
+                    raise ValueError("mask has fewer than ceil(rows/32) words")
+        check(load().mqvs_search(self._h, _ptr(q), 0, B, int(k), _ptr(mask), mask_dev, _ptr(scores), _ptr(ids), 0))
+        return scores, ids
+
+    def search_device(self, q, k: int, out_scores, out_ids, mask=None, id_base: int = 0, stream: int = 0) -> None:
+        """All-device variant on a caller stream (torch tensors; plumbing only)."""
+        B = q.shape[0]
+        check(load().mqvs_search_async(self._h, _ptr(q), B, int(k), _ptr(mask), int(id_base), _ptr(out_scores),
+                                       _ptr(out_ids), _vp(stream)))
+
+    def get_rows(self, row_ids) -> np.ndarray:
+        row_ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+        out = np.empty((row_ids.shape[0], self.dim), np.float32)
+        check(load().mqvs_get_rows(self._h, _ptr(row_ids), row_ids.shape[0], _ptr(out)))
+        return out
+
+    def save(self, path: str) -> None:
+        check(load().mqvs_save(self._h, os.fsencode(path)))
+
+    def load_file(self, path: str) -> None:
+        check(load().mqvs_load(self._h, os.fsencode(path)))
+
+    def stats(self) -> dict:
+        st = Stats()
+        check(load().mqvs_get_stats(self._h, ctypes.byref(st)))
+        return st.as_dict()
+
+    def set_path(self, path: int) -> None:
+        check(load().mqvs_set_path(self._h, int(path)))
+
+
+def merge_candidates(device: int, scores, ids, out_scores, out_ids, stream: int = 0) -> None:
+    """scores/ids [W, B, k] device tensors -> out [B, k] device tensors."""
+    W, B, k = scores.shape
+    check(load().mqvs_merge_candidates(int(device), _ptr(scores), _ptr(ids), W, B, k, _ptr(out_scores), _ptr(out_ids),
+                                       _vp(stream)))

@@ -1,0 +1,502 @@
+// api.cu -- the C ABI of libmqvs.so (include/mqvs.h): store lifetime, ingest, search orchestration, persistence.
+// No torch types, no exceptions across the boundary; CUDA errors become MQVS_E_CUDA with a thread-local message.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mqvs.h"
+#include "launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? MQVS_E_OOM : MQVS_E_CUDA;                    \
+            cudaGetLastError();                                                                          \
+            return fail(code_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return MQVS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = std::max(need, (size_t)4096);
+        CU(cudaMalloc(&p, want));
+        bytes = want;
+        return MQVS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+size_t elem_size(int dtype) { return dtype == MQVS_F32 ? 4 : 2; }
+
+}  // namespace
+
+struct mqvs_store {
+    std::mutex mu;
+    int dev = 0;
+    int dim = 0;
+    int dtype = MQVS_F32;
+    int sm_count = 148;
+    int path = 0;
+    void* rows = nullptr;
+    uint64_t n = 0, cap = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_pending = false;
+    DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
+    unsigned long long* bad_dev = nullptr;
+    unsigned long long* bad_host = nullptr;  // pinned
+    mqvs_stats stats{};
+
+    size_t row_bytes() const { return (size_t)MQVS_DIM_PAD * elem_size(dtype); }
+};
+
+namespace {
+
+int grow(mqvs_store* s, uint64_t need_rows) {
+    if (need_rows <= s->cap) return MQVS_OK;
+    if (need_rows > 0xfffffff0ull) return fail(MQVS_E_INVALID, "a shard holds at most 2^32-16 rows");
+    uint64_t want = std::max<uint64_t>(need_rows, std::max<uint64_t>(1024, s->cap + s->cap / 2));
+    void* fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, want * s->row_bytes());
+    if (e != cudaSuccess && want > need_rows) {  // retry with the exact size before giving up
+        cudaGetLastError();
+        want = need_rows;
+        e = cudaMalloc(&fresh, want * s->row_bytes());
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MQVS_E_OOM, "cudaMalloc of %llu rows (%.2f GB) failed: %s", (unsigned long long)want,
+                    want * s->row_bytes() / 1e9, cudaGetErrorString(e));
+    }
+    if (s->n) CU(cudaMemcpyAsync(fresh, s->rows, s->n * s->row_bytes(), cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (s->rows) cudaFree(s->rows);
+    s->rows = fresh;
+    s->cap = want;
+    return MQVS_OK;
+}
+
+// finish the event bookkeeping of the previous search (blocking searches do it immediately)
+void settle_events(mqvs_store* s) {
+    if (!s->ev_pending) return;
+    if (cudaEventSynchronize(s->ev[3]) == cudaSuccess) {
+        float total = 0.f, scan = 0.f;
+        cudaEventElapsedTime(&total, s->ev[0], s->ev[3]);
+        cudaEventElapsedTime(&scan, s->ev[1], s->ev[2]);
+        s->stats.last_search_ms = total;
+        s->stats.last_scan_ms = scan;
+        s->stats.scan_ms += scan;
+    } else {
+        cudaGetLastError();
+    }
+    s->ev_pending = false;
+}
+
+// Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
+int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
+                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st) {
+    using namespace mqvs;
+    settle_events(s);
+    const int gmax = scan_max_grid(s->sm_count);
+    int rc;
+    if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
+    if ((rc = s->cand.ensure((size_t)B * gmax * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
+    launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
+    CU(cudaMemsetAsync(s->cand.p, 0, (size_t)B * gmax * k * sizeof(uint64_t), st));
+    s->stats.kernel_launches += 1;
+
+    CU(cudaEventRecord(s->ev[1], st));
+    uint32_t passes = 0;
+    for (int b0 = 0; b0 < B;) {
+        int nq = 0, grid = 0;
+        scan_plan(s->dtype, B - b0, k, s->sm_count, &nq, &grid);
+        launch_scan_simt(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)b0 * MQVS_DIM_PAD, nq,
+                         mask_dev, k, (uint64_t*)s->cand.p + (size_t)b0 * gmax * k, gmax, grid, st);
+        b0 += nq;
+        ++passes;
+    }
+    CU(cudaEventRecord(s->ev[2], st));
+    launch_merge_keys((const uint64_t*)s->cand.p, B, gmax * k, k, id_base, out_scores_dev, out_ids_dev, st);
+    CU(cudaEventRecord(s->ev[3], st));
+    CU(cudaGetLastError());
+
+    s->ev_pending = true;
+    s->stats.kernel_launches += passes + 1;
+    s->stats.scan_launches += passes;
+    s->stats.scan_bytes += (uint64_t)passes * s->n * s->row_bytes();
+    s->stats.last_scan_passes = passes;
+    s->stats.last_path = 0;
+    s->stats.searches += 1;
+    s->stats.queries += (uint64_t)B;
+    return MQVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+MQVS_API int mqvs_version(void) { return MQVS_VERSION; }
+
+MQVS_API const char* mqvs_last_error(void) { return g_err.c_str(); }
+
+MQVS_API int mqvs_device_count(int* out) {
+    if (!out) return fail(MQVS_E_INVALID, "out is NULL");
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    *out = n;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out) {
+    if (!out) return fail(MQVS_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_dev != 1)
+        return fail(MQVS_E_INVALID, "one device per handle: shard rows across ranks (one process per GPU) and merge "
+                                    "with mqvs_merge_candidates; got n_dev=%d", n_dev);
+    if (dim < 1 || dim > MQVS_DIM_PAD) return fail(MQVS_E_INVALID, "dim must be in [1, %d], got %d", MQVS_DIM_PAD, dim);
+    if (store_dtype != MQVS_F32 && store_dtype != MQVS_BF16) return fail(MQVS_E_INVALID, "unknown store_dtype %d", store_dtype);
+    int dev = dev_ids ? dev_ids[0] : 0;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (dev < 0 || dev >= count) return fail(MQVS_E_INVALID, "device %d not present (%d visible)", dev, count);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(MQVS_E_CUDA, "libmqvs is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    mqvs_store* s = new (std::nothrow) mqvs_store();
+    if (!s) return fail(MQVS_E_OOM, "host allocation failed");
+    s->dev = dev;
+    s->dim = dim;
+    s->dtype = store_dtype;
+    s->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int rc) {
+        mqvs_destroy(s);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "stream creation failed"));
+    for (auto& e : s->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
+    if (cudaMalloc(&s->bad_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
+    if (cudaMallocHost(&s->bad_host, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
+    if (capacity_rows) {
+        int rc = grow(s, capacity_rows);
+        if (rc != MQVS_OK) return bail(rc);
+    }
+    *out = s;
+    return MQVS_OK;
+}
+
+MQVS_API void mqvs_destroy(mqvs_t* s) {
+    if (!s) return;
+    cudaSetDevice(s->dev);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf}) b->release();
+    if (s->rows) cudaFree(s->rows);
+    if (s->bad_dev) cudaFree(s->bad_dev);
+    if (s->bad_host) cudaFreeHost(s->bad_host);
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->st) cudaStreamDestroy(s->st);
+    cudaGetLastError();
+    delete s;
+}
+
+MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out) {
+    if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    *out = s->n;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_reserve(mqvs_t* s, uint64_t capacity_rows) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    return grow(s, capacity_rows);
+}
+
+static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uint64_t seed, uint64_t first_index,
+                      uint64_t n, uint64_t* first_row_out) {
+    using namespace mqvs;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    if (first_row_out) *first_row_out = s->n;
+    if (n == 0) return MQVS_OK;
+    int rc = grow(s, s->n + n);
+    if (rc != MQVS_OK) return rc;
+    char* dst = (char*)s->rows + s->n * s->row_bytes();
+    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), s->st));
+    uint64_t launches = 0;
+    if (synth) {
+        launch_synth_normalize(seed, first_index, n, s->dim, s->dtype, dst, s->bad_dev, s->st);
+        launches = 1;
+    } else if (x_is_device) {
+        launch_normalize((const float*)x, n, s->dim, s->dtype, dst, s->bad_dev, s->st);
+        launches = 1;
+    } else {
+        const uint64_t chunk = 65536;
+        if ((rc = s->stage.ensure((size_t)std::min(n, chunk) * s->dim * sizeof(float))) != MQVS_OK) return rc;
+        for (uint64_t r = 0; r < n; r += chunk) {
+            uint64_t m = std::min(chunk, n - r);
+            CU(cudaMemcpyAsync(s->stage.p, (const float*)x + r * s->dim, (size_t)m * s->dim * sizeof(float),
+                               cudaMemcpyHostToDevice, s->st));
+            launch_normalize((const float*)s->stage.p, m, s->dim, s->dtype, dst + r * s->row_bytes(), s->bad_dev, s->st);
+            CU(cudaStreamSynchronize(s->st));  // staging buffer is reused
+            ++launches;
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.kernel_launches += launches;
+    if (*s->bad_host)
+        return fail(MQVS_E_INVALID, "%llu of %llu embeddings have a non-finite norm; nothing was added",
+                    *s->bad_host, (unsigned long long)n);
+    s->n += n;
+    s->stats.rows = s->n;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_add(mqvs_t* s, const void* x, int x_dtype, int x_is_device, uint64_t n, uint64_t* first_row_out) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (n && !x) return fail(MQVS_E_INVALID, "x is NULL");
+    if (x_dtype != MQVS_F32) return fail(MQVS_E_INVALID, "embeddings must be fp32 (x_dtype=%d)", x_dtype);
+    return add_common(s, x, x_is_device, false, 0, 0, n, first_row_out);
+}
+
+MQVS_API int mqvs_add_synthetic(mqvs_t* s, uint64_t seed, uint64_t first_index, uint64_t n, uint64_t* first_row_out) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    return add_common(s, nullptr, 1, true, seed, first_index, n, first_row_out);
+}
+
+static int check_search_args(mqvs_t* s, const float* q, int B, int k, const void* out_scores, const void* out_ids) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (B < 0) return fail(MQVS_E_INVALID, "B must be >= 0, got %d", B);
+    if (k < 1 || k > MQVS_MAX_K) return fail(MQVS_E_INVALID, "k must be in [1, %d], got %d", MQVS_MAX_K, k);
+    if (B && (!q || !out_scores || !out_ids)) return fail(MQVS_E_INVALID, "NULL query or output buffer");
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
+                float* out_scores, int64_t* out_ids, int out_is_device) {
+    int rc = check_search_args(s, q, B, k, out_scores, out_ids);
+    if (rc != MQVS_OK) return rc;
+    if (B == 0) return MQVS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    const float* q_dev = q;
+    if (!q_is_device) {
+        if ((rc = s->qraw.ensure((size_t)B * s->dim * sizeof(float))) != MQVS_OK) return rc;
+        CU(cudaMemcpyAsync(s->qraw.p, q, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->st));
+        q_dev = (const float*)s->qraw.p;
+    }
+    const uint32_t* mask_dev = mask;
+    if (mask && !mask_is_device) {
+        size_t bytes = (size_t)((s->n + 31) / 32) * sizeof(uint32_t);
+        if ((rc = s->maskbuf.ensure(bytes)) != MQVS_OK) return rc;
+        CU(cudaMemcpyAsync(s->maskbuf.p, mask, bytes, cudaMemcpyHostToDevice, s->st));
+        mask_dev = (const uint32_t*)s->maskbuf.p;
+    }
+    float* os = out_scores;
+    int64_t* oi = out_ids;
+    if (!out_is_device) {
+        if ((rc = s->out_s.ensure((size_t)B * k * sizeof(float))) != MQVS_OK) return rc;
+        if ((rc = s->out_i.ensure((size_t)B * k * sizeof(int64_t))) != MQVS_OK) return rc;
+        os = (float*)s->out_s.p;
+        oi = (int64_t*)s->out_i.p;
+    }
+    if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st)) != MQVS_OK) return rc;
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
+    }
+    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    settle_events(s);
+    if (*s->bad_host) return fail(MQVS_E_INVALID, "%llu of %d queries have a non-finite norm", *s->bad_host, B);
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
+                      float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    int rc = check_search_args(s, q_dev, B, k, out_scores_dev, out_ids_dev);
+    if (rc != MQVS_OK) return rc;
+    if (B == 0) return MQVS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    return enqueue_search(s, q_dev, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, (cudaStream_t)cuda_stream);
+}
+
+MQVS_API int mqvs_merge_candidates(int device, const float* scores_dev, const int64_t* ids_dev, int W, int B, int k,
+                          float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    if (W < 1 || B < 0 || k < 1 || k > MQVS_MAX_K || (long long)W * k > 16384)
+        return fail(MQVS_E_INVALID, "bad merge shape W=%d B=%d k=%d (need W*k <= 16384)", W, B, k);
+    if (B == 0) return MQVS_OK;
+    if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev) return fail(MQVS_E_INVALID, "NULL buffer");
+    CU(cudaSetDevice(device));
+    mqvs::launch_merge_candidates(scores_dev, ids_dev, W, B, k, out_scores_dev, out_ids_dev, (cudaStream_t)cuda_stream);
+    CU(cudaGetLastError());
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float* out_host) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (n == 0) return MQVS_OK;
+    if (!row_ids || !out_host) return fail(MQVS_E_INVALID, "NULL buffer");
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (uint64_t i = 0; i < n; ++i)
+        if (row_ids[i] < 0 || (uint64_t)row_ids[i] >= s->n)
+            return fail(MQVS_E_INVALID, "row id %lld out of range [0, %llu)", (long long)row_ids[i], (unsigned long long)s->n);
+    CU(cudaSetDevice(s->dev));
+    int rc;
+    if ((rc = s->idbuf.ensure(n * sizeof(int64_t))) != MQVS_OK) return rc;
+    if ((rc = s->gatherbuf.ensure(n * s->dim * sizeof(float))) != MQVS_OK) return rc;
+    CU(cudaMemcpyAsync(s->idbuf.p, row_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, s->st));
+    mqvs::launch_gather_rows(s->rows, s->dtype, (const int64_t*)s->idbuf.p, n, s->dim, (float*)s->gatherbuf.p, s->st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_host, s->gatherbuf.p, n * s->dim * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.kernel_launches += 1;
+    return MQVS_OK;
+}
+
+namespace {
+struct FileHeader {
+    char magic[8];
+    uint32_t version, dim, dtype, dim_pad;
+    uint64_t rows;
+};
+}  // namespace
+
+MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
+    if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(MQVS_E_IO, "cannot open %s for writing", tmp.c_str());
+    FileHeader h{};
+    memcpy(h.magic, "MQVSROW1", 8);
+    h.version = MQVS_VERSION;
+    h.dim = (uint32_t)s->dim;
+    h.dtype = (uint32_t)s->dtype;
+    h.dim_pad = MQVS_DIM_PAD;
+    h.rows = s->n;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const uint64_t chunk = 65536;
+    std::vector<char> host((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(s->n, 1)) * s->row_bytes());
+    for (uint64_t r = 0; ok && r < s->n; r += chunk) {
+        uint64_t m = std::min(chunk, s->n - r);
+        cudaError_t e = cudaMemcpy(host.data(), (char*)s->rows + r * s->row_bytes(), m * s->row_bytes(), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            fclose(f);
+            remove(tmp.c_str());
+            return fail(MQVS_E_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+        }
+        ok = fwrite(host.data(), s->row_bytes(), m, f) == m;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return fail(MQVS_E_IO, "writing %s failed", path);
+    }
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
+    if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(MQVS_E_IO, "cannot open %s", path);
+    FileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MQVSROW1", 8) != 0) {
+        fclose(f);
+        return fail(MQVS_E_IO, "%s is not an mqvs row file", path);
+    }
+    if ((int)h.dim != s->dim || (int)h.dtype != s->dtype || h.dim_pad != MQVS_DIM_PAD) {
+        fclose(f);
+        return fail(MQVS_E_INVALID, "%s holds dim=%u dtype=%u, store is dim=%d dtype=%d", path, h.dim, h.dtype, s->dim, s->dtype);
+    }
+    s->n = 0;
+    int rc = grow(s, h.rows);
+    if (rc != MQVS_OK) {
+        fclose(f);
+        return rc;
+    }
+    const uint64_t chunk = 65536;
+    std::vector<char> host((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(h.rows, 1)) * s->row_bytes());
+    for (uint64_t r = 0; r < h.rows; r += chunk) {
+        uint64_t m = std::min(chunk, h.rows - r);
+        if (fread(host.data(), s->row_bytes(), m, f) != m) {
+            fclose(f);
+            return fail(MQVS_E_IO, "%s is truncated", path);
+        }
+        cudaError_t e = cudaMemcpy((char*)s->rows + r * s->row_bytes(), host.data(), m * s->row_bytes(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            fclose(f);
+            return fail(MQVS_E_CUDA, "host-to-device copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    fclose(f);
+    s->n = h.rows;
+    s->stats.rows = s->n;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
+    if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    cudaSetDevice(s->dev);
+    settle_events(s);
+    s->stats.rows = s->n;
+    *out = s->stats;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_set_path(mqvs_t* s, int path) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (path < 0 || path > 2) return fail(MQVS_E_INVALID, "path must be 0, 1 or 2");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->path = path;
+    return MQVS_OK;
+}
+
+}  // extern "C"

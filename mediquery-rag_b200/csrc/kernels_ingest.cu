@@ -1,0 +1,139 @@
+// kernels_ingest.cu -- K1: fused L2-normalise + fp32/bf16 pack (one warp per row), and the row gather.
+//
+// Replaces the work hidden behind collection.upsert(embeddings=...) in Chroma.from_documents
+// (/root/reference/src/ingest_medical.py:106-110): rows arrive as fp32 [n, dim], leave as unit rows of
+// 768 elements (zero-padded) in the store's dtype.  HBM-bound: reads 4*dim, writes 768*sizeof(elem) per row.
+#include "common.cuh"
+#include "launch.h"
+
+namespace mqvs {
+
+namespace {
+
+constexpr int kIngestWarps = 8;
+
+struct MemSource {
+    const float* x;
+    int dim;
+    bool vec4;  // dim % 4 == 0 and base 16-byte aligned
+    __device__ __forceinline__ void load(uint64_t row, int lane, float4 (&v)[kChunks]) const {
+        const float* p = x + row * (uint64_t)dim;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            int j = c * 128 + lane * 4;
+            if (vec4 && j + 3 < dim) {
+                v[c] = ld_stream_f4(p + j);
+            } else {
+                v[c].x = j + 0 < dim ? p[j + 0] : 0.0f;
+                v[c].y = j + 1 < dim ? p[j + 1] : 0.0f;
+                v[c].z = j + 2 < dim ? p[j + 2] : 0.0f;
+                v[c].w = j + 3 < dim ? p[j + 3] : 0.0f;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float synth_value(uint64_t seed, uint64_t idx) {
+    return __fsub_rn(__fmul_rn((float)(splitmix64(seed, idx) >> 40), 1.0f / 8388608.0f), 1.0f);
+}
+
+struct SynthSource {
+    uint64_t seed, first_index;
+    int dim;
+    __device__ __forceinline__ void load(uint64_t row, int lane, float4 (&v)[kChunks]) const {
+        uint64_t base = (first_index + row) * (uint64_t)dim;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            int j = c * 128 + lane * 4;
+            v[c].x = j + 0 < dim ? synth_value(seed, base + j + 0) : 0.0f;
+            v[c].y = j + 1 < dim ? synth_value(seed, base + j + 1) : 0.0f;
+            v[c].z = j + 2 < dim ? synth_value(seed, base + j + 2) : 0.0f;
+            v[c].w = j + 3 < dim ? synth_value(seed, base + j + 3) : 0.0f;
+        }
+    }
+};
+
+template <typename Source, typename OutT>
+__global__ void __launch_bounds__(kIngestWarps * 32)
+normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned long long* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * kIngestWarps;
+    for (uint64_t row = (uint64_t)blockIdx.x * kIngestWarps + (threadIdx.x >> 5); row < n; row += warps_total) {
+        float4 v[kChunks];
+        src.load(row, lane, v);
+        float ss = warp_butterfly_sum(lane_dot(v, v));
+        bool ok = isfinite(ss);
+        float inv = ok ? __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ss), kEps)) : 0.0f;
+        if (!ok && lane == 0) atomicAdd(bad, 1ull);
+        OutT* o = out + row * (uint64_t)kDim;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            float4 y;
+            y.x = ok ? __fmul_rn(v[c].x, inv) : 0.0f;
+            y.y = ok ? __fmul_rn(v[c].y, inv) : 0.0f;
+            y.z = ok ? __fmul_rn(v[c].z, inv) : 0.0f;
+            y.w = ok ? __fmul_rn(v[c].w, inv) : 0.0f;
+            if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + c * 128 + lane * 4) = y;
+            } else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(y.x, y.y);
+                __nv_bfloat162 b = __floats2bfloat162_rn(y.z, y.w);
+                uint2 w;
+                w.x = *reinterpret_cast<uint32_t*>(&a);
+                w.y = *reinterpret_cast<uint32_t*>(&b);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o) + c * 128 + lane * 4) = w;
+            }
+        }
+    }
+}
+
+template <typename Source>
+void launch_k1(Source src, uint64_t n, int out_dtype, void* out, unsigned long long* bad, cudaStream_t st) {
+    if (n == 0) return;
+    uint64_t blocks = (n + kIngestWarps - 1) / kIngestWarps;
+    int grid = (int)(blocks < 148ull * 16 ? blocks : 148ull * 16);
+    if (out_dtype == MQVS_F32)
+        normalize_pack_kernel<Source, float><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (float*)out, bad);
+    else
+        normalize_pack_kernel<Source, __nv_bfloat16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (__nv_bfloat16*)out, bad);
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ rows, const int64_t* __restrict__ ids, uint64_t n, int dim,
+                                   float* __restrict__ out) {
+    uint64_t i = blockIdx.x;
+    if (i >= n) return;
+    const T* r = rows + (uint64_t)ids[i] * kDim;
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) out[i * (uint64_t)dim + j] = (float)r[j];
+}
+
+}  // namespace
+
+void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
+                      cudaStream_t st) {
+    MemSource src{x, dim, (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)};
+    launch_k1(src, n, out_dtype, out, bad, st);
+}
+
+void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int dim, int out_dtype, void* out,
+                            unsigned long long* bad, cudaStream_t st) {
+    SynthSource src{seed, first_index, dim};
+    launch_k1(src, n, out_dtype, out, bad, st);
+}
+
+void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,
+                        cudaStream_t st) {
+    if (n == 0) return;
+    if (dtype == MQVS_F32)
+        gather_rows_kernel<float><<<(unsigned)n, 128, 0, st>>>((const float*)rows, ids, n, dim, out);
+    else
+        gather_rows_kernel<__nv_bfloat16><<<(unsigned)n, 128, 0, st>>>((const __nv_bfloat16*)rows, ids, n, dim, out);
+}
+
+}  // namespace mqvs

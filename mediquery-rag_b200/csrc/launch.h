@@ -1,0 +1,37 @@
+// launch.h -- host-callable launchers of the libmqvs kernels (defined in the kernels_*.cu files).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mqvs {
+
+// K1: L2-normalise + pack.  x [n, dim] fp32 (device) -> out [n, 768] fp32 or bf16, zero-padded; counts
+// rows whose squared norm is not finite into *bad (and stores them as zeros).
+void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
+                      cudaStream_t st);
+// Same K1 fed by the counter-based generator instead of memory.
+void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int dim, int out_dtype, void* out,
+                            unsigned long long* bad, cudaStream_t st);
+
+// K2 (SIMT) + K3: exact fp32 scan of `n_rows` stored rows against nq (<= scan_max_queries_per_pass) normalised
+// queries, fused per-warp top-k with optional allow-mask; writes per-CTA sorted candidate keys
+// cand[q][cta][k].  Returns the grid size used (number of CTAs) so the merge knows the layout.
+// scan_plan: how many of the `nq_remaining` queries the next pass takes and the grid it runs with;
+// scan_max_grid: upper bound of that grid over all passes (the candidate buffer's per-query stride).
+void scan_plan(int dtype, int nq_remaining, int k, int sm_count, int* nq_pass, int* grid);
+int scan_max_grid(int sm_count);
+void launch_scan_simt(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
+                      int k, uint64_t* cand, int cand_stride, int grid, cudaStream_t st);
+
+// Merge: keys_in [B][m] (any order, 0 = empty) -> best k per query as (score, id + id_base); (-inf, -1) fill.
+void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_base, float* out_scores,
+                       int64_t* out_ids, cudaStream_t st);
+// Cross-shard merge of already-decoded candidates [W, B, k] -> [B, k].
+void launch_merge_candidates(const float* scores, const int64_t* ids, int W, int B, int k, float* out_scores,
+                             int64_t* out_ids, cudaStream_t st);
+// Gather stored rows as fp32 [n, dim].
+void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,
+                        cudaStream_t st);
+
+}  // namespace mqvs
