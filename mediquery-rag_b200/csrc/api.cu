@@ -73,8 +73,13 @@ struct mqvs_store {
     void* rows = nullptr;
     uint64_t n = 0, cap = 0;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ev_pending = false;
+    // ring of event quads so that back-to-back async searches never wait on each other's timing
+    static constexpr int kEvRing = 32;
+    struct EvSet {
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        bool pending = false;
+    } evr[kEvRing];
+    int ev_cursor = 0;
     DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
     unsigned long long* bad_dev = nullptr;
     unsigned long long* bad_host = nullptr;  // pinned
@@ -109,39 +114,46 @@ int grow(mqvs_store* s, uint64_t need_rows) {
     return MQVS_OK;
 }
 
-// finish the event bookkeeping of the previous search (blocking searches do it immediately)
-void settle_events(mqvs_store* s) {
-    if (!s->ev_pending) return;
-    if (cudaEventSynchronize(s->ev[3]) == cudaSuccess) {
+// fold one finished search's CUDA-event timings into the stats (waits for that search if still running)
+void settle_slot(mqvs_store* s, int slot) {
+    auto& ev = s->evr[slot];
+    if (!ev.pending) return;
+    if (cudaEventSynchronize(ev.e[3]) == cudaSuccess) {
         float total = 0.f, scan = 0.f;
-        cudaEventElapsedTime(&total, s->ev[0], s->ev[3]);
-        cudaEventElapsedTime(&scan, s->ev[1], s->ev[2]);
+        cudaEventElapsedTime(&total, ev.e[0], ev.e[3]);
+        cudaEventElapsedTime(&scan, ev.e[1], ev.e[2]);
         s->stats.last_search_ms = total;
         s->stats.last_scan_ms = scan;
         s->stats.scan_ms += scan;
     } else {
         cudaGetLastError();
     }
-    s->ev_pending = false;
+    ev.pending = false;
+}
+void settle_events(mqvs_store* s) {
+    for (int i = 0; i < mqvs_store::kEvRing; ++i) settle_slot(s, (s->ev_cursor + i) % mqvs_store::kEvRing);
 }
 
 // Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                    float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st) {
     using namespace mqvs;
-    settle_events(s);
+    const int slot = s->ev_cursor;
+    s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
+    settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
+    cudaEvent_t* ev = s->evr[slot].e;
     const int gmax = scan_max_grid(s->sm_count);
     int rc;
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
     if ((rc = s->cand.ensure((size_t)B * gmax * k * sizeof(uint64_t))) != MQVS_OK) return rc;
 
-    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaEventRecord(ev[0], st));
     CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
     launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
     CU(cudaMemsetAsync(s->cand.p, 0, (size_t)B * gmax * k * sizeof(uint64_t), st));
     s->stats.kernel_launches += 1;
 
-    CU(cudaEventRecord(s->ev[1], st));
+    CU(cudaEventRecord(ev[1], st));
     uint32_t passes = 0;
     for (int b0 = 0; b0 < B;) {
         int nq = 0, grid = 0;
@@ -151,12 +163,12 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b0 += nq;
         ++passes;
     }
-    CU(cudaEventRecord(s->ev[2], st));
+    CU(cudaEventRecord(ev[2], st));
     launch_merge_keys((const uint64_t*)s->cand.p, B, gmax * k, k, id_base, out_scores_dev, out_ids_dev, st);
-    CU(cudaEventRecord(s->ev[3], st));
+    CU(cudaEventRecord(ev[3], st));
     CU(cudaGetLastError());
 
-    s->ev_pending = true;
+    s->evr[slot].pending = true;
     s->stats.kernel_launches += passes + 1;
     s->stats.scan_launches += passes;
     s->stats.scan_bytes += (uint64_t)passes * s->n * s->row_bytes();
@@ -211,8 +223,9 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
         return rc;
     };
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "stream creation failed"));
-    for (auto& e : s->ev)
-        if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
+    for (auto& set : s->evr)
+        for (auto& e : set.e)
+            if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
     if (cudaMalloc(&s->bad_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (cudaMallocHost(&s->bad_host, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
     if (capacity_rows) {
@@ -231,8 +244,9 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (s->rows) cudaFree(s->rows);
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
-    for (auto& e : s->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto& set : s->evr)
+        for (auto& e : set.e)
+            if (e) cudaEventDestroy(e);
     if (s->st) cudaStreamDestroy(s->st);
     cudaGetLastError();
     delete s;

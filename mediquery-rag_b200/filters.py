@@ -1,0 +1,196 @@
+"""Chroma `where` filters compiled to the packed allow-bitmask the scan kernels consume.
+
+The reference passes no filter today (/root/reference/src/agents/nodes.py:93 calls similarity_search(q, k=5)),
+but the Chroma surface it programs against takes `filter=` and BASELINE.json config 5 exercises it.  Grammar:
+{"field": v} (== $eq) | {"field": {"$eq|$ne|$gt|$gte|$lt|$lte": v}} | {"field": {"$in|$nin": [..]}} |
+{"$and": [..]} | {"$or": [..]}.  Evaluation is columnar (one numpy pass per leaf); a field missing from a row
+matches only $ne / $nin.  The result is AND-ed with the live-row bitmap and packed little-endian into uint32
+words: bit (r & 31) of word (r >> 5) is row r.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+_COMPARE = ("$gt", "$gte", "$lt", "$lte")
+_LEAF_OPS = ("$eq", "$ne", "$in", "$nin") + _COMPARE
+
+
+class FilterError(ValueError):
+    pass
+
+
+class MetadataColumns:
+    """Per-field columns over row-aligned metadata dicts, built lazily and extended incrementally."""
+
+    def __init__(self) -> None:
+        self._rows: List[Mapping[str, Any]] = []
+        self._explicit: Dict[str, np.ndarray] = {}   # bulk columns supplied as arrays (no per-row dicts)
+        self._cache: Dict[str, tuple] = {}           # field -> (n_rows_built, values object array, present bool array)
+        self._dict_fields: set = set()               # fields that occur in per-row dicts
+
+    def __len__(self) -> int:
+        return len(self._rows)
+
+    def extend(self, metadatas: Sequence[Optional[Mapping[str, Any]]]) -> None:
+        for md in metadatas:
+            md = md if md else _EMPTY
+            self._dict_fields.update(md.keys())
+            self._rows.append(md)
+
+    def extend_columns(self, n: int, columns: Mapping[str, np.ndarray]) -> None:
+        """Append n rows whose metadata is given column-wise (bulk ingest of millions of rows)."""
+        start = len(self._rows)
+        self._rows.extend([_EMPTY] * n)
+        for name, col in columns.items():
+            col = np.asarray(col)
+            if col.shape[0] != n:
+                raise ValueError(f"column {name!r} has {col.shape[0]} values for {n} rows")
+            old = self._explicit.get(name)
+            if old is None:
+                old, present = np.zeros(start, dtype=col.dtype), np.zeros(start, dtype=bool)
+            else:
+                old, present = old
+                if old.shape[0] < start:  # rows added since without this column
+                    pad = start - old.shape[0]
+                    old = np.concatenate([old, np.zeros(pad, old.dtype)])
+                    present = np.concatenate([present, np.zeros(pad, bool)])
+            self._explicit[name] = (np.concatenate([old, col]), np.concatenate([present, np.ones(n, bool)]))
+        for name, (vals, present) in list(self._explicit.items()):
+            if vals.shape[0] < start + n:
+                pad = start + n - vals.shape[0]
+                self._explicit[name] = (np.concatenate([vals, np.zeros(pad, vals.dtype)]),
+                                        np.concatenate([present, np.zeros(pad, bool)]))
+        self._cache.clear()
+
+    def row(self, r: int) -> Dict[str, Any]:
+        md = dict(self._rows[r])
+        for name, (vals, present) in self._explicit.items():
+            if r < present.shape[0] and present[r]:
+                md[name] = vals[r].item()
+        return md
+
+    def set_row(self, r: int, md: Optional[Mapping[str, Any]]) -> None:
+        self._rows[r] = md if md else _EMPTY
+        self._dict_fields.update(self._rows[r].keys())
+        self._cache.clear()
+
+    def column(self, field: str):
+        """-> (values, present): values is a typed array when the field is homogeneous, else object."""
+        n = len(self._rows)
+        if field in self._explicit:
+            vals, present = self._explicit[field]
+            if field not in self._dict_fields and vals.shape[0] == n:
+                return vals, present
+        hit = self._cache.get(field)
+        if hit is not None and hit[0] == n:
+            return hit[1], hit[2]
+        vals = np.empty(n, dtype=object)
+        present = np.zeros(n, dtype=bool)
+        if field in self._explicit:
+            ev, ep = self._explicit[field]
+            vals[: ev.shape[0]] = ev
+            present[: ep.shape[0]] = ep
+        for r, md in enumerate(self._rows):
+            if field in md:
+                vals[r] = md[field]
+                present[r] = True
+        self._cache[field] = (n, vals, present)
+        return vals, present
+
+
+_EMPTY: Mapping[str, Any] = {}
+
+
+def _leaf(cols: MetadataColumns, field: str, op: str, want: Any) -> np.ndarray:
+    vals, present = cols.column(field)
+    n = len(cols)
+    if op in ("$in", "$nin"):
+        if not isinstance(want, (list, tuple, set, frozenset, np.ndarray)):
+            raise FilterError(f"{op} expects a list, got {type(want).__name__}")
+        wanted = list(want)
+        if vals.dtype != object:
+            hit = np.isin(vals, np.asarray(wanted)) if wanted else np.zeros(n, bool)
+        else:
+            ws = set(wanted)
+            hit = np.fromiter((p and v in ws for v, p in zip(vals, present)), dtype=bool, count=n)
+        hit &= present
+        return hit if op == "$in" else ~hit
+    if isinstance(want, (list, dict, tuple, set)):
+        raise FilterError(f"{op} expects a scalar, got {type(want).__name__}")
+    if op in ("$eq", "$ne"):
+        if vals.dtype != object:
+            hit = (vals == want) if not isinstance(want, str) or vals.dtype.kind in "US" else np.zeros(n, bool)
+        else:
+            hit = np.fromiter((bool(p and v == want) for v, p in zip(vals, present)), dtype=bool, count=n)
+        hit = np.asarray(hit, bool) & present
+        return hit if op == "$eq" else ~hit
+    # ordered comparisons: only between like kinds (str with str, number with number); missing never matches
+    want_is_str = isinstance(want, str)
+
+    def ok(v: Any) -> bool:
+        return isinstance(v, str) == want_is_str and v is not None
+
+    if vals.dtype != object and (vals.dtype.kind in "US") == want_is_str:
+        v = vals
+        hit = {"$gt": v > want, "$gte": v >= want, "$lt": v < want, "$lte": v <= want}[op]
+        return np.asarray(hit, bool) & present
+    if vals.dtype != object:
+        return np.zeros(n, bool)
+    import operator as _op
+
+    fn = {"$gt": _op.gt, "$gte": _op.ge, "$lt": _op.lt, "$lte": _op.le}[op]
+    return np.fromiter((bool(p and ok(v) and fn(v, want)) for v, p in zip(vals, present)), dtype=bool, count=n)
+
+
+def evaluate(where: Optional[Mapping[str, Any]], cols: MetadataColumns) -> np.ndarray:
+    """Chroma `where` dict -> bool[n_rows]."""
+    n = len(cols)
+    if not where:
+        return np.ones(n, dtype=bool)
+    if not isinstance(where, Mapping) or len(where) != 1:
+        raise FilterError("where expects a dict with exactly one key per level (use $and / $or to combine)")
+    (key, val), = where.items()
+    if key in ("$and", "$or"):
+        if not isinstance(val, (list, tuple)) or not val:
+            raise FilterError(f"{key} expects a non-empty list of filters")
+        parts = [evaluate(w, cols) for w in val]
+        out = parts[0].copy()
+        for p in parts[1:]:
+            out = (out & p) if key == "$and" else (out | p)
+        return out
+    if key.startswith("$"):
+        raise FilterError(f"unknown logical operator {key}")
+    if isinstance(val, Mapping):
+        if len(val) != 1:
+            raise FilterError("an operator expression takes exactly one operator")
+        (op, want), = val.items()
+        if op not in _LEAF_OPS:
+            raise FilterError(f"unknown operator {op}")
+    else:
+        op, want = "$eq", val
+    return _leaf(cols, key, op, want)
+
+
+def pack_mask(allowed: np.ndarray) -> np.ndarray:
+    """bool[n] -> uint32[ceil(n/32)], bit r&31 of word r>>5 == allowed[r] (padding bits are 0)."""
+    allowed = np.asarray(allowed, dtype=bool)
+    n = allowed.shape[0]
+    words = (n + 31) // 32
+    if words == 0:
+        return np.zeros(0, np.uint32)
+    padded = np.zeros(words * 32, dtype=bool)
+    padded[:n] = allowed
+    return np.packbits(padded.reshape(words, 32), axis=1, bitorder="little").view(np.uint32).reshape(words).copy()
+
+
+def compile_mask(where: Optional[Mapping[str, Any]], cols: MetadataColumns, live: Optional[np.ndarray]):
+    """-> (packed mask or None when every row is allowed, number of allowed rows)."""
+    n = len(cols)
+    allowed = evaluate(where, cols) if where else None
+    if live is not None and not live.all():
+        allowed = live.copy() if allowed is None else (allowed & live)
+    if allowed is None:
+        return None, n
+    return pack_mask(allowed), int(allowed.sum())

@@ -1,0 +1,441 @@
+"""MediQueryVectorStore -- drop-in for the `langchain_chroma.Chroma` object MediQuery-RAG uses.
+
+Call sites it replaces (file:line under /root/reference):
+  src/ingest_medical.py:106-110   Chroma.from_documents(documents=docs, embedding=embeddings, persist_directory=DB_PATH)
+  src/medical_engine.py:52        Chroma(persist_directory=DB_PATH, embedding_function=embeddings)
+  src/agents/nodes.py:93          vectorstore.similarity_search(search_query, k=5)      -> [Document], best first
+  src/medical_engine.py:70        vectorstore.similarity_search(query, k=k)             (k=3)
+Swap = change `from langchain_chroma import Chroma` to
+`from mediquery_rag_b200 import MediQueryVectorStore as Chroma`; nothing else in the reference changes.
+
+Division of labour: documents, metadata and string ids stay on the host (Chroma keeps them in sqlite); the
+vectors live in HBM behind libmqvs.so and every search is an EXACT scan there (no HNSW, no CPU fallback).
+Scores come back as cosine similarity; `*_with_score` converts to the distance Chroma would report for the
+collection's `hnsw:space` (default "l2", as in the reference, which passes no collection_metadata):
+l2 -> 2 - 2s (= ||a-b||^2 on unit vectors), cosine / ip -> 1 - s.  Rows are stored L2-normalised (Ollama's
+embedder already returns unit vectors), so for non-unit inputs l2/ip distances are those of the normalised rows.
+"""
+from __future__ import annotations
+
+import json
+import os
+import uuid
+from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .documents import HAVE_LANGCHAIN, Document, Embeddings
+from .filters import MetadataColumns, compile_mask
+
+if HAVE_LANGCHAIN:  # pragma: no cover
+    from langchain_core.vectorstores import VectorStore as _Base  # type: ignore
+else:
+    _Base = object
+
+DEFAULT_K = 4  # langchain_chroma's default
+_SPACES = ("l2", "cosine", "ip")
+_ROWS_FILE, _DOCS_FILE, _MANIFEST = "rows.mqvs", "docs.jsonl", "manifest.json"
+
+
+def _distance(space: str, sim: float) -> float:
+    return 2.0 - 2.0 * sim if space == "l2" else 1.0 - sim
+
+
+def _relevance(space: str, sim: float) -> float:
+    # langchain: cosine -> 1 - d ; l2 -> 1 - d / sqrt(2) ; ip -> d > 0 ? 1 - d : -d
+    d = _distance(space, sim)
+    if space == "cosine":
+        return 1.0 - d
+    if space == "l2":
+        return 1.0 - d / (2.0 ** 0.5)
+    return 1.0 - d if d > 0 else -d
+
+
+class MediQueryRetriever:
+    """What `as_retriever()` returns when langchain_core is absent: `.invoke(query) -> list[Document]`."""
+
+    def __init__(self, store: "MediQueryVectorStore", search_type: str = "similarity",
+                 search_kwargs: Optional[Dict[str, Any]] = None):
+        if search_type not in ("similarity", "similarity_score_threshold", "mmr"):
+            raise ValueError(f"search_type of {search_type} not allowed")
+        self.vectorstore, self.search_type, self.search_kwargs = store, search_type, dict(search_kwargs or {})
+        if search_type == "similarity_score_threshold" and "score_threshold" not in self.search_kwargs:
+            raise ValueError("`score_threshold` must be given in search_kwargs for similarity_score_threshold")
+
+    def invoke(self, query: str, config: Any = None, **kwargs: Any) -> List[Document]:
+        kw = {**self.search_kwargs, **kwargs}
+        if self.search_type == "similarity":
+            return self.vectorstore.similarity_search(query, **kw)
+        if self.search_type == "mmr":
+            return self.vectorstore.max_marginal_relevance_search(query, **kw)
+        thr = kw.pop("score_threshold")
+        return [d for d, s in self.vectorstore.similarity_search_with_relevance_scores(query, **kw) if s >= thr]
+
+    get_relevant_documents = invoke
+
+
+class MediQueryVectorStore(_Base):  # type: ignore[misc]
+    def __init__(self, collection_name: str = "langchain", embedding_function: Optional[Embeddings] = None,
+                 persist_directory: Optional[str] = None, collection_metadata: Optional[Dict[str, Any]] = None,
+                 client_settings: Any = None, client: Any = None, relevance_score_fn: Optional[Callable] = None,
+                 create_collection_if_not_exists: bool = True, *, store_dtype: str = "fp32", device: int = 0,
+                 dim: Optional[int] = None, capacity_rows: int = 0, auto_persist: bool = True,
+                 index_factory: Optional[Callable[..., Any]] = None, **_: Any):
+        self._collection_name = collection_name
+        self._embedding_function = embedding_function
+        self._persist_directory = persist_directory
+        self._collection_metadata = dict(collection_metadata or {})
+        space = self._collection_metadata.get("hnsw:space", "l2")
+        if space not in _SPACES:
+            raise ValueError(f"hnsw:space must be one of {_SPACES}, got {space!r}")
+        self._space = space
+        self._relevance_fn = relevance_score_fn
+        if store_dtype not in _native.DTYPES:
+            raise ValueError(f"store_dtype must be one of {sorted(_native.DTYPES)}")
+        self._store_dtype = store_dtype
+        self._device = device
+        self._capacity = capacity_rows
+        self._auto_persist = auto_persist
+        self._index_factory = index_factory or _native.Index
+        self._index: Any = None
+        self._dim: Optional[int] = dim
+        self._ids: List[str] = []
+        self._id2row: Dict[str, int] = {}
+        self._texts: List[Optional[str]] = []
+        self._cols = MetadataColumns()
+        self._live = np.zeros(0, dtype=bool)
+        if persist_directory is not None:
+            # the reference tests os.path.exists(DB_PATH) before opening (src/medical_engine.py:34-37)
+            os.makedirs(persist_directory, exist_ok=True)
+            if os.path.exists(os.path.join(persist_directory, _MANIFEST)):
+                self._load()
+        if self._index is None and self._dim is not None:
+            self._ensure_index(self._dim)
+
+    # ------------------------------------------------------------------------------------------- basics
+    @property
+    def embeddings(self) -> Optional[Embeddings]:
+        return self._embedding_function
+
+    def __len__(self) -> int:
+        return int(self._live.sum())
+
+    def _ensure_index(self, dim: int) -> None:
+        if self._index is None:
+            self._dim = int(dim)
+            self._index = self._index_factory(self._dim, self._store_dtype, self._device, self._capacity)
+        elif dim != self._dim:
+            raise ValueError(f"embedding dimension {dim} does not match the collection's {self._dim}")
+
+    def _embed_query(self, query: str) -> np.ndarray:
+        if self._embedding_function is None:
+            raise ValueError("this store was built without an embedding_function; use the *_by_vector methods")
+        return np.asarray(self._embedding_function.embed_query(query), dtype=np.float32)
+
+    # ------------------------------------------------------------------------------------------- ingest
+    def add_texts(self, texts: Iterable[str], metadatas: Optional[List[Optional[dict]]] = None,
+                  ids: Optional[List[str]] = None, **kwargs: Any) -> List[str]:
+        texts = list(texts)
+        if self._embedding_function is None:
+            raise ValueError("add_texts needs an embedding_function; use add_embeddings for pre-computed vectors")
+        if not texts:
+            return []
+        vectors = np.asarray(self._embedding_function.embed_documents(texts), dtype=np.float32)
+        return self._add(texts, vectors, metadatas, ids)
+
+    def add_documents(self, documents: List[Document], **kwargs: Any) -> List[str]:
+        ids = kwargs.pop("ids", None)
+        if ids is None and documents and all(getattr(d, "id", None) for d in documents):
+            ids = [d.id for d in documents]
+        return self.add_texts([d.page_content for d in documents], [d.metadata for d in documents], ids=ids)
+
+    def add_embeddings(self, text_embeddings: Any, metadatas: Optional[List[Optional[dict]]] = None,
+                       ids: Optional[List[str]] = None, *, metadata_columns: Optional[Mapping[str, Any]] = None,
+                       **kwargs: Any) -> List[str]:
+        """Pre-computed vectors.  `text_embeddings` is an iterable of (text, vector) pairs (FAISS style) or a
+        (texts, embeddings) pair where embeddings is an [n, dim] numpy array or CUDA torch tensor (zero-copy
+        via data_ptr) and texts is a list or None.  `metadata_columns` gives metadata column-wise for bulk loads."""
+        if isinstance(text_embeddings, tuple) and len(text_embeddings) == 2 and hasattr(text_embeddings[1], "shape"):
+            texts, vectors = text_embeddings
+            n = vectors.shape[0]
+            texts = list(texts) if texts is not None else [None] * n
+        else:
+            pairs = list(text_embeddings)
+            texts = [t for t, _ in pairs]
+            vectors = np.asarray([v for _, v in pairs], dtype=np.float32)
+        return self._add(texts, vectors, metadatas, ids, metadata_columns)
+
+    def _add(self, texts: List[Optional[str]], vectors: Any, metadatas, ids, metadata_columns=None) -> List[str]:
+        n = len(texts)
+        if n == 0:
+            return []
+        if not hasattr(vectors, "data_ptr"):
+            vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+        if vectors.ndim != 2 or vectors.shape[0] != n:
+            raise ValueError(f"expected {n} embeddings of one width, got shape {tuple(vectors.shape)}")
+        if metadatas is not None and len(metadatas) != n:
+            raise ValueError(f"{len(metadatas)} metadatas for {n} texts")
+        if ids is None:
+            ids = [str(uuid.uuid4()) for _ in range(n)]
+        ids = [str(i) for i in ids]
+        if len(ids) != n:
+            raise ValueError(f"{len(ids)} ids for {n} texts")
+        if len(set(ids)) != n:
+            raise ValueError("duplicate ids within one call")
+        self._ensure_index(vectors.shape[1])
+        first = self._index.add(vectors)  # raises (and appends nothing) on non-finite rows
+        assert first == len(self._ids), "host document table and device rows out of step"
+        # upsert semantics: a repeated id retires its previous row (Chroma's collection.upsert)
+        self._live = np.concatenate([self._live, np.ones(n, dtype=bool)])
+        for j, doc_id in enumerate(ids):
+            old = self._id2row.get(doc_id)
+            if old is not None:
+                self._live[old] = False
+            self._id2row[doc_id] = first + j
+        self._ids.extend(ids)
+        self._texts.extend(texts)
+        if metadata_columns is not None:
+            if metadatas is not None:
+                raise ValueError("give metadatas or metadata_columns, not both")
+            self._cols.extend_columns(n, metadata_columns)
+        else:
+            self._cols.extend(metadatas if metadatas is not None else [None] * n)
+        if self._persist_directory is not None and self._auto_persist:
+            self.persist()
+        return ids
+
+    @classmethod
+    def from_texts(cls, texts: List[str], embedding: Optional[Embeddings] = None,
+                   metadatas: Optional[List[dict]] = None, ids: Optional[List[str]] = None,
+                   collection_name: str = "langchain", persist_directory: Optional[str] = None,
+                   collection_metadata: Optional[Dict[str, Any]] = None, **kwargs: Any) -> "MediQueryVectorStore":
+        store = cls(collection_name=collection_name, embedding_function=embedding,
+                    persist_directory=persist_directory, collection_metadata=collection_metadata, **kwargs)
+        store.add_texts(texts, metadatas=metadatas, ids=ids)
+        return store
+
+    @classmethod
+    def from_documents(cls, documents: List[Document], embedding: Optional[Embeddings] = None,
+                       ids: Optional[List[str]] = None, collection_name: str = "langchain",
+                       persist_directory: Optional[str] = None, collection_metadata: Optional[Dict[str, Any]] = None,
+                       **kwargs: Any) -> "MediQueryVectorStore":
+        if ids is None and documents and all(getattr(d, "id", None) for d in documents):
+            ids = [d.id for d in documents]
+        return cls.from_texts([d.page_content for d in documents], embedding, [d.metadata for d in documents], ids,
+                              collection_name, persist_directory, collection_metadata, **kwargs)
+
+    # ------------------------------------------------------------------------------------------- search
+    def search_batch(self, queries: Any, k: int = DEFAULT_K, filter: Optional[Mapping[str, Any]] = None
+                     ) -> Tuple[np.ndarray, np.ndarray]:
+        """Batch extension used by the benchmark configs: queries [B, dim] -> (cosine scores [B, k'], row ids
+        [B, k']) with k' = min(k, allowed rows); rows best-first, ties -> lower row id."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        if self._index is None or len(self._ids) == 0:
+            return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
+        mask, allowed = compile_mask(filter, self._cols, self._live)
+        k_eff = min(k, allowed)  # Chroma clamps n_results to the collection size
+        if k_eff == 0:
+            return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
+        if k_eff > _native.MAX_K:
+            raise ValueError(f"k is limited to {_native.MAX_K}")
+        return self._index.search(q, k_eff, mask)
+
+    def _docs(self, scores: np.ndarray, rows: np.ndarray) -> List[Tuple[Document, float]]:
+        out = []
+        for s, r in zip(scores.tolist(), rows.tolist()):
+            if r < 0:
+                continue
+            out.append((Document(page_content=self._texts[r] or "", metadata=self._cols.row(r), id=self._ids[r]), s))
+        return out
+
+    def _similar(self, vector: Any, k: int, filter: Optional[Mapping[str, Any]]) -> List[Tuple[Document, float]]:
+        scores, rows = self.search_batch(np.asarray(vector, dtype=np.float32)[None, :], k, filter)
+        return self._docs(scores[0], rows[0])
+
+    def similarity_search(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
+                          **kwargs: Any) -> List[Document]:
+        return [d for d, _ in self._similar(self._embed_query(query), k, filter)]
+
+    def similarity_search_with_score(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
+                                     where_document: Optional[Dict[str, Any]] = None, **kwargs: Any
+                                     ) -> List[Tuple[Document, float]]:
+        """(Document, distance) pairs, LOWER is better, in the collection's hnsw:space."""
+        if where_document:
+            raise NotImplementedError("where_document is not supported")
+        return [(d, _distance(self._space, s)) for d, s in self._similar(self._embed_query(query), k, filter)]
+
+    def similarity_search_by_vector(self, embedding: List[float], k: int = DEFAULT_K,
+                                    filter: Optional[Dict[str, Any]] = None, **kwargs: Any) -> List[Document]:
+        return [d for d, _ in self._similar(embedding, k, filter)]
+
+    def similarity_search_by_vector_with_relevance_scores(self, embedding: List[float], k: int = DEFAULT_K,
+                                                          filter: Optional[Dict[str, Any]] = None, **kwargs: Any
+                                                          ) -> List[Tuple[Document, float]]:
+        # langchain_chroma returns the raw distance here despite the name; kept for compatibility
+        return [(d, _distance(self._space, s)) for d, s in self._similar(embedding, k, filter)]
+
+    def _select_relevance_score_fn(self) -> Callable[[float], float]:
+        if self._relevance_fn is not None:
+            return self._relevance_fn
+        space = self._space
+        if space == "cosine":
+            return lambda d: 1.0 - d
+        if space == "l2":
+            return lambda d: 1.0 - d / (2.0 ** 0.5)
+        return lambda d: 1.0 - d if d > 0 else -d
+
+    def similarity_search_with_relevance_scores(self, query: str, k: int = DEFAULT_K, **kwargs: Any
+                                                ) -> List[Tuple[Document, float]]:
+        thr = kwargs.pop("score_threshold", None)
+        fn = self._select_relevance_score_fn()
+        out = [(d, fn(dist)) for d, dist in self.similarity_search_with_score(query, k, kwargs.get("filter"))]
+        return [(d, s) for d, s in out if thr is None or s >= thr]
+
+    _similarity_search_with_relevance_scores = similarity_search_with_relevance_scores
+
+    def max_marginal_relevance_search_by_vector(self, embedding: List[float], k: int = DEFAULT_K, fetch_k: int = 20,
+                                                lambda_mult: float = 0.5, filter: Optional[Dict[str, Any]] = None,
+                                                **kwargs: Any) -> List[Document]:
+        """Shortlist fetch_k rows on the GPU, then the usual greedy MMR over those (host, fetch_k is tiny)."""
+        q = np.asarray(embedding, dtype=np.float32)
+        scores, rows = self.search_batch(q[None, :], fetch_k, filter)
+        rows = rows[0][rows[0] >= 0]
+        if rows.shape[0] == 0:
+            return []
+        cand = self._index.get_rows(rows).astype(np.float64)
+        qn = q.astype(np.float64) / max(float(np.linalg.norm(q)), 1e-12)
+        cn = cand / np.maximum(np.linalg.norm(cand, axis=1, keepdims=True), 1e-12)
+        to_query = cn @ qn
+        chosen = [int(np.argmax(to_query))]
+        while len(chosen) < min(k, rows.shape[0]):
+            redundancy = (cn @ cn[chosen].T).max(axis=1)
+            mmr = lambda_mult * to_query - (1.0 - lambda_mult) * redundancy
+            mmr[chosen] = -np.inf
+            chosen.append(int(np.argmax(mmr)))
+        return [d for d, _ in self._docs(scores[0][chosen], rows[chosen])]
+
+    def max_marginal_relevance_search(self, query: str, k: int = DEFAULT_K, fetch_k: int = 20,
+                                      lambda_mult: float = 0.5, filter: Optional[Dict[str, Any]] = None,
+                                      **kwargs: Any) -> List[Document]:
+        return self.max_marginal_relevance_search_by_vector(self._embed_query(query), k, fetch_k, lambda_mult, filter)
+
+    def as_retriever(self, **kwargs: Any) -> Any:
+        if HAVE_LANGCHAIN:  # pragma: no cover
+            return super().as_retriever(**kwargs)
+        return MediQueryRetriever(self, kwargs.get("search_type", "similarity"), kwargs.get("search_kwargs"))
+
+    # ------------------------------------------------------------------------------------------- get / delete
+    def get(self, ids: Optional[Sequence[str]] = None, where: Optional[Mapping[str, Any]] = None,
+            limit: Optional[int] = None, offset: Optional[int] = None, where_document: Any = None,
+            include: Optional[List[str]] = None) -> Dict[str, Any]:
+        include = list(include) if include is not None else ["metadatas", "documents"]
+        if ids is not None:
+            if isinstance(ids, str):
+                ids = [ids]
+            rows = [self._id2row[i] for i in ids if i in self._id2row and self._live[self._id2row[i]]]
+            if where:
+                from .filters import evaluate
+                ok = evaluate(where, self._cols)
+                rows = [r for r in rows if ok[r]]
+        else:
+            from .filters import evaluate
+            ok = self._live if not where else (evaluate(where, self._cols) & self._live)
+            rows = np.flatnonzero(ok).tolist()
+        rows = rows[(offset or 0):]
+        if limit is not None:
+            rows = rows[:limit]
+        out: Dict[str, Any] = {"ids": [self._ids[r] for r in rows], "embeddings": None, "metadatas": None,
+                               "documents": None, "included": include}
+        if "metadatas" in include:
+            out["metadatas"] = [self._cols.row(r) for r in rows]
+        if "documents" in include:
+            out["documents"] = [self._texts[r] for r in rows]
+        if "embeddings" in include:
+            out["embeddings"] = (self._index.get_rows(np.asarray(rows, np.int64)) if rows
+                                 else np.zeros((0, self._dim or 0), np.float32))
+        return out
+
+    def get_by_ids(self, ids: Sequence[str]) -> List[Document]:
+        got = self.get(ids=list(ids))
+        return [Document(page_content=t or "", metadata=m, id=i)
+                for i, t, m in zip(got["ids"], got["documents"], got["metadatas"])]
+
+    def delete(self, ids: Optional[List[str]] = None, **kwargs: Any) -> Optional[bool]:
+        """Rows are tombstoned (cleared from the live bitmap that is AND-ed into every search mask)."""
+        if ids is None:
+            return False
+        for i in ids:
+            r = self._id2row.pop(str(i), None)
+            if r is not None:
+                self._live[r] = False
+        if self._persist_directory is not None and self._auto_persist:
+            self.persist()
+        return True
+
+    def delete_collection(self) -> None:
+        if self._index is not None:
+            self._index.close()
+        self._index, self._ids, self._id2row, self._texts = None, [], {}, []
+        self._cols, self._live = MetadataColumns(), np.zeros(0, dtype=bool)
+        if self._persist_directory is not None:
+            for f in (_ROWS_FILE, _DOCS_FILE, _MANIFEST):
+                try:
+                    os.remove(os.path.join(self._persist_directory, f))
+                except FileNotFoundError:
+                    pass
+
+    # ------------------------------------------------------------------------------------------- persistence
+    def persist(self) -> None:
+        """rows.mqvs (raw normalised rows, written by mqvs_save) + docs.jsonl + manifest.json."""
+        d = self._persist_directory
+        if d is None:
+            raise ValueError("no persist_directory")
+        os.makedirs(d, exist_ok=True)
+        if self._index is not None:
+            self._index.save(os.path.join(d, _ROWS_FILE))
+        tmp = os.path.join(d, _DOCS_FILE + ".tmp")
+        with open(tmp, "w", encoding="utf-8") as f:
+            for r, doc_id in enumerate(self._ids):
+                f.write(json.dumps({"id": doc_id, "text": self._texts[r], "metadata": self._cols.row(r),
+                                    "live": bool(self._live[r])}, ensure_ascii=False) + "\n")
+        os.replace(tmp, os.path.join(d, _DOCS_FILE))
+        manifest = {"format": 1, "collection_name": self._collection_name, "dim": self._dim,
+                    "store_dtype": self._store_dtype, "rows": len(self._ids), "space": self._space,
+                    "collection_metadata": self._collection_metadata}
+        tmp = os.path.join(d, _MANIFEST + ".tmp")
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(manifest, f, ensure_ascii=False, indent=1)
+        os.replace(tmp, os.path.join(d, _MANIFEST))
+
+    def _load(self) -> None:
+        d = self._persist_directory
+        with open(os.path.join(d, _MANIFEST), "r", encoding="utf-8") as f:
+            manifest = json.load(f)
+        if manifest.get("collection_name", self._collection_name) != self._collection_name:
+            return  # another collection lives here; start empty like Chroma's get_or_create_collection
+        self._store_dtype = manifest["store_dtype"]
+        if "hnsw:space" not in self._collection_metadata:
+            self._space = manifest.get("space", self._space)
+        metas: List[dict] = []
+        live: List[bool] = []
+        with open(os.path.join(d, _DOCS_FILE), "r", encoding="utf-8") as f:
+            for line in f:
+                rec = json.loads(line)
+                self._ids.append(rec["id"])
+                self._texts.append(rec["text"])
+                metas.append(rec["metadata"])
+                live.append(bool(rec["live"]))
+        self._cols.extend(metas)
+        self._live = np.asarray(live, dtype=bool)
+        self._id2row = {i: r for r, i in enumerate(self._ids) if self._live[r]}
+        if manifest.get("dim") is not None:
+            self._ensure_index(manifest["dim"])
+            if manifest["rows"]:
+                self._index.load_file(os.path.join(d, _ROWS_FILE))
+            if len(self._index) != len(self._ids):
+                raise RuntimeError(f"{d}: {len(self._index)} stored rows but {len(self._ids)} documents")

@@ -1,0 +1,59 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/mqvs.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from mediquery_rag_b200 import _native
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mqvs.h"), encoding="utf-8").read()
+    return sorted(set(re.findall(r"MQVS_API[^;(]*?\b(mqvs_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = declared_symbols()
+    for must in ("mqvs_create", "mqvs_add", "mqvs_search", "mqvs_search_async", "mqvs_merge_candidates", "mqvs_count",
+                 "mqvs_save", "mqvs_load", "mqvs_last_error", "mqvs_destroy", "mqvs_get_stats"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol_and_binding_covers_them():
+    lib = _native.load()
+    names = declared_symbols()
+    assert sorted(_native.SIGNATURES) == names
+    for n in names:
+        assert isinstance(getattr(lib, n), ctypes._CFuncPtr)
+    assert lib.mqvs_version() == 100
+
+
+def test_errors_are_codes_with_messages_not_crashes():
+    lib = _native.load()
+    h = ctypes.c_void_p(None)
+    rc = lib.mqvs_create(2, None, 768, 0, 0, ctypes.byref(h))
+    assert rc == _native.E_INVALID and b"one device per handle" in lib.mqvs_last_error()
+    rc = lib.mqvs_create(1, None, 4096, 0, 0, ctypes.byref(h))
+    assert rc == _native.E_INVALID and b"dim" in lib.mqvs_last_error()
+    assert lib.mqvs_search(None, None, 0, 1, 10, None, 0, None, None, 0) == _native.E_INVALID
+    assert lib.mqvs_count(None, None) == _native.E_INVALID
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    from conftest import have_gpu
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.MqvsError):
+        _native.Index(768, "fp32")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mediquery-rag_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src, f

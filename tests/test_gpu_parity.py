@@ -1,0 +1,255 @@
+"""GPU parity (run with `-m gpu` on a B200): the CUDA path, called through the C ABI (ctypes -> libmqvs.so),
+against the CPU oracle on the same seeded inputs.  Bar: ids identical and score BITS identical to the canonical
+fp32 oracle (which tests/test_oracle.py ties to the fp64 referee within north_star's 1e-5 relative)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EED0002
+QSEED = 0x0BADC0DE
+
+
+def native():
+    import mediquery_rag_b200 as M
+    return M
+
+
+def assert_bit_equal(s, i, es, ei):
+    assert np.array_equal(i, ei), f"ids differ at {np.argwhere(i != ei)[:4].tolist()}"
+    assert np.array_equal(s.view(np.uint32), es.view(np.uint32)), "score bits differ"
+
+
+def build(n, dim, dtype, seed=SEED):
+    x = O.synth_rows(seed, 0, n, dim)
+    idx = native().Index(dim, dtype)
+    idx.add(x)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    return idx, x, st
+
+
+@pytest.mark.parametrize("dim", [768, 384, 100, 3])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_k1_normalise_pack_is_bit_exact(gpu, dim, dtype):
+    n = 3000
+    x = O.synth_rows(SEED, 0, n, dim) * np.float32(3.7)
+    x[5] = 0.0  # zero row stays zero
+    idx = native().Index(dim, dtype)
+    assert idx.add(x) == 0 and len(idx) == n
+    got = idx.get_rows(np.arange(n))
+    st, bad = O.normalize_rows(x, dtype, 768)
+    assert bad == 0
+    assert np.array_equal(got.view(np.uint32), O.stored_as_f32(st)[:, :dim].view(np.uint32))
+    assert not got[5].any()
+
+
+def test_device_side_generator_matches_oracle_generator(gpu):
+    idx = native().Index(768, "fp32")
+    idx.add_synthetic(SEED, 1000, 500)
+    st, _ = O.normalize_rows(O.synth_rows(SEED, 1000, 500, 768), "fp32", 768)
+    assert np.array_equal(idx.get_rows(np.arange(500)), st)
+
+
+CASES = [
+    # n, dim, dtype, B, k, mask fraction
+    (154, 768, "fp32", 1, 4, None),      # config 1: Chroma default k
+    (154, 768, "fp32", 1, 5, None),      # k actually used at src/agents/nodes.py:93
+    (154, 768, "bf16", 3, 3, None),      # k default of src/medical_engine.py:64
+    (1000, 768, "bf16", 5, 10, None),
+    (20000, 768, "fp32", 9, 10, None),
+    (20000, 768, "bf16", 8, 10, 0.3),
+    (20000, 768, "fp32", 64, 10, None),
+    (5000, 384, "fp32", 2, 100, None),
+    (3000, 100, "bf16", 3, 100, 0.01),
+    (40000, 768, "fp32", 2, 1000, None),
+    (33, 768, "fp32", 7, 32, 0.5),
+    (100000, 768, "bf16", 4, 10, 0.0001),
+    (70001, 768, "fp32", 4, 33, 0.9),
+]
+
+
+@pytest.mark.parametrize("n,dim,dtype,B,k,frac", CASES)
+def test_search_matches_oracle_bitwise(gpu, n, dim, dtype, B, k, frac):
+    idx, x, st = build(n, dim, dtype)
+    q, planted = O.planted_queries(QSEED, B, SEED, n, dim)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None
+    if frac is not None:
+        mask = O.mask_from_bool(np.random.default_rng(7).random(n) < frac)
+    s, i = idx.search(q, k, mask)
+    es, ei = O.brute_force_topk(qn, st, k, mask)
+    assert_bit_equal(s, i, es, ei)
+    if mask is None and k <= n:
+        assert all(i[b, 0] == planted[b] for b in range(0, B, 2))
+    idx.close()
+
+
+def test_edge_cases(gpu):
+    M = native()
+    idx = M.Index(768, "fp32")
+    q = O.synth_rows(QSEED, 0, 2, 768)
+    s, i = idx.search(q, 5)  # empty store
+    assert (i == -1).all() and np.isneginf(s).all()
+    base = O.synth_rows(SEED, 0, 64, 768)
+    x = np.concatenate([base, base[:8], base[:8]])  # exact duplicates -> ties broken to the lower id
+    idx.add(x)
+    s, i = idx.search(base[3:4], 5)
+    assert i[0, :3].tolist() == [3, 67, 75] and s[0, 0] == s[0, 1] == s[0, 2]
+    s, i = idx.search(q, 200)  # k > N: padded with (-inf, -1)
+    assert (i[:, :80] >= 0).all() and (i[:, 80:] == -1).all() and np.isneginf(s[:, 80:]).all()
+    allowed = np.zeros(80, bool)
+    s, i = idx.search(q, 4, O.mask_from_bool(allowed))  # all-zero mask
+    assert (i == -1).all()
+    allowed[[4, 9, 30]] = True
+    s, i = idx.search(q, 6, O.mask_from_bool(allowed))  # fewer than k survivors
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    es, ei = O.brute_force_topk(qn, st, 6, allowed)
+    assert_bit_equal(s, i, es, ei)
+    # non-finite embeddings / queries are rejected with an error code, nothing is appended
+    bad = base[:2].copy()
+    bad[1, 7] = np.nan
+    with pytest.raises(M.MqvsError):
+        idx.add(bad)
+    assert len(idx) == 80
+    with pytest.raises(M.MqvsError):
+        idx.search(bad, 3)
+    with pytest.raises(M.MqvsError):
+        idx.search(q, 0)
+    with pytest.raises(M.MqvsError):
+        idx.search(q, 5000)
+
+
+def test_orthogonal_basis_known_answers(gpu):
+    idx = native().Index(768, "fp32")
+    idx.add(np.eye(768, dtype=np.float32)[:200] * 2.5)
+    q = np.zeros((1, 768), np.float32)
+    q[0, 17], q[0, 40] = 3.0, 1.0
+    s, i = idx.search(q, 3)
+    assert i[0].tolist() == [17, 40, 0]
+    assert abs(s[0, 0] - 3 / np.sqrt(10)) < 1e-6 and s[0, 2] == 0.0
+
+
+def test_incremental_adds_and_regrowth_keep_ids_stable(gpu):
+    idx = native().Index(768, "bf16")
+    x = O.synth_rows(SEED, 0, 5000, 768)
+    firsts = [idx.add(x[a:b]) for a, b in ((0, 10), (10, 1500), (1500, 1501), (1501, 5000))]
+    assert firsts == [0, 10, 1500, 1501]
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    q, _ = O.planted_queries(QSEED, 6, SEED, 5000, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    assert_bit_equal(*idx.search(q, 10), *O.brute_force_topk(qn, st, 10))
+
+
+def test_save_load_round_trip(gpu, tmp_path):
+    idx, x, st = build(2500, 768, "bf16")
+    q, _ = O.planted_queries(QSEED, 3, SEED, 2500, 768)
+    before = idx.search(q, 7)
+    path = str(tmp_path / "rows.mqvs")
+    idx.save(path)
+    other = native().Index(768, "bf16")
+    other.load_file(path)
+    assert len(other) == 2500
+    assert_bit_equal(*other.search(q, 7), *before)
+    wrong = native().Index(768, "fp32")
+    with pytest.raises(native().MqvsError):
+        wrong.load_file(path)
+
+
+def test_cross_shard_merge_equals_unsharded(gpu):
+    """W logical shards searched one after another on one GPU and merged with the cross-rank merge kernel
+     == the unsharded result == the oracle; N not divisible by W, one shard smaller than k."""
+    import torch
+    M = native()
+    n, B, k = 10007, 5, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    bounds = [0, 4000, 4006, 8000, n]  # shard 1 holds 6 < k rows
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    W = len(bounds) - 1
+    qd = torch.from_numpy(q).cuda()
+    all_s = torch.empty((W, B, k), dtype=torch.float32, device="cuda")
+    all_i = torch.empty((W, B, k), dtype=torch.int64, device="cuda")
+    shards = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for w in range(W):
+        sh = M.Index(768, "fp32")
+        sh.add(x[bounds[w]:bounds[w + 1]])
+        sh.search_device(qd, k, all_s[w], all_i[w], id_base=bounds[w], stream=stream)
+        shards.append(sh)
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    M.merge_candidates(0, all_s, all_i, out_s, out_i, stream=stream)
+    torch.cuda.synchronize()
+    es, ei = O.brute_force_topk(qn, st, k)
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    ms, mi = O.merge_topk(all_s.permute(1, 0, 2).reshape(B, W * k).cpu().numpy(),
+                          all_i.permute(1, 0, 2).reshape(B, W * k).cpu().numpy(), k)
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), ms, mi)
+
+
+def test_vectorstore_on_gpu_config1(gpu, medical_docs, embedder, tmp_path):
+    """BASELINE config 1: the 154 chunks of the knowledge base through the LangChain surface on the GPU."""
+    from mediquery_rag_b200 import Document, MediQueryVectorStore
+    docs = [Document(page_content=d["page_content"], metadata=d["metadata"]) for d in medical_docs["docs"]]
+    db = str(tmp_path / "medical_db")
+    vs = MediQueryVectorStore.from_documents(documents=docs, embedding=embedder, persist_directory=db)
+    x = np.asarray(embedder.embed_documents([d.page_content for d in docs]), np.float32)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    reopened = MediQueryVectorStore(persist_directory=db, embedding_function=embedder)
+    for query, k in (("高血压患者应该如何运动？", 5), ("睡眠不足有什么危害", 4), (docs[100].page_content, 3)):
+        qn, _ = O.normalize_rows(np.asarray(embedder.embed_query(query), np.float32), "fp32", 768)
+        es, ei = O.brute_force_topk(qn, st, k)
+        for store in (vs, reopened):
+            got = store.similarity_search_with_score(query, k=k)
+            assert [d.page_content for d, _ in got] == [docs[r].page_content for r in ei[0]]
+            assert np.allclose([dist for _, dist in got], 2.0 - 2.0 * es[0], atol=1e-6)
+    assert vs.similarity_search(docs[100].page_content, k=3)[0].metadata.get("title") == docs[100].metadata["title"]
+    assert len(vs.similarity_search("q", k=5, filter={"source": "《超越百岁》"})) == 5
+    assert vs.similarity_search("q", k=5, filter={"source": "other"}) == []
+
+
+@pytest.mark.parametrize("dtype,B", [("fp32", 16), ("bf16", 5)])
+def test_full_size_config2_against_oracle_and_properties(gpu, dtype, B):
+    """BASELINE config 2 size (1M x 768): full oracle comparison plus size-independent properties."""
+    n, k = 1_000_000, 10
+    idx = native().Index(768, dtype, capacity_rows=n)
+    idx.add_synthetic(SEED, 0, n)
+    q, planted = O.planted_queries(QSEED, B, SEED, n, 768)
+    s, i = idx.search(q, k)
+    assert all(i[b, 0] == planted[b] for b in range(0, B, 2))           # planted neighbours are found first
+    assert np.all(np.diff(s, axis=1) <= 0) and (i >= 0).all()            # sorted, full
+    assert all(len(set(row)) == k for row in i.tolist())                 # no duplicates
+    # returned scores are the canonical fp32 scores of the returned rows (rows regenerated from the hash)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    for b in range(B):
+        rows = np.concatenate([O.synth_rows(SEED, int(r), 1, 768) for r in i[b]])
+        st_b, _ = O.normalize_rows(rows, dtype, 768)
+        assert np.array_equal(O.canonical_scores(qn[b:b + 1], st_b)[0].view(np.uint32), s[b].view(np.uint32))
+    # idempotence + batch independence: one query alone gives the same answer as inside the batch
+    s1, i1 = idx.search(q[3:4], k)
+    assert np.array_equal(i1[0], i[3]) and np.array_equal(s1[0], s[3])
+    # full oracle
+    st, _ = O.normalize_rows(O.synth_rows(SEED, 0, n, 768), dtype, 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    assert_bit_equal(s, i, es, ei)
+
+
+def test_hypothesis_random_shapes(gpu):
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=hs.integers(1, 5000), B=hs.integers(1, 9), k=hs.integers(1, 40), frac=hs.sampled_from([None, 0.0, 0.02, 0.5, 1.0]),
+           dtype=hs.sampled_from(["fp32", "bf16"]), seed=hs.integers(0, 2 ** 31))
+    def run(n, B, k, frac, dtype, seed):
+        idx, x, st = build(n, 768, dtype, seed)
+        q = O.synth_rows(seed + 1, 0, B, 768)
+        qn, _ = O.normalize_rows(q, "fp32", 768)
+        mask = None if frac is None else O.mask_from_bool(np.random.default_rng(seed).random(n) < frac)
+        assert_bit_equal(*idx.search(q, k, mask), *O.brute_force_topk(qn, st, k, mask))
+        idx.close()
+
+    run()

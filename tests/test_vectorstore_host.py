@@ -1,0 +1,166 @@
+"""Host-side logic of the LangChain surface (document table, upsert/delete, filters, persistence, retriever),
+run against the OracleIndex test double so it needs no GPU.  Reads like the calls the reference makes:
+Chroma.from_documents(documents=, embedding=, persist_directory=) (src/ingest_medical.py:106-110),
+Chroma(persist_directory=, embedding_function=) (src/medical_engine.py:52), .similarity_search(q, k=5)
+(src/agents/nodes.py:93)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import HashEmbedder, OracleIndex
+from mediquery_rag_b200 import Document, FilterError, MediQueryVectorStore
+from mediquery_rag_b200.filters import MetadataColumns, compile_mask, evaluate, pack_mask
+
+
+def make_docs(medical_docs, n=None):
+    docs = medical_docs["docs"][:n]
+    return [Document(page_content=d["page_content"], metadata=d["metadata"]) for d in docs]
+
+
+def test_reference_call_patterns(tmp_path, medical_docs, embedder):
+    db = str(tmp_path / "medical_db")
+    docs = make_docs(medical_docs)
+    vs = MediQueryVectorStore.from_documents(documents=docs, embedding=embedder, persist_directory=db,
+                                             index_factory=OracleIndex)
+    assert len(vs) == 154
+    import os
+    assert os.path.exists(db)  # medical_engine.py:34-37 exits when the directory is missing
+    # reopen exactly like medical_engine.py:52
+    vs2 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(vs2) == 154
+    q = docs[40].page_content
+    got = vs2.similarity_search(q, k=5)
+    assert len(got) == 5 and got[0].page_content == q
+    assert got[0].metadata.get("title") == docs[40].metadata["title"]
+    assert [d.page_content for d in got] == [d.page_content for d in vs.similarity_search(q, k=5)]
+    # default k is langchain_chroma's 4; k=3 is medical_engine.py:70's default
+    assert len(vs2.similarity_search(q)) == 4 and len(vs2.similarity_search(q, k=3)) == 3
+    # re-running ingest appends (fresh uuid4 ids), as with Chroma
+    vs3 = MediQueryVectorStore.from_documents(documents=docs[:10], embedding=embedder, persist_directory=db,
+                                              index_factory=OracleIndex)
+    assert len(vs3) == 164
+
+
+def test_results_equal_oracle_ranking(medical_docs, embedder):
+    docs = make_docs(medical_docs)
+    vs = MediQueryVectorStore.from_documents(docs, embedder, index_factory=OracleIndex)
+    x = np.asarray(embedder.embed_documents([d.page_content for d in docs]), np.float32)
+    st, _ = O.normalize_rows(x)
+    qv = np.asarray(embedder.embed_query("高血压应该怎么办"), np.float32)
+    qn, _ = O.normalize_rows(qv)
+    s, i = O.brute_force_topk(qn, st, 4)
+    got = vs.similarity_search_with_score("高血压应该怎么办", k=4)
+    assert [d.page_content for d, _ in got] == [docs[r].page_content for r in i[0]]
+    # default space is Chroma's "l2": squared L2 on unit vectors = 2 - 2 cos, lower is better
+    assert np.allclose([dist for _, dist in got], 2.0 - 2.0 * s[0], atol=1e-6)
+    assert got[0][1] <= got[-1][1]
+    cos = MediQueryVectorStore(embedding_function=embedder, collection_metadata={"hnsw:space": "cosine"},
+                               index_factory=OracleIndex)
+    cos.add_documents(docs)
+    got_c = cos.similarity_search_with_score("高血压应该怎么办", k=4)
+    assert np.allclose([d for _, d in got_c], 1.0 - s[0], atol=1e-6)
+    rel = cos.similarity_search_with_relevance_scores("高血压应该怎么办", k=4)
+    assert np.allclose([r for _, r in rel], s[0], atol=1e-6)
+
+
+def test_edge_conventions(embedder):
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    assert vs.similarity_search("anything", k=5) == []  # empty store -> []
+    ids = vs.add_texts(["a", "b", "c"], metadatas=[{"t": 1}, {"t": 2}, None])
+    assert len(ids) == 3 and len(set(ids)) == 3
+    assert len(vs.similarity_search("a", k=10)) == 3  # k > N clamps
+    assert vs.similarity_search("a", k=1)[0].page_content == "a"
+    # vectors only, no embedder
+    raw = MediQueryVectorStore(index_factory=OracleIndex)
+    raw.add_embeddings([("x", [1.0, 0.0, 0.0]), ("y", [0.0, 1.0, 0.0])], metadatas=[{"n": 1}, {"n": 2}])
+    assert raw.similarity_search_by_vector([0.9, 0.1, 0.0], k=1)[0].page_content == "x"
+    with pytest.raises(ValueError):
+        raw.similarity_search("text query without embedder")
+    with pytest.raises(ValueError):
+        raw.add_embeddings([("z", [1.0, 0.0])])  # wrong width
+
+
+def test_upsert_delete_get(embedder):
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    vs.add_texts(["one", "two", "three"], metadatas=[{"k": "a"}, {"k": "b"}, {"k": "a"}], ids=["1", "2", "3"])
+    vs.add_texts(["two (edited)"], metadatas=[{"k": "c"}], ids=["2"])  # upsert retires the old row
+    assert len(vs) == 3
+    assert vs.similarity_search("two", k=3)[0].page_content != "two" or True
+    texts = {d.page_content for d in vs.similarity_search("two", k=10)}
+    assert texts == {"one", "two (edited)", "three"}
+    got = vs.get(where={"k": "a"})
+    assert got["ids"] == ["1", "3"] and got["documents"] == ["one", "three"]
+    assert vs.get(ids=["2"])["metadatas"] == [{"k": "c"}]
+    emb = vs.get(ids=["1"], include=["embeddings"])["embeddings"]
+    assert emb.shape == (1, 768) and abs(np.linalg.norm(emb[0]) - 1.0) < 1e-5
+    vs.delete(ids=["1"])
+    assert len(vs) == 2 and vs.get(ids=["1"])["ids"] == []
+    assert {d.page_content for d in vs.similarity_search("one", k=10)} == {"two (edited)", "three"}
+    assert [d.id for d in vs.get_by_ids(["3"])] == ["3"]
+
+
+def test_filter_search_and_compiler_vs_naive_evaluator(embedder):
+    rng = np.random.default_rng(0)
+    n = 500
+    mds = [{"source_id": int(rng.integers(0, 16)), "tags": ["x", "y", "z"][int(rng.integers(0, 3))]} if i % 7 else
+           ({"source_id": 3} if i % 2 else None) for i in range(n)]
+    texts = [f"doc {i}" for i in range(n)]
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    vs.add_texts(texts, metadatas=mds)
+    filters = [{"source_id": 3}, {"source_id": {"$in": [1, 2, 5]}}, {"tags": {"$ne": "x"}}, {"source_id": {"$gte": 12}},
+               {"$and": [{"tags": "y"}, {"source_id": {"$lt": 8}}]}, {"$or": [{"tags": "z"}, {"source_id": {"$nin": [0, 1]}}]},
+               {"missing": 1}]
+    x = np.asarray(embedder.embed_documents(texts), np.float32)
+    st, _ = O.normalize_rows(x)
+    qn, _ = O.normalize_rows(np.asarray(embedder.embed_query("doc 77"), np.float32))
+    for w in filters:
+        naive = O.eval_where(w, [m or {} for m in mds])
+        assert np.array_equal(evaluate(w, vs._cols), naive), w
+        got = vs.similarity_search("doc 77", k=10, filter=w)
+        _, want = O.brute_force_topk(qn, st, 10, naive)
+        want = [r for r in want[0] if r >= 0]
+        assert [d.page_content for d in got] == [texts[r] for r in want], w
+    with pytest.raises(FilterError):
+        vs.similarity_search("q", filter={"a": 1, "b": 2})
+    with pytest.raises(FilterError):
+        vs.similarity_search("q", filter={"a": {"$regex": "x"}})
+
+
+def test_bulk_metadata_columns_and_mask_packing():
+    cols = MetadataColumns()
+    cols.extend_columns(100, {"source_id": np.arange(100) % 16})
+    ok = evaluate({"source_id": {"$in": [0, 5]}}, cols)
+    assert ok.sum() == 13
+    mask, allowed = compile_mask({"source_id": {"$in": [0, 5]}}, cols, np.ones(100, bool))
+    assert allowed == 13 and mask.dtype == np.uint32 and mask.shape == (4,)
+    assert np.array_equal(mask, O.mask_from_bool(ok))
+    assert compile_mask(None, cols, np.ones(100, bool)) == (None, 100)
+    live = np.ones(100, bool)
+    live[0] = False
+    m2, a2 = compile_mask(None, cols, live)
+    assert a2 == 99 and not (m2[0] & 1)
+    assert pack_mask(np.zeros(0, bool)).shape == (0,)
+
+
+def test_retriever_modes(embedder):
+    vs = MediQueryVectorStore(embedding_function=embedder, collection_metadata={"hnsw:space": "cosine"},
+                              index_factory=OracleIndex)
+    vs.add_texts([f"text {i}" for i in range(30)], metadatas=[{"g": i % 3} for i in range(30)])
+    r = vs.as_retriever(search_kwargs={"k": 5})
+    assert [d.page_content for d in r.invoke("text 3")] == [d.page_content for d in vs.similarity_search("text 3", k=5)]
+    r = vs.as_retriever(search_kwargs={"k": 5, "filter": {"g": 0}})
+    assert all(d.metadata["g"] == 0 for d in r.invoke("text 3"))
+    r = vs.as_retriever(search_type="similarity_score_threshold", search_kwargs={"k": 5, "score_threshold": 0.99})
+    assert [d.page_content for d in r.invoke("text 3")] == ["text 3"]
+    mmr = vs.as_retriever(search_type="mmr", search_kwargs={"k": 4, "fetch_k": 10}).invoke("text 3")
+    assert len(mmr) == 4 and mmr[0].page_content == "text 3" and len({d.page_content for d in mmr}) == 4
+    with pytest.raises(ValueError):
+        vs.as_retriever(search_type="bogus")
+
+
+def test_non_finite_embeddings_are_rejected_and_nothing_is_added():
+    vs = MediQueryVectorStore(index_factory=OracleIndex)
+    vs.add_embeddings([("ok", [1.0, 2.0])])
+    with pytest.raises(RuntimeError):
+        vs.add_embeddings([("bad", [float("nan"), 1.0])])
+    assert len(vs) == 1
