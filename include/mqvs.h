@@ -52,6 +52,7 @@ typedef struct mqvs_stats {
     double   last_scan_ms;       /* device time of the last search's scan launches */
     uint32_t last_scan_passes;   /* corpus passes the last search needed */
     uint32_t last_path;          /* 0 = SIMT fp32 scan, 1 = tensor-core shortlist + fp32 rescoring */
+    uint64_t exact_fallbacks;    /* queries whose tensor-core shortlist could not be proven exact and were re-run on the SIMT scan */
 } mqvs_stats;
 
 MQVS_API int mqvs_version(void);

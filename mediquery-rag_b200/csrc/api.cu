@@ -14,6 +14,7 @@
 
 #include "../../include/mqvs.h"
 #include "launch.h"
+#include "tc.h"
 
 namespace {
 
@@ -81,6 +82,10 @@ struct mqvs_store {
     } evr[kEvRing];
     int ev_cursor = 0;
     DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
+    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys;  // tensor-core path scratch
+    uint32_t* flags_host = nullptr;                      // pinned [1 + max B]: flag_count, flags[B]
+    size_t flags_host_n = 0;
+    uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
     unsigned long long* bad_dev = nullptr;
     unsigned long long* bad_host = nullptr;  // pinned
     mqvs_stats stats{};
@@ -134,6 +139,38 @@ void settle_events(mqvs_store* s) {
     for (int i = 0; i < mqvs_store::kEvRing; ++i) settle_slot(s, (s->ev_cursor + i) % mqvs_store::kEvRing);
 }
 
+// Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
+bool use_tensor_path(const mqvs_store* s, int B, int k) {
+    if (s->path == 1) return false;
+    if (k > 128 || s->n < 4096) return false;
+    if (s->path == 2) return true;
+    return B >= 16 && s->n >= 65536;
+}
+
+// Exact SIMT scan of queries [b0, b0 + nb) of s->qn into out rows [b0, ...).  Returns passes launched.
+int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
+                 int64_t* out_ids_dev, cudaStream_t st, uint32_t* passes_out) {
+    using namespace mqvs;
+    const int gmax = scan_max_grid(s->sm_count);
+    int rc;
+    if ((rc = s->cand.ensure((size_t)nb * gmax * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+    CU(cudaMemsetAsync(s->cand.p, 0, (size_t)nb * gmax * k * sizeof(uint64_t), st));
+    uint32_t passes = 0;
+    for (int b = 0; b < nb;) {
+        int nq = 0, grid = 0;
+        scan_plan(s->dtype, nb - b, k, s->sm_count, &nq, &grid);
+        launch_scan_simt(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)(b0 + b) * MQVS_DIM_PAD, nq,
+                         mask_dev, k, (uint64_t*)s->cand.p + (size_t)b * gmax * k, gmax, grid, st);
+        b += nq;
+        ++passes;
+    }
+    launch_merge_keys((const uint64_t*)s->cand.p, nb, gmax * k, k, id_base, out_scores_dev + (size_t)b0 * k,
+                      out_ids_dev + (size_t)b0 * k, st);
+    CU(cudaGetLastError());
+    *passes_out = passes;
+    return MQVS_OK;
+}
+
 // Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                    float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st) {
@@ -142,38 +179,62 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
-    const int gmax = scan_max_grid(s->sm_count);
+    const bool tensor = use_tensor_path(s, B, k);
+    tc::Plan plan{};
     int rc;
+    if (tensor) {
+        plan = tc::plan(k, B, s->sm_count);
+        const size_t small = (size_t)plan.b_pad * (sizeof(float) * 2 + sizeof(uint32_t) * 2) + 64;
+        if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
+        if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
+        if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
+        if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
+        if ((rc = s->tc_keys.ensure((size_t)B * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
+    }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
-    if ((rc = s->cand.ensure((size_t)B * gmax * k * sizeof(uint64_t))) != MQVS_OK) return rc;
 
     CU(cudaEventRecord(ev[0], st));
     CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
     launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
-    CU(cudaMemsetAsync(s->cand.p, 0, (size_t)B * gmax * k * sizeof(uint64_t), st));
     s->stats.kernel_launches += 1;
-
-    CU(cudaEventRecord(ev[1], st));
     uint32_t passes = 0;
-    for (int b0 = 0; b0 < B;) {
-        int nq = 0, grid = 0;
-        scan_plan(s->dtype, B - b0, k, s->sm_count, &nq, &grid);
-        launch_scan_simt(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)b0 * MQVS_DIM_PAD, nq,
-                         mask_dev, k, (uint64_t*)s->cand.p + (size_t)b0 * gmax * k, gmax, grid, st);
-        b0 += nq;
-        ++passes;
+    if (tensor) {
+        tc::Buffers b{};
+        char* sm = (char*)s->tc_small.p;
+        b.q_op = s->tc_qop.p;
+        b.eps = (float*)sm;
+        b.tau_tilde = b.eps + plan.b_pad;
+        b.tau = (uint32_t*)(b.tau_tilde + plan.b_pad);
+        b.flag_count = b.tau + plan.b_pad;       // flag_count immediately followed by flags[B]: one D2H copy
+        b.flags = b.flag_count + 1;
+        b.cnt = (uint32_t*)s->tc_cnt.p;
+        b.lists = (uint64_t*)s->tc_lists.p;
+        b.short_keys = (uint64_t*)s->tc_keys.p;
+        b.exact_keys = b.short_keys + (size_t)B * plan.kprime;
+        s->last_flags_dev = b.flag_count;
+        CU(cudaEventRecord(ev[1], st));
+        const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
+                                     id_base, out_scores_dev, out_ids_dev, st);
+        if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
+        CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
+        passes = 1;
+        s->stats.kernel_launches += tc::kLaunchesPerSearch;
+        s->stats.last_path = 1;
+    } else {
+        CU(cudaEventRecord(ev[1], st));
+        // scan launches are bracketed together with the (tiny) candidate memset
+        if ((rc = enqueue_simt(s, 0, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, &passes)) != MQVS_OK) return rc;
+        CU(cudaEventRecord(ev[2], st));
+        s->stats.kernel_launches += passes + 1;
+        s->stats.last_path = 0;
     }
-    CU(cudaEventRecord(ev[2], st));
-    launch_merge_keys((const uint64_t*)s->cand.p, B, gmax * k, k, id_base, out_scores_dev, out_ids_dev, st);
     CU(cudaEventRecord(ev[3], st));
     CU(cudaGetLastError());
 
     s->evr[slot].pending = true;
-    s->stats.kernel_launches += passes + 1;
     s->stats.scan_launches += passes;
     s->stats.scan_bytes += (uint64_t)passes * s->n * s->row_bytes();
     s->stats.last_scan_passes = passes;
-    s->stats.last_path = 0;
     s->stats.searches += 1;
     s->stats.queries += (uint64_t)B;
     return MQVS_OK;
@@ -240,7 +301,10 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (!s) return;
     cudaSetDevice(s->dev);
     if (s->st) cudaStreamSynchronize(s->st);
-    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf}) b->release();
+    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
+                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys})
+        b->release();
+    if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->rows) cudaFree(s->rows);
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
@@ -362,9 +426,35 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
     }
     CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    const bool tensor = s->stats.last_path == 1;
+    if (tensor) {
+        if (s->flags_host_n < (size_t)B + 1) {
+            if (s->flags_host) cudaFreeHost(s->flags_host);
+            s->flags_host = nullptr;
+            s->flags_host_n = 0;
+            CU(cudaMallocHost(&s->flags_host, ((size_t)B + 1) * sizeof(uint32_t)));
+            s->flags_host_n = (size_t)B + 1;
+        }
+        CU(cudaMemcpyAsync(s->flags_host, s->last_flags_dev, ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
+    }
     CU(cudaStreamSynchronize(s->st));
-    settle_events(s);
     if (*s->bad_host) return fail(MQVS_E_INVALID, "%llu of %d queries have a non-finite norm", *s->bad_host, B);
+    if (tensor && s->flags_host[0]) {
+        // exactness margin not proven for these queries: re-run them on the exact scan
+        for (int b = 0; b < B; ++b) {
+            if (!s->flags_host[1 + b]) continue;
+            uint32_t passes = 0;
+            if ((rc = enqueue_simt(s, b, 1, k, mask_dev, 0, os, oi, s->st, &passes)) != MQVS_OK) return rc;
+            s->stats.kernel_launches += passes + 1;
+            s->stats.exact_fallbacks += 1;
+        }
+        if (!out_is_device) {
+            CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+            CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
+        }
+        CU(cudaStreamSynchronize(s->st));
+    }
+    settle_events(s);
     return MQVS_OK;
 }
 

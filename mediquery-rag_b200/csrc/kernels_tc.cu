@@ -1,0 +1,579 @@
+// kernels_tc.cu -- K2' (tensor-core scoring) + K3 (fused shortlist epilogue) + K4 (exact fp32 rescoring).
+//
+// For query batches where the contraction [B, 768] x [768, N] is real GEMM work, scoring runs on the 5th-gen
+// tensor cores: tcgen05.mma (kind::f16 for bf16 rows with bf16-rounded queries, kind::tf32 for fp32 rows),
+// operands staged by TMA into 128B-swizzled shared memory through a 4-stage mbarrier ring, fp32 accumulators in
+// TMEM, double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// Orientation: QUERIES on the MMA M axis (TMEM lanes), CORPUS rows on N (TMEM columns).  After tcgen05.ld each
+// epilogue thread owns one query and walks that query's scores for 256 corpus rows in registers: one compare per
+// score against a per-query threshold held in a register.  Survivors are appended to a thread-private list
+// in global memory ([cta][query][CAP] 64-bit keys); when a list passes CAP-32 entries the warp sorts it in
+// registers (bitonic, CAP/32 keys per lane), keeps the best k' and raises the threshold, which is shared across
+// CTAs through an atomicMax on tau[query] -- every CTA filters with the tightest bound any CTA has proven.
+// The score matrix (B x N; 164 GB at 4096 x 10M) is never materialised.
+//
+// The tensor-core scores are approximate (bf16-rounded queries / tf32 operands), so they only SHORTLIST.
+// K4 recomputes the k' best candidates per query in the canonical fp32 order (common.cuh) and the final top-k
+// is taken from those exact scores.  Exactness is checked, not assumed: every discarded row had an approximate
+// score <= tau~, hence an exact score <= tau~ + eps (eps = rigorous bound on |approx - exact|); if the k-th exact
+// score does not exceed tau~ + eps the query is flagged and re-run on the exact SIMT scan (kernels_scan.cu).
+//
+// Roofline: HBM while B is small (corpus streamed once per batch), tensor pipe for large B:
+// 2 * N * 768 * B flop per batch.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "launch.h"
+#include "tc.h"
+
+namespace mqvs {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ geometry
+constexpr int BM = 128;           // queries per tile  (TMEM lanes)
+constexpr int BN = 256;           // corpus rows per tile (TMEM columns)
+constexpr int kStages = 4;
+constexpr int kRowBytes = 128;    // one swizzle-128B row of a K-chunk
+constexpr int kABytes = BM * kRowBytes;
+constexpr int kBBytes = BN * kRowBytes;
+constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
+constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+template <typename T>
+struct Kind;
+template <>
+struct Kind<__nv_bfloat16> {  // kind::f16, bf16 x bf16 -> fp32, K = 16 per instruction
+    static constexpr int kElemsPerChunk = 64, kFmt = 1;
+    static constexpr bool kTf32 = false;
+};
+template <>
+struct Kind<float> {  // kind::tf32, fp32 data read as tf32, K = 8 per instruction
+    static constexpr int kElemsPerChunk = 32, kFmt = 2;
+    static constexpr bool kTf32 = true;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if constexpr (kTf32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ uint32_t ord_u32(float s) {
+    if (s == 0.0f) s = 0.0f;
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+constexpr uint32_t kOrdNegInf = 0x007FFFFFu;  // ord_u32(-inf)
+
+// ------------------------------------------------------------------------------------------ warp bitonic
+// Sort 32*KPL keys held as element e = r*32 + lane, DESCENDING in e.
+template <int KPL>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * KPL; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool desc = (((r << 5) | lane) & size) == 0;
+                        uint64_t a = key[r], b = key[r | rs];
+                        bool swap = desc ? (a < b) : (a > b);
+                        key[r] = swap ? b : a;
+                        key[r | rs] = swap ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], stride);
+                    const bool lower = (lane & stride) == 0;
+                    const bool desc = (((r << 5) | lane) & size) == 0;
+                    const bool take_max = (lower == desc);
+                    uint64_t mx = key[r] > other ? key[r] : other;
+                    uint64_t mn = key[r] > other ? other : key[r];
+                    key[r] = take_max ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+struct ScoreArgs {
+    uint32_t n_rows;        // valid corpus rows
+    uint32_t n_queries;     // valid queries (B); lanes beyond are padding
+    uint32_t m_tiles;       // ceil(B / 128)
+    uint32_t n_tiles;       // ceil(n_rows / 256)
+    const uint32_t* mask;   // optional allow-mask over rows (device), or nullptr
+    uint32_t* tau;          // [B_pad] shared per-query threshold, order-preserving uint, atomicMax
+    uint32_t* cnt;          // [grid][B_pad] list lengths
+    uint64_t* lists;        // [grid][B_pad][CAP]
+    uint32_t b_pad;
+};
+
+template <typename T, int CAP, int KPRIME>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScoreArgs a) {
+    using K = Kind<T>;
+    constexpr int kChunks768 = kDim / K::kElemsPerChunk;  // 12 (bf16) or 24 (tf32) K-chunks per tile
+    constexpr int KPL = CAP / 32;
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + (size_t)kStages * kStageBytes);
+    // bars[0..S): full, [S..2S): empty, [2S..2S+2): tmem_full, [2S+2..2S+4): tmem_empty
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const uint32_t total_work = a.n_tiles > blockIdx.x ? ((a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * a.m_tiles : 0;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t nt = blockIdx.x; nt < a.n_tiles; nt += gridDim.x)
+                for (uint32_t mt = 0; mt < a.m_tiles; ++mt)
+                    for (int kc = 0; kc < kChunks768; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                        mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                        tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(mt * BM));
+                        tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = 0; w < total_work; ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kc = 0; kc < kChunks768; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)  // 4 x 32-byte K-slices inside the 128-byte swizzle row
+                        tcgen05_mma<K::kTf32>(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                    tcgen05_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold + shortlist =====================
+        const int quad = warp & 3;  // TMEM lanes 32*quad .. 32*quad+31 are this warp's
+        uint32_t w = 0;
+        for (uint32_t nt = blockIdx.x; nt < a.n_tiles; nt += gridDim.x)
+            for (uint32_t mt = 0; mt < a.m_tiles; ++mt, ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                const uint32_t q = mt * BM + quad * 32 + lane;
+                const bool q_ok = q < a.n_queries;
+                const size_t slot = (size_t)blockIdx.x * a.b_pad + q;
+                uint64_t* lst = a.lists + slot * CAP;
+                uint32_t cnt = q_ok ? a.cnt[slot] : 0;
+                float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
+
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    const uint32_t row0 = nt * BN + ch * 32;
+                    if (row0 >= a.n_rows) break;  // uniform
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + ch * 32, v);
+                    uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
+                    if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (s >= tau && (mw & (1u << j))) {
+                            if (cnt < CAP) lst[cnt] = pack_key(s, row0 + j);
+                            ++cnt;
+                        }
+                    }
+                    // lists that could overflow on the next chunk are compacted now (warp-cooperative)
+                    unsigned todo = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        __syncwarp();
+                        const uint64_t* L = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)lst, src));
+                        const uint32_t c = min(__shfl_sync(0xffffffffu, cnt, src), (uint32_t)CAP);
+                        uint64_t key[KPL];
+#pragma unroll
+                        for (int r = 0; r < KPL; ++r) key[r] = (uint32_t)(r * 32 + lane) < c ? __ldcg(L + r * 32 + lane) : 0ull;
+                        warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+                        for (int r = 0; r < KPL; ++r)
+                            if (r * 32 + lane < KPRIME) const_cast<uint64_t*>(L)[r * 32 + lane] = key[r];
+                        const uint64_t kth = __shfl_sync(0xffffffffu, key[(KPRIME - 1) >> 5], (KPRIME - 1) & 31);
+                        if (lane == src) {
+                            cnt = KPRIME;  // c > CAP - 32 >= KPRIME, so the list is full down to its k'-th entry
+                            const uint32_t t = (uint32_t)(kth >> 32);
+                            atomicMax(a.tau + q, t);
+                            tau = fmaxf(tau, ord_to_float(t));
+                        }
+                        __syncwarp();
+                    }
+                }
+                // accumulator fully read -> hand TMEM back to the MMA warp
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (q_ok) a.cnt[slot] = cnt;
+            }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ prep
+// Normalised fp32 queries -> operand matrix [b_pad, 768] (bf16-rounded or fp32 copy), zero rows for padding,
+// and eps[q], the rigorous bound on |tensor-core score - exact fp32 score| for unit-norm rows.
+template <typename T>
+__global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_pad, T* __restrict__ q_op,
+                                    float* __restrict__ eps, uint32_t* __restrict__ tau, uint32_t* __restrict__ flag_count) {
+    const int q = blockIdx.x, lane = threadIdx.x;  // one warp per query row
+    if (q == 0 && lane == 0) *flag_count = 0;
+    float err2 = 0.f;
+    for (int j = lane; j < kDim; j += 32) {
+        float v = q < B ? qn[(size_t)q * kDim + j] : 0.f;
+        if constexpr (sizeof(T) == 2) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            q_op[(size_t)q * kDim + j] = h;
+            float d = v - __bfloat162float(h);
+            err2 += d * d;
+        } else {
+            q_op[(size_t)q * kDim + j] = v;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, m);
+    if (lane == 0) {
+        // bf16 rows: stored rows are exact operands, only the query is rounded: |err| <= ||dq|| * ||x||, with
+        // ||x|| <= 1 + 2^-8 after bf16 rounding of a unit row.  tf32: both operands lose 13 mantissa bits:
+        // |err| <= 2^-10 (||q|| ||x||) * 2 + second order.  Both get 2e-5 for fp32 accumulation-order effects.
+        float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 2e-5f : 2.0f * 0.0009765625f * 1.001f + 2e-5f;
+        eps[q] = e;
+        tau[q] = kOrdNegInf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ select + rescore
+constexpr int kSelThreads = 256;
+
+// One CTA per query: union of that query's per-CTA lists -> best kp (= k') approximate keys, plus tau~.
+__global__ void __launch_bounds__(kSelThreads)
+select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ tau,
+                    int grid_ctas, int b_pad, int cap, int kp, uint64_t* __restrict__ short_keys, float* __restrict__ tau_tilde) {
+    constexpr int kBuf = 2048;
+    __shared__ uint64_t buf[kBuf];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+    __syncthreads();
+    int fill = kp;  // [0, kp) holds the running best
+    uint32_t total = 0;
+    for (int g = 0; g < grid_ctas; ++g) {
+        const size_t slot = (size_t)g * b_pad + q;
+        const int c = min((int)cnt[slot], cap);
+        if (c == 0) continue;
+        if (fill + c > kBuf) {
+            block_bitonic_sort_desc(buf, kBuf);
+            for (int i = kp + threadIdx.x; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+            __syncthreads();
+            fill = kp;
+        }
+        const uint64_t* L = lists + slot * cap;
+        for (int i = threadIdx.x; i < c; i += kSelThreads) buf[fill + i] = __ldcg(L + i);
+        fill += c;
+        total += c;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(buf, kBuf);
+    for (int i = threadIdx.x; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = buf[i];
+    if (threadIdx.x == 0) {
+        // everything discarded anywhere scored <= max(shared threshold, k'-th kept score when the union overflowed)
+        float t = ord_to_float(tau[q]);
+        if (total > (uint32_t)kp && buf[kp - 1]) t = fmaxf(t, key_score(buf[kp - 1]));
+        tau_tilde[q] = t;
+    }
+}
+
+// K4: one warp per (query, shortlisted row): canonical fp32 dot -> exact key.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rescore_kernel(const T* __restrict__ rows, const float* __restrict__ qn, const uint64_t* __restrict__ short_keys,
+               int B, int kp, uint64_t* __restrict__ exact_keys) {
+    const int lane = threadIdx.x & 31;
+    const size_t item = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= (size_t)B * kp) return;
+    const int q = (int)(item / kp);
+    const uint64_t key = short_keys[item];
+    if (key == 0ull) {
+        if (lane == 0) exact_keys[item] = 0ull;
+        return;
+    }
+    const uint32_t id = key_id(key);
+    RowFrag<T> x;
+    x.load(rows + (size_t)id * kDim, lane);
+    float4 qv[kChunks], xv[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        qv[c] = *reinterpret_cast<const float4*>(qn + (size_t)q * kDim + c * 128 + lane * 4);
+        xv[c] = x.get(c);
+    }
+    const float s = warp_butterfly_sum(lane_dot(qv, xv));
+    if (lane == 0) exact_keys[item] = pack_key(s, id);
+}
+
+// Per query: sort the kp exact keys, emit top-k, verify the exactness margin.
+__global__ void __launch_bounds__(kSelThreads)
+finalize_kernel(const uint64_t* __restrict__ exact_keys, const float* __restrict__ tau_tilde, const float* __restrict__ eps,
+                int kp, int k, int64_t id_base, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                uint32_t* __restrict__ flags, uint32_t* __restrict__ flag_count) {
+    __shared__ uint64_t buf[256];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < kp; i += kSelThreads) buf[i] = exact_keys[(size_t)q * kp + i];
+    block_bitonic_sort_desc(buf, kp);
+    for (int j = threadIdx.x; j < k; j += kSelThreads) {
+        const uint64_t key = j < kp ? buf[j] : 0ull;
+        out_scores[(size_t)q * k + j] = key ? key_score(key) : -INFINITY;
+        out_ids[(size_t)q * k + j] = key ? (int64_t)key_id(key) + id_base : -1;
+    }
+    if (threadIdx.x == 0) {
+        const float tt = tau_tilde[q];
+        bool ok = true;
+        if (tt != -INFINITY) {  // something was discarded: the k-th exact score must clear every discarded row's bound
+            const uint64_t kth = (k <= kp) ? buf[k - 1] : 0ull;
+            ok = kth != 0ull && key_score(kth) > tt + eps[q];
+        }
+        flags[q] = ok ? 0u : 1u;
+        if (!ok) atomicAdd(flag_count, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// [rows, 768] row-major matrix, box = one 128-byte K-chunk x box_rows rows, 128B swizzle.
+bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int dtype, int box_rows) {
+    auto enc = get_encode();
+    if (!enc || rows == 0) return false;
+    const bool f32 = dtype == MQVS_F32;
+    cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kDim * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int CAP, int KPRIME>
+cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a, int grid, cudaStream_t st) {
+    auto kern = tc_score_kernel<T, CAP, KPRIME>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kThreads, kSmemBytes, st>>>(mq, mx, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+Plan plan(int k, int B, int sm_count) {
+    Plan p{};
+    p.kprime = k <= 10 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : 256));
+    p.cap = p.kprime <= 64 ? 128 : 2 * p.kprime;
+    p.b_pad = (B + BM - 1) / BM * BM;
+    p.grid = sm_count;
+    return p;
+}
+
+size_t op_bytes(const Plan& p, int dtype) { return (size_t)p.b_pad * kDim * (dtype == MQVS_F32 ? 4 : 2); }
+size_t lists_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * p.cap * sizeof(uint64_t); }
+size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint32_t); }
+
+const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
+                   int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+    CUtensorMap mq, mx;
+    if (!make_map(&mq, b.q_op, (uint64_t)p.b_pad, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
+    if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
+    if (dtype == MQVS_F32)
+        prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps, b.tau, b.flag_count);
+    else
+        prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps, b.tau, b.flag_count);
+    if (cudaMemsetAsync(b.cnt, 0, cnt_bytes(p), st) != cudaSuccess) return "cudaMemsetAsync failed";
+
+    ScoreArgs a{};
+    a.n_rows = n_rows;
+    a.n_queries = (uint32_t)B;
+    a.m_tiles = (uint32_t)(p.b_pad / BM);
+    a.n_tiles = (n_rows + BN - 1) / BN;
+    a.mask = mask;
+    a.tau = b.tau;
+    a.cnt = b.cnt;
+    a.lists = b.lists;
+    a.b_pad = (uint32_t)p.b_pad;
+    const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.n_tiles);
+    cudaError_t e = cudaSuccess;
+#define MQVS_TC(CAP_, KP_)                                                                                  \
+    if (p.cap == CAP_ && p.kprime == KP_)                                                                   \
+        e = dtype == MQVS_F32 ? launch_score<float, CAP_, KP_>(mq, mx, a, grid, st)                         \
+                              : launch_score<__nv_bfloat16, CAP_, KP_>(mq, mx, a, grid, st);
+    MQVS_TC(128, 32)
+    MQVS_TC(128, 64)
+    MQVS_TC(256, 128)
+    MQVS_TC(512, 256)
+#undef MQVS_TC
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+
+    select_lists_kernel<<<B, kSelThreads, 0, st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap, p.kprime, b.short_keys, b.tau_tilde);
+    const size_t items = (size_t)B * p.kprime;
+    const unsigned rs_grid = (unsigned)((items + 7) / 8);
+    if (dtype == MQVS_F32)
+        rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+    else
+        rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+    finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps, p.kprime, k, id_base, out_scores, out_ids,
+                                               b.flags, b.flag_count);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace tc
+}  // namespace mqvs

@@ -1,0 +1,42 @@
+// tc.h -- host interface of the tensor-core search path (kernels_tc.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mqvs {
+namespace tc {
+
+struct Plan {
+    int kprime;  // shortlist size per query (k' > k): rescored exactly
+    int cap;     // per-(CTA, query) candidate list capacity
+    int b_pad;   // queries padded to a multiple of 128
+    int grid;    // persistent CTAs (one per SM)
+};
+
+struct Buffers {       // all device memory, owned by the store handle
+    void* q_op;        // [b_pad, 768] query operand matrix (bf16 or fp32)
+    float* eps;        // [b_pad]
+    uint32_t* tau;     // [b_pad]
+    uint32_t* cnt;     // [grid, b_pad]
+    uint64_t* lists;   // [grid, b_pad, cap]
+    uint64_t* short_keys;  // [B, kprime]
+    uint64_t* exact_keys;  // [B, kprime]
+    float* tau_tilde;  // [B]
+    uint32_t* flags;   // [B] 1 = exactness margin not proven, needs the exact scan
+    uint32_t* flag_count;
+};
+
+Plan plan(int k, int B, int sm_count);
+size_t op_bytes(const Plan& p, int dtype);
+size_t lists_bytes(const Plan& p);
+size_t cnt_bytes(const Plan& p);
+
+// Enqueue the whole tensor-core search on `st`.  Returns nullptr or an error message.
+const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
+                   int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st);
+
+constexpr int kLaunchesPerSearch = 5;  // prep, score, select, rescore, finalize
+
+}  // namespace tc
+}  // namespace mqvs
