@@ -184,12 +184,12 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     int rc;
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
-        const size_t small = (size_t)plan.b_pad * (sizeof(float) * 2 + sizeof(uint32_t) * 2) + 64;
+        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 16) * sizeof(uint32_t);
         if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
         if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
-        if ((rc = s->tc_keys.ensure((size_t)B * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
+        if ((rc = s->tc_keys.ensure((size_t)plan.b_pad * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
     }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
 
@@ -202,15 +202,15 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         tc::Buffers b{};
         char* sm = (char*)s->tc_small.p;
         b.q_op = s->tc_qop.p;
-        b.eps = (float*)sm;
-        b.tau_tilde = b.eps + plan.b_pad;
+        b.tau_tilde = (float*)sm;
         b.tau = (uint32_t*)(b.tau_tilde + plan.b_pad);
-        b.flag_count = b.tau + plan.b_pad;       // flag_count immediately followed by flags[B]: one D2H copy
+        b.eps = (float*)(b.tau + plan.b_pad);    // [B]
+        b.flag_count = (uint32_t*)(b.eps + B);   // flag_count immediately followed by flags[B]: one D2H copy
         b.flags = b.flag_count + 1;
         b.cnt = (uint32_t*)s->tc_cnt.p;
         b.lists = (uint64_t*)s->tc_lists.p;
         b.short_keys = (uint64_t*)s->tc_keys.p;
-        b.exact_keys = b.short_keys + (size_t)B * plan.kprime;
+        b.exact_keys = b.short_keys + (size_t)plan.b_pad * plan.kprime;
         s->last_flags_dev = b.flag_count;
         CU(cudaEventRecord(ev[1], st));
         const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
@@ -218,7 +218,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
         passes = 1;
-        s->stats.kernel_launches += tc::kLaunchesPerSearch;
+        s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B);
         s->stats.last_path = 1;
     } else {
         CU(cudaEventRecord(ev[1], st));

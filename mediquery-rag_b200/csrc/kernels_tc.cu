@@ -43,6 +43,9 @@ constexpr int kBBytes = BN * kRowBytes;
 constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
 constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
+constexpr int kMaxQueriesPerLaunch = 4096;
+constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
+constexpr uint32_t kSegmentGrowth = 16;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 template <typename T>
@@ -88,6 +91,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// Contiguous L2 prefetch (no tensor map): pulls whole corpus rows into L2 in address order, so HBM sees long
+// sequential bursts instead of the 128-byte column slices the swizzled TMA boxes ask for.
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -119,6 +127,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// max of 32 fp32 values held as raw bits: 16 three-input max instructions, depth 4
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+    float a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        a[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float b0 = fmax3(a[0], a[1], a[2]), b1 = fmax3(a[3], a[4], a[5]), b2 = fmax3(a[6], a[7], a[8]);
+    const float b3 = fmaxf(a[9], a[10]);
+    return fmaxf(fmax3(b0, b1, b2), b3);
 }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
@@ -184,8 +209,11 @@ struct ScoreArgs {
     uint32_t n_rows;        // valid corpus rows
     uint32_t n_queries;     // valid queries (B); lanes beyond are padding
     uint32_t m_tiles;       // ceil(B / 128)
-    uint32_t n_tiles;       // ceil(n_rows / 256)
+    uint32_t tile_begin;    // this launch scores corpus tiles [tile_begin, tile_end) (256 rows each)
+    uint32_t tile_end;
     const uint32_t* mask;   // optional allow-mask over rows (device), or nullptr
+    const uint8_t* rows;    // corpus base (for the contiguous L2 prefetch)
+    uint32_t prefetch;      // 1: prefetch the CTA's next corpus tile into L2 while the current one is consumed
     uint32_t* tau;          // [B_pad] shared per-query threshold, order-preserving uint, atomicMax
     uint32_t* cnt;          // [grid][B_pad] list lengths
     uint64_t* lists;        // [grid][B_pad][CAP]
@@ -234,15 +262,24 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const uint32_t total_work = a.n_tiles > blockIdx.x ? ((a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * a.m_tiles : 0;
+    const uint32_t first_tile = a.tile_begin + blockIdx.x;
+    const uint32_t total_work = a.tile_end > first_tile ? ((a.tile_end - first_tile + gridDim.x - 1) / gridDim.x) * a.m_tiles : 0;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t nt = blockIdx.x; nt < a.n_tiles; nt += gridDim.x)
+            constexpr uint32_t kTileBytes = BN * kDim * sizeof(T);
+            constexpr uint32_t kSlice = kTileBytes / kChunks768;  // one slice of the next tile per K-chunk of this one
+            for (uint32_t nt = first_tile; nt < a.tile_end; nt += gridDim.x)
                 for (uint32_t mt = 0; mt < a.m_tiles; ++mt)
                     for (int kc = 0; kc < kChunks768; ++kc) {
+                        if (a.prefetch && mt == 0) {
+                            const uint32_t nxt = nt + gridDim.x;
+                            const uint64_t off = (uint64_t)nxt * kTileBytes + (uint64_t)kc * kSlice;
+                            const uint64_t end = (uint64_t)a.n_rows * kDim * sizeof(T);
+                            if (nxt < a.tile_end && off + kSlice <= end) l2_prefetch(a.rows + off, kSlice);
+                        }
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                         mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
@@ -278,7 +315,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ===================== epilogue: threshold + shortlist =====================
         const int quad = warp & 3;  // TMEM lanes 32*quad .. 32*quad+31 are this warp's
         uint32_t w = 0;
-        for (uint32_t nt = blockIdx.x; nt < a.n_tiles; nt += gridDim.x)
+        for (uint32_t nt = first_tile; nt < a.tile_end; nt += gridDim.x)
             for (uint32_t mt = 0; mt < a.m_tiles; ++mt, ++w) {
                 const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
                 const uint32_t q = mt * BM + quad * 32 + lane;
@@ -298,14 +335,20 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     uint32_t v[32];
                     __syncwarp();
                     tmem_ld32(taddr + ch * 32, v);
-                    uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
-                    if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
+                    // fast reject: one 3-input max tree per 32 scores, one compare.  (Masked / out-of-range rows are
+                    // not excluded here -- that only makes the test conservative; the slow path applies the mask.)
+                    const unsigned hit = __ballot_sync(0xffffffffu, max32(v) >= tau);
+                    if (hit == 0u) continue;
+                    if (hit & (1u << lane)) {
+                        uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
+                        if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (s >= tau && (mw & (1u << j))) {
-                            if (cnt < CAP) lst[cnt] = pack_key(s, row0 + j);
-                            ++cnt;
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]);
+                            if (s >= tau && (mw & (1u << j))) {
+                                if (cnt < CAP) lst[cnt] = pack_key(s, row0 + j);
+                                ++cnt;
+                            }
                         }
                     }
                     // lists that could overflow on the next chunk are compacted now (warp-cooperative)
@@ -354,9 +397,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // and eps[q], the rigorous bound on |tensor-core score - exact fp32 score| for unit-norm rows.
 template <typename T>
 __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_pad, T* __restrict__ q_op,
-                                    float* __restrict__ eps, uint32_t* __restrict__ tau, uint32_t* __restrict__ flag_count) {
+                                    float* __restrict__ eps, uint32_t* __restrict__ tau) {
     const int q = blockIdx.x, lane = threadIdx.x;  // one warp per query row
-    if (q == 0 && lane == 0) *flag_count = 0;
     float err2 = 0.f;
     for (int j = lane; j < kDim; j += 32) {
         float v = q < B ? qn[(size_t)q * kDim + j] : 0.f;
@@ -376,7 +418,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_p
         // ||x|| <= 1 + 2^-8 after bf16 rounding of a unit row.  tf32: both operands lose 13 mantissa bits:
         // |err| <= 2^-10 (||q|| ||x||) * 2 + second order.  Both get 2e-5 for fp32 accumulation-order effects.
         float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 2e-5f : 2.0f * 0.0009765625f * 1.001f + 2e-5f;
-        eps[q] = e;
+        if (q < B) eps[q] = e;
         tau[q] = kOrdNegInf;
     }
 }
@@ -384,40 +426,58 @@ __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_p
 // ------------------------------------------------------------------------------------------ select + rescore
 constexpr int kSelThreads = 256;
 
-// One CTA per query: union of that query's per-CTA lists -> best kp (= k') approximate keys, plus tau~.
+// One CTA per query, run after every corpus segment: (running shortlist of earlier segments) U (this segment's
+// per-CTA lists) -> new running shortlist of the kp (= k') best approximate keys, and tau[q] raised to the k'-th
+// best score of everything seen so far -- the threshold the next segment's epilogue filters with.  Entries that
+// cannot beat the current k'-th key are dropped before they reach the sort buffer, and only the filled part of
+// the buffer is sorted, so after the first segment a call costs a few microseconds.
 __global__ void __launch_bounds__(kSelThreads)
-select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ tau,
-                    int grid_ctas, int b_pad, int cap, int kp, uint64_t* __restrict__ short_keys, float* __restrict__ tau_tilde) {
+select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tau,
+                    int grid_ctas, int b_pad, int cap, int kp, int first_segment, uint64_t* __restrict__ short_keys,
+                    float* __restrict__ tau_tilde) {
     constexpr int kBuf = 2048;
+    constexpr int kMaxLists = 256;  // >= number of CTAs of the score kernel (one per SM)
     __shared__ uint64_t buf[kBuf];
-    const int q = blockIdx.x;
-    for (int i = threadIdx.x; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+    __shared__ int cnt_s[kMaxLists];
+    __shared__ int fill_s;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kBuf; i += kSelThreads)
+        buf[i] = (i < kp && !first_segment) ? short_keys[(size_t)q * kp + i] : 0ull;
+    for (int g = tid; g < kMaxLists; g += kSelThreads)
+        cnt_s[g] = g < grid_ctas ? min((int)cnt[(size_t)g * b_pad + q], cap) : 0;
+    if (tid == 0) fill_s = kp;
     __syncthreads();
-    int fill = kp;  // [0, kp) holds the running best
-    uint32_t total = 0;
-    for (int g = 0; g < grid_ctas; ++g) {
-        const size_t slot = (size_t)g * b_pad + q;
-        const int c = min((int)cnt[slot], cap);
-        if (c == 0) continue;
-        if (fill + c > kBuf) {
-            block_bitonic_sort_desc(buf, kBuf);
-            for (int i = kp + threadIdx.x; i < kBuf; i += kSelThreads) buf[i] = 0ull;
-            __syncthreads();
-            fill = kp;
+    uint64_t floor_key = buf[kp - 1];  // sorted by the previous call; 0 = shortlist not full yet
+    int g0 = 0;
+    while (g0 < grid_ctas) {
+        // batch [g0, g1): as many lists as fit in the buffer even if every entry survives the filter
+        int g1 = g0, room = kBuf - fill_s;
+        while (g1 < grid_ctas && cnt_s[g1] <= room) room -= cnt_s[g1++];
+        for (int g = g0 + warp; g < g1; g += kSelThreads / 32) {  // one warp per list
+            const int c = cnt_s[g];
+            const uint64_t* L = lists + ((size_t)g * b_pad + q) * cap;
+            for (int i = lane; i < c; i += 32) {
+                const uint64_t key = __ldcg(L + i);
+                if (key > floor_key) buf[atomicAdd(&fill_s, 1)] = key;
+            }
         }
-        const uint64_t* L = lists + slot * cap;
-        for (int i = threadIdx.x; i < c; i += kSelThreads) buf[fill + i] = __ldcg(L + i);
-        fill += c;
-        total += c;
+        __syncthreads();
+        const int n_sort = max(2 * kp, next_pow2(fill_s));  // untouched slots beyond fill_s are zero
+        block_bitonic_sort_desc(buf, n_sort);
+        floor_key = buf[kp - 1];
+        __syncthreads();
+        for (int i = kp + tid; i < n_sort; i += kSelThreads) buf[i] = 0ull;
+        if (tid == 0) fill_s = kp;
+        __syncthreads();
+        g0 = g1;
     }
-    __syncthreads();
-    block_bitonic_sort_desc(buf, kBuf);
-    for (int i = threadIdx.x; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = buf[i];
-    if (threadIdx.x == 0) {
-        // everything discarded anywhere scored <= max(shared threshold, k'-th kept score when the union overflowed)
-        float t = ord_to_float(tau[q]);
-        if (total > (uint32_t)kp && buf[kp - 1]) t = fmaxf(t, key_score(buf[kp - 1]));
-        tau_tilde[q] = t;
+    for (int i = tid; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = buf[i];
+    if (tid == 0) {
+        // every row discarded so far (epilogue filter, list compaction, this selection) scored <= the k'-th best
+        uint32_t t = tau[q];
+        if (buf[kp - 1]) t = max(t, (uint32_t)(buf[kp - 1] >> 32));
+        tau[q] = t;
+        tau_tilde[q] = ord_to_float(t);
     }
 }
 
@@ -518,8 +578,9 @@ cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const Sco
 Plan plan(int k, int B, int sm_count) {
     Plan p{};
     p.kprime = k <= 10 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : 256));
-    p.cap = p.kprime <= 64 ? 128 : 2 * p.kprime;
-    p.b_pad = (B + BM - 1) / BM * BM;
+    p.cap = 512;  // the first segment appends a whole 256-row tile per (CTA, query) without compaction
+    const int chunk = B < kMaxQueriesPerLaunch ? B : kMaxQueriesPerLaunch;
+    p.b_pad = (chunk + BM - 1) / BM * BM;
     p.grid = sm_count;
     return p;
 }
@@ -528,50 +589,78 @@ size_t op_bytes(const Plan& p, int dtype) { return (size_t)p.b_pad * kDim * (dty
 size_t lists_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * p.cap * sizeof(uint64_t); }
 size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint32_t); }
 
-const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
-                   int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
+    uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
+    for (uint32_t end = kFirstSegmentTiles; ; end *= kSegmentGrowth) { ++segs; if (end >= tiles) break; }
+    const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
+    return chunks * (int)(1 + 2 * segs + 2);
+}
+
+const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn_all, int B_all,
+                   int k, const uint32_t* mask, int64_t id_base, float* out_scores_all, int64_t* out_ids_all, cudaStream_t st) {
     CUtensorMap mq, mx;
     if (!make_map(&mq, b.q_op, (uint64_t)p.b_pad, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
-    if (dtype == MQVS_F32)
-        prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps, b.tau, b.flag_count);
-    else
-        prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps, b.tau, b.flag_count);
-    if (cudaMemsetAsync(b.cnt, 0, cnt_bytes(p), st) != cudaSuccess) return "cudaMemsetAsync failed";
+    const uint32_t n_tiles = (n_rows + BN - 1) / BN;
+    if (cudaMemsetAsync(b.flag_count, 0, sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
 
-    ScoreArgs a{};
-    a.n_rows = n_rows;
-    a.n_queries = (uint32_t)B;
-    a.m_tiles = (uint32_t)(p.b_pad / BM);
-    a.n_tiles = (n_rows + BN - 1) / BN;
-    a.mask = mask;
-    a.tau = b.tau;
-    a.cnt = b.cnt;
-    a.lists = b.lists;
-    a.b_pad = (uint32_t)p.b_pad;
-    const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.n_tiles);
-    cudaError_t e = cudaSuccess;
-#define MQVS_TC(CAP_, KP_)                                                                                  \
-    if (p.cap == CAP_ && p.kprime == KP_)                                                                   \
-        e = dtype == MQVS_F32 ? launch_score<float, CAP_, KP_>(mq, mx, a, grid, st)                         \
-                              : launch_score<__nv_bfloat16, CAP_, KP_>(mq, mx, a, grid, st);
-    MQVS_TC(128, 32)
-    MQVS_TC(128, 64)
-    MQVS_TC(256, 128)
-    MQVS_TC(512, 256)
+    // queries are processed kMaxQueriesPerLaunch at a time (bounds the candidate-list memory)
+    for (int q0 = 0; q0 < B_all; q0 += kMaxQueriesPerLaunch) {
+        const int B = std::min(kMaxQueriesPerLaunch, B_all - q0);
+        const int b_pad = (B + BM - 1) / BM * BM;
+        const float* qn = qn_all + (size_t)q0 * kDim;
+        if (dtype == MQVS_F32)
+            prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps + q0, b.tau);
+        else
+            prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps + q0, b.tau);
+
+        ScoreArgs a{};
+        a.n_rows = n_rows;
+        a.n_queries = (uint32_t)B;
+        a.m_tiles = (uint32_t)(b_pad / BM);
+        a.mask = mask;
+        a.rows = (const uint8_t*)rows;
+        a.prefetch = 0u;  // measured slower on B200 (r01: 0.86 -> 1.16 ms at 1M x 768 fp32, B=64): kept switchable, off
+        a.tau = b.tau;
+        a.cnt = b.cnt;
+        a.lists = b.lists;
+        a.b_pad = (uint32_t)p.b_pad;
+        // Corpus segments of geometrically growing size.  After each one the per-query threshold becomes the k'-th
+        // best score over EVERYTHING scored so far (select_lists_kernel), so a segment 16x larger than all before it
+        // appends only ~15 k' candidates per query instead of re-learning its threshold in every CTA.
+        uint32_t begin = 0;
+        for (uint32_t end = kFirstSegmentTiles; begin < n_tiles; end *= kSegmentGrowth) {
+            a.tile_begin = begin;
+            a.tile_end = std::min(end, n_tiles);
+            const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
+            if (cudaMemsetAsync(b.cnt, 0, (size_t)grid * p.b_pad * sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
+            cudaError_t e = cudaSuccess;
+#define MQVS_TC(KP_)                                                                          \
+    if (p.kprime == KP_)                                                                      \
+        e = dtype == MQVS_F32 ? launch_score<float, 512, KP_>(mq, mx, a, grid, st)            \
+                              : launch_score<__nv_bfloat16, 512, KP_>(mq, mx, a, grid, st);
+            MQVS_TC(32)
+            MQVS_TC(64)
+            MQVS_TC(128)
+            MQVS_TC(256)
 #undef MQVS_TC
-    if (e != cudaSuccess) return cudaGetErrorString(e);
+            if (e != cudaSuccess) return cudaGetErrorString(e);
+            select_lists_kernel<<<B, kSelThreads, 0, st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap, p.kprime, begin == 0,
+                                                           b.short_keys, b.tau_tilde);
+            begin = a.tile_end;
+        }
 
-    select_lists_kernel<<<B, kSelThreads, 0, st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap, p.kprime, b.short_keys, b.tau_tilde);
-    const size_t items = (size_t)B * p.kprime;
-    const unsigned rs_grid = (unsigned)((items + 7) / 8);
-    if (dtype == MQVS_F32)
-        rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
-    else
-        rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
-    finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps, p.kprime, k, id_base, out_scores, out_ids,
-                                               b.flags, b.flag_count);
-    e = cudaGetLastError();
+        const size_t items = (size_t)B * p.kprime;
+        const unsigned rs_grid = (unsigned)((items + 7) / 8);
+        if (dtype == MQVS_F32)
+            rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+        else
+            rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+        finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps + q0, p.kprime, k, id_base,
+                                                   out_scores_all + (size_t)q0 * k, out_ids_all + (size_t)q0 * k,
+                                                   b.flags + q0, b.flag_count);
+    }
+    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

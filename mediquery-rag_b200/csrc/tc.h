@@ -16,13 +16,13 @@ struct Plan {
 
 struct Buffers {       // all device memory, owned by the store handle
     void* q_op;        // [b_pad, 768] query operand matrix (bf16 or fp32)
-    float* eps;        // [b_pad]
+    float* eps;        // [B]
     uint32_t* tau;     // [b_pad]
     uint32_t* cnt;     // [grid, b_pad]
     uint64_t* lists;   // [grid, b_pad, cap]
-    uint64_t* short_keys;  // [B, kprime]
-    uint64_t* exact_keys;  // [B, kprime]
-    float* tau_tilde;  // [B]
+    uint64_t* short_keys;  // [b_pad, kprime]
+    uint64_t* exact_keys;  // [b_pad, kprime]
+    float* tau_tilde;  // [b_pad]
     uint32_t* flags;   // [B] 1 = exactness margin not proven, needs the exact scan
     uint32_t* flag_count;
 };
@@ -36,7 +36,7 @@ size_t cnt_bytes(const Plan& p);
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
                    int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
-constexpr int kLaunchesPerSearch = 5;  // prep, score, select, rescore, finalize
+int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize
 
 }  // namespace tc
 }  // namespace mqvs
