@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "20", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -300,7 +300,9 @@ def main():
                    "ingest_s": round(ingest_s, 3), "scan_passes_per_step": scan_launches / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "scan_simt_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                     "kernel": ("tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, "
+                                "bracketed together)" if st1["last_path"] == 1 else "scan_simt_kernel"),
+                     "algorithmic_bytes_per_launch": algo_bytes,
                      "avg_launch_ms": avg_launch_ms, "scan_share_of_step": scan_ms / ms_total if ms_total else None,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 768 * 4, "d2h_bytes_per_step": B * k * 12},

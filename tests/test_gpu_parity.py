@@ -253,3 +253,90 @@ def test_hypothesis_random_shapes(gpu):
         idx.close()
 
     run()
+
+
+# ------------------------------------------------------------------------------------------ tensor-core path
+TC_CASES = [
+    # n, dtype, B, k, mask fraction   (path forced to the tcgen05 shortlist + fp32 rescoring pipeline)
+    (8192, "bf16", 16, 10, None),
+    (8192, "fp32", 16, 10, None),
+    (50000, "bf16", 100, 10, None),
+    (50000, "fp32", 130, 10, None),
+    (100003, "bf16", 300, 100, None),     # k' = 256, ragged last corpus tile, 3 query tiles
+    (100003, "fp32", 64, 32, None),
+    (70000, "bf16", 64, 10, 0.3),
+    (70000, "fp32", 33, 64, 0.05),
+    (300000, "bf16", 512, 10, None),
+    (4096, "bf16", 1, 5, None),           # smallest store the path accepts, single query
+    (65536, "fp32", 128, 128, 0.001),     # fewer allowed rows (about 65) than k: padded results
+]
+
+
+@pytest.mark.parametrize("n,dtype,B,k,frac", TC_CASES)
+def test_tensor_core_path_matches_oracle_bitwise(gpu, n, dtype, B, k, frac):
+    idx, x, st = build(n, 768, dtype, seed=0x5EED0003)
+    idx.set_path(2)
+    q, planted = O.planted_queries(QSEED, B, 0x5EED0003, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(11).random(n) < frac)
+    s, i = idx.search(q, k, mask)
+    assert idx.stats()["last_path"] == 1
+    assert_bit_equal(s, i, *O.brute_force_topk(qn, st, k, mask))
+    idx.close()
+
+
+def test_tensor_core_path_falls_back_to_exact_scan_when_margin_cannot_be_proven(gpu):
+    """300 exact copies of the best row: the k'-th approximate score ties the k-th, the margin check must flag the
+    query and the exact SIMT scan must repair it -- same ids (lowest row ids of the tie) as the oracle."""
+    n = 20000
+    x = O.synth_rows(SEED, 0, n, 768)
+    x[5000:5300] = x[123]
+    idx = native().Index(768, "bf16")
+    idx.add(x)
+    idx.set_path(2)
+    q = np.stack([x[123] + 0.01 * x[7], x[9000], x[123]])
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    s, i = idx.search(q, 10)
+    assert_bit_equal(s, i, *O.brute_force_topk(qn, st, 10))
+    stats = idx.stats()
+    assert stats["last_path"] == 1 and stats["exact_fallbacks"] >= 2
+
+
+def test_auto_path_choice_and_agreement_between_paths(gpu):
+    n = 131072
+    idx = native().Index(768, "bf16", capacity_rows=n)
+    idx.add_synthetic(SEED, 0, n)
+    q, _ = O.planted_queries(QSEED, 48, SEED, n, 768)
+    idx.set_path(0)
+    auto = idx.search(q, 10)
+    assert idx.stats()["last_path"] == 1          # batch >= 16 on a large store -> tensor cores
+    small = idx.search(q[:4], 10)
+    assert idx.stats()["last_path"] == 0          # small batch -> bandwidth-bound SIMT scan
+    idx.set_path(1)
+    simt = idx.search(q, 10)
+    assert_bit_equal(*auto, *simt)
+    assert_bit_equal(small[0], small[1], simt[0][:4], simt[1][:4])
+
+
+def test_full_size_config3_shape_properties(gpu):
+    """BASELINE config 3 (10M x 768 bf16, k=100, tensor cores + fp32 rerank) at a batch the test can afford;
+    size-independent checks: planted neighbours first, sorted, scores = canonical fp32 of the returned rows,
+    and agreement with the exact SIMT scan on a subset of the queries."""
+    n, B, k = 10_000_000, 256, 100
+    idx = native().Index(768, "bf16", capacity_rows=n)
+    idx.add_synthetic(0x5EED0003, 0, n)
+    q, planted = O.planted_queries(QSEED, B, 0x5EED0003, n, 768)
+    s, i = idx.search(q, k)
+    st = idx.stats()
+    assert st["last_path"] == 1 and st["exact_fallbacks"] == 0
+    assert all(i[b, 0] == planted[b] for b in range(0, B, 2))
+    assert np.all(np.diff(s, axis=1) <= 0) and (i >= 0).all()
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    for b in (0, 1, 77):
+        rows = np.concatenate([O.synth_rows(0x5EED0003, int(r), 1, 768) for r in i[b]])
+        st_b, _ = O.normalize_rows(rows, "bf16", 768)
+        assert np.array_equal(O.canonical_scores(qn[b:b + 1], st_b)[0].view(np.uint32), s[b].view(np.uint32))
+    idx.set_path(1)
+    es, ei = idx.search(q[:6], k)
+    assert_bit_equal(s[:6], i[:6], es, ei)
