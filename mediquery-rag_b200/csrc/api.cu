@@ -144,7 +144,11 @@ bool use_tensor_path(const mqvs_store* s, int B, int k) {
     if (s->path == 1) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2) return true;
-    return B >= 16 && s->n >= 65536;
+    // measured on B200 (profiles/r01_*): the register-resident SIMT scan holds the HBM roofline for 1 query (bf16 rows)
+    // or 1-2 queries (fp32 rows); beyond that its multi-query variants fall to 2-3.4 TB/s while the tensor path streams
+    // the corpus once for up to 128 queries at 4.8-7 TB/s.
+    const int simt_max = s->dtype == MQVS_F32 ? 2 : 1;
+    return B > simt_max && s->n >= 65536;
 }
 
 // Exact SIMT scan of queries [b0, b0 + nb) of s->qn into out rows [b0, ...).  Returns passes launched.

@@ -45,7 +45,12 @@ constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + 
 constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
 constexpr int kMaxQueriesPerLaunch = 4096;
 constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
-constexpr uint32_t kSegmentGrowth = 16;
+// A segment g times larger than everything before it appends about g * k' candidates per query, spread over the
+// CTAs; g is chosen so that a (CTA, query) list expects <= ~200 appends (no compaction; lists hold 512).
+__host__ inline uint32_t segment_growth(int kprime, int grid) {
+    const uint32_t g = (uint32_t)(200ll * grid / kprime);
+    return g < 16u ? 16u : (g > 1024u ? 1024u : g);
+}
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 template <typename T>
@@ -591,7 +596,7 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
-    for (uint32_t end = kFirstSegmentTiles; ; end *= kSegmentGrowth) { ++segs; if (end >= tiles) break; }
+    for (uint64_t end = kFirstSegmentTiles; ; end *= segment_growth(p.kprime, p.grid)) { ++segs; if (end >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
     return chunks * (int)(1 + 2 * segs + 2);
 }
@@ -626,12 +631,12 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.lists = b.lists;
         a.b_pad = (uint32_t)p.b_pad;
         // Corpus segments of geometrically growing size.  After each one the per-query threshold becomes the k'-th
-        // best score over EVERYTHING scored so far (select_lists_kernel), so a segment 16x larger than all before it
-        // appends only ~15 k' candidates per query instead of re-learning its threshold in every CTA.
+        // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
+        // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
         uint32_t begin = 0;
-        for (uint32_t end = kFirstSegmentTiles; begin < n_tiles; end *= kSegmentGrowth) {
+        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end *= segment_growth(p.kprime, p.grid)) {
             a.tile_begin = begin;
-            a.tile_end = std::min(end, n_tiles);
+            a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
             const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
             if (cudaMemsetAsync(b.cnt, 0, (size_t)grid * p.b_pad * sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
             cudaError_t e = cudaSuccess;

@@ -310,13 +310,16 @@ def test_auto_path_choice_and_agreement_between_paths(gpu):
     q, _ = O.planted_queries(QSEED, 48, SEED, n, 768)
     idx.set_path(0)
     auto = idx.search(q, 10)
-    assert idx.stats()["last_path"] == 1          # batch >= 16 on a large store -> tensor cores
-    small = idx.search(q[:4], 10)
-    assert idx.stats()["last_path"] == 0          # small batch -> bandwidth-bound SIMT scan
+    assert idx.stats()["last_path"] == 1          # a real batch on a large store -> tensor cores
+    mid = idx.search(q[:4], 10)
+    assert idx.stats()["last_path"] == 1
+    single = idx.search(q[:1], 10)
+    assert idx.stats()["last_path"] == 0          # single query -> bandwidth-bound SIMT scan
     idx.set_path(1)
     simt = idx.search(q, 10)
     assert_bit_equal(*auto, *simt)
-    assert_bit_equal(small[0], small[1], simt[0][:4], simt[1][:4])
+    assert_bit_equal(mid[0], mid[1], simt[0][:4], simt[1][:4])
+    assert_bit_equal(single[0], single[1], simt[0][:1], simt[1][:1])
 
 
 def test_full_size_config3_shape_properties(gpu):
