@@ -44,12 +44,15 @@ constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
 constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
 constexpr int kMaxQueriesPerLaunch = 4096;
-constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
-// A segment g times larger than everything before it appends about g * k' candidates per query, spread over the
-// CTAs; g is chosen so that a (CTA, query) list expects <= ~200 appends (no compaction; lists hold 512).
-__host__ inline uint32_t segment_growth(int kprime, int grid) {
-    const uint32_t g = (uint32_t)(200ll * grid / kprime);
-    return g < 16u ? 16u : (g > 1024u ? 1024u : g);
+constexpr uint32_t kFirstSegmentTiles = 7;   // 1792 rows: the cold segment's 7 x 256 candidates per query fill exactly
+                                             // one selection batch; the second segment is one tile per CTA
+// Each segment is 16x everything before it.  What matters is hits per warp-chunk (32 queries x 32 rows = 1024 scores
+// against thresholds learnt on S rows: ~1024 k'/S), not appends per list: growing faster (measured: 2 segments instead
+// of 3 on 1M rows) sends most chunks down the slow path and costs 1.6x at batch 4096.
+__host__ inline uint32_t segment_growth(int /*kprime*/, int /*grid*/) { return 16u; }
+// segment ends (in tiles): 7, 7 + grid, then x16 each
+__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid) {
+    return end == kFirstSegmentTiles ? end + (uint64_t)grid : end * segment_growth(kprime, grid);
 }
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -139,9 +142,8 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// max of 32 fp32 values held as raw bits: 16 three-input max instructions, depth 4
-__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
-    float a[11];
+// max of 32 fp32 values held as raw bits: 16 three-input max instructions, depth 4; a[i] = max of triple i
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float (&a)[11]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i)
         a[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
@@ -342,17 +344,34 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     tmem_ld32(taddr + ch * 32, v);
                     // fast reject: one 3-input max tree per 32 scores, one compare.  (Masked / out-of-range rows are
                     // not excluded here -- that only makes the test conservative; the slow path applies the mask.)
-                    const unsigned hit = __ballot_sync(0xffffffffu, max32(v) >= tau);
+                    float grp[11];
+                    const float mx = max32(v, grp);
+                    const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
                     if (hit == 0u) continue;
-                    if (hit & (1u << lane)) {
+                    if (mx >= tau) {
+                        // slow path, cost proportional to the number of hits: find the triples that hold one, then
+                        // test only their elements (mask / out-of-range rows are excluded here)
                         uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
                         if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
+                        unsigned gm = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]);
+                        for (int i = 0; i < 11; ++i) gm |= grp[i] >= tau ? (1u << i) : 0u;
+                        auto offer = [&](uint32_t bits, int j) {
+                            const float s = __uint_as_float(bits);
                             if (s >= tau && (mw & (1u << j))) {
                                 if (cnt < CAP) lst[cnt] = pack_key(s, row0 + j);
                                 ++cnt;
+                            }
+                        };
+                        while (gm) {
+                            const int g = __ffs(gm) - 1;
+                            gm &= gm - 1;
+                            switch (g) {
+#define MQVS_TRIPLE(G_) case G_: offer(v[3 * G_], 3 * G_); offer(v[3 * G_ + 1], 3 * G_ + 1); offer(v[3 * G_ + 2], 3 * G_ + 2); break;
+                                MQVS_TRIPLE(0) MQVS_TRIPLE(1) MQVS_TRIPLE(2) MQVS_TRIPLE(3) MQVS_TRIPLE(4)
+                                MQVS_TRIPLE(5) MQVS_TRIPLE(6) MQVS_TRIPLE(7) MQVS_TRIPLE(8) MQVS_TRIPLE(9)
+#undef MQVS_TRIPLE
+                                default: offer(v[30], 30); offer(v[31], 31); break;
                             }
                         }
                     }
@@ -441,30 +460,46 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
                     int grid_ctas, int b_pad, int cap, int kp, int first_segment, uint64_t* __restrict__ short_keys,
                     float* __restrict__ tau_tilde) {
     constexpr int kBuf = 2048;
-    constexpr int kMaxLists = 256;  // >= number of CTAs of the score kernel (one per SM)
+    constexpr int kMaxLists = kSelThreads;  // >= number of CTAs of the score kernel (one per SM)
     __shared__ uint64_t buf[kBuf];
-    __shared__ int cnt_s[kMaxLists];
+    __shared__ int pre_s[kMaxLists + 1];    // exclusive prefix sum of the list lengths
+    __shared__ int warp_tot[kSelThreads / 32];
     __shared__ int fill_s;
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < kBuf; i += kSelThreads)
-        buf[i] = (i < kp && !first_segment) ? short_keys[(size_t)q * kp + i] : 0ull;
-    for (int g = tid; g < kMaxLists; g += kSelThreads)
-        cnt_s[g] = g < grid_ctas ? min((int)cnt[(size_t)g * b_pad + q], cap) : 0;
+    // list lengths -> block-wide exclusive scan (one list per thread)
+    const int mine = tid < grid_ctas ? min((int)cnt[(size_t)tid * b_pad + q], cap) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    const int n_sort0 = first_segment ? 0 : kp;
+    for (int i = tid; i < kBuf; i += kSelThreads) buf[i] = i < n_sort0 ? short_keys[(size_t)q * kp + i] : 0ull;
     if (tid == 0) fill_s = kp;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    pre_s[tid + 1] = base + incl;
+    if (tid == 0) pre_s[0] = 0;
     __syncthreads();
     uint64_t floor_key = buf[kp - 1];  // sorted by the previous call; 0 = shortlist not full yet
     int g0 = 0;
     while (g0 < grid_ctas) {
         // batch [g0, g1): as many lists as fit in the buffer even if every entry survives the filter
-        int g1 = g0, room = kBuf - fill_s;
-        while (g1 < grid_ctas && cnt_s[g1] <= room) room -= cnt_s[g1++];
-        for (int g = g0 + warp; g < g1; g += kSelThreads / 32) {  // one warp per list
-            const int c = cnt_s[g];
-            const uint64_t* L = lists + ((size_t)g * b_pad + q) * cap;
-            for (int i = lane; i < c; i += 32) {
-                const uint64_t key = __ldcg(L + i);
-                if (key > floor_key) buf[atomicAdd(&fill_s, 1)] = key;
+        const int room = kBuf - kp;
+        int g1 = g0;
+        while (g1 < grid_ctas && pre_s[g1 + 1] - pre_s[g0] <= room) ++g1;
+        const int first = pre_s[g0], total = pre_s[g1] - first;
+        for (int idx = tid; idx < total; idx += kSelThreads) {  // all entries of the batch, independent loads
+            int lo = g0, hi = g1;                               // list g with pre_s[g] <= first + idx < pre_s[g + 1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre_s[mid] <= first + idx) lo = mid; else hi = mid;
             }
+            const uint64_t key = __ldcg(lists + ((size_t)lo * b_pad + q) * cap + (first + idx - pre_s[lo]));
+            if (key > floor_key) buf[atomicAdd(&fill_s, 1)] = key;
         }
         __syncthreads();
         const int n_sort = max(2 * kp, next_pow2(fill_s));  // untouched slots beyond fill_s are zero
@@ -596,7 +631,7 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
-    for (uint64_t end = kFirstSegmentTiles; ; end *= segment_growth(p.kprime, p.grid)) { ++segs; if (end >= tiles) break; }
+    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end, p.kprime, p.grid)) { ++segs; if (end >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
     return chunks * (int)(1 + 2 * segs + 2);
 }
@@ -634,7 +669,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
         // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
         uint32_t begin = 0;
-        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end *= segment_growth(p.kprime, p.grid)) {
+        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end, p.kprime, p.grid)) {
             a.tile_begin = begin;
             a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
             const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
