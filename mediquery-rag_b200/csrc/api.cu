@@ -459,6 +459,7 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         CU(cudaStreamSynchronize(s->st));
     }
     settle_events(s);
+    mqvs::tc::trace_dump();
     return MQVS_OK;
 }
 

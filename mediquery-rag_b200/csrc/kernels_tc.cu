@@ -25,6 +25,10 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "launch.h"
@@ -43,18 +47,19 @@ constexpr int kBBytes = BN * kRowBytes;
 constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
 constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
+constexpr int kStageChunkBytes = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32 scores x 32 lanes) staging for the hit path
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStageChunkBytes;
 constexpr int kMaxQueriesPerLaunch = 4096;
-constexpr uint32_t kFirstSegmentTiles = 7;   // 1792 rows: the cold segment's 7 x 256 candidates per query fill exactly
-                                             // one selection batch; the second segment is one tile per CTA
+constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
 // Each segment is 16x everything before it.  What matters is hits per warp-chunk (32 queries x 32 rows = 1024 scores
 // against thresholds learnt on S rows: ~1024 k'/S), not appends per list: growing faster (measured: 2 segments instead
 // of 3 on 1M rows) sends most chunks down the slow path and costs 1.6x at batch 4096.
 __host__ inline uint32_t segment_growth(int /*kprime*/, int /*grid*/) { return 16u; }
-// segment ends (in tiles): 7, 7 + grid, then x16 each
-__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid) {
-    return end == kFirstSegmentTiles ? end + (uint64_t)grid : end * segment_growth(kprime, grid);
+// segment ends (in tiles): 16, 256, 4096, ... (measured alternatives on 1M rows, r01: 2 segments -> 1.3-1.6x slower,
+// 7 / +grid / x16 -> no gain)
+__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid, uint32_t /*m_tiles*/) {
+    return end * segment_growth(kprime, grid);
 }
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 template <typename T>
 struct Kind;
@@ -142,7 +147,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// max of 32 fp32 values held as raw bits: 16 three-input max instructions, depth 4; a[i] = max of triple i
+// max of 32 fp32 values held as raw bits: 16 three-input max instructions, depth 4
 __device__ __forceinline__ float max32(const uint32_t (&v)[32], float (&a)[11]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i)
@@ -244,6 +249,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint32_t* hit_stage = reinterpret_cast<uint32_t*>(smem_al + (size_t)kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -348,32 +354,28 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     const float mx = max32(v, grp);
                     const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
                     if (hit == 0u) continue;
-                    if (mx >= tau) {
-                        // slow path, cost proportional to the number of hits: find the triples that hold one, then
-                        // test only their elements (mask / out-of-range rows are excluded here)
+                    {
+                        // hit path (some lane of the warp has a survivor): branch-free pass mask per lane, the chunk
+                        // staged in shared memory so survivors can be fetched with a dynamic index -- cost is
+                        // ~100 straight-line instructions + a few per survivor, instead of 32 divergent tests
+                        uint32_t* st = hit_stage + (warp - 2) * 1024;
+                        uint32_t pm = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            st[j * 32 + lane] = v[j];
+                            pm |= __uint_as_float(v[j]) >= tau ? (1u << j) : 0u;
+                        }
                         uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
                         if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
-                        unsigned gm = 0;
-#pragma unroll
-                        for (int i = 0; i < 11; ++i) gm |= grp[i] >= tau ? (1u << i) : 0u;
-                        auto offer = [&](uint32_t bits, int j) {
-                            const float s = __uint_as_float(bits);
-                            if (s >= tau && (mw & (1u << j))) {
-                                if (cnt < CAP) lst[cnt] = pack_key(s, row0 + j);
-                                ++cnt;
-                            }
-                        };
-                        while (gm) {
-                            const int g = __ffs(gm) - 1;
-                            gm &= gm - 1;
-                            switch (g) {
-#define MQVS_TRIPLE(G_) case G_: offer(v[3 * G_], 3 * G_); offer(v[3 * G_ + 1], 3 * G_ + 1); offer(v[3 * G_ + 2], 3 * G_ + 2); break;
-                                MQVS_TRIPLE(0) MQVS_TRIPLE(1) MQVS_TRIPLE(2) MQVS_TRIPLE(3) MQVS_TRIPLE(4)
-                                MQVS_TRIPLE(5) MQVS_TRIPLE(6) MQVS_TRIPLE(7) MQVS_TRIPLE(8) MQVS_TRIPLE(9)
-#undef MQVS_TRIPLE
-                                default: offer(v[30], 30); offer(v[31], 31); break;
-                            }
+                        pm &= mw;
+                        __syncwarp();
+                        while (pm) {
+                            const int j = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            if (cnt < CAP) lst[cnt] = pack_key(__uint_as_float(st[j * 32 + lane]), row0 + j);
+                            ++cnt;
                         }
+                        __syncwarp();
                     }
                     // lists that could overflow on the next chunk are compacted now (warp-cooperative)
                     unsigned todo = __ballot_sync(0xffffffffu, cnt > CAP - 32);
@@ -604,6 +606,19 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int dtype, int 
     return r == CUDA_SUCCESS;
 }
 
+// MQVS_TRACE=1: CUDA events after every launch of a tensor-core search, printed by trace_dump() (developer aid)
+struct Trace {
+    bool on = getenv("MQVS_TRACE") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    void mark(const char* what, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(what, e);
+    }
+} g_trace;
+
 template <typename T, int CAP, int KPRIME>
 cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a, int grid, cudaStream_t st) {
     auto kern = tc_score_kernel<T, CAP, KPRIME>;
@@ -631,7 +646,8 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
-    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end, p.kprime, p.grid)) { ++segs; if (end >= tiles) break; }
+    const uint32_t m_tiles = (uint32_t)((std::min(B, kMaxQueriesPerLaunch) + BM - 1) / BM);
+    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end, p.kprime, p.grid, m_tiles)) { ++segs; if (end >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
     return chunks * (int)(1 + 2 * segs + 2);
 }
@@ -644,6 +660,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
     const uint32_t n_tiles = (n_rows + BN - 1) / BN;
     if (cudaMemsetAsync(b.flag_count, 0, sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
 
+    g_trace.mark("begin", st);
     // queries are processed kMaxQueriesPerLaunch at a time (bounds the candidate-list memory)
     for (int q0 = 0; q0 < B_all; q0 += kMaxQueriesPerLaunch) {
         const int B = std::min(kMaxQueriesPerLaunch, B_all - q0);
@@ -654,6 +671,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         else
             prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps + q0, b.tau);
 
+        g_trace.mark("prep", st);
         ScoreArgs a{};
         a.n_rows = n_rows;
         a.n_queries = (uint32_t)B;
@@ -669,7 +687,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
         // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
         uint32_t begin = 0;
-        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end, p.kprime, p.grid)) {
+        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end, p.kprime, p.grid, a.m_tiles)) {
             a.tile_begin = begin;
             a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
             const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
@@ -685,8 +703,10 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
             MQVS_TC(256)
 #undef MQVS_TC
             if (e != cudaSuccess) return cudaGetErrorString(e);
+            g_trace.mark("score", st);
             select_lists_kernel<<<B, kSelThreads, 0, st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap, p.kprime, begin == 0,
                                                            b.short_keys, b.tau_tilde);
+            g_trace.mark("select", st);
             begin = a.tile_end;
         }
 
@@ -699,9 +719,22 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps + q0, p.kprime, k, id_base,
                                                    out_scores_all + (size_t)q0 * k, out_ids_all + (size_t)q0 * k,
                                                    b.flags + q0, b.flag_count);
+        g_trace.mark("rescore+finalize", st);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+void trace_dump() {
+    if (!g_trace.on || g_trace.marks.empty()) return;
+    cudaEventSynchronize(g_trace.marks.back().second);
+    for (size_t i = 1; i < g_trace.marks.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_trace.marks[i - 1].second, g_trace.marks[i].second);
+        fprintf(stderr, "[mqvs trace] %-18s %8.1f us\n", g_trace.marks[i].first, ms * 1e3f);
+    }
+    for (auto& m : g_trace.marks) cudaEventDestroy(m.second);
+    g_trace.marks.clear();
 }
 
 }  // namespace tc

@@ -36,6 +36,7 @@ size_t cnt_bytes(const Plan& p);
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
                    int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
+void trace_dump();  // MQVS_TRACE=1 developer aid: per-launch timings of the last searches to stderr
 int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize
 
 }  // namespace tc
