@@ -53,6 +53,8 @@ typedef struct mqvs_stats {
     uint32_t last_scan_passes;   /* corpus passes the last search needed */
     uint32_t last_path;          /* 0 = SIMT fp32 scan, 1 = tensor-core shortlist + fp32 rescoring */
     uint64_t exact_fallbacks;    /* queries whose tensor-core shortlist could not be proven exact and were re-run on the SIMT scan */
+    uint64_t unrepaired;         /* mqvs_search_async only: flagged queries beyond the 64 the device repair pass takes per call
+                                    (their results are approximate; the blocking mqvs_search repairs every one) */
 } mqvs_stats;
 
 MQVS_API int mqvs_version(void);

@@ -82,13 +82,17 @@ struct mqvs_store {
     } evr[kEvRing];
     int ev_cursor = 0;
     DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
-    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys;  // tensor-core path scratch
+    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand;  // tensor-core path scratch
+    static constexpr int kMaxDeviceFix = 64;             // flagged queries repaired on the device per search
+    uint32_t* fix_dev = nullptr;                         // [kMaxDeviceFix] list + [1] count
+    unsigned long long* fix_counters = nullptr;          // device [2]: repaired on device, left to the host
     uint32_t* flags_host = nullptr;                      // pinned [1 + max B]: flag_count, flags[B]
     size_t flags_host_n = 0;
     uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
     unsigned long long* bad_dev = nullptr;
     unsigned long long* bad_host = nullptr;  // pinned
     mqvs_stats stats{};
+    uint64_t host_fallbacks = 0;
 
     size_t row_bytes() const { return (size_t)MQVS_DIM_PAD * elem_size(dtype); }
 };
@@ -194,6 +198,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_keys.ensure((size_t)plan.b_pad * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
+        if ((rc = s->tc_fixcand.ensure((size_t)mqvs_store::kMaxDeviceFix * scan_fix_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
     }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
 
@@ -221,8 +226,16 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
                                      id_base, out_scores_dev, out_ids_dev, st);
         if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
+        // queries whose shortlist was not proven exact are re-scanned exactly, driven from the device (no host sync)
+        uint32_t* fix_list = s->fix_dev;
+        uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
+        launch_compact_flags(b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n, s->fix_counters, st);
+        launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, fix_list, fix_n, mask_dev, k,
+                        (uint64_t*)s->tc_fixcand.p, s->sm_count, st);
+        launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
+                         fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
         passes = 1;
-        s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B);
+        s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B) + 3;
         s->stats.last_path = 1;
     } else {
         CU(cudaEventRecord(ev[1], st));
@@ -293,6 +306,10 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
             if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
     if (cudaMalloc(&s->bad_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (cudaMallocHost(&s->bad_host, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
+    if (cudaMalloc(&s->fix_dev, (mqvs_store::kMaxDeviceFix + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&s->fix_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->fix_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+        return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (capacity_rows) {
         int rc = grow(s, capacity_rows);
         if (rc != MQVS_OK) return bail(rc);
@@ -306,8 +323,10 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     cudaSetDevice(s->dev);
     if (s->st) cudaStreamSynchronize(s->st);
     for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
-                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys})
+                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand})
         b->release();
+    if (s->fix_dev) cudaFree(s->fix_dev);
+    if (s->fix_counters) cudaFree(s->fix_counters);
     if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->rows) cudaFree(s->rows);
     if (s->bad_dev) cudaFree(s->bad_dev);
@@ -443,14 +462,14 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     }
     CU(cudaStreamSynchronize(s->st));
     if (*s->bad_host) return fail(MQVS_E_INVALID, "%llu of %d queries have a non-finite norm", *s->bad_host, B);
-    if (tensor && s->flags_host[0]) {
-        // exactness margin not proven for these queries: re-run them on the exact scan
+    if (tensor && s->flags_host[0] > (uint32_t)mqvs_store::kMaxDeviceFix) {
+        // more flagged queries than the device repair pass takes: re-run the rest on the exact scan from here
         for (int b = 0; b < B; ++b) {
-            if (!s->flags_host[1 + b]) continue;
+            if (!s->flags_host[1 + b]) continue;  // flags of device-repaired queries were cleared
             uint32_t passes = 0;
             if ((rc = enqueue_simt(s, b, 1, k, mask_dev, 0, os, oi, s->st, &passes)) != MQVS_OK) return rc;
             s->stats.kernel_launches += passes + 1;
-            s->stats.exact_fallbacks += 1;
+            s->host_fallbacks += 1;
         }
         if (!out_is_device) {
             CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
@@ -596,6 +615,10 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
     cudaSetDevice(s->dev);
     settle_events(s);
     s->stats.rows = s->n;
+    unsigned long long c[2] = {0, 0};
+    if (s->fix_counters && cudaMemcpy(c, s->fix_counters, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
+    s->stats.exact_fallbacks = c[0] + s->host_fallbacks;  // async callers: c[1] - host_fallbacks queries stayed unrepaired
+    s->stats.unrepaired = c[1] > s->host_fallbacks ? c[1] - s->host_fallbacks : 0;
     *out = s->stats;
     return MQVS_OK;
 }

@@ -58,10 +58,9 @@ struct TopK {
 };
 
 template <typename T, int QB, int KPL, int U>
-__global__ void __launch_bounds__(kScanThreads)
-scan_simt_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
-                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride) {
-    extern __shared__ __align__(16) uint64_t smem_keys[];  // [QB][sort_n]
+__device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
+                                          const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand,
+                                          int cand_stride, uint64_t* smem_keys) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
@@ -127,6 +126,31 @@ scan_simt_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __res
     }
 }
 
+template <typename T, int QB, int KPL, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_simt_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
+                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride) {
+    extern __shared__ __align__(16) uint64_t smem_keys[];  // [QB][sort_n]
+    scan_body<T, QB, KPL, U>(rows, n_rows, qn, nq, mask, k, cand, cand_stride, smem_keys);
+}
+
+// Device-driven repair pass of the tensor-core path: re-scans the corpus exactly for the (few) queries whose
+// shortlist could not be proven exact.  The list lives in device memory, so no host round trip is needed; with an
+// empty list every CTA returns at once.
+template <typename T, int KPL, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn_all,
+                const uint32_t* __restrict__ fix_list, const uint32_t* __restrict__ fix_n,
+                const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride) {
+    extern __shared__ __align__(16) uint64_t smem_keys[];
+    const uint32_t n = *fix_n;
+    for (uint32_t f = 0; f < n; ++f) {
+        scan_body<T, 1, KPL, U>(rows, n_rows, qn_all + (size_t)fix_list[f] * kDim, 1, mask, k,
+                                cand + (size_t)f * cand_stride * k, cand_stride, smem_keys);
+        __syncthreads();
+    }
+}
+
 struct ScanCfg {
     int qb, kpl;
 };
@@ -165,6 +189,24 @@ size_t scan_smem(const ScanCfg& c, int k) { return (size_t)c.qb * next_pow2(kSca
 constexpr int kMaxCtasPerSm = 3;
 
 }  // namespace
+
+int scan_fix_grid(int sm_count) { return sm_count * 2; }
+
+void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* fix_list,
+                     const uint32_t* fix_n, const uint32_t* mask, int k, uint64_t* cand, int sm_count, cudaStream_t st) {
+    const int kpl = k <= 32 ? 1 : 4;  // the tensor path serves k <= 128
+    const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
+    const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
+#define MQVS_FIX(T_, KPL_, U_)                                                                                   \
+    scan_fix_kernel<T_, KPL_, U_><<<grid, kScanThreads, smem, st>>>((const T_*)rows, n_rows, qn_all, fix_list, fix_n, \
+                                                                     mask, k, cand, stride)
+    if (dtype == MQVS_F32) {
+        if (kpl == 1) MQVS_FIX(float, 1, 2); else MQVS_FIX(float, 4, 2);
+    } else {
+        if (kpl == 1) MQVS_FIX(__nv_bfloat16, 1, 4); else MQVS_FIX(__nv_bfloat16, 4, 4);
+    }
+#undef MQVS_FIX
+}
 
 void scan_plan(int dtype, int nq_remaining, int k, int sm_count, int* nq_pass, int* grid) {
     ScanCfg c = pick_cfg(nq_remaining, k);

@@ -32,6 +32,54 @@ merge_keys_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, in
     }
 }
 
+// Repair pass of the tensor-core path: block f merges the exact-scan candidates of flagged query fix_list[f] into
+// that query's output row and clears its flag.  Same body as merge_keys_kernel, indirect through the device list.
+__global__ void __launch_bounds__(kSelThreads)
+merge_fix_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, int buf_n, int64_t id_base,
+                 const uint32_t* __restrict__ fix_list, const uint32_t* __restrict__ fix_n, uint32_t* __restrict__ flags,
+                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) uint64_t buf[];
+    if (blockIdx.x >= *fix_n) return;
+    const uint32_t q = fix_list[blockIdx.x];
+    const uint64_t* in = keys_in + (size_t)blockIdx.x * m;
+    const int chunk = buf_n - kp;
+    for (int i = threadIdx.x; i < kp; i += kSelThreads) buf[i] = 0ull;
+    for (int base = 0; base < m; base += chunk) {
+        for (int i = threadIdx.x; i < chunk; i += kSelThreads) buf[kp + i] = (base + i < m) ? in[base + i] : 0ull;
+        block_bitonic_sort_desc(buf, buf_n);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += kSelThreads) {
+        uint64_t key = buf[j];
+        size_t o = (size_t)q * k + j;
+        out_scores[o] = key ? key_score(key) : -INFINITY;
+        out_ids[o] = key ? (int64_t)key_id(key) + id_base : -1;
+    }
+    if (threadIdx.x == 0) flags[q] = 0u;
+}
+
+// flags[B] -> fix_list (first `max_fix` flagged queries), *fix_n, and the running repair counters
+__global__ void compact_flags_kernel(const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
+                                     uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t n_s;
+    if (threadIdx.x == 0) n_s = 0;
+    __syncthreads();
+    uint32_t flagged = 0;
+    for (int q = threadIdx.x; q < B; q += blockDim.x)
+        if (flags[q]) {
+            ++flagged;
+            uint32_t slot = atomicAdd(&n_s, 1u);
+            if (slot < (uint32_t)max_fix) fix_list[slot] = (uint32_t)q;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n = n_s < (uint32_t)max_fix ? n_s : (uint32_t)max_fix;
+        *fix_n = n;
+        atomicAdd(counters + 0, (unsigned long long)n);          // repaired on the device
+        atomicAdd(counters + 1, (unsigned long long)(n_s - n));  // left flagged (host repairs them in the blocking call)
+    }
+}
+
 // Cross-shard merge with 64-bit ids: entries are (order-preserving score bits, id); sorted by score desc, id asc.
 struct Cand {
     uint32_t ord;  // 0 == empty
@@ -97,6 +145,20 @@ void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_
     if (next_pow2(kp + m) < buf_n) buf_n = next_pow2(kp + m) > 2 * kp ? next_pow2(kp + m) : 2 * kp;
     size_t smem = (size_t)buf_n * sizeof(uint64_t);
     merge_keys_kernel<<<B, kSelThreads, smem, st>>>(keys_in, m, k, kp, buf_n, id_base, out_scores, out_ids);
+}
+
+void launch_compact_flags(const uint32_t* flags, int B, int max_fix, uint32_t* fix_list, uint32_t* fix_n,
+                          unsigned long long* counters, cudaStream_t st) {
+    compact_flags_kernel<<<1, 256, 0, st>>>(flags, B, max_fix, fix_list, fix_n, counters);
+}
+
+void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
+                      const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+    int kp = next_pow2(k);
+    int buf_n = kp * 2 > 2048 ? kp * 2 : 2048;
+    size_t smem = (size_t)buf_n * sizeof(uint64_t);
+    merge_fix_kernel<<<max_fix, kSelThreads, smem, st>>>(keys_in, m, k, kp, buf_n, id_base, fix_list, fix_n, flags,
+                                                         out_scores, out_ids);
 }
 
 void launch_merge_candidates(const float* scores, const int64_t* ids, int W, int B, int k, float* out_scores,

@@ -54,10 +54,15 @@ constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thre
 // Each segment is 16x everything before it.  What matters is hits per warp-chunk (32 queries x 32 rows = 1024 scores
 // against thresholds learnt on S rows: ~1024 k'/S), not appends per list: growing faster (measured: 2 segments instead
 // of 3 on 1M rows) sends most chunks down the slow path and costs 1.6x at batch 4096.
-__host__ inline uint32_t segment_growth(int /*kprime*/, int /*grid*/) { return 16u; }
+__host__ inline uint32_t segment_growth(int /*kprime*/, int /*grid*/) {
+    static const uint32_t g = getenv("MQVS_SEG_GROWTH") ? (uint32_t)atoi(getenv("MQVS_SEG_GROWTH")) : 16u;  // tuning knob
+    return g < 2u ? 2u : g;
+}
 // segment ends (in tiles): 16, 256, 4096, ... (measured alternatives on 1M rows, r01: 2 segments -> 1.3-1.6x slower,
 // 7 / +grid / x16 -> no gain)
-__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid, uint32_t /*m_tiles*/) {
+__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid, uint32_t m_tiles) {
+    static const uint32_t g1 = getenv("MQVS_SEG_GROWTH_B128") ? (uint32_t)atoi(getenv("MQVS_SEG_GROWTH_B128")) : 0u;
+    if (m_tiles == 1 && g1 >= 2u) return end * g1;
     return end * segment_growth(kprime, grid);
 }
 

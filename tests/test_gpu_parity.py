@@ -343,3 +343,30 @@ def test_full_size_config3_shape_properties(gpu):
     idx.set_path(1)
     es, ei = idx.search(q[:6], k)
     assert_bit_equal(s[:6], i[:6], es, ei)
+
+
+def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacity(gpu):
+    """mqvs_search_async cannot ask the host, so flagged queries are re-scanned by a device-driven pass (up to 64 per
+    call); the blocking call additionally repairs any number.  100 queries all aimed at a 300-fold duplicated row."""
+    import torch
+    n, B, k = 20000, 100, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x[5000:5300] = x[123]
+    noise = O.synth_rows(77, 0, B, 768)
+    q = x[123][None, :] + 0.01 * noise
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    idx = native().Index(768, "bf16")
+    idx.add(x)
+    idx.set_path(2)
+    s, i = idx.search(q, k)                       # blocking: device repairs 64, host repairs the other 36
+    assert_bit_equal(s, i, es, ei)
+    assert idx.stats()["exact_fallbacks"] >= B and idx.stats()["unrepaired"] == 0
+    qd = torch.from_numpy(q[:40]).cuda()          # async, within the device pass' capacity
+    out_s = torch.empty((40, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((40, k), dtype=torch.int64, device="cuda")
+    idx.search_device(qd, k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es[:40], ei[:40])
+    assert idx.stats()["unrepaired"] == 0
