@@ -31,23 +31,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CORPUS_SEED = {"c2": 0x5EED0002, "c3": 0x5EED0003, "c4": 0x5EED0004}
+CORPUS_SEED = {"c2": 0x5EED0002, "c3": 0x5EED0003, "c4": 0x5EED0004, "c5": 0x5EED0005}
 QUERY_SEED = 0x0BADC0DE
 WORKLOADS = {
     "c2": dict(rows=1_000_000, dtype="fp32", k=10, batch=64, desc="config2: 1M x 768 fp32, k=10, exact cosine, 1 GPU"),
     "c3": dict(rows=10_000_000, dtype="bf16", k=100, batch=4096, desc="config3: 10M x 768 bf16, k=100, 1 GPU"),
     "c4": dict(rows=100_000_000, dtype="bf16", k=10, batch=64, desc="config4: 100M x 768 bf16 row-sharded, k=10"),
+    "c5": dict(rows=10_000_000, dtype="bf16", k=10, batch=16384,
+               desc="config5: 10M x 768 bf16 row-sharded + Chroma-style where-filter as a fused bitmask, k=10"),
 }
+MASK_SEED = 0xF117E4
 ELEM = {"fp32": 4, "bf16": 2}
 
 
 def peaks():
+    """-> dict(hbm GB/s, tensor TFLOP/s burst + sustained, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+        return {"hbm": float(p["hbm_gbs"]), "tf_burst": float(p["bf16_tflops"]),
+                "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
 
 
 class ClockSampler:
@@ -114,6 +120,12 @@ def cpu_port_qps(workload: str, rows: int, batch: int, k: int, steps: int, warmu
     return batch * steps / dt, cores, dt / steps
 
 
+def cpu_sample_rows(rows: int, batch: int) -> int:
+    """Rows the CPU legs scan per step: the whole corpus when that is <= ~1.5 TFLOP and <= 4M rows, else a slice."""
+    cap = int(1.5e12 / (2 * 768 * max(batch, 1)))
+    return max(50_000, min(rows, 4_000_000, cap))
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU retrieval arithmetic (oracle port; chromadb cannot be installed
     offline here) on the host cores, same config / metric / unit."""
@@ -123,11 +135,9 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     rows = wl["rows"]
     sample = f"full {rows} rows x {args.batch} queries per step"
-    if rows > 4_000_000:  # bound host memory/time: scan a slice, scale QPS by the row ratio
-        rows_s = 2_000_000
+    rows_s = cpu_sample_rows(rows, args.batch)
+    if rows_s < rows:  # bound host memory/time: scan a slice, scale QPS by the row ratio
         sample = f"{rows_s} of {rows} rows x {args.batch} queries per step, QPS scaled by {rows_s}/{rows}"
-    else:
-        rows_s = rows
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
     qps, cores, s_per_step = cpu_port_qps(args.workload, rows_s, args.batch, wl["k"], steps, warmup)
     qps *= rows_s / rows
@@ -153,6 +163,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=str, default=None, help="comma-separated extra batch sizes to report")
+    ap.add_argument("--selectivity", type=float, default=0.1, help="c5: fraction of rows the where-filter allows")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
@@ -196,8 +207,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # config 5: a synthetic categorical metadata column source_id in {0..99} (hash of the row id), filtered with the
+    # Chroma grammar {"source_id": {"$in": [...]}} through the product's where -> bitmask compiler
+    def build_mask(selectivity):
+        from mediquery_rag_b200.filters import MetadataColumns, compile_mask
+        lo, hi = sh.lo, sh.hi
+        ids = (O._splitmix64_np(MASK_SEED, np.arange(lo, hi, dtype=np.uint64)) % np.uint64(100)).astype(np.int64)
+        cols = MetadataColumns()
+        cols.extend_columns(hi - lo, {"source_id": ids})
+        where = {"source_id": {"$in": list(range(max(1, round(selectivity * 100))))}}
+        words, allowed = compile_mask(where, cols, None)
+        return torch.from_numpy(words.view(np.int32)).to(dev), allowed, where
+
+    mask_dev, mask_info = None, None
+    if args.workload == "c5":
+        mask_dev, allowed, where = build_mask(args.selectivity)
+        mask_info = {"where": str(where)[:60] + "...", "selectivity": args.selectivity, "allowed_rows_rank0": allowed}
+
     def step_device(q):
-        return sh.search(q, k)
+        return sh.search(q, k, mask_dev)
 
     def timed(fn, steps):
         barrier()
@@ -229,7 +257,11 @@ def main():
 
     # correctness guard on the timed configuration: planted neighbours must come first
     ids = out[1].cpu().numpy()
-    assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
+    if mask_dev is None:
+        assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
+    else:  # every returned row must carry an allowed source_id
+        got = ids[ids >= 0].astype(np.uint64)
+        assert ((O._splitmix64_np(MASK_SEED, got) % np.uint64(100)) < max(1, round(args.selectivity * 100))).all()
 
     # ---- e2e: public API, host buffers; H2D of the queries and D2H of the results inside the timed region
     q_np_pinned = q_pinned.numpy()
@@ -238,10 +270,10 @@ def main():
 
     def step_e2e():
         if world == 1:
-            return sh.index.search(q_np_pinned, k)  # mqvs_search: host in, host out, blocking
+            return sh.index.search(q_np_pinned, k, mask_dev)  # mqvs_search: host in, host out, blocking
         qd = q_pinned.to(dev, non_blocking=True) if rank == 0 else torch.empty_like(q_dev)
         dist.broadcast(qd, 0)
-        s, i = sh.search(qd, k)
+        s, i = sh.search(qd, k, mask_dev)
         if rank == 0:
             res_s.copy_(s, non_blocking=True)
             res_i.copy_(i, non_blocking=True)
@@ -275,20 +307,48 @@ def main():
         sweep.append({"batch": b, "qps": b * n_steps / (ms_b / 1e3), "ms_per_step": ms_b / n_steps,
                       "scan_gbps_per_gpu": sh.local_rows * 768 * ELEM[wl["dtype"]] / 1e9 / (scan_b / 1e3) if scan_b else None})
 
+    sel_sweep = []
+    if args.workload == "c5":
+        for sel in (0.5, 0.1, 0.01):
+            m_dev, allowed, _ = build_mask(sel)
+            for _ in range(2):
+                sh.search(q_dev, k, m_dev)
+            n_steps = max(3, args.steps // 2)
+            ms_s, _ = timed(lambda: sh.search(q_dev, k, m_dev), n_steps)
+            sel_sweep.append({"selectivity": sel, "qps": B * n_steps / (ms_s / 1e3), "ms_per_step": ms_s / n_steps})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    algo_bytes = sh.local_rows * 768 * ELEM[wl["dtype"]]  # per scan launch on this rank
+    pk = peaks()
+    algo_bytes = sh.local_rows * 768 * ELEM[wl["dtype"]]  # corpus bytes one scan streams on this rank
     avg_launch_ms = scan_ms / max(1, scan_launches)
-    achieved = algo_bytes / 1e9 / (avg_launch_ms / 1e3) if avg_launch_ms else 0.0
+    kernel = ("tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, "
+              "bracketed together)" if st1["last_path"] == 1 else "scan_simt_kernel")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload)
+            traffic = json.load(f).get(f"{args.workload}_b{B}")
+    # intensity = B flop per corpus byte (bf16) or B/2 (fp32): above the ridge the tensor pipe bounds the search
+    ridge = pk["tf_burst"] * 1e3 / pk["hbm"] * (1 if wl["dtype"] == "bf16" else 2)
+    if B >= ridge:
+        flops = 2.0 * sh.local_rows * 768 * B
+        achieved = flops / 1e12 / (avg_launch_ms / 1e3) if avg_launch_ms else 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tf_burst"], "traffic": traffic, "peak_source": pk["src"] + " bf16_tflops (burst)",
+                    "frac_of_sustained": achieved / pk["tf_sustained"], "kernel": kernel,
+                    "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg_launch_ms,
+                    "scan_share_of_step": scan_ms / ms_total if ms_total else None}
+    else:
+        achieved = algo_bytes / 1e9 / (avg_launch_ms / 1e3) if avg_launch_ms else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " hbm_gbs",
+                    "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,
+                    "scan_share_of_step": scan_ms / ms_total if ms_total else None,
+                    "frac_of_nominal_8TBps": achieved / 8000.0}
 
     line = {
         "metric": "queries_per_sec_exact_top%d" % k, "value": value, "unit": "queries/s", "n_gpus": world,
@@ -298,20 +358,17 @@ def main():
                    "store_dtype": wl["dtype"], "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (corpus per GPU %.2f GB vs 126 MB L2); no flush needed" % (algo_bytes / 1e9),
                    "ingest_s": round(ingest_s, 3), "scan_passes_per_step": scan_launches / args.steps},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, "
-                                "bracketed together)" if st1["last_path"] == 1 else "scan_simt_kernel"),
-                     "algorithmic_bytes_per_launch": algo_bytes,
-                     "avg_launch_ms": avg_launch_ms, "scan_share_of_step": scan_ms / ms_total if ms_total else None,
-                     "frac_of_nominal_8TBps": achieved / 8000.0},
+        "roofline": roofline,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 768 * 4, "d2h_bytes_per_step": B * k * 12},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if sweep:
         line["sweep"] = sweep
+    if mask_info:
+        line["config"]["filter"] = mask_info
+        line["selectivity_sweep"] = sel_sweep
     if world == 1 and not args.no_cpu_baseline:
-        rows_s = rows if rows <= 4_000_000 else 2_000_000
+        rows_s = cpu_sample_rows(rows, B)
         qps, cores, s_per = cpu_port_qps(args.workload, rows_s, B, k, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": qps * rows_s / rows, "unit": "queries/s", "cores": cores, "kind": "port",
                                 "sample": f"numpy sgemm+partition, {rows_s} rows x {B} queries x 3 steps ({s_per:.2f} s/step)"
