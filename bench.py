@@ -44,6 +44,15 @@ MASK_SEED = 0xF117E4
 ELEM = {"fp32": 4, "bf16": 2}
 
 
+def splitmix64_np(seed: int, idx: np.ndarray) -> np.ndarray:
+    """Counter-based hash used for the synthetic metadata column of config 5 (host-side input generation)."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (idx.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
 def peaks():
     """-> dict(hbm GB/s, tensor TFLOP/s burst + sustained, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -104,6 +113,12 @@ def host_corpus(workload: str, rows: int):
 def cpu_port_qps(workload: str, rows: int, batch: int, k: int, steps: int, warmup: int):
     """numpy sgemm + partition over the same rows, all host threads; returns (qps, cores, sample description)."""
     import oracle as O
+    cores = len(os.sched_getaffinity(0))
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     wl = WORKLOADS[workload]
     st = host_corpus(workload, rows)
     if wl["dtype"] == "bf16":  # same stored values the GPU scans: bf16-rounded rows, upcast
@@ -116,14 +131,13 @@ def cpu_port_qps(workload: str, rows: int, batch: int, k: int, steps: int, warmu
     for _ in range(steps):
         O.sgemm_topk(qn, st, k)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
     return batch * steps / dt, cores, dt / steps
 
 
 def cpu_sample_rows(rows: int, batch: int) -> int:
-    """Rows the CPU legs scan per step: the whole corpus when that is <= ~1.5 TFLOP and <= 4M rows, else a slice."""
+    """Rows the CPU legs scan per step: the whole corpus when that is <= ~1.5 TFLOP and <= 2M rows, else a slice."""
     cap = int(1.5e12 / (2 * 768 * max(batch, 1)))
-    return max(50_000, min(rows, 4_000_000, cap))
+    return max(50_000, min(rows, 2_000_000, cap))
 
 
 def run_reference(args):
@@ -164,6 +178,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=str, default=None, help="comma-separated extra batch sizes to report")
     ap.add_argument("--selectivity", type=float, default=0.1, help="c5: fraction of rows the where-filter allows")
+    ap.add_argument("--no-scaling-base", action="store_true",
+                    help="N=1 default run: skip the extra config-4 (100M x 768 bf16) measurement on this one GPU")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
@@ -212,7 +228,7 @@ def main():
     def build_mask(selectivity):
         from mediquery_rag_b200.filters import MetadataColumns, compile_mask
         lo, hi = sh.lo, sh.hi
-        ids = (O._splitmix64_np(MASK_SEED, np.arange(lo, hi, dtype=np.uint64)) % np.uint64(100)).astype(np.int64)
+        ids = (splitmix64_np(MASK_SEED, np.arange(lo, hi, dtype=np.uint64)) % np.uint64(100)).astype(np.int64)
         cols = MetadataColumns()
         cols.extend_columns(hi - lo, {"source_id": ids})
         where = {"source_id": {"$in": list(range(max(1, round(selectivity * 100))))}}
@@ -261,7 +277,7 @@ def main():
         assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
     else:  # every returned row must carry an allowed source_id
         got = ids[ids >= 0].astype(np.uint64)
-        assert ((O._splitmix64_np(MASK_SEED, got) % np.uint64(100)) < max(1, round(args.selectivity * 100))).all()
+        assert ((splitmix64_np(MASK_SEED, got) % np.uint64(100)) < max(1, round(args.selectivity * 100))).all()
 
     # ---- e2e: public API, host buffers; H2D of the queries and D2H of the results inside the timed region
     q_np_pinned = q_pinned.numpy()
@@ -367,6 +383,36 @@ def main():
     if mask_info:
         line["config"]["filter"] = mask_info
         line["selectivity_sweep"] = sel_sweep
+    # N=1 default run only: the multi-GPU runs use config 4 (strong scaling over a fixed 100M-row corpus), so the
+    # same corpus is also measured here on ONE GPU (153.6 GB of the 180 GB) -- the base point of that scaling curve.
+    if world == 1 and args.workload == "c2" and not args.rows and not args.no_scaling_base:
+        try:
+            del sh
+            torch.cuda.empty_cache()
+            c4 = WORKLOADS["c4"]
+            sh4 = ShardedIndex(768, c4["dtype"], c4["rows"])
+            sh4.add_synthetic(CORPUS_SEED["c4"])
+            base = {"workload": c4["desc"] + " on 1 GPU", "rows": c4["rows"], "k": c4["k"], "points": []}
+            for b in (1, c4["batch"]):
+                qb, pl = O.planted_queries(QUERY_SEED, b, CORPUS_SEED["c4"], c4["rows"], 768)
+                qb_dev = torch.from_numpy(qb).to(dev)
+                for _ in range(2):
+                    o4 = sh4.search(qb_dev, c4["k"])
+                torch.cuda.synchronize()
+                assert all(int(o4[1][j, 0]) == pl[j] for j in range(0, b, 2))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    sh4.search(qb_dev, c4["k"])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                base["points"].append({"batch": b, "qps": b / (ms / 1e3), "ms_per_step": ms,
+                                       "scan_gbps": c4["rows"] * 768 * 2 / 1e9 / (ms / 1e3)})
+            line["scaling_base_config4_n1"] = base
+            del sh4
+        except Exception as exc:  # e.g. not enough free HBM on a shared box
+            line["scaling_base_config4_n1"] = {"unavailable": str(exc)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         rows_s = cpu_sample_rows(rows, B)
         qps, cores, s_per = cpu_port_qps(args.workload, rows_s, B, k, steps=3, warmup=1)

@@ -173,6 +173,30 @@ def evaluate(where: Optional[Mapping[str, Any]], cols: MetadataColumns) -> np.nd
     return _leaf(cols, key, op, want)
 
 
+def evaluate_document(where_document: Optional[Mapping[str, Any]], texts: Sequence[Optional[str]]) -> np.ndarray:
+    """Chroma `where_document`: {"$contains": s} | {"$not_contains": s} | {"$and": [..]} | {"$or": [..]} -> bool[n]."""
+    n = len(texts)
+    if not where_document:
+        return np.ones(n, dtype=bool)
+    if not isinstance(where_document, Mapping) or len(where_document) != 1:
+        raise FilterError("where_document expects a dict with exactly one key per level")
+    (op, val), = where_document.items()
+    if op in ("$and", "$or"):
+        if not isinstance(val, (list, tuple)) or not val:
+            raise FilterError(f"{op} expects a non-empty list of filters")
+        parts = [evaluate_document(w, texts) for w in val]
+        out = parts[0].copy()
+        for p in parts[1:]:
+            out = (out & p) if op == "$and" else (out | p)
+        return out
+    if op in ("$contains", "$not_contains"):
+        if not isinstance(val, str):
+            raise FilterError(f"{op} expects a string")
+        hit = np.fromiter((t is not None and val in t for t in texts), dtype=bool, count=n)
+        return hit if op == "$contains" else ~hit
+    raise FilterError(f"unknown where_document operator {op}")
+
+
 def pack_mask(allowed: np.ndarray) -> np.ndarray:
     """bool[n] -> uint32[ceil(n/32)], bit r&31 of word r>>5 == allowed[r] (padding bits are 0)."""
     allowed = np.asarray(allowed, dtype=bool)
@@ -185,10 +209,14 @@ def pack_mask(allowed: np.ndarray) -> np.ndarray:
     return np.packbits(padded.reshape(words, 32), axis=1, bitorder="little").view(np.uint32).reshape(words).copy()
 
 
-def compile_mask(where: Optional[Mapping[str, Any]], cols: MetadataColumns, live: Optional[np.ndarray]):
+def compile_mask(where: Optional[Mapping[str, Any]], cols: MetadataColumns, live: Optional[np.ndarray],
+                 where_document: Optional[Mapping[str, Any]] = None, texts: Optional[Sequence[Optional[str]]] = None):
     """-> (packed mask or None when every row is allowed, number of allowed rows)."""
     n = len(cols)
     allowed = evaluate(where, cols) if where else None
+    if where_document:
+        doc_ok = evaluate_document(where_document, texts if texts is not None else [None] * n)
+        allowed = doc_ok if allowed is None else (allowed & doc_ok)
     if live is not None and not live.all():
         allowed = live.copy() if allowed is None else (allowed & live)
     if allowed is None:

@@ -226,8 +226,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                               collection_name, persist_directory, collection_metadata, **kwargs)
 
     # ------------------------------------------------------------------------------------------- search
-    def search_batch(self, queries: Any, k: int = DEFAULT_K, filter: Optional[Mapping[str, Any]] = None
-                     ) -> Tuple[np.ndarray, np.ndarray]:
+    def search_batch(self, queries: Any, k: int = DEFAULT_K, filter: Optional[Mapping[str, Any]] = None,
+                     where_document: Optional[Mapping[str, Any]] = None) -> Tuple[np.ndarray, np.ndarray]:
         """Batch extension used by the benchmark configs: queries [B, dim] -> (cosine scores [B, k'], row ids
         [B, k']) with k' = min(k, allowed rows); rows best-first, ties -> lower row id."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -237,7 +237,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             raise ValueError("k must be >= 1")
         if self._index is None or len(self._ids) == 0:
             return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
-        mask, allowed = compile_mask(filter, self._cols, self._live)
+        mask, allowed = compile_mask(filter, self._cols, self._live, where_document, self._texts)
         k_eff = min(k, allowed)  # Chroma clamps n_results to the collection size
         if k_eff == 0:
             return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
@@ -253,25 +253,25 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             out.append((Document(page_content=self._texts[r] or "", metadata=self._cols.row(r), id=self._ids[r]), s))
         return out
 
-    def _similar(self, vector: Any, k: int, filter: Optional[Mapping[str, Any]]) -> List[Tuple[Document, float]]:
-        scores, rows = self.search_batch(np.asarray(vector, dtype=np.float32)[None, :], k, filter)
+    def _similar(self, vector: Any, k: int, filter: Optional[Mapping[str, Any]],
+                 where_document: Optional[Mapping[str, Any]] = None) -> List[Tuple[Document, float]]:
+        scores, rows = self.search_batch(np.asarray(vector, dtype=np.float32)[None, :], k, filter, where_document)
         return self._docs(scores[0], rows[0])
 
     def similarity_search(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
                           **kwargs: Any) -> List[Document]:
-        return [d for d, _ in self._similar(self._embed_query(query), k, filter)]
+        return [d for d, _ in self._similar(self._embed_query(query), k, filter, kwargs.get("where_document"))]
 
     def similarity_search_with_score(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
                                      where_document: Optional[Dict[str, Any]] = None, **kwargs: Any
                                      ) -> List[Tuple[Document, float]]:
         """(Document, distance) pairs, LOWER is better, in the collection's hnsw:space."""
-        if where_document:
-            raise NotImplementedError("where_document is not supported")
-        return [(d, _distance(self._space, s)) for d, s in self._similar(self._embed_query(query), k, filter)]
+        return [(d, _distance(self._space, s))
+                for d, s in self._similar(self._embed_query(query), k, filter, where_document)]
 
     def similarity_search_by_vector(self, embedding: List[float], k: int = DEFAULT_K,
                                     filter: Optional[Dict[str, Any]] = None, **kwargs: Any) -> List[Document]:
-        return [d for d, _ in self._similar(embedding, k, filter)]
+        return [d for d, _ in self._similar(embedding, k, filter, kwargs.get("where_document"))]
 
     def similarity_search_by_vector_with_relevance_scores(self, embedding: List[float], k: int = DEFAULT_K,
                                                           filter: Optional[Dict[str, Any]] = None, **kwargs: Any

@@ -164,3 +164,16 @@ def test_non_finite_embeddings_are_rejected_and_nothing_is_added():
     with pytest.raises(RuntimeError):
         vs.add_embeddings([("bad", [float("nan"), 1.0])])
     assert len(vs) == 1
+
+
+def test_where_document_contains(embedder):
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    vs.add_texts(["运动 降低 血压", "睡眠 与 记忆", "运动 与 睡眠", "饮食"], metadatas=[{"g": 1}, {"g": 1}, {"g": 2}, {"g": 2}])
+    got = vs.similarity_search("q", k=10, where_document={"$contains": "运动"})
+    assert {d.page_content for d in got} == {"运动 降低 血压", "运动 与 睡眠"}
+    got = vs.similarity_search_with_score("q", k=10, filter={"g": 2}, where_document={"$not_contains": "运动"})
+    assert [d.page_content for d, _ in got] == ["饮食"]
+    got = vs.similarity_search("q", k=10, where_document={"$or": [{"$contains": "饮食"}, {"$and": [{"$contains": "睡眠"}, {"$contains": "记忆"}]}]})
+    assert {d.page_content for d in got} == {"饮食", "睡眠 与 记忆"}
+    with pytest.raises(FilterError):
+        vs.similarity_search("q", where_document={"$regex": "x"})

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Real multi-GPU parity (run under torchrun on W GPUs): the row-sharded NCCL path == the CPU oracle, bit for bit.
+Covers N not divisible by W, a shard smaller than k, a where-mask, both store dtypes and both search paths."""
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle as O
+from mediquery_rag_b200.sharded import ShardedIndex
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+W = dist.get_world_size()
+SEED, QSEED = 0x5EED0004, 0x0BADC0DE
+results = []
+for n, dtype, B, k, frac in [(200_003, "bf16", 1, 10, None), (200_003, "bf16", 37, 10, None), (200_003, "fp32", 64, 100, 0.2),
+                             (70, "fp32", 3, 40, None), (300_000, "bf16", 300, 10, 0.01), (131_072 * W + 5, "bf16", 16, 10, None)]:
+    sh = ShardedIndex(768, dtype, n)
+    sh.add_synthetic(SEED)
+    q, planted = O.planted_queries(QSEED, B, SEED, n, 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(3).random(n) < frac)
+    lm = sh.local_mask(mask)
+    lm_dev = None if lm is None else torch.from_numpy(lm.view(np.int32)).to(dev)
+    s, i = sh.search(torch.from_numpy(q).to(dev), k, lm_dev)
+    torch.cuda.synchronize()
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    if rank == 0:
+        st, _ = O.normalize_rows(O.synth_rows(SEED, 0, n, 768), dtype, 768)
+        qn, _ = O.normalize_rows(q, "fp32", 768)
+        es, ei = O.brute_force_topk(qn, st, k, mask)
+        ok = bool(np.array_equal(i, ei) and np.array_equal(s.view(np.uint32), es.view(np.uint32)))
+        results.append(dict(world=W, n=n, dtype=dtype, B=B, k=k, mask=frac, bounds=sh.bounds[:3], path=sh.index.stats()["last_path"], bit_exact=ok))
+        print(results[-1], flush=True)
+    # every rank must hold the same answer
+    chk = torch.from_numpy(i.astype(np.int64)).to(dev)
+    ref = chk.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(chk, ref), f"rank {rank} disagrees with rank 0"
+    del sh
+if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(results, open(f"gpurun_out/multi_gpu_parity_w{W}.json", "w"), indent=1)
+    print("MULTI-GPU PARITY", "OK" if all(r["bit_exact"] for r in results) else "FAILED")
+dist.destroy_process_group()
