@@ -11,7 +11,7 @@
  * corpus in HBM, scratch, streams.  Every function returns MQVS_OK (0) or a negative code and never throws;
  * mqvs_last_error() gives the thread-local message.  A handle is not re-entrant (one call at a time per
  * handle, enforced by an internal mutex) but may be used from any host thread.
- * "is_device" flags say whether a pointer is device memory on the store's first device (1) or host (0).
+ * "is_device" flags say whether a pointer is device memory on the store's device (1) or host (0).
  */
 #ifndef MQVS_H_
 #define MQVS_H_
@@ -62,7 +62,11 @@ MQVS_API const char* mqvs_last_error(void);
 MQVS_API int mqvs_device_count(int* out);
 
 /* Chroma(persist_directory=..., embedding_function=...) -- src/medical_engine.py:52 -- and the collection
- * Chroma.from_documents creates -- src/ingest_medical.py:106-110.  dim <= MQVS_DIM_PAD. */
+ * Chroma.from_documents creates -- src/ingest_medical.py:106-110.  dim <= MQVS_DIM_PAD.
+ * One handle owns one row shard on ONE device: n_dev must be 1 and dev_ids[0] names the device (NULL = device 0).
+ * A corpus spread over several GPUs is one handle per process/GPU plus mqvs_merge_candidates after the all-gather
+ * (mediquery-rag_b200/sharded.py); the (n_dev, dev_ids) form is kept so a single-process variant can be added
+ * without changing the ABI. */
 MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out);
 MQVS_API void mqvs_destroy(mqvs_t* s);
 MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out);
@@ -88,7 +92,8 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
 
 /* Same, enqueued on `cuda_stream` (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) with all
  * buffers on the device; returns after enqueueing.  id_base is added to every returned id (row-sharded
- * stores: the rank's first global row). */
+ * stores: the rank's first global row).  Scratch belongs to the handle: enqueue the next call on the same stream
+ * (or after this one has finished).  Non-finite queries are not reported here (use mqvs_search to validate). */
 MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                       float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 
