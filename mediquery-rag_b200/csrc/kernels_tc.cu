@@ -51,22 +51,12 @@ constexpr int kStageChunkBytes = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32 sco
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStageChunkBytes;
 constexpr int kMaxQueriesPerLaunch = 4096;
 constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
-// Each segment is 16x everything before it.  What matters is hits per warp-chunk (32 queries x 32 rows = 1024 scores
-// against thresholds learnt on S rows: ~1024 k'/S), not appends per list: growing faster (measured: 2 segments instead
-// of 3 on 1M rows) sends most chunks down the slow path and costs 1.6x at batch 4096.
-__host__ inline uint32_t segment_growth(int /*kprime*/, int /*grid*/) {
-    static const uint32_t g = getenv("MQVS_SEG_GROWTH") ? (uint32_t)atoi(getenv("MQVS_SEG_GROWTH")) : 16u;  // tuning knob
-    return g < 2u ? 2u : g;
-}
-// segment ends (in tiles): 16, 256, 4096, ... (measured alternatives on 1M rows, r01: 2 segments -> 1.3-1.6x slower,
-// 7 / +grid / x16 -> no gain)
-__host__ inline uint64_t next_segment_end(uint64_t end, int kprime, int grid, uint32_t m_tiles) {
-    static const uint32_t g1 = getenv("MQVS_SEG_GROWTH_B128") ? (uint32_t)atoi(getenv("MQVS_SEG_GROWTH_B128")) : 0u;
-    static const int one_per_cta = getenv("MQVS_SEG_ONE_PER_CTA") ? atoi(getenv("MQVS_SEG_ONE_PER_CTA")) : 0;
-    if (m_tiles == 1 && g1 >= 2u) return end * g1;
-    if (one_per_cta && (int)m_tiles <= one_per_cta && end == kFirstSegmentTiles) return end + (uint64_t)grid;  // one tile per CTA
-    return end * segment_growth(kprime, grid);
-}
+// Corpus segments end at 16, 256, 4096, ... tiles: each is 16x everything before it.  What matters is hits per
+// warp-chunk (32 queries x 32 rows = 1024 scores against thresholds learnt on S rows: ~1024 k'/S), not appends per
+// list.  Measured alternatives on B200 (r01, 1M and 10M rows): growth 8 / 32 / 64, a two-segment schedule for a single
+// query tile, and "second segment = one tile per CTA" were all equal or slower.
+constexpr uint32_t kSegmentGrowth = 16;
+__host__ inline uint64_t next_segment_end(uint64_t end) { return end * kSegmentGrowth; }
 
 template <typename T>
 struct Kind;
@@ -110,11 +100,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
-}
-// Contiguous L2 prefetch (no tensor map): pulls whole corpus rows into L2 in address order, so HBM sees long
-// sequential bursts instead of the 128-byte column slices the swizzled TMA boxes ask for.
-__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -231,8 +216,6 @@ struct ScoreArgs {
     uint32_t tile_begin;    // this launch scores corpus tiles [tile_begin, tile_end) (256 rows each)
     uint32_t tile_end;
     const uint32_t* mask;   // optional allow-mask over rows (device), or nullptr
-    const uint8_t* rows;    // corpus base (for the contiguous L2 prefetch)
-    uint32_t prefetch;      // 1: prefetch the CTA's next corpus tile into L2 while the current one is consumed
     uint32_t* tau;          // [B_pad] shared per-query threshold, order-preserving uint, atomicMax
     uint32_t* cnt;          // [grid][B_pad] list lengths
     uint64_t* lists;        // [grid][B_pad][CAP]
@@ -289,17 +272,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            constexpr uint32_t kTileBytes = BN * kDim * sizeof(T);
-            constexpr uint32_t kSlice = kTileBytes / kChunks768;  // one slice of the next tile per K-chunk of this one
             for (uint32_t nt = first_tile; nt < a.tile_end; nt += gridDim.x)
                 for (uint32_t mt = 0; mt < a.m_tiles; ++mt)
                     for (int kc = 0; kc < kChunks768; ++kc) {
-                        if (a.prefetch && mt == 0) {
-                            const uint32_t nxt = nt + gridDim.x;
-                            const uint64_t off = (uint64_t)nxt * kTileBytes + (uint64_t)kc * kSlice;
-                            const uint64_t end = (uint64_t)a.n_rows * kDim * sizeof(T);
-                            if (nxt < a.tile_end && off + kSlice <= end) l2_prefetch(a.rows + off, kSlice);
-                        }
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                         mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
@@ -654,8 +629,7 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
-    const uint32_t m_tiles = (uint32_t)((std::min(B, kMaxQueriesPerLaunch) + BM - 1) / BM);
-    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end, p.kprime, p.grid, m_tiles)) { ++segs; if (end >= tiles) break; }
+    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end)) { ++segs; if (end >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
     return chunks * (int)(1 + 2 * segs + 2);
 }
@@ -685,8 +659,6 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.n_queries = (uint32_t)B;
         a.m_tiles = (uint32_t)(b_pad / BM);
         a.mask = mask;
-        a.rows = (const uint8_t*)rows;
-        a.prefetch = 0u;  // measured slower on B200 (r01: 0.86 -> 1.16 ms at 1M x 768 fp32, B=64): kept switchable, off
         a.tau = b.tau;
         a.cnt = b.cnt;
         a.lists = b.lists;
@@ -695,7 +667,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
         // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
         uint32_t begin = 0;
-        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end, p.kprime, p.grid, a.m_tiles)) {
+        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end)) {
             a.tile_begin = begin;
             a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
             const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
