@@ -115,8 +115,14 @@ int grow(mqvs_store* s, uint64_t need_rows) {
         return fail(MQVS_E_OOM, "cudaMalloc of %llu rows (%.2f GB) failed: %s", (unsigned long long)want,
                     want * s->row_bytes() / 1e9, cudaGetErrorString(e));
     }
-    if (s->n) CU(cudaMemcpyAsync(fresh, s->rows, s->n * s->row_bytes(), cudaMemcpyDeviceToDevice, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    cudaError_t ce = cudaSuccess;
+    if (s->n) ce = cudaMemcpyAsync(fresh, s->rows, s->n * s->row_bytes(), cudaMemcpyDeviceToDevice, s->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->st);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(fresh);
+        return fail(MQVS_E_CUDA, "moving %llu rows to the larger allocation failed: %s", (unsigned long long)s->n, cudaGetErrorString(ce));
+    }
     if (s->rows) cudaFree(s->rows);
     s->rows = fresh;
     s->cap = want;
