@@ -139,7 +139,7 @@ def cpu_port_qps(workload: str, rows: int, batch: int, k: int, steps: int, warmu
 def cpu_sample_rows(rows: int, batch: int) -> int:
     """Rows the CPU legs scan per step: the whole corpus when that is <= ~1.5 TFLOP and <= 2M rows, else a slice."""
     cap = int(1.5e12 / (2 * 768 * max(batch, 1)))
-    return max(50_000, min(rows, 2_000_000, cap))
+    return min(rows, max(50_000, min(2_000_000, cap)))
 
 
 def run_reference(args):
