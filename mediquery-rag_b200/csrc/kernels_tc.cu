@@ -55,8 +55,12 @@ constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thre
 // warp-chunk (32 queries x 32 rows = 1024 scores against thresholds learnt on S rows: ~1024 k'/S), not appends per
 // list.  Measured alternatives on B200 (r01, 1M and 10M rows): growth 8 / 32 / 64, a two-segment schedule for a single
 // query tile, and "second segment = one tile per CTA" were all equal or slower.
+// (also measured and rejected: a cold segment of one tile on EVERY CTA + 32x growth for B <= 256 -- two segments up to
+// 1.2M rows -- 0.61 -> 0.68 ms at config 2, B=64: the cold tiles and the higher hit rate of the big segment cost more
+// than the launches saved.)
 constexpr uint32_t kSegmentGrowth = 16;
-__host__ inline uint64_t next_segment_end(uint64_t end) { return end * kSegmentGrowth; }
+__host__ inline uint64_t first_segment_end(uint32_t /*m_tiles*/, int /*grid*/) { return kFirstSegmentTiles; }
+__host__ inline uint64_t next_segment_end(uint64_t end, uint32_t /*m_tiles*/) { return end * kSegmentGrowth; }
 
 template <typename T>
 struct Kind;
@@ -470,7 +474,57 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
     if (tid == 0) pre_s[0] = 0;
     __syncthreads();
     uint64_t floor_key = buf[kp - 1];  // sorted by the previous call; 0 = shortlist not full yet
+    const int grand_total = pre_s[grid_ctas];
     int g0 = 0;
+    if (floor_key == 0ull && grand_total > kBuf - kp) {
+        // Cold call with far more candidates than the buffer holds (one whole tile from every CTA): sort the first
+        // buffer-full to get a pivot (its k'-th key), then ONE filtered pass over everything else.  A pivot from 1792
+        // keys lets ~k'/1792 of the rest through; should they overflow the buffer anyway, the batch loop below redoes
+        // the pass safely (correct for any data, just slower).
+        int g1 = 0;
+        while (g1 < grid_ctas && pre_s[g1 + 1] <= kBuf - kp) ++g1;
+        for (int idx = tid; idx < pre_s[g1]; idx += kSelThreads) {
+            int lo = 0, hi = g1;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre_s[mid] <= idx) lo = mid; else hi = mid;
+            }
+            buf[kp + idx] = __ldcg(lists + ((size_t)lo * b_pad + q) * cap + (idx - pre_s[lo]));
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(buf, kBuf);
+        const uint64_t pivot = buf[kp - 1];
+        __syncthreads();
+        for (int i = kp + tid; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+        if (tid == 0) fill_s = kp;
+        __syncthreads();
+        const int first = pre_s[g1], total = grand_total - first;
+        for (int idx = tid; idx < total; idx += kSelThreads) {
+            int lo = g1, hi = grid_ctas;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre_s[mid] <= first + idx) lo = mid; else hi = mid;
+            }
+            const uint64_t key = __ldcg(lists + ((size_t)lo * b_pad + q) * cap + (first + idx - pre_s[lo]));
+            if (key > pivot) {
+                const int slot = atomicAdd(&fill_s, 1);
+                if (slot < kBuf) buf[slot] = key;
+            }
+        }
+        __syncthreads();
+        if (fill_s <= kBuf) {
+            block_bitonic_sort_desc(buf, max(2 * kp, next_pow2(fill_s)));
+            floor_key = buf[kp - 1];
+            g0 = grid_ctas;  // done
+        } else {  // overflow: keep the pivot batch's winners as the running best and redo the rest in safe batches
+            __syncthreads();
+            for (int i = kp + tid; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+            if (tid == 0) fill_s = kp;
+            floor_key = pivot;
+            g0 = g1;
+        }
+        __syncthreads();
+    }
     while (g0 < grid_ctas) {
         // batch [g0, g1): as many lists as fit in the buffer even if every entry survives the filter
         const int room = kBuf - kp;
@@ -629,7 +683,8 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
-    for (uint64_t end = kFirstSegmentTiles; ; end = next_segment_end(end)) { ++segs; if (end >= tiles) break; }
+    const uint32_t m_tiles = (uint32_t)((std::min(B, kMaxQueriesPerLaunch) + BM - 1) / BM);
+    for (uint64_t end = first_segment_end(m_tiles, p.grid); ; end = next_segment_end(end, m_tiles)) { ++segs; if (end >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
     return chunks * (int)(1 + 2 * segs + 2);
 }
@@ -667,7 +722,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
         // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
         uint32_t begin = 0;
-        for (uint64_t end = kFirstSegmentTiles; begin < n_tiles; end = next_segment_end(end)) {
+        for (uint64_t end = first_segment_end(a.m_tiles, p.grid); begin < n_tiles; end = next_segment_end(end, a.m_tiles)) {
             a.tile_begin = begin;
             a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
             const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);

@@ -370,3 +370,23 @@ def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacit
     torch.cuda.synchronize()
     assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es[:40], ei[:40])
     assert idx.stats()["unrepaired"] == 0
+
+
+def test_hypothesis_random_shapes_tensor_path(gpu):
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=12, deadline=None)
+    @given(n=hs.integers(4096, 40000), B=hs.integers(1, 200), k=hs.integers(1, 128),
+           frac=hs.sampled_from([None, 0.0, 0.003, 0.5, 1.0]), dtype=hs.sampled_from(["fp32", "bf16"]), seed=hs.integers(0, 2 ** 31))
+    def run(n, B, k, frac, dtype, seed):
+        idx, x, st = build(n, 768, dtype, seed)
+        idx.set_path(2)
+        q = O.synth_rows(seed + 1, 0, B, 768)
+        qn, _ = O.normalize_rows(q, "fp32", 768)
+        mask = None if frac is None else O.mask_from_bool(np.random.default_rng(seed).random(n) < frac)
+        got = idx.search(q, k, mask)
+        assert idx.stats()["last_path"] == 1
+        assert_bit_equal(*got, *O.brute_force_topk(qn, st, k, mask))
+        idx.close()
+
+    run()
