@@ -89,8 +89,11 @@ struct mqvs_store {
     uint32_t* flags_host = nullptr;                      // pinned [1 + max B]: flag_count, flags[B]
     size_t flags_host_n = 0;
     uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
-    unsigned long long* bad_dev = nullptr;
-    unsigned long long* bad_host = nullptr;  // pinned
+    unsigned long long* bad_dev = nullptr;   // [0] = non-finite rows counted by K1, [1] = epoch of the last fused
+    unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits)
+    unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
+    unsigned int epoch = 0;                  // id of the last fused search
+    bool last_fused = false;
     mqvs_stats stats{};
     uint64_t host_fallbacks = 0;
 
@@ -151,7 +154,7 @@ void settle_events(mqvs_store* s) {
 
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
 bool use_tensor_path(const mqvs_store* s, int B, int k) {
-    if (s->path == 1) return false;
+    if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2) return true;
     // measured on B200 (profiles/r01_*): the register-resident SIMT scan holds the HBM roofline for 1 query (bf16 rows)
@@ -194,8 +197,31 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
     const bool tensor = use_tensor_path(s, B, k);
+    const bool fused = !tensor && s->path != 3 && scan_fused_ok(B, k);
+    s->last_fused = fused;
     tc::Plan plan{};
     int rc;
+    if (fused) {
+        // latency path: normalisation, scan, top-k and the final merge in one launch
+        if ((rc = s->cand.ensure((size_t)B * scan_fused_max_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+        CU(cudaEventRecord(ev[0], st));
+        CU(cudaEventRecord(ev[1], st));
+        launch_scan_fused(s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, B, mask_dev, k, (uint64_t*)s->cand.p,
+                          out_scores_dev, out_ids_dev, id_base, s->ticket_dev, (unsigned int*)(s->bad_dev + 1), ++s->epoch,
+                          s->sm_count, st);
+        CU(cudaEventRecord(ev[2], st));
+        CU(cudaEventRecord(ev[3], st));
+        CU(cudaGetLastError());
+        s->evr[slot].pending = true;
+        s->stats.kernel_launches += 1;
+        s->stats.scan_launches += 1;
+        s->stats.scan_bytes += s->n * s->row_bytes();
+        s->stats.last_scan_passes = 1;
+        s->stats.last_path = 0;
+        s->stats.searches += 1;
+        s->stats.queries += (uint64_t)B;
+        return MQVS_OK;
+    }
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
         const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 16) * sizeof(uint32_t);
@@ -310,8 +336,12 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     for (auto& set : s->evr)
         for (auto& e : set.e)
             if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
-    if (cudaMalloc(&s->bad_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
-    if (cudaMallocHost(&s->bad_host, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
+    if (cudaMalloc(&s->bad_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->bad_dev, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&s->ticket_dev, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(s->ticket_dev, 0, sizeof(unsigned int)) != cudaSuccess)
+        return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
+    if (cudaMallocHost(&s->bad_host, 2 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
     if (cudaMalloc(&s->fix_dev, (mqvs_store::kMaxDeviceFix + 1) * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&s->fix_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(s->fix_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
@@ -336,6 +366,7 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->rows) cudaFree(s->rows);
     if (s->bad_dev) cudaFree(s->bad_dev);
+    if (s->ticket_dev) cudaFree(s->ticket_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
     for (auto& set : s->evr)
         for (auto& e : set.e)
@@ -454,7 +485,7 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
     }
-    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
     const bool tensor = s->stats.last_path == 1;
     if (tensor) {
         if (s->flags_host_n < (size_t)B + 1) {
@@ -467,7 +498,8 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         CU(cudaMemcpyAsync(s->flags_host, s->last_flags_dev, ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
     }
     CU(cudaStreamSynchronize(s->st));
-    if (*s->bad_host) return fail(MQVS_E_INVALID, "%llu of %d queries have a non-finite norm", *s->bad_host, B);
+    if (s->last_fused ? (unsigned int)s->bad_host[1] == s->epoch : s->bad_host[0] != 0)
+        return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
     if (tensor && s->flags_host[0] > (uint32_t)mqvs_store::kMaxDeviceFix) {
         // more flagged queries than the device repair pass takes: re-run the rest on the exact scan from here
         for (int b = 0; b < B; ++b) {
@@ -631,7 +663,7 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
 
 MQVS_API int mqvs_set_path(mqvs_t* s, int path) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
-    if (path < 0 || path > 2) return fail(MQVS_E_INVALID, "path must be 0, 1 or 2");
+    if (path < 0 || path > 3) return fail(MQVS_E_INVALID, "path must be 0, 1, 2 or 3");
     std::lock_guard<std::mutex> lk(s->mu);
     s->path = path;
     return MQVS_OK;

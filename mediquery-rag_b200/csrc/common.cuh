@@ -113,6 +113,38 @@ __device__ __forceinline__ float lane_dot(const float4 (&q)[kChunks], const floa
     return acc;
 }
 
+// One lane's canonical share of an fp32 vector of `dim` <= kDim elements (zeros beyond dim).  vec4: dim % 4 == 0 and
+// the vector is 16-byte aligned, so the share can be fetched as 128-bit loads.
+__device__ __forceinline__ void load_lane_share(const float* p, int dim, bool vec4, int lane, float4 (&v)[kChunks]) {
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const int j = c * 128 + lane * 4;
+        if (vec4 && j + 3 < dim) {
+            v[c] = ld_stream_f4(p + j);
+        } else {
+            v[c].x = j + 0 < dim ? p[j + 0] : 0.0f;
+            v[c].y = j + 1 < dim ? p[j + 1] : 0.0f;
+            v[c].z = j + 2 < dim ? p[j + 2] : 0.0f;
+            v[c].w = j + 3 < dim ? p[j + 3] : 0.0f;
+        }
+    }
+}
+// K1's arithmetic on a lane share (whole warp participates): v <- v / max(||v||, eps) in the canonical order.
+// Returns false (and zeroes v) when the squared norm is not finite.
+__device__ __forceinline__ bool normalize_lane_share(float4 (&v)[kChunks]) {
+    const float ss = warp_butterfly_sum(lane_dot(v, v));
+    const bool ok = isfinite(ss);
+    const float inv = ok ? __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ss), kEps)) : 0.0f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        v[c].x = ok ? __fmul_rn(v[c].x, inv) : 0.0f;
+        v[c].y = ok ? __fmul_rn(v[c].y, inv) : 0.0f;
+        v[c].z = ok ? __fmul_rn(v[c].z, inv) : 0.0f;
+        v[c].w = ok ? __fmul_rn(v[c].w, inv) : 0.0f;
+    }
+    return ok;
+}
+
 // ---------------------------------------------------------------------------------------------- sort
 // Block-wide bitonic sort of n (power of two) 64-bit keys in shared memory, DESCENDING.
 __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* s, int n) {
@@ -128,6 +160,60 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* s, int n) {
                     s[lo] = b;
                     s[hi] = a;
                 }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Sort-free top-k for small k (<= 32) by a 256-thread block: each of the 8 warps repeatedly extracts the maximum of its
+// slice of the m <= kPerLane * 256 candidate keys (register-resident, warp-shuffle max), then warp 0 does the same over
+// the 8 x k winners.  `win` is 8 * 32 keys of shared memory.  Keys are unique (they embed the row id) or 0 (= empty).
+template <int kPerLane>
+__device__ __forceinline__ uint64_t warp_pop_max(uint64_t (&ks)[kPerLane]) {
+    uint64_t best = ks[0];
+#pragma unroll
+    for (int r = 1; r < kPerLane; ++r) best = ks[r] > best ? ks[r] : best;
+    uint64_t top = best;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, top, o);
+        top = other > top ? other : top;
+    }
+    if (top != 0ull && best == top) {  // exactly one lane owns it
+        bool done = false;
+#pragma unroll
+        for (int r = 0; r < kPerLane; ++r)
+            if (!done && ks[r] == top) { ks[r] = 0ull; done = true; }
+    }
+    return top;
+}
+template <int kPerLane>
+__device__ __forceinline__ void block_select_small(const uint64_t* __restrict__ in, int m, int k, int64_t id_base,
+                                                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                                                   uint64_t* win) {
+    static_assert(kPerLane >= 8, "the final round holds 8 x k winners");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t key[kPerLane];
+#pragma unroll
+    for (int r = 0; r < kPerLane; ++r) {
+        const int i = (r * 8 + warp) * 32 + lane;  // coalesced, warps interleaved
+        key[r] = i < m ? __ldcg(in + i) : 0ull;
+    }
+    for (int j = 0; j < k; ++j) {
+        const uint64_t top = warp_pop_max<kPerLane>(key);
+        if (lane == 0) win[warp * 32 + j] = top;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t fin[kPerLane];
+#pragma unroll
+        for (int r = 0; r < kPerLane; ++r) fin[r] = (r < 8 && lane < k) ? win[r * 32 + lane] : 0ull;
+        for (int j = 0; j < k; ++j) {
+            const uint64_t top = warp_pop_max<kPerLane>(fin);
+            if (lane == 0) {
+                out_scores[j] = top ? key_score(top) : -INFINITY;
+                out_ids[j] = top ? (int64_t)key_id(top) + id_base : -1;
             }
         }
     }

@@ -17,19 +17,7 @@ struct MemSource {
     int dim;
     bool vec4;  // dim % 4 == 0 and base 16-byte aligned
     __device__ __forceinline__ void load(uint64_t row, int lane, float4 (&v)[kChunks]) const {
-        const float* p = x + row * (uint64_t)dim;
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            int j = c * 128 + lane * 4;
-            if (vec4 && j + 3 < dim) {
-                v[c] = ld_stream_f4(p + j);
-            } else {
-                v[c].x = j + 0 < dim ? p[j + 0] : 0.0f;
-                v[c].y = j + 1 < dim ? p[j + 1] : 0.0f;
-                v[c].z = j + 2 < dim ? p[j + 2] : 0.0f;
-                v[c].w = j + 3 < dim ? p[j + 3] : 0.0f;
-            }
-        }
+        load_lane_share(x + row * (uint64_t)dim, dim, vec4, lane, v);
     }
 };
 
@@ -67,18 +55,12 @@ normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned l
     for (uint64_t row = (uint64_t)blockIdx.x * kIngestWarps + (threadIdx.x >> 5); row < n; row += warps_total) {
         float4 v[kChunks];
         src.load(row, lane, v);
-        float ss = warp_butterfly_sum(lane_dot(v, v));
-        bool ok = isfinite(ss);
-        float inv = ok ? __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ss), kEps)) : 0.0f;
+        const bool ok = normalize_lane_share(v);
         if (!ok && lane == 0) atomicAdd(bad, 1ull);
         OutT* o = out + row * (uint64_t)kDim;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
-            float4 y;
-            y.x = ok ? __fmul_rn(v[c].x, inv) : 0.0f;
-            y.y = ok ? __fmul_rn(v[c].y, inv) : 0.0f;
-            y.z = ok ? __fmul_rn(v[c].z, inv) : 0.0f;
-            y.w = ok ? __fmul_rn(v[c].w, inv) : 0.0f;
+            const float4 y = v[c];
             if constexpr (sizeof(OutT) == 4) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + c * 128 + lane * 4) = y;
             } else {

@@ -57,28 +57,13 @@ struct TopK {
     }
 };
 
+// The row walk shared by every SIMT kernel: warp `gw` of `warps_total` visits groups of U consecutive rows in
+// ascending order, scores them against the QB register-resident queries and offers them to the warp's top-k lists.
 template <typename T, int QB, int KPL, int U>
-__device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
-                                          const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand,
-                                          int cand_stride, uint64_t* smem_keys) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-
-    // queries -> registers (lane's canonical share); missing queries are zero and never written out
-    float4 q[QB][kChunks];
-#pragma unroll
-    for (int b = 0; b < QB; ++b)
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c)
-            q[b][c] = b < nq ? *reinterpret_cast<const float4*>(qn + (size_t)b * kDim + c * 128 + lane * 4)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-
-    TopK<QB, KPL> top;
-    top.init(k, lane);
-
+__device__ __forceinline__ void scan_rows(const T* __restrict__ rows, uint32_t n_rows, const float4 (&q)[QB][kChunks],
+                                          const uint32_t* __restrict__ mask, TopK<QB, KPL>& top, int lane) {
     const uint32_t warps_total = gridDim.x * kScanWarps;
-    const uint32_t gw = blockIdx.x * kScanWarps + warp;
-    // each warp walks groups of U consecutive rows, ascending
+    const uint32_t gw = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
     for (uint64_t r0 = (uint64_t)gw * U; r0 < n_rows; r0 += (uint64_t)warps_total * U) {
         RowFrag<T> x[U];
         bool live[U];
@@ -105,8 +90,12 @@ __device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n
             }
         }
     }
+}
 
-    // CTA-level reduction: all warps' lists of query b -> sort -> best k
+// CTA-level reduction: all warps' lists of query b -> sort -> the CTA's best k, written to cand[b][blockIdx.x][k].
+template <int QB, int KPL>
+__device__ __forceinline__ void cta_reduce(const TopK<QB, KPL>& top, int nq, int k, uint64_t* __restrict__ cand,
+                                           int cand_stride, uint64_t* smem_keys, int lane, int warp) {
     const int sort_n = next_pow2(kScanWarps * k);
     for (int i = threadIdx.x; i < QB * sort_n; i += kScanThreads) smem_keys[i] = 0ull;
     __syncthreads();
@@ -124,6 +113,80 @@ __device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n
         uint64_t* out = cand + ((size_t)b * cand_stride + blockIdx.x) * k;
         for (int j = threadIdx.x; j < k; j += kScanThreads) out[j] = s[j];
     }
+}
+
+template <typename T, int QB, int KPL, int U>
+__device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
+                                          const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand,
+                                          int cand_stride, uint64_t* smem_keys) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // queries -> registers (lane's canonical share); missing queries are zero and never written out
+    float4 q[QB][kChunks];
+#pragma unroll
+    for (int b = 0; b < QB; ++b)
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+            q[b][c] = b < nq ? *reinterpret_cast<const float4*>(qn + (size_t)b * kDim + c * 128 + lane * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    TopK<QB, KPL> top;
+    top.init(k, lane);
+    scan_rows<T, QB, KPL, U>(rows, n_rows, q, mask, top, lane);
+    cta_reduce<QB, KPL>(top, nq, k, cand, cand_stride, smem_keys, lane, warp);
+}
+
+// ------------------------------------------------------------------------------------------------ latency path
+// One launch for the whole search when B <= 4 and k <= 16 (the reference's own regime: one query, k = 3..5,
+// /root/reference/src/agents/nodes.py:93): each warp normalises the raw queries itself (K1's arithmetic, so the
+// result is bit-identical), the scan runs as above, and the LAST CTA to finish (atomic ticket) merges the per-CTA
+// candidates and writes the final scores/ids -- no separate normalise, memset or merge launches.
+struct FusedArgs {
+    const float* q_raw;      // [nq, dim] fp32, un-normalised
+    int dim;
+    int vec4;
+    float* out_scores;       // [nq, k]
+    int64_t* out_ids;
+    int64_t id_base;
+    unsigned int* ticket;    // zero on entry; the last CTA leaves it zero again
+    unsigned int* bad_epoch; // raised to `epoch` (atomicMax) when a query has a non-finite norm
+    unsigned int epoch;
+};
+
+template <typename T, int QB, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_fused_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uint32_t* __restrict__ mask, int k,
+                  uint64_t* __restrict__ cand, FusedArgs a) {
+    __shared__ __align__(16) uint64_t smem_keys[QB * 128];  // next_pow2(8 warps * k), k <= 16
+    __shared__ uint64_t win[8 * 32];
+    __shared__ unsigned int s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 q[QB][kChunks];
+#pragma unroll
+    for (int b = 0; b < QB; ++b) {
+        if (b < nq) {
+            load_lane_share(a.q_raw + (size_t)b * a.dim, a.dim, a.vec4 != 0, lane, q[b]);
+            const bool ok = normalize_lane_share(q[b]);
+            if (!ok && blockIdx.x == 0 && warp == 0 && lane == 0) atomicMax(a.bad_epoch, a.epoch);
+        } else {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) q[b][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    TopK<QB, 1> top;
+    top.init(k, lane);
+    scan_rows<T, QB, 1, U>(rows, n_rows, q, mask, top, lane);
+    cta_reduce<QB, 1>(top, nq, k, cand, (int)gridDim.x, smem_keys, lane, warp);
+    // publish this CTA's candidates, take a ticket; the last CTA merges
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    for (int b = 0; b < nq; ++b)
+        block_select_small<24>(cand + (size_t)b * gridDim.x * k, (int)gridDim.x * k, k, a.id_base,
+                               a.out_scores + (size_t)b * k, a.out_ids + (size_t)b * k, win);
+    if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
 template <typename T, int QB, int KPL, int U>
@@ -189,6 +252,41 @@ size_t scan_smem(const ScanCfg& c, int k) { return (size_t)c.qb * next_pow2(kSca
 constexpr int kMaxCtasPerSm = 3;
 
 }  // namespace
+
+bool scan_fused_ok(int B, int k) { return B >= 1 && B <= 4 && k <= 16; }
+
+template <typename T, int QB, int U>
+int launch_fused_t(const void* rows, uint32_t n_rows, int nq, const uint32_t* mask, int k, uint64_t* cand, int sm_count,
+                   const FusedArgs& a, cudaStream_t st) {
+    auto kern = scan_fused_kernel<T, QB, U>;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    const int grid = sm_count * (occ < 2 ? occ : 2);  // <= 296 CTAs: grid * k <= 4736 keys for the in-kernel merge
+    kern<<<grid, kScanThreads, 0, st>>>((const T*)rows, n_rows, nq, mask, k, cand, a);
+    return grid;
+}
+
+int scan_fused_max_grid(int sm_count) { return sm_count * 2; }
+
+void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float* q_raw, int dim, int nq,
+                       const uint32_t* mask, int k, uint64_t* cand, float* out_scores, int64_t* out_ids, int64_t id_base,
+                       unsigned int* ticket, unsigned int* bad_epoch, unsigned int epoch, int sm_count, cudaStream_t st) {
+    FusedArgs a{q_raw, dim, (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0,
+                out_scores, out_ids, id_base, ticket, bad_epoch, epoch};
+    const int qb = nq >= 3 ? 4 : nq;  // 1, 2 or 4 register-resident queries
+#define MQVS_FUSED(T_, U_)                                                                                     \
+    (qb == 1   ? launch_fused_t<T_, 1, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st)                     \
+     : qb == 2 ? launch_fused_t<T_, 2, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st)                     \
+               : launch_fused_t<T_, 4, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st))
+    if (dtype == MQVS_F32)
+        MQVS_FUSED(float, 2);
+    else
+        MQVS_FUSED(__nv_bfloat16, 4);
+#undef MQVS_FUSED
+}
 
 int scan_fix_grid(int sm_count) { return sm_count * 2; }
 

@@ -32,61 +32,15 @@ merge_keys_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, in
     }
 }
 
-// Small-k variant (k <= 32): no sort.  Each of the 8 warps repeatedly extracts the maximum of its slice of the candidates
-// (register-resident, kPerLane keys per lane, warp-shuffle argmax), then warp 0 does the same over the 8 x k winners.
-// For the batch-1 latency path this replaces three 2048-key bitonic sorts (~25 us) by ~3 us.
+// Small-k variant (k <= 32): no sort (block_select_small, common.cuh).  For the batch-1 latency path this replaces
+// three 2048-key bitonic sorts (~25 us) by ~3 us.
 template <int kPerLane>
 __global__ void __launch_bounds__(kSelThreads)
 merge_keys_small_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int64_t id_base,
                         float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
     __shared__ uint64_t win[8 * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t* in = keys_in + (size_t)blockIdx.x * m;
-    uint64_t key[kPerLane];
-#pragma unroll
-    for (int r = 0; r < kPerLane; ++r) {
-        const int i = (r * 8 + warp) * 32 + lane;  // coalesced, warps interleaved
-        key[r] = i < m ? in[i] : 0ull;
-    }
-    auto pop_max = [&](uint64_t (&ks)[kPerLane]) {
-        uint64_t best = ks[0];
-#pragma unroll
-        for (int r = 1; r < kPerLane; ++r) best = ks[r] > best ? ks[r] : best;
-        uint64_t top = best;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, top, o);
-            top = other > top ? other : top;
-        }
-        if (top != 0ull && best == top) {  // keys are unique (they embed the row id): exactly one lane owns it
-            bool done = false;
-#pragma unroll
-            for (int r = 0; r < kPerLane; ++r)
-                if (!done && ks[r] == top) { ks[r] = 0ull; done = true; }
-        }
-        return top;
-    };
-    for (int j = 0; j < k; ++j) {
-        const uint64_t top = pop_max(key);
-        if (lane == 0) win[warp * 32 + j] = top;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        uint64_t fin[kPerLane];
-#pragma unroll
-        for (int r = 0; r < kPerLane; ++r) fin[r] = 0ull;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)  // 8 warps x k winners; kPerLane >= 8 is guaranteed by the launcher
-            fin[r] = lane < k ? win[r * 32 + lane] : 0ull;
-        for (int j = 0; j < k; ++j) {
-            const uint64_t top = pop_max(fin);
-            if (lane == 0) {
-                const size_t o = (size_t)blockIdx.x * k + j;
-                out_scores[o] = top ? key_score(top) : -INFINITY;
-                out_ids[o] = top ? (int64_t)key_id(top) + id_base : -1;
-            }
-        }
-    }
+    block_select_small<kPerLane>(keys_in + (size_t)blockIdx.x * m, m, k, id_base, out_scores + (size_t)blockIdx.x * k,
+                                 out_ids + (size_t)blockIdx.x * k, win);
 }
 
 // Repair pass of the tensor-core path: block f merges the exact-scan candidates of flagged query fix_list[f] into

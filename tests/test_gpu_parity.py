@@ -390,3 +390,32 @@ def test_hypothesis_random_shapes_tensor_path(gpu):
         idx.close()
 
     run()
+
+
+@pytest.mark.parametrize("n,dim,dtype,B,k,frac", [(154, 768, "fp32", 1, 5, None), (154, 768, "bf16", 4, 16, None),
+                                                  (7, 768, "fp32", 2, 10, None), (50000, 300, "bf16", 3, 4, 0.2),
+                                                  (300000, 768, "fp32", 1, 10, None), (300000, 768, "fp32", 2, 3, 0.001)])
+def test_single_launch_latency_path_equals_multi_launch_path_and_oracle(gpu, n, dim, dtype, B, k, frac):
+    """B <= 4, k <= 16 searches run as ONE kernel (in-kernel query normalisation, last-CTA merge); path 3 forces the
+    classic normalise + scan + merge launches.  Both must equal the oracle bit for bit; non-finite queries still raise."""
+    idx, x, st = build(n, dim, dtype)
+    q, _ = O.planted_queries(QSEED, B, SEED, n, dim)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(5).random(n) < frac)
+    want = O.brute_force_topk(qn, st, k, mask)
+    idx.set_path(1)
+    launches0 = idx.stats()["kernel_launches"]
+    fused = idx.search(q, k, mask)
+    assert idx.stats()["kernel_launches"] - launches0 == 1       # the whole search was one launch
+    fused2 = idx.search(q, k, mask)                               # the ticket resets itself
+    idx.set_path(3)
+    classic = idx.search(q, k, mask)
+    assert_bit_equal(*fused, *want)
+    assert_bit_equal(*fused2, *want)
+    assert_bit_equal(*classic, *want)
+    idx.set_path(1)
+    bad = q.copy()
+    bad[B - 1, 0] = np.inf
+    with pytest.raises(native().MqvsError):
+        idx.search(bad, k)
+    assert_bit_equal(*idx.search(q, k, mask), *want)              # and the handle keeps working afterwards
