@@ -55,6 +55,28 @@ def splitmix64_np(seed: int, idx: np.ndarray) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
+def synth_rows_np(seed: int, first_row: int, n: int, dim: int = 768) -> np.ndarray:
+    """Host copy of the counter-based generator libmqvs uses on the device (mqvs_add_synthetic):
+    v[r, c] = uniform[-1, 1) from splitmix64(seed, r * dim + c).  Keeps the measured arm free of oracle/ imports."""
+    idx = (np.arange(first_row, first_row + n, dtype=np.uint64)[:, None] * np.uint64(dim)
+           + np.arange(dim, dtype=np.uint64)[None, :])
+    z = splitmix64_np(seed, idx)
+    return (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
+
+
+def planted_queries_np(query_seed: int, B: int, corpus_seed: int, n_rows: int, dim: int = 768, noise: float = 0.05):
+    """B synthetic queries; even-numbered ones are a (known) corpus row plus 5 % noise, so their top-1 is known."""
+    q = synth_rows_np(query_seed, 0, B, dim)
+    planted = np.full(B, -1, np.int64)
+    pick = splitmix64_np(query_seed ^ 0xA5A5A5A5, np.arange(B, dtype=np.uint64)) % np.uint64(max(n_rows, 1))
+    for b in range(0, B, 2):
+        t = int(pick[b])
+        row = synth_rows_np(corpus_seed, t, 1, dim)[0]
+        q[b] = row / np.linalg.norm(row) + np.float32(noise) * (q[b] / np.linalg.norm(q[b]))
+        planted[b] = t
+    return q, planted
+
+
 def peaks():
     """-> dict(hbm GB/s, tensor TFLOP/s burst + sustained, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -215,8 +237,7 @@ def main():
     torch.cuda.synchronize()
     ingest_s = time.perf_counter() - t0
 
-    import oracle as O  # query generation only (host-side synthetic inputs); never on the measured path
-    q_host_np, planted = O.planted_queries(QUERY_SEED, B, CORPUS_SEED[args.workload], rows, 768)
+    q_host_np, planted = planted_queries_np(QUERY_SEED, B, CORPUS_SEED[args.workload], rows)
     q_pinned = torch.from_numpy(q_host_np).pin_memory()
     q_dev = q_pinned.to(dev)
 
@@ -313,7 +334,7 @@ def main():
     # ---- optional sweep over other batch sizes (device-resident), reported beside the headline
     sweep = []
     for b in [int(v) for v in args.sweep.split(",")] if args.sweep else []:
-        qb, _ = O.planted_queries(QUERY_SEED, b, CORPUS_SEED[args.workload], rows, 768)
+        qb, _ = planted_queries_np(QUERY_SEED, b, CORPUS_SEED[args.workload], rows)
         qb_dev = torch.from_numpy(qb).to(dev)
         for _ in range(3):
             sh.search(qb_dev, k)
@@ -397,7 +418,7 @@ def main():
             sh4.add_synthetic(CORPUS_SEED["c4"])
             base = {"workload": c4["desc"] + " on 1 GPU", "rows": c4["rows"], "k": c4["k"], "points": []}
             for b in (1, c4["batch"]):
-                qb, pl = O.planted_queries(QUERY_SEED, b, CORPUS_SEED["c4"], c4["rows"], 768)
+                qb, pl = planted_queries_np(QUERY_SEED, b, CORPUS_SEED["c4"], c4["rows"])
                 qb_dev = torch.from_numpy(qb).to(dev)
                 for _ in range(2):
                     o4 = sh4.search(qb_dev, c4["k"])
