@@ -431,3 +431,26 @@ def test_tensor_path_batches_larger_than_one_launch_chunk(gpu):
     s, i = idx.search(q, k)
     assert idx.stats()["last_path"] == 1
     assert_bit_equal(s, i, *O.brute_force_topk(qn, st, k))
+
+
+@pytest.mark.parametrize("dtype,k", [("bf16", 10), ("fp32", 100)])
+def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k):
+    """Rows ordered by INCREASING similarity to the queries: thresholds learnt on earlier segments never filter anything,
+    every score is appended, the per-(CTA, query) lists overflow and the warp-sort compaction path runs for real."""
+    n, B = 160_000, 16
+    rng = np.random.default_rng(42)
+    q0 = rng.standard_normal(768).astype(np.float32)
+    q0 /= np.linalg.norm(q0)
+    t = (np.arange(n, dtype=np.float32) / n * 0.9)[:, None]
+    x = (1.0 - t) * O.synth_rows(SEED, 0, n, 768) / np.sqrt(256.0).astype(np.float32) + t * q0[None, :]
+    q = q0[None, :] + 0.02 * rng.standard_normal((B, 768)).astype(np.float32)
+    idx = native().Index(768, dtype)
+    idx.add(x)
+    idx.set_path(2)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    s, i = idx.search(q, k)
+    assert idx.stats()["last_path"] == 1
+    es, ei = O.brute_force_topk(qn, st, k)
+    assert (ei[:, 0] > n - 20000).all()         # the best rows really are among the last ones
+    assert_bit_equal(s, i, es, ei)
