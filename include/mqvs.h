@@ -111,7 +111,8 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path);
 
 MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);
 /* 0 = choose by batch size, 1 = force the SIMT fp32 scan, 2 = force the tensor-core path,
- * 3 = SIMT scan without the single-launch latency kernel (tests compare the two) */
+ * 3 = SIMT scan without the single-launch latency kernel, 4 = tensor-core path without the single-launch pipeline
+ * for B <= 128 (tests compare the variants) */
 MQVS_API int mqvs_set_path(mqvs_t* s, int path);
 
 #ifdef __cplusplus

@@ -82,7 +82,7 @@ struct mqvs_store {
     } evr[kEvRing];
     int ev_cursor = 0;
     DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
-    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand;  // tensor-core path scratch
+    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
     static constexpr int kMaxDeviceFix = 64;             // flagged queries repaired on the device per search
     uint32_t* fix_dev = nullptr;                         // [kMaxDeviceFix] list + [1] count
     unsigned long long* fix_counters = nullptr;          // device [2]: repaired on device, left to the host
@@ -93,7 +93,7 @@ struct mqvs_store {
     unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits)
     unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
     unsigned int epoch = 0;                  // id of the last fused search
-    bool last_fused = false;
+    bool last_fused = false;                 // the last search reported non-finite queries through the epoch word
     mqvs_stats stats{};
     uint64_t host_fallbacks = 0;
 
@@ -156,7 +156,7 @@ void settle_events(mqvs_store* s) {
 bool use_tensor_path(const mqvs_store* s, int B, int k) {
     if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
-    if (s->path == 2) return true;
+    if (s->path == 2 || s->path == 4) return true;
     // measured on B200 (profiles/r01_*): the register-resident SIMT scan holds the HBM roofline for 1 query (bf16 rows)
     // or 1-2 queries (fp32 rows); beyond that its multi-query variants fall to 2-3.4 TB/s while the tensor path streams
     // the corpus once for up to 128 queries at 4.8-7 TB/s.
@@ -222,25 +222,23 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->stats.queries += (uint64_t)B;
         return MQVS_OK;
     }
+    // single-launch tensor pipeline for one query tile (B <= 128); path 4 = keep the segmented pipeline (tests compare)
+    const bool tc_one = tensor && s->path != 4 && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
-        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 16) * sizeof(uint32_t);
+        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 32) * sizeof(uint32_t);
         if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
         if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_keys.ensure((size_t)plan.b_pad * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
         if ((rc = s->tc_fixcand.ensure((size_t)mqvs_store::kMaxDeviceFix * scan_fix_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+        if (tc_one && (rc = s->tc_cmax.ensure(tc::cmax_bytes(plan))) != MQVS_OK) return rc;
     }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
 
-    CU(cudaEventRecord(ev[0], st));
-    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
-    launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
-    s->stats.kernel_launches += 1;
-    uint32_t passes = 0;
+    tc::Buffers b{};
     if (tensor) {
-        tc::Buffers b{};
         char* sm = (char*)s->tc_small.p;
         b.q_op = s->tc_qop.p;
         b.tau_tilde = (float*)sm;
@@ -248,17 +246,16 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.eps = (float*)(b.tau + plan.b_pad);    // [B]
         b.flag_count = (uint32_t*)(b.eps + B);   // flag_count immediately followed by flags[B]: one D2H copy
         b.flags = b.flag_count + 1;
+        b.gbar = (unsigned int*)(b.flags + B);
         b.cnt = (uint32_t*)s->tc_cnt.p;
         b.lists = (uint64_t*)s->tc_lists.p;
         b.short_keys = (uint64_t*)s->tc_keys.p;
         b.exact_keys = b.short_keys + (size_t)plan.b_pad * plan.kprime;
+        b.cmax = (uint32_t*)s->tc_cmax.p;
         s->last_flags_dev = b.flag_count;
-        CU(cudaEventRecord(ev[1], st));
-        const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
-                                     id_base, out_scores_dev, out_ids_dev, st);
-        if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
-        CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
-        // queries whose shortlist was not proven exact are re-scanned exactly, driven from the device (no host sync)
+    }
+    // queries whose shortlist was not proven exact are re-scanned exactly, driven from the device (no host sync)
+    auto enqueue_repair = [&]() {
         uint32_t* fix_list = s->fix_dev;
         uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
         launch_compact_flags(b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n, s->fix_counters, st);
@@ -266,6 +263,42 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
                         (uint64_t*)s->tc_fixcand.p, s->sm_count, st);
         launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
                          fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
+    };
+    if (tc_one) {
+        s->last_fused = true;  // non-finite queries are reported through the epoch word, as on the latency path
+        CU(cudaEventRecord(ev[0], st));
+        CU(cudaEventRecord(ev[1], st));
+        const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
+                                           mask_dev, id_base, out_scores_dev, out_ids_dev, (unsigned int*)(s->bad_dev + 1),
+                                           ++s->epoch, st);
+        if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
+        CU(cudaEventRecord(ev[2], st));  // brackets prep + the single scan/select/rescore launch
+        enqueue_repair();
+        CU(cudaEventRecord(ev[3], st));
+        CU(cudaGetLastError());
+        s->evr[slot].pending = true;
+        s->stats.kernel_launches += 2 + 3;
+        s->stats.scan_launches += 1;
+        s->stats.scan_bytes += s->n * s->row_bytes();
+        s->stats.last_scan_passes = 1;
+        s->stats.last_path = 1;
+        s->stats.searches += 1;
+        s->stats.queries += (uint64_t)B;
+        return MQVS_OK;
+    }
+
+    CU(cudaEventRecord(ev[0], st));
+    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
+    launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
+    s->stats.kernel_launches += 1;
+    uint32_t passes = 0;
+    if (tensor) {
+        CU(cudaEventRecord(ev[1], st));
+        const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
+                                     id_base, out_scores_dev, out_ids_dev, st);
+        if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
+        CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
+        enqueue_repair();
         passes = 1;
         s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B) + 3;
         s->stats.last_path = 1;
@@ -359,7 +392,7 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     cudaSetDevice(s->dev);
     if (s->st) cudaStreamSynchronize(s->st);
     for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
-                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand})
+                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand, &s->tc_cmax})
         b->release();
     if (s->fix_dev) cudaFree(s->fix_dev);
     if (s->fix_counters) cudaFree(s->fix_counters);
@@ -663,7 +696,7 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
 
 MQVS_API int mqvs_set_path(mqvs_t* s, int path) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
-    if (path < 0 || path > 3) return fail(MQVS_E_INVALID, "path must be 0, 1, 2 or 3");
+    if (path < 0 || path > 4) return fail(MQVS_E_INVALID, "path must be 0..4");
     std::lock_guard<std::mutex> lk(s->mu);
     s->path = path;
     return MQVS_OK;

@@ -178,36 +178,112 @@ constexpr uint32_t kOrdNegInf = 0x007FFFFFu;  // ord_u32(-inf)
 
 // ------------------------------------------------------------------------------------------ warp bitonic
 // Sort 32*KPL keys held as element e = r*32 + lane, DESCENDING in e.
+// Deliberately NOT fully unrolled: the 36-45 compare-exchange stages, straight-line, are 50-150 KB of code that runs
+// once per call -- measured on B200, fetching it cold cost ~10 us per sort (instruction-cache misses), several times
+// the arithmetic.  Stages that exchange between lanes share one loop body; only the register-to-register stages
+// (partner = another register of the same lane) are unrolled, because their register indices must be constants.
 template <int KPL>
 __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
-#pragma unroll
+#pragma unroll 1
     for (int size = 2; size <= 32 * KPL; size <<= 1) {
+        if (size > 32) {
 #pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int rs = stride >> 5;
+            for (int rs = KPL >> 1; rs >= 1; rs >>= 1) {
+                if ((rs << 5) < size) {  // stride = 32 * rs <= size / 2
 #pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    if ((r & rs) == 0) {
-                        const bool desc = (((r << 5) | lane) & size) == 0;
-                        uint64_t a = key[r], b = key[r | rs];
-                        bool swap = desc ? (a < b) : (a > b);
-                        key[r] = swap ? b : a;
-                        key[r | rs] = swap ? a : b;
+                    for (int r = 0; r < KPL; ++r) {
+                        if ((r & rs) == 0) {
+                            const bool desc = (((r << 5) | lane) & size) == 0;
+                            const uint64_t a = key[r], b = key[r | rs];
+                            const bool swap = desc ? (a < b) : (a > b);
+                            key[r] = swap ? b : a;
+                            key[r | rs] = swap ? a : b;
+                        }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], stride);
-                    const bool lower = (lane & stride) == 0;
-                    const bool desc = (((r << 5) | lane) & size) == 0;
-                    const bool take_max = (lower == desc);
-                    uint64_t mx = key[r] > other ? key[r] : other;
-                    uint64_t mn = key[r] > other ? other : key[r];
-                    key[r] = take_max ? mx : mn;
-                }
             }
+        }
+#pragma unroll 1
+        for (int stride = size > 32 ? 16 : (size >> 1); stride > 0; stride >>= 1) {
+            const bool lower = (lane & stride) == 0;
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) {
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], stride);
+                const bool desc = (((r << 5) | lane) & size) == 0;
+                const bool take_max = (lower == desc);
+                const uint64_t mx = key[r] > other ? key[r] : other;
+                const uint64_t mn = key[r] > other ? other : key[r];
+                key[r] = take_max ? mx : mn;
+            }
+        }
+    }
+}
+
+// One 128 x 256 accumulator tile, seen by the epilogue thread that owns TMEM lane (= query) `taddr >> 16`: threshold
+// test of this query's 256 scores, survivors appended to the thread's private list, lists about to overflow compacted.
+template <int CAP, int KPRIME>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0, uint32_t n_rows,
+                                              const uint32_t* __restrict__ mask, uint32_t* st, uint32_t* tau_glob_q, int lane,
+                                              float& tau, uint32_t& cnt, uint64_t* lst) {
+    constexpr int KPL = CAP / 32;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        const uint32_t row0 = tile_row0 + ch * 32;
+        if (row0 >= n_rows) break;  // uniform
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(taddr + ch * 32, v);
+        // fast reject: one 3-input max tree per 32 scores, one compare.  (Masked / out-of-range rows are
+        // not excluded here -- that only makes the test conservative; the slow path applies the mask.)
+        float grp[11];
+        const float mx = max32(v, grp);
+        const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
+        if (hit == 0u) continue;
+        {
+            // hit path (some lane of the warp has a survivor): branch-free pass mask per lane, the chunk
+            // staged in shared memory so survivors can be fetched with a dynamic index -- cost is
+            // ~100 straight-line instructions + a few per survivor, instead of 32 divergent tests
+            uint32_t pm = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                st[j * 32 + lane] = v[j];
+                pm |= __uint_as_float(v[j]) >= tau ? (1u << j) : 0u;
+            }
+            uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
+            if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
+            pm &= mw;
+            __syncwarp();
+            while (pm) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                if (cnt < CAP) lst[cnt] = pack_key(__uint_as_float(st[j * 32 + lane]), row0 + j);
+                ++cnt;
+            }
+            __syncwarp();
+        }
+        // lists that could overflow on the next chunk are compacted now (warp-cooperative)
+        unsigned todo = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            __syncwarp();
+            const uint64_t* L = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)lst, src));
+            const uint32_t c = min(__shfl_sync(0xffffffffu, cnt, src), (uint32_t)CAP);
+            uint64_t key[KPL];
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) key[r] = (uint32_t)(r * 32 + lane) < c ? __ldcg(L + r * 32 + lane) : 0ull;
+            warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+            for (int r = 0; r < KPL; ++r)
+                if (r * 32 + lane < KPRIME) const_cast<uint64_t*>(L)[r * 32 + lane] = key[r];
+            const uint64_t kth = __shfl_sync(0xffffffffu, key[(KPRIME - 1) >> 5], (KPRIME - 1) & 31);
+            if (lane == src) {
+                cnt = KPRIME;  // c > CAP - 32 >= KPRIME, so the list is full down to its k'-th entry
+                const uint32_t t = (uint32_t)(kth >> 32);
+                atomicMax(tau_glob_q, t);
+                tau = fmaxf(tau, ord_to_float(t));
+            }
+            __syncwarp();
         }
     }
 }
@@ -231,7 +307,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScoreArgs a) {
     using K = Kind<T>;
     constexpr int kChunks768 = kDim / K::kElemsPerChunk;  // 12 (bf16) or 24 (tf32) K-chunks per tile
-    constexpr int KPL = CAP / 32;
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -327,67 +402,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    const uint32_t row0 = nt * BN + ch * 32;
-                    if (row0 >= a.n_rows) break;  // uniform
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld32(taddr + ch * 32, v);
-                    // fast reject: one 3-input max tree per 32 scores, one compare.  (Masked / out-of-range rows are
-                    // not excluded here -- that only makes the test conservative; the slow path applies the mask.)
-                    float grp[11];
-                    const float mx = max32(v, grp);
-                    const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
-                    if (hit == 0u) continue;
-                    {
-                        // hit path (some lane of the warp has a survivor): branch-free pass mask per lane, the chunk
-                        // staged in shared memory so survivors can be fetched with a dynamic index -- cost is
-                        // ~100 straight-line instructions + a few per survivor, instead of 32 divergent tests
-                        uint32_t* st = hit_stage + (warp - 2) * 1024;
-                        uint32_t pm = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            st[j * 32 + lane] = v[j];
-                            pm |= __uint_as_float(v[j]) >= tau ? (1u << j) : 0u;
-                        }
-                        uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
-                        if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
-                        pm &= mw;
-                        __syncwarp();
-                        while (pm) {
-                            const int j = __ffs(pm) - 1;
-                            pm &= pm - 1;
-                            if (cnt < CAP) lst[cnt] = pack_key(__uint_as_float(st[j * 32 + lane]), row0 + j);
-                            ++cnt;
-                        }
-                        __syncwarp();
-                    }
-                    // lists that could overflow on the next chunk are compacted now (warp-cooperative)
-                    unsigned todo = __ballot_sync(0xffffffffu, cnt > CAP - 32);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        __syncwarp();
-                        const uint64_t* L = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)lst, src));
-                        const uint32_t c = min(__shfl_sync(0xffffffffu, cnt, src), (uint32_t)CAP);
-                        uint64_t key[KPL];
-#pragma unroll
-                        for (int r = 0; r < KPL; ++r) key[r] = (uint32_t)(r * 32 + lane) < c ? __ldcg(L + r * 32 + lane) : 0ull;
-                        warp_sort_desc<KPL>(key, lane);
-#pragma unroll
-                        for (int r = 0; r < KPL; ++r)
-                            if (r * 32 + lane < KPRIME) const_cast<uint64_t*>(L)[r * 32 + lane] = key[r];
-                        const uint64_t kth = __shfl_sync(0xffffffffu, key[(KPRIME - 1) >> 5], (KPRIME - 1) & 31);
-                        if (lane == src) {
-                            cnt = KPRIME;  // c > CAP - 32 >= KPRIME, so the list is full down to its k'-th entry
-                            const uint32_t t = (uint32_t)(kth >> 32);
-                            atomicMax(a.tau + q, t);
-                            tau = fmaxf(tau, ord_to_float(t));
-                        }
-                        __syncwarp();
-                    }
-                }
+                epilogue_tile<CAP, KPRIME>(taddr, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024, a.tau + q, lane, tau, cnt, lst);
                 // accumulator fully read -> hand TMEM back to the MMA warp
                 tcgen05_fence_before();
                 __syncwarp();
@@ -444,19 +459,17 @@ constexpr int kSelThreads = 256;
 // best score of everything seen so far -- the threshold the next segment's epilogue filters with.  Entries that
 // cannot beat the current k'-th key are dropped before they reach the sort buffer, and only the filled part of
 // the buffer is sorted, so after the first segment a call costs a few microseconds.
-__global__ void __launch_bounds__(kSelThreads)
-select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tau,
-                    int grid_ctas, int b_pad, int cap, int kp, int first_segment, uint64_t* __restrict__ short_keys,
-                    float* __restrict__ tau_tilde) {
+// Body shared by select_lists_kernel (NT = 256, one CTA per query) and the tail of tc_fused_kernel (NT = 192).
+// Leaves the kp best keys, sorted descending, in buf[0, kp).  buf: 2048 keys; pre_s: NT + 1; warp_tot: NT / 32.
+template <int NT>
+__device__ __forceinline__ void select_lists_body(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt,
+                                                  int grid_ctas, int b_pad, int cap, int kp, const uint64_t* __restrict__ prev_keys,
+                                                  int q, uint64_t* buf, int* pre_s, int* warp_tot, int* fill_sp) {
     constexpr int kBuf = 2048;
-    constexpr int kMaxLists = kSelThreads;  // >= number of CTAs of the score kernel (one per SM)
-    __shared__ uint64_t buf[kBuf];
-    __shared__ int pre_s[kMaxLists + 1];    // exclusive prefix sum of the list lengths
-    __shared__ int warp_tot[kSelThreads / 32];
-    __shared__ int fill_s;
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // list lengths -> block-wide exclusive scan (one list per thread)
-    const int mine = tid < grid_ctas ? min((int)cnt[(size_t)tid * b_pad + q], cap) : 0;
+    int& fill_s = *fill_sp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // list lengths -> block-wide exclusive scan (one list per thread; grid_ctas <= NT)
+    const int mine = tid < grid_ctas ? min((int)__ldcg(cnt + (size_t)tid * b_pad + q), cap) : 0;
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -464,8 +477,8 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
         if (lane >= d) incl += o;
     }
     if (lane == 31) warp_tot[warp] = incl;
-    const int n_sort0 = first_segment ? 0 : kp;
-    for (int i = tid; i < kBuf; i += kSelThreads) buf[i] = i < n_sort0 ? short_keys[(size_t)q * kp + i] : 0ull;
+    const int n_sort0 = prev_keys ? kp : 0;
+    for (int i = tid; i < kBuf; i += NT) buf[i] = i < n_sort0 ? prev_keys[(size_t)q * kp + i] : 0ull;
     if (tid == 0) fill_s = kp;
     __syncthreads();
     int base = 0;
@@ -483,7 +496,7 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
         // the pass safely (correct for any data, just slower).
         int g1 = 0;
         while (g1 < grid_ctas && pre_s[g1 + 1] <= kBuf - kp) ++g1;
-        for (int idx = tid; idx < pre_s[g1]; idx += kSelThreads) {
+        for (int idx = tid; idx < pre_s[g1]; idx += NT) {
             int lo = 0, hi = g1;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -495,11 +508,11 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
         block_bitonic_sort_desc(buf, kBuf);
         const uint64_t pivot = buf[kp - 1];
         __syncthreads();
-        for (int i = kp + tid; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+        for (int i = kp + tid; i < kBuf; i += NT) buf[i] = 0ull;
         if (tid == 0) fill_s = kp;
         __syncthreads();
         const int first = pre_s[g1], total = grand_total - first;
-        for (int idx = tid; idx < total; idx += kSelThreads) {
+        for (int idx = tid; idx < total; idx += NT) {
             int lo = g1, hi = grid_ctas;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -518,7 +531,7 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
             g0 = grid_ctas;  // done
         } else {  // overflow: keep the pivot batch's winners as the running best and redo the rest in safe batches
             __syncthreads();
-            for (int i = kp + tid; i < kBuf; i += kSelThreads) buf[i] = 0ull;
+            for (int i = kp + tid; i < kBuf; i += NT) buf[i] = 0ull;
             if (tid == 0) fill_s = kp;
             floor_key = pivot;
             g0 = g1;
@@ -531,8 +544,8 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
         int g1 = g0;
         while (g1 < grid_ctas && pre_s[g1 + 1] - pre_s[g0] <= room) ++g1;
         const int first = pre_s[g0], total = pre_s[g1] - first;
-        for (int idx = tid; idx < total; idx += kSelThreads) {  // all entries of the batch, independent loads
-            int lo = g0, hi = g1;                               // list g with pre_s[g] <= first + idx < pre_s[g + 1]
+        for (int idx = tid; idx < total; idx += NT) {  // all entries of the batch, independent loads
+            int lo = g0, hi = g1;                       // list g with pre_s[g] <= first + idx < pre_s[g + 1]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (pre_s[mid] <= first + idx) lo = mid; else hi = mid;
@@ -545,11 +558,24 @@ select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restri
         block_bitonic_sort_desc(buf, n_sort);
         floor_key = buf[kp - 1];
         __syncthreads();
-        for (int i = kp + tid; i < n_sort; i += kSelThreads) buf[i] = 0ull;
+        for (int i = kp + tid; i < n_sort; i += NT) buf[i] = 0ull;
         if (tid == 0) fill_s = kp;
         __syncthreads();
         g0 = g1;
     }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tau,
+                    int grid_ctas, int b_pad, int cap, int kp, int first_segment, uint64_t* __restrict__ short_keys,
+                    float* __restrict__ tau_tilde) {
+    __shared__ uint64_t buf[2048];
+    __shared__ int pre_s[kSelThreads + 1];    // exclusive prefix sum of the list lengths (<= one list per thread)
+    __shared__ int warp_tot[kSelThreads / 32];
+    __shared__ int fill_s;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    select_lists_body<kSelThreads>(lists, cnt, grid_ctas, b_pad, cap, kp, first_segment ? nullptr : short_keys, q, buf, pre_s,
+                                   warp_tot, &fill_s);
     for (int i = tid; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = buf[i];
     if (tid == 0) {
         // every row discarded so far (epilogue filter, list compaction, this selection) scored <= the k'-th best
@@ -613,6 +639,470 @@ finalize_kernel(const uint64_t* __restrict__ exact_keys, const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------ single-launch pipeline
+// ---- tail of tc_fused_kernel: CTA c turns the G per-CTA lists of query c into the final top-k.
+// Selection runs in registers (warp bitonic sorts, no block barriers per compare stage): a shared-memory bitonic sort of
+// 2048 keys costs ~20 us of barrier latency, which at one query per CTA would be the whole tail.
+// Warp w sorts keys [w * 32 * KPL, (w + 1) * 32 * KPL) of the flattened lists and writes its kp best to out[w * kp ...].
+template <int KPL>
+__device__ __forceinline__ void tail_gather_sort(const uint64_t* __restrict__ lists, const int* pre_s, int G, int q, int cap,
+                                                 int total, int kp, uint64_t* out, int warp, int lane) {
+    uint64_t key[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int idx = (warp * KPL + r) * 32 + lane;
+        key[r] = 0ull;
+        if (idx < total) {
+            int lo = 0, hi = G;  // list g with pre_s[g] <= idx < pre_s[g + 1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre_s[mid] <= idx) lo = mid; else hi = mid;
+            }
+            key[r] = __ldcg(lists + ((size_t)lo * BM + q) * cap + (idx - pre_s[lo]));
+        }
+    }
+    warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r)
+        if (r * 32 + lane < kp) out[warp * kp + r * 32 + lane] = key[r];
+    if (32 * KPL < kp)
+        for (int e = 32 * KPL + lane; e < kp; e += 32) out[warp * kp + e] = 0ull;
+}
+// Warp `warp` sorts src[warp * 32 * KPL ...] (n valid keys overall) and writes its kp best to dst[warp * kp ...].
+template <int KPL>
+__device__ __forceinline__ void tail_merge_sort(const uint64_t* src, int n, int kp, uint64_t* dst, int warp, int lane) {
+    uint64_t key[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int idx = (warp * KPL + r) * 32 + lane;
+        key[r] = idx < n ? src[idx] : 0ull;
+    }
+    warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r)
+        if (r * 32 + lane < kp) dst[warp * kp + r * 32 + lane] = key[r];
+}
+
+struct FusedArgs;
+template <typename T, int CAP, int KPRIME>
+__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al);
+
+// Batches of up to 128 queries (one query tile) are HBM-bound: the corpus is streamed once and the tensor pipe idles
+// most of the time, so what the segmented pipeline above pays for -- two short cold segments and three selection
+// launches, ~200 us next to a 425 us scan at 1M x 768 fp32 -- is pure latency.  tc_fused_kernel does the whole search
+// in ONE cooperative launch of one persistent CTA per SM:
+//   1. every CTA scores its first tile; the epilogue reads the accumulator once and publishes, per query, the maximum
+//      of each 32-row chunk (8 per CTA, masked and out-of-range rows excluded);
+//   2. grid barrier; CTA c takes query c and finds the k'-th largest of the G*8 chunk maxima.  The chunks are disjoint,
+//      so at least k' allowed rows score >= that value: a valid threshold tau, within a few ranks of the exact k'-th
+//      best of the first G*256 rows.  Second grid barrier publishes tau[0..B);
+//   3. the first tile -- still in TMEM -- is read again against tau, then the CTA streams its remaining tiles exactly as
+//      tc_score_kernel does (the TMA and MMA warps never stop: the second accumulator covers the barriers);
+//   4. third grid barrier; CTA c merges the G per-CTA lists of query c, rescoring its k' best rows in the canonical fp32
+//      order, sorts, writes the top-k and checks the exactness margin (select_lists + rescore + finalize above).
+struct FusedArgs {
+    uint32_t n_rows, n_queries, n_tiles, ncols;  // ncols = gridDim.x * 8 chunk maxima per query
+    const uint32_t* mask;
+    uint32_t* tau;         // [128]: -inf on entry (prep)
+    uint32_t* cmax;        // [128][ncols] order-preserving chunk maxima, 0 = no row
+    uint32_t* cnt;         // [grid][128]
+    uint64_t* lists;       // [grid][128][CAP]
+    unsigned int* gbar;    // [3] grid barrier counters, zero on entry (prep)
+    const void* rows;      // corpus, for the exact rescoring
+    const float* qn;       // [B][768] normalised fp32 queries
+    const float* eps;      // [B]
+    int k;
+    long long id_base;
+    float* out_scores;
+    int64_t* out_ids;
+    uint32_t* flags;
+    uint32_t* flag_count;
+    unsigned long long* dbg;  // MQVS_TRACE only: [grid][16] globaltimer stamps of the phases, else nullptr
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MQVS_STAMP(i_) do { if (a.dbg) a.dbg[blockIdx.x * 16 + (i_)] = globaltimer_ns(); } while (0)
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// One thread per CTA: publish this CTA's writes, arrive, wait for all `expected` CTAs (cooperative launch: co-resident).
+__device__ __forceinline__ void grid_arrive_and_wait(unsigned int* ctr, unsigned int expected) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ctr) < expected) {
+        __nanosleep(40);
+        if (clock64() - t0 > 6000000000ll) __trap();  // seconds: a lost CTA must fail loudly, never hang the device
+    }
+    __threadfence();
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
+// k-th largest of n <= 1280 values (global, written by other CTAs before a grid barrier), by the 128 epilogue threads:
+// binary search over the 32 key bits, one count + named barrier per bit.  Every thread returns the same value.
+__device__ __forceinline__ uint32_t kth_largest_u32(const uint32_t* __restrict__ vals, int n, int kth, int et, int* s_cnt) {
+    uint32_t v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = i * 128 + et < n ? __ldcg(vals + i * 128 + et) : 0u;
+    uint32_t lo = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = lo | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) c += v[i] >= cand ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        int* sc = s_cnt + ((bit & 1) << 2);
+        if ((et & 31) == 0) sc[et >> 5] = c;
+        epi_bar_sync();
+        if (sc[0] + sc[1] + sc[2] + sc[3] >= kth) lo = cand;
+    }
+    return lo;
+}
+
+template <typename T, int CAP, int KPRIME>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const FusedArgs a) {
+    using K = Kind<T>;
+    constexpr int kChunks768 = kDim / K::kElemsPerChunk;
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + (size_t)kStages * kStageBytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    int* s_cnt = reinterpret_cast<int*>(smem_al + (size_t)kStages * kStageBytes + 128);  // [2][4]
+    uint32_t* hit_stage = reinterpret_cast<uint32_t*>(smem_al + (size_t)kStages * kStageBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t G = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const uint32_t first_tile = blockIdx.x;
+    const uint32_t n_my = first_tile < a.n_tiles ? (a.n_tiles - first_tile + G - 1) / G : 0;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G)
+                for (int kc = 0; kc < kChunks768; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                    tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, 0);
+                    tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = 0; w < n_my; ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kc = 0; kc < kChunks768; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma<K::kTf32>(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                    tcgen05_commit(bar_empty + 8 * stage);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int quad = warp & 3;
+        const int et = (int)threadIdx.x - 64;  // 0..127
+        const uint32_t q = quad * 32 + lane;
+        const bool q_ok = q < a.n_queries;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint64_t* lst = a.lists + ((size_t)blockIdx.x * BM + q) * CAP;
+        uint32_t cnt = 0;
+
+        // ---- 1. chunk maxima of the first tile
+        uint32_t* my_cmax = a.cmax + (size_t)q * a.ncols + blockIdx.x * 8;
+        if (et == 0) MQVS_STAMP(0);
+        if (n_my > 0) {
+            mbar_wait(bar_tfull, 0);
+            tcgen05_fence_after();
+            if (et == 0) MQVS_STAMP(1);
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                const uint32_t row0 = first_tile * BN + ch * 32;
+                uint32_t ord = 0u;
+                if (row0 < a.n_rows) {  // uniform
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(lane_taddr + ch * 32, v);
+                    uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
+                    if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);
+                    ord = mw ? ord_u32(m) : 0u;
+                }
+                if (q_ok) my_cmax[ch] = ord;
+            }
+        } else if (q_ok) {
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch) my_cmax[ch] = 0u;
+        }
+        __threadfence();
+        epi_bar_sync();
+        if (et == 0) { MQVS_STAMP(2); grid_arrive_and_wait(a.gbar + 0, G); MQVS_STAMP(3); }
+        epi_bar_sync();
+
+        // ---- 2. CTA c: tau[c] = k'-th largest chunk maximum of query c
+        if (blockIdx.x < a.n_queries) {
+            const uint32_t t = kth_largest_u32(a.cmax + (size_t)blockIdx.x * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
+            if (et == 0) a.tau[blockIdx.x] = t > kOrdNegInf ? t : kOrdNegInf;
+        }
+        __threadfence();
+        epi_bar_sync();
+        if (et == 0) { MQVS_STAMP(4); grid_arrive_and_wait(a.gbar + 1, G); MQVS_STAMP(5); }
+        epi_bar_sync();
+        float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
+
+        // ---- 3. first tile again, now against tau, then the rest of this CTA's tiles
+        uint32_t w = 0;
+        for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G, ++w) {
+            const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+            if (w > 0) {
+                if (q_ok) tau = fmaxf(tau, ord_to_float(__ldcg(a.tau + q)));  // raised by list compactions anywhere
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tcgen05_fence_after();
+            }
+            epilogue_tile<CAP, KPRIME>(lane_taddr + acc * BN, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024,
+                                       a.tau + q, lane, tau, cnt, lst);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (q_ok) a.cnt[(size_t)blockIdx.x * BM + q] = cnt;
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+
+    // ---- 4. all lists are complete once every CTA is here; CTA c finishes query c
+    __threadfence();
+    if (threadIdx.x == 0) { MQVS_STAMP(6); grid_arrive_and_wait(a.gbar + 2, G); MQVS_STAMP(7); }
+    __syncthreads();
+    if (blockIdx.x >= a.n_queries) return;
+    fused_tail<T, CAP, KPRIME>(a, (int)G, smem_al);
+}
+
+template <typename T, int CAP, int KPRIME>
+__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al) {
+    constexpr int NW = kThreads / 32;
+    // the operand ring is idle now (every TMA load was consumed by an MMA that has retired): reuse it
+    uint64_t* sA = reinterpret_cast<uint64_t*>(smem_al);  // 2048 keys
+    uint64_t* sB = sA + 2048;                             // 2048 keys
+    uint64_t* ex = sB + 2048;                             // KPRIME exact keys
+    int* pre_s = reinterpret_cast<int*>(ex + 256);        // kThreads + 1
+    int* warp_tot = pre_s + kThreads + 1;                 // NW
+    int* fill_s = warp_tot + NW;
+    const int qf = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // list lengths -> exclusive prefix sum (one list per thread)
+    const int mine = tid < G ? min((int)__ldcg(a.cnt + (size_t)tid * BM + qf), CAP) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    pre_s[tid + 1] = base + incl;
+    if (tid == 0) pre_s[0] = 0;
+    __syncthreads();
+    const int total = pre_s[G];
+
+    const uint64_t* top;  // the KPRIME best approximate keys, sorted descending
+    if (total <= NW * 512) {
+        if (total <= NW * 128)
+            tail_gather_sort<4>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
+        else if (total <= NW * 256)
+            tail_gather_sort<8>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
+        else
+            tail_gather_sort<16>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
+        uint64_t* src = sA;
+        uint64_t* dst = sB;
+        int n = NW * KPRIME;
+        for (;;) {
+            __syncthreads();
+            const int nchunks = n <= 256 ? 1 : (n + 511) / 512;
+            if (warp < nchunks) {
+                if (n <= 256) tail_merge_sort<8>(src, n, KPRIME, dst, warp, lane);
+                else tail_merge_sort<16>(src, n, KPRIME, dst, warp, lane);
+            }
+            if (nchunks == 1) break;
+            n = nchunks * KPRIME;
+            uint64_t* t = src; src = dst; dst = t;
+        }
+        __syncthreads();
+        top = dst;
+    } else {  // lists that overflowed the register path (adversarial orderings): the general streaming selection
+        select_lists_body<kThreads>(a.lists, a.cnt, G, BM, CAP, KPRIME, nullptr, qf, sA, pre_s, warp_tot, fill_s);
+        top = sA;
+    }
+    // every row not in top[0, k') scored <= tt: it was filtered by tau, dropped by a compaction (which raised tau to its
+    // k'-th key) or ranked behind the k'-th key here
+    uint32_t t = __ldcg(a.tau + qf);
+    if (top[KPRIME - 1]) t = max(t, (uint32_t)(top[KPRIME - 1] >> 32));
+    const float tt = ord_to_float(t);
+    if (tid == 0) MQVS_STAMP(8);
+
+    // K4: canonical fp32 rescoring, one warp per row, three rows in flight per warp
+    const T* rows = reinterpret_cast<const T*>(a.rows);
+    float4 qv[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) qv[c] = *reinterpret_cast<const float4*>(a.qn + (size_t)qf * kDim + c * 128 + lane * 4);
+    constexpr int kInFlight = 3;
+    for (int i0 = warp * kInFlight; i0 < KPRIME; i0 += NW * kInFlight) {
+        uint64_t key[kInFlight];
+        RowFrag<T> x[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            key[u] = i0 + u < KPRIME ? top[i0 + u] : 0ull;
+            if (key[u] != 0ull) x[u].load(rows + (size_t)key_id(key[u]) * kDim, lane);  // warp-uniform
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            uint64_t out = 0ull;
+            if (key[u] != 0ull) {
+                float4 xv[kChunks];
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) xv[c] = x[u].get(c);
+                out = pack_key(warp_butterfly_sum(lane_dot(qv, xv)), key_id(key[u]));
+            }
+            if (lane == 0 && i0 + u < KPRIME) ex[i0 + u] = out;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) MQVS_STAMP(9);
+    if (warp == 0) {  // final order by exact score: one warp, KPRIME / 32 keys per lane
+        constexpr int KPL = KPRIME / 32;
+        uint64_t key[KPL];
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) key[r] = ex[r * 32 + lane];
+        warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const int j = r * 32 + lane;
+            if (j < a.k) {
+                a.out_scores[(size_t)qf * a.k + j] = key[r] ? key_score(key[r]) : -INFINITY;
+                a.out_ids[(size_t)qf * a.k + j] = key[r] ? (int64_t)key_id(key[r]) + a.id_base : -1;
+            }
+            if (j == a.k - 1) {  // the thread holding the k-th exact key checks the margin
+                bool ok = true;
+                if (tt != -INFINITY) ok = key[r] != 0ull && key_score(key[r]) > tt + a.eps[qf];
+                a.flags[qf] = ok ? 0u : 1u;
+                if (!ok) atomicAdd(a.flag_count, 1u);
+            }
+        }
+        if (lane == 0) MQVS_STAMP(10);
+    }
+}
+
+// Raw queries -> everything tc_fused_kernel needs, in one launch: K1's normalisation (bit-identical: same lane shares,
+// same order), the fp32 copy the exact rescoring reads, the tensor-core operand matrix (bf16-rounded or fp32) padded to
+// 128 rows, eps[q], tau = -inf, and the zeroed grid-barrier counters / flag count.
+template <typename T>
+__global__ void __launch_bounds__(128)
+prep_fused_kernel(const float* __restrict__ q_raw, int dim, int vec4, int B, float* __restrict__ qn, T* __restrict__ q_op,
+                  float* __restrict__ eps, uint32_t* __restrict__ tau, unsigned int* __restrict__ gbar,
+                  uint32_t* __restrict__ flag_count, unsigned int* __restrict__ bad_epoch, unsigned int epoch) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        gbar[0] = gbar[1] = gbar[2] = 0u;
+        *flag_count = 0u;
+    }
+    float4 v[kChunks];
+    if (q < B) {
+        load_lane_share(q_raw + (size_t)q * dim, dim, vec4 != 0, lane, v);
+        if (!normalize_lane_share(v) && lane == 0) atomicMax(bad_epoch, epoch);
+    } else {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float err2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const size_t o = (size_t)q * kDim + c * 128 + lane * 4;
+        if (q < B) *reinterpret_cast<float4*>(qn + o) = v[c];
+        if constexpr (sizeof(T) == 2) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[c].x), h1 = __float2bfloat16_rn(v[c].y);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(v[c].z), h3 = __float2bfloat16_rn(v[c].w);
+            const float d0 = v[c].x - __bfloat162float(h0), d1 = v[c].y - __bfloat162float(h1);
+            const float d2 = v[c].z - __bfloat162float(h2), d3 = v[c].w - __bfloat162float(h3);
+            err2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            uint2 pk;
+            pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            *reinterpret_cast<uint2*>(q_op + o) = pk;
+        } else {
+            *reinterpret_cast<float4*>(q_op + o) = v[c];
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, m);
+    if (lane == 0) {
+        // same bounds as prep_queries_kernel
+        const float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 1e-4f : 2.0f * 0.0009765625f * 1.001f + 1e-4f;
+        if (q < B) eps[q] = e;
+        tau[q] = kOrdNegInf;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 
@@ -647,6 +1137,13 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int dtype, int 
 struct Trace {
     bool on = getenv("MQVS_TRACE") != nullptr;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    unsigned long long* dbg = nullptr;  // [grid][8] phase stamps of the last tc_fused_kernel launch
+    int dbg_grid = 0;
+    unsigned long long* fused_dbg(int grid) {
+        if (!dbg && cudaMalloc(&dbg, 256 * 16 * sizeof(unsigned long long)) != cudaSuccess) dbg = nullptr;
+        dbg_grid = grid;
+        return dbg;
+    }
     void mark(const char* what, cudaStream_t st) {
         if (!on) return;
         cudaEvent_t e;
@@ -760,6 +1257,78 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+bool fused_ok(int B, int k, int sm_count) {
+    // one query tile; one list / 8 chunk maxima per CTA must fit select_lists_body<192> and kth_largest_u32 (1280 values);
+    // CTA c finishes query c, so there must be at least B CTAs
+    return B >= 1 && B <= BM && k <= 128 && sm_count >= BM && sm_count <= 160;
+}
+size_t cmax_bytes(const Plan& p) { return (size_t)BM * p.grid * 8 * sizeof(uint32_t); }
+
+namespace {
+template <typename T, int KP>
+cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const FusedArgs& a, int grid, cudaStream_t st) {
+    auto kern = tc_fused_kernel<T, 512, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&mq, (void*)&mx, (void*)&a};
+    // cooperative: the grid barriers need every CTA resident (one per SM), whatever else shares the device
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, kSmemBytes, st);
+}
+}  // namespace
+
+const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
+                         int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
+                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st) {
+    CUtensorMap mq, mx;
+    if (!make_map(&mq, b.q_op, (uint64_t)BM, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
+    if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
+    g_trace.mark("begin", st);
+    const int vec4 = (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0;
+    if (dtype == MQVS_F32)
+        prep_fused_kernel<float><<<BM / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (float*)b.q_op, b.eps, b.tau, b.gbar,
+                                                         b.flag_count, bad_epoch, epoch);
+    else
+        prep_fused_kernel<__nv_bfloat16><<<BM / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (__nv_bfloat16*)b.q_op, b.eps, b.tau,
+                                                                 b.gbar, b.flag_count, bad_epoch, epoch);
+    g_trace.mark("prep", st);
+    FusedArgs a{};
+    a.n_rows = n_rows;
+    a.n_queries = (uint32_t)B;
+    a.n_tiles = (n_rows + BN - 1) / BN;
+    a.ncols = (uint32_t)p.grid * 8;
+    a.mask = mask;
+    a.tau = b.tau;
+    a.cmax = b.cmax;
+    a.cnt = b.cnt;
+    a.lists = b.lists;
+    a.gbar = b.gbar;
+    a.rows = rows;
+    a.qn = qn;
+    a.eps = b.eps;
+    a.k = k;
+    a.id_base = id_base;
+    a.out_scores = out_scores;
+    a.out_ids = out_ids;
+    a.flags = b.flags;
+    a.flag_count = b.flag_count;
+    a.dbg = g_trace.on ? g_trace.fused_dbg(p.grid) : nullptr;
+    if (a.dbg) cudaMemsetAsync(a.dbg, 0, 256 * 16 * sizeof(unsigned long long), st);
+    cudaError_t e = cudaSuccess;
+#define MQVS_TCF(KP_)                                                                          \
+    if (p.kprime == KP_)                                                                       \
+        e = dtype == MQVS_F32 ? launch_fused<float, KP_>(mq, mx, a, p.grid, st)                \
+                              : launch_fused<__nv_bfloat16, KP_>(mq, mx, a, p.grid, st);
+    MQVS_TCF(32)
+    MQVS_TCF(64)
+    MQVS_TCF(128)
+    MQVS_TCF(256)
+#undef MQVS_TCF
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    g_trace.mark("fused", st);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 void trace_dump() {
     if (!g_trace.on || g_trace.marks.empty()) return;
     cudaEventSynchronize(g_trace.marks.back().second);
@@ -770,6 +1339,27 @@ void trace_dump() {
     }
     for (auto& m : g_trace.marks) cudaEventDestroy(m.second);
     g_trace.marks.clear();
+    if (g_trace.dbg && g_trace.dbg_grid > 0) {
+        // phase stamps of the last single-launch search, relative to the earliest CTA start: min / median / max over CTAs
+        const int G = g_trace.dbg_grid;
+        std::vector<unsigned long long> h((size_t)G * 16);
+        if (cudaMemcpy(h.data(), g_trace.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            unsigned long long t0 = ~0ull;
+            for (int c = 0; c < G; ++c) t0 = std::min(t0, h[(size_t)c * 16]);
+            static const char* names[11] = {"epilogue start", "first tile scored", "chunk maxima out", "barrier 1 passed",
+                                            "tau selected", "barrier 2 passed", "scan done", "barrier 3 passed",
+                                            "shortlist selected", "rescored", "results written"};
+            for (int i = 0; i < 11; ++i) {
+                std::vector<double> v;
+                for (int c = 0; c < G; ++c)
+                    if (h[(size_t)c * 16 + i] >= t0) v.push_back((double)(h[(size_t)c * 16 + i] - t0) * 1e-3);
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, "[mqvs trace]   %-18s min %8.1f  med %8.1f  max %8.1f us\n", names[i], v.front(), v[v.size() / 2], v.back());
+            }
+        }
+        g_trace.dbg_grid = 0;
+    }
 }
 
 }  // namespace tc

@@ -25,6 +25,8 @@ struct Buffers {       // all device memory, owned by the store handle
     float* tau_tilde;  // [b_pad]
     uint32_t* flags;   // [B] 1 = exactness margin not proven, needs the exact scan
     uint32_t* flag_count;
+    uint32_t* cmax;    // single-launch pipeline: [128][grid * 8] chunk maxima of every CTA's first tile
+    unsigned int* gbar;  // single-launch pipeline: [3] grid barrier counters
 };
 
 Plan plan(int k, int B, int sm_count);
@@ -35,6 +37,14 @@ size_t cnt_bytes(const Plan& p);
 // Enqueue the whole tensor-core search on `st`.  Returns nullptr or an error message.
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
                    int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st);
+
+// Single-launch pipeline for B <= 128 (one query tile): prep kernel + one cooperative persistent kernel that learns the
+// thresholds, scans, selects, rescores and finalizes.  Takes the RAW queries (normalises them into qn itself).
+bool fused_ok(int B, int k, int sm_count);
+size_t cmax_bytes(const Plan& p);
+const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
+                         int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
+                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st);
 
 void trace_dump();  // MQVS_TRACE=1 developer aid: per-launch timings of the last searches to stderr
 int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize

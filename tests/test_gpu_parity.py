@@ -269,13 +269,20 @@ TC_CASES = [
     (300000, "bf16", 512, 10, None),
     (4096, "bf16", 1, 5, None),           # smallest store the path accepts, single query
     (65536, "fp32", 128, 128, 0.001),     # fewer allowed rows (about 65) than k: padded results
+    (37000, "bf16", 128, 10, None),       # fewer corpus tiles (145) than CTAs: some CTAs own no tile at all
+    (200001, "fp32", 7, 1, 0.02),         # k = 1, ragged tail, sparse mask
+    (151552, "bf16", 96, 100, None),      # exactly 4 tiles per CTA (148 x 4 x 256 rows), k' = 256
 ]
 
 
-@pytest.mark.parametrize("n,dtype,B,k,frac", TC_CASES)
-def test_tensor_core_path_matches_oracle_bitwise(gpu, n, dtype, B, k, frac):
+# path 2 = tensor-core path (single cooperative launch for B <= 128, segmented pipeline above); 4 = always segmented
+TC_CASES_PATHS = [c + (2,) for c in TC_CASES] + [c + (4,) for c in TC_CASES if c[2] <= 128]
+
+
+@pytest.mark.parametrize("n,dtype,B,k,frac,path", TC_CASES_PATHS)
+def test_tensor_core_path_matches_oracle_bitwise(gpu, n, dtype, B, k, frac, path):
     idx, x, st = build(n, 768, dtype, seed=0x5EED0003)
-    idx.set_path(2)
+    idx.set_path(path)
     q, planted = O.planted_queries(QSEED, B, 0x5EED0003, n, 768)
     qn, _ = O.normalize_rows(q, "fp32", 768)
     mask = None if frac is None else O.mask_from_bool(np.random.default_rng(11).random(n) < frac)
@@ -380,7 +387,7 @@ def test_hypothesis_random_shapes_tensor_path(gpu):
            frac=hs.sampled_from([None, 0.0, 0.003, 0.5, 1.0]), dtype=hs.sampled_from(["fp32", "bf16"]), seed=hs.integers(0, 2 ** 31))
     def run(n, B, k, frac, dtype, seed):
         idx, x, st = build(n, 768, dtype, seed)
-        idx.set_path(2)
+        idx.set_path(2 if seed % 3 else 4)
         q = O.synth_rows(seed + 1, 0, B, 768)
         qn, _ = O.normalize_rows(q, "fp32", 768)
         mask = None if frac is None else O.mask_from_bool(np.random.default_rng(seed).random(n) < frac)
@@ -433,8 +440,9 @@ def test_tensor_path_batches_larger_than_one_launch_chunk(gpu):
     assert_bit_equal(s, i, *O.brute_force_topk(qn, st, k))
 
 
+@pytest.mark.parametrize("path", [2, 4])
 @pytest.mark.parametrize("dtype,k", [("bf16", 10), ("fp32", 100)])
-def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k):
+def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k, path):
     """Rows ordered by INCREASING similarity to the queries: thresholds learnt on earlier segments never filter anything,
     every score is appended, the per-(CTA, query) lists overflow and the warp-sort compaction path runs for real."""
     n, B = 160_000, 16
@@ -446,7 +454,7 @@ def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k):
     q = q0[None, :] + 0.02 * rng.standard_normal((B, 768)).astype(np.float32)
     idx = native().Index(768, dtype)
     idx.add(x)
-    idx.set_path(2)
+    idx.set_path(path)
     st, _ = O.normalize_rows(x, dtype, 768)
     qn, _ = O.normalize_rows(q, "fp32", 768)
     s, i = idx.search(q, k)
@@ -454,3 +462,41 @@ def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k):
     es, ei = O.brute_force_topk(qn, st, k)
     assert (ei[:, 0] > n - 20000).all()         # the best rows really are among the last ones
     assert_bit_equal(s, i, es, ei)
+
+
+def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segmented_one(gpu):
+    """B <= 128 on the tensor path: prep kernel + ONE cooperative persistent kernel (threshold learning through grid
+    barriers, scan, selection, fp32 rescoring, margin check) + the three device-driven repair launches.  Must agree bit
+    for bit with the segmented pipeline (path 4), the exact SIMT scan (path 1) and the oracle; repeated calls on one
+    handle reuse the barrier counters; a non-finite query still raises and leaves the handle usable."""
+    n, B, k = 300_000, 64, 10
+    idx = native().Index(768, "fp32", capacity_rows=n)
+    idx.add_synthetic(SEED, 0, n)
+    q, planted = O.planted_queries(QSEED, B, SEED, n, 768)
+    idx.set_path(0)
+    l0 = idx.stats()["kernel_launches"]
+    one = idx.search(q, k)
+    st = idx.stats()
+    assert st["last_path"] == 1 and st["kernel_launches"] - l0 == 5 and st["exact_fallbacks"] == 0
+    again = idx.search(q, k)
+    assert all(one[1][b, 0] == planted[b] for b in range(0, B, 2))
+    idx.set_path(4)
+    seg = idx.search(q, k)
+    idx.set_path(1)
+    simt = idx.search(q, k)
+    assert_bit_equal(*one, *simt)
+    assert_bit_equal(*again, *simt)
+    assert_bit_equal(*seg, *simt)
+    idx.set_path(0)
+    bad = q.copy()
+    bad[17, 5] = np.nan
+    with pytest.raises(native().MqvsError):
+        idx.search(bad, k)
+    assert_bit_equal(*idx.search(q, k), *simt)
+    # ragged batch sizes around the tile / warp boundaries
+    for b in (3, 31, 33, 127, 128):
+        got = idx.search(q[:1].repeat(b, axis=0) + 0.01 * O.synth_rows(b, 0, b, 768), k)
+        idx.set_path(1)
+        want = idx.search(q[:1].repeat(b, axis=0) + 0.01 * O.synth_rows(b, 0, b, 768), k)
+        idx.set_path(0)
+        assert_bit_equal(*got, *want)
