@@ -364,8 +364,11 @@ def main():
     pk = peaks()
     algo_bytes = sh.local_rows * 768 * ELEM[wl["dtype"]]  # corpus bytes one scan streams on this rank
     avg_launch_ms = scan_ms / max(1, scan_launches)
-    kernel = ("tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, "
-              "bracketed together)" if st1["last_path"] == 1 else "scan_simt_kernel")
+    kernel = {0: "scan_simt_kernel (+ candidate memset, bracketed together)",
+              1: "scan_fused_kernel (single-launch SIMT search)",
+              2: "tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, bracketed together)",
+              3: "prep_fused_kernel + tc_fused_kernel (one cooperative launch: tcgen05 scoring of the whole corpus, in-kernel "
+                 "threshold learning, selection, fp32 rescoring; bracketed together)"}[st1["last_pipeline"]]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):

@@ -55,6 +55,10 @@ typedef struct mqvs_stats {
     uint64_t exact_fallbacks;    /* queries whose tensor-core shortlist could not be proven exact and were re-run on the SIMT scan */
     uint64_t unrepaired;         /* mqvs_search_async only: flagged queries beyond the 64 the device repair pass takes per call
                                     (their results are approximate; the blocking mqvs_search repairs every one) */
+    uint32_t last_pipeline;      /* how the last search ran: 0 = SIMT scan, normalise + scan(s) + merge launches; 1 = SIMT scan, one
+                                    launch (B <= 4, k <= 16); 2 = tensor cores, corpus segments + selection launches;
+                                    3 = tensor cores, one cooperative launch (B <= 128) */
+    uint32_t reserved_;
 } mqvs_stats;
 
 MQVS_API int mqvs_version(void);

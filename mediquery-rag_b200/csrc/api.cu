@@ -218,6 +218,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->stats.scan_bytes += s->n * s->row_bytes();
         s->stats.last_scan_passes = 1;
         s->stats.last_path = 0;
+        s->stats.last_pipeline = 1;
         s->stats.searches += 1;
         s->stats.queries += (uint64_t)B;
         return MQVS_OK;
@@ -282,6 +283,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->stats.scan_bytes += s->n * s->row_bytes();
         s->stats.last_scan_passes = 1;
         s->stats.last_path = 1;
+        s->stats.last_pipeline = 3;
         s->stats.searches += 1;
         s->stats.queries += (uint64_t)B;
         return MQVS_OK;
@@ -302,6 +304,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         passes = 1;
         s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B) + 3;
         s->stats.last_path = 1;
+        s->stats.last_pipeline = 2;
     } else {
         CU(cudaEventRecord(ev[1], st));
         // scan launches are bracketed together with the (tiny) candidate memset
@@ -309,6 +312,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         CU(cudaEventRecord(ev[2], st));
         s->stats.kernel_launches += passes + 1;
         s->stats.last_path = 0;
+        s->stats.last_pipeline = 0;
     }
     CU(cudaEventRecord(ev[3], st));
     CU(cudaGetLastError());

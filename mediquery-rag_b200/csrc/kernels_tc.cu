@@ -221,10 +221,19 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
 
 // One 128 x 256 accumulator tile, seen by the epilogue thread that owns TMEM lane (= query) `taddr >> 16`: threshold
 // test of this query's 256 scores, survivors appended to the thread's private list, lists about to overflow compacted.
-template <int CAP, int KPRIME>
+// The 8 largest chunk maxima (order-preserving bits; one chunk = 32 consecutive rows, masked rows excluded) this
+// (CTA, query) has seen, unsorted, mirrored in global memory slot by slot: tc_fused_kernel's threshold refresh reads them.
+struct ChunkTop {
+    uint32_t v[8];
+    uint32_t mn;     // min of v
+    uint32_t* out;   // this thread's 8 slots of cmax
+    bool on;         // record chunks of the tile being processed
+};
+
+template <int CAP, int KPRIME, bool TRACK = false>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0, uint32_t n_rows,
                                               const uint32_t* __restrict__ mask, uint32_t* st, uint32_t* tau_glob_q, int lane,
-                                              float& tau, uint32_t& cnt, uint64_t* lst) {
+                                              float& tau, uint32_t& cnt, uint64_t* lst, ChunkTop* trk = nullptr) {
     constexpr int KPL = CAP / 32;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
@@ -252,6 +261,31 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
             uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
             if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
             pm &= mw;
+            if constexpr (TRACK) {
+                if (pm != 0u && trk->on) {  // this chunk's best allowed row clears tau: is it among this thread's 8 best chunks?
+                    float m = mx;
+                    if (mw != 0xffffffffu) {
+                        m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);
+                    }
+                    const uint32_t o = ord_u32(m);
+                    if (o > trk->mn) {
+                        bool done = false;
+                        uint32_t nm = 0xffffffffu;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (!done && trk->v[i] == trk->mn) {  // replace ONE slot: a reader never sees a chunk twice
+                                trk->v[i] = o;
+                                trk->out[i] = o;
+                                done = true;
+                            }
+                            nm = min(nm, trk->v[i]);
+                        }
+                        trk->mn = nm;
+                    }
+                }
+            }
             __syncwarp();
             while (pm) {
                 const int j = __ffs(pm) - 1;
@@ -640,49 +674,6 @@ finalize_kernel(const uint64_t* __restrict__ exact_keys, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ single-launch pipeline
-// ---- tail of tc_fused_kernel: CTA c turns the G per-CTA lists of query c into the final top-k.
-// Selection runs in registers (warp bitonic sorts, no block barriers per compare stage): a shared-memory bitonic sort of
-// 2048 keys costs ~20 us of barrier latency, which at one query per CTA would be the whole tail.
-// Warp w sorts keys [w * 32 * KPL, (w + 1) * 32 * KPL) of the flattened lists and writes its kp best to out[w * kp ...].
-template <int KPL>
-__device__ __forceinline__ void tail_gather_sort(const uint64_t* __restrict__ lists, const int* pre_s, int G, int q, int cap,
-                                                 int total, int kp, uint64_t* out, int warp, int lane) {
-    uint64_t key[KPL];
-#pragma unroll
-    for (int r = 0; r < KPL; ++r) {
-        const int idx = (warp * KPL + r) * 32 + lane;
-        key[r] = 0ull;
-        if (idx < total) {
-            int lo = 0, hi = G;  // list g with pre_s[g] <= idx < pre_s[g + 1]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (pre_s[mid] <= idx) lo = mid; else hi = mid;
-            }
-            key[r] = __ldcg(lists + ((size_t)lo * BM + q) * cap + (idx - pre_s[lo]));
-        }
-    }
-    warp_sort_desc<KPL>(key, lane);
-#pragma unroll
-    for (int r = 0; r < KPL; ++r)
-        if (r * 32 + lane < kp) out[warp * kp + r * 32 + lane] = key[r];
-    if (32 * KPL < kp)
-        for (int e = 32 * KPL + lane; e < kp; e += 32) out[warp * kp + e] = 0ull;
-}
-// Warp `warp` sorts src[warp * 32 * KPL ...] (n valid keys overall) and writes its kp best to dst[warp * kp ...].
-template <int KPL>
-__device__ __forceinline__ void tail_merge_sort(const uint64_t* src, int n, int kp, uint64_t* dst, int warp, int lane) {
-    uint64_t key[KPL];
-#pragma unroll
-    for (int r = 0; r < KPL; ++r) {
-        const int idx = (warp * KPL + r) * 32 + lane;
-        key[r] = idx < n ? src[idx] : 0ull;
-    }
-    warp_sort_desc<KPL>(key, lane);
-#pragma unroll
-    for (int r = 0; r < KPL; ++r)
-        if (r * 32 + lane < kp) dst[warp * kp + r * 32 + lane] = key[r];
-}
-
 struct FusedArgs;
 template <typename T, int CAP, int KPRIME>
 __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al);
@@ -861,7 +852,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t cnt = 0;
 
         // ---- 1. chunk maxima of the first tile
-        uint32_t* my_cmax = a.cmax + (size_t)q * a.ncols + blockIdx.x * 8;
+        uint32_t* my_cmax = a.cmax + (size_t)(q_ok ? q : 0) * a.ncols + blockIdx.x * 8;
+        ChunkTop trk;
+        trk.out = my_cmax;
+        trk.on = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) trk.v[i] = 0u;
         if (et == 0) MQVS_STAMP(0);
         if (n_my > 0) {
             mbar_wait(bar_tfull, 0);
@@ -883,6 +879,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     ord = mw ? ord_u32(m) : 0u;
                 }
                 if (q_ok) my_cmax[ch] = ord;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i == ch) trk.v[i] = ord;
             }
         } else if (q_ok) {
 #pragma unroll
@@ -903,6 +902,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (et == 0) { MQVS_STAMP(4); grid_arrive_and_wait(a.gbar + 1, G); MQVS_STAMP(5); }
         epi_bar_sync();
         float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
+        trk.mn = trk.v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) trk.mn = min(trk.mn, trk.v[i]);
 
         // ---- 3. first tile again, now against tau, then the rest of this CTA's tiles
         uint32_t w = 0;
@@ -913,11 +915,21 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tcgen05_fence_after();
             }
-            epilogue_tile<CAP, KPRIME>(lane_taddr + acc * BN, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024,
-                                       a.tau + q, lane, tau, cnt, lst);
+            trk.on = w > 0 && q_ok;  // the first tile's chunks are already in trk
+            epilogue_tile<CAP, KPRIME, true>(lane_taddr + acc * BN, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024,
+                                             a.tau + q, lane, tau, cnt, lst, &trk);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            // Threshold refresh after 2, 4, 8, ... tiles and after the last one: every (CTA, query) mirrors its 8 largest chunk maxima so far in
+            // cmax, so the k'-th largest of a query's G*8 slots is a valid threshold that tightens as the scan proceeds
+            // (a query then collects ~k' candidates per doubling of the rows scanned instead of k' N / (256 G)).  Slots are
+            // replaced one word at a time and a chunk is only ever written to one slot, so whatever mix of old and new
+            // values the reader sees, distinct slots are distinct chunks, i.e. distinct rows scoring at least that much.
+            if (blockIdx.x < a.n_queries && w >= 1 && (((w + 1) & w) == 0 || w + 1 == n_my)) {
+                const uint32_t t = kth_largest_u32(a.cmax + (size_t)blockIdx.x * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
+                if (et == 0 && t > kOrdNegInf) atomicMax(a.tau + blockIdx.x, t);
+            }
         }
         if (q_ok) a.cnt[(size_t)blockIdx.x * BM + q] = cnt;
     }
@@ -937,16 +949,22 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     fused_tail<T, CAP, KPRIME>(a, (int)G, smem_al);
 }
 
+// ---- tail of tc_fused_kernel: CTA c turns the G per-CTA lists of query c into the final top-k.
+// No sort of approximate keys: after the last threshold refresh tau[q] is within a few ranks of the k'-th best score, so
+// the candidates that still clear it (~k', counted) ARE the shortlist.  All of them are rescored exactly, and the output
+// order comes from ranking each exact key against the others (keys are unique: they embed the row id).  A sorting
+// network on one warp costs 10+ us here (single-warp issue latency); this tail is ~6 us at k = 10.
 template <typename T, int CAP, int KPRIME>
 __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al) {
     constexpr int NW = kThreads / 32;
+    constexpr int kCcap = 1024;  // shortlist capacity of the direct path (>= 2 k' with room for ties)
     // the operand ring is idle now (every TMA load was consumed by an MMA that has retired): reuse it
-    uint64_t* sA = reinterpret_cast<uint64_t*>(smem_al);  // 2048 keys
-    uint64_t* sB = sA + 2048;                             // 2048 keys
-    uint64_t* ex = sB + 2048;                             // KPRIME exact keys
-    int* pre_s = reinterpret_cast<int*>(ex + 256);        // kThreads + 1
+    uint64_t* C = reinterpret_cast<uint64_t*>(smem_al);   // 2048 keys (direct path uses kCcap; the fallback all of it)
+    uint64_t* ex = C + 2048;                              // kCcap exact keys
+    int* pre_s = reinterpret_cast<int*>(ex + kCcap);      // kThreads + 1
     int* warp_tot = pre_s + kThreads + 1;                 // NW
     int* fill_s = warp_tot + NW;
+    int* valid_s = fill_s + 1;
     const int qf = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // list lengths -> exclusive prefix sum (one list per thread)
@@ -958,6 +976,7 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
         if (lane >= d) incl += o;
     }
     if (lane == 31) warp_tot[warp] = incl;
+    if (tid == 0) { *fill_s = 0; *valid_s = 0; }
     __syncthreads();
     int base = 0;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
@@ -966,53 +985,47 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
     __syncthreads();
     const int total = pre_s[G];
 
-    const uint64_t* top;  // the KPRIME best approximate keys, sorted descending
-    if (total <= NW * 512) {
-        if (total <= NW * 128)
-            tail_gather_sort<4>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
-        else if (total <= NW * 256)
-            tail_gather_sort<8>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
-        else
-            tail_gather_sort<16>(a.lists, pre_s, G, qf, CAP, total, KPRIME, sA, warp, lane);
-        uint64_t* src = sA;
-        uint64_t* dst = sB;
-        int n = NW * KPRIME;
-        for (;;) {
-            __syncthreads();
-            const int nchunks = n <= 256 ? 1 : (n + 511) / 512;
-            if (warp < nchunks) {
-                if (n <= 256) tail_merge_sort<8>(src, n, KPRIME, dst, warp, lane);
-                else tail_merge_sort<16>(src, n, KPRIME, dst, warp, lane);
-            }
-            if (nchunks == 1) break;
-            n = nchunks * KPRIME;
-            uint64_t* t = src; src = dst; dst = t;
+    // every row that is not a candidate scored < tau[q] (filtered) or <= tau[q] (dropped by a list compaction, which
+    // raised tau[q] to its k'-th key), so tau[q] bounds the approximate score of everything outside the shortlist
+    uint32_t tq = __ldcg(a.tau + qf);
+    for (int idx = tid; idx < total; idx += kThreads) {
+        int lo = 0, hi = G;  // list g with pre_s[g] <= idx < pre_s[g + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre_s[mid] <= idx) lo = mid; else hi = mid;
         }
-        __syncthreads();
-        top = dst;
-    } else {  // lists that overflowed the register path (adversarial orderings): the general streaming selection
-        select_lists_body<kThreads>(a.lists, a.cnt, G, BM, CAP, KPRIME, nullptr, qf, sA, pre_s, warp_tot, fill_s);
-        top = sA;
+        const uint64_t key = __ldcg(a.lists + ((size_t)lo * BM + qf) * CAP + (idx - pre_s[lo]));
+        if ((uint32_t)(key >> 32) >= tq) {
+            const int slot = atomicAdd(fill_s, 1);
+            if (slot < kCcap) C[slot] = key;
+        }
     }
-    // every row not in top[0, k') scored <= tt: it was filtered by tau, dropped by a compaction (which raised tau to its
-    // k'-th key) or ranked behind the k'-th key here
-    uint32_t t = __ldcg(a.tau + qf);
-    if (top[KPRIME - 1]) t = max(t, (uint32_t)(top[KPRIME - 1] >> 32));
-    const float tt = ord_to_float(t);
+    __syncthreads();
+    int nC = *fill_s;
+    if (nC > kCcap) {
+        // far more survivors than k' (hundreds of exact ties, adversarial orderings): the general streaming selection
+        // picks the k' best approximate keys; its k'-th key then bounds everything it left out
+        __syncthreads();
+        select_lists_body<kThreads>(a.lists, a.cnt, G, BM, CAP, KPRIME, nullptr, qf, C, pre_s, warp_tot, fill_s);
+        if (C[KPRIME - 1]) tq = max(tq, (uint32_t)(C[KPRIME - 1] >> 32));
+        nC = KPRIME;
+    }
+    const float tt = ord_to_float(tq);
     if (tid == 0) MQVS_STAMP(8);
 
-    // K4: canonical fp32 rescoring, one warp per row, three rows in flight per warp
+    // K4: canonical fp32 rescoring, one warp per row, four rows in flight per warp
     const T* rows = reinterpret_cast<const T*>(a.rows);
     float4 qv[kChunks];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) qv[c] = *reinterpret_cast<const float4*>(a.qn + (size_t)qf * kDim + c * 128 + lane * 4);
-    constexpr int kInFlight = 3;
-    for (int i0 = warp * kInFlight; i0 < KPRIME; i0 += NW * kInFlight) {
+    constexpr int kInFlight = 4;
+    int n_valid = 0;
+    for (int i0 = warp * kInFlight; i0 < nC; i0 += NW * kInFlight) {
         uint64_t key[kInFlight];
         RowFrag<T> x[kInFlight];
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
-            key[u] = i0 + u < KPRIME ? top[i0 + u] : 0ull;
+            key[u] = i0 + u < nC ? C[i0 + u] : 0ull;
             if (key[u] != 0ull) x[u].load(rows + (size_t)key_id(key[u]) * kDim, lane);  // warp-uniform
         }
 #pragma unroll
@@ -1023,34 +1036,42 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) xv[c] = x[u].get(c);
                 out = pack_key(warp_butterfly_sum(lane_dot(qv, xv)), key_id(key[u]));
+                ++n_valid;
             }
-            if (lane == 0 && i0 + u < KPRIME) ex[i0 + u] = out;
+            if (lane == 0 && i0 + u < nC) ex[i0 + u] = out;
         }
     }
+    if (lane == 0 && n_valid) atomicAdd(valid_s, n_valid);
     __syncthreads();
     if (tid == 0) MQVS_STAMP(9);
-    if (warp == 0) {  // final order by exact score: one warp, KPRIME / 32 keys per lane
-        constexpr int KPL = KPRIME / 32;
-        uint64_t key[KPL];
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) key[r] = ex[r * 32 + lane];
-        warp_sort_desc<KPL>(key, lane);
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) {
-            const int j = r * 32 + lane;
-            if (j < a.k) {
-                a.out_scores[(size_t)qf * a.k + j] = key[r] ? key_score(key[r]) : -INFINITY;
-                a.out_ids[(size_t)qf * a.k + j] = key[r] ? (int64_t)key_id(key[r]) + a.id_base : -1;
-            }
-            if (j == a.k - 1) {  // the thread holding the k-th exact key checks the margin
-                bool ok = true;
-                if (tt != -INFINITY) ok = key[r] != 0ull && key_score(key[r]) > tt + a.eps[qf];
-                a.flags[qf] = ok ? 0u : 1u;
-                if (!ok) atomicAdd(a.flag_count, 1u);
-            }
+
+    // rank of each exact key among the others = its output position
+    const int n_valid_all = *valid_s;
+    for (int i = tid; i < nC; i += kThreads) {
+        const uint64_t e = ex[i];
+        if (e == 0ull) continue;
+        int rank = 0;
+        for (int j = 0; j < nC; ++j) rank += ex[j] > e ? 1 : 0;
+        if (rank < a.k) {
+            a.out_scores[(size_t)qf * a.k + rank] = key_score(e);
+            a.out_ids[(size_t)qf * a.k + rank] = (int64_t)key_id(e) + a.id_base;
         }
-        if (lane == 0) MQVS_STAMP(10);
+        if (rank == a.k - 1) {  // the k-th exact score must clear the bound of everything outside the shortlist
+            const bool ok = tt == -INFINITY || key_score(e) > tt + a.eps[qf];
+            a.flags[qf] = ok ? 0u : 1u;
+            if (!ok) atomicAdd(a.flag_count, 1u);
+        }
     }
+    for (int j = n_valid_all + tid; j < a.k; j += kThreads) {  // fewer candidates than k: pad
+        a.out_scores[(size_t)qf * a.k + j] = -INFINITY;
+        a.out_ids[(size_t)qf * a.k + j] = -1;
+    }
+    if (tid == 0 && n_valid_all < a.k) {
+        const bool ok = tt == -INFINITY;  // nothing was ever discarded: the candidates are all the allowed rows
+        a.flags[qf] = ok ? 0u : 1u;
+        if (!ok) atomicAdd(a.flag_count, 1u);
+    }
+    if (tid == 0) MQVS_STAMP(10);
 }
 
 // Raw queries -> everything tc_fused_kernel needs, in one launch: K1's normalisation (bit-identical: same lane shares,

@@ -292,22 +292,28 @@ def test_tensor_core_path_matches_oracle_bitwise(gpu, n, dtype, B, k, frac, path
     idx.close()
 
 
-def test_tensor_core_path_falls_back_to_exact_scan_when_margin_cannot_be_proven(gpu):
-    """300 exact copies of the best row: the k'-th approximate score ties the k-th, the margin check must flag the
-    query and the exact SIMT scan must repair it -- same ids (lowest row ids of the tie) as the oracle."""
+@pytest.mark.parametrize("path,dups,must_repair", [(4, 300, True), (2, 300, False), (2, 1500, True)])
+def test_tensor_core_path_falls_back_to_exact_scan_when_margin_cannot_be_proven(gpu, path, dups, must_repair):
+    """Hundreds of exact copies of the best row.  Segmented pipeline (path 4): the k'-th approximate score ties the k-th,
+    the margin check must flag the query and the exact SIMT scan must repair it.  Single-launch pipeline (path 2): every
+    candidate above the learnt threshold is rescored, so 300 ties are resolved exactly without a repair; 1500 ties
+    overflow its shortlist, the streaming selection takes over and the margin check flags the query.  In every case:
+    same ids (lowest row ids of the tie) and score bits as the oracle."""
     n = 20000
     x = O.synth_rows(SEED, 0, n, 768)
-    x[5000:5300] = x[123]
+    x[5000:5000 + dups] = x[123]
     idx = native().Index(768, "bf16")
     idx.add(x)
-    idx.set_path(2)
+    idx.set_path(path)
     q = np.stack([x[123] + 0.01 * x[7], x[9000], x[123]])
     qn, _ = O.normalize_rows(q, "fp32", 768)
     st, _ = O.normalize_rows(x, "bf16", 768)
     s, i = idx.search(q, 10)
     assert_bit_equal(s, i, *O.brute_force_topk(qn, st, 10))
     stats = idx.stats()
-    assert stats["last_path"] == 1 and stats["exact_fallbacks"] >= 2
+    assert stats["last_path"] == 1
+    if must_repair:
+        assert stats["exact_fallbacks"] >= 2
 
 
 def test_auto_path_choice_and_agreement_between_paths(gpu):
@@ -352,13 +358,15 @@ def test_full_size_config3_shape_properties(gpu):
     assert_bit_equal(s[:6], i[:6], es, ei)
 
 
-def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacity(gpu):
+@pytest.mark.parametrize("path,dups", [(4, 300), (2, 1500)])
+def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacity(gpu, path, dups):
     """mqvs_search_async cannot ask the host, so flagged queries are re-scanned by a device-driven pass (up to 64 per
-    call); the blocking call additionally repairs any number.  100 queries all aimed at a 300-fold duplicated row."""
+    call); the blocking call additionally repairs any number.  100 queries all aimed at a many-fold duplicated row
+    (enough copies to defeat the shortlist of the pipeline under test)."""
     import torch
     n, B, k = 20000, 100, 10
     x = O.synth_rows(SEED, 0, n, 768)
-    x[5000:5300] = x[123]
+    x[5000:5000 + dups] = x[123]
     noise = O.synth_rows(77, 0, B, 768)
     q = x[123][None, :] + 0.01 * noise
     qn, _ = O.normalize_rows(q, "fp32", 768)
@@ -366,7 +374,7 @@ def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacit
     es, ei = O.brute_force_topk(qn, st, k)
     idx = native().Index(768, "bf16")
     idx.add(x)
-    idx.set_path(2)
+    idx.set_path(path)
     s, i = idx.search(q, k)                       # blocking: device repairs 64, host repairs the other 36
     assert_bit_equal(s, i, es, ei)
     assert idx.stats()["exact_fallbacks"] >= B and idx.stats()["unrepaired"] == 0
