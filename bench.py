@@ -6,7 +6,8 @@
 A "step" is one search of a batch of B queries over the whole corpus.
   N = 1 (default)  workload c2 = BASELINE config 2: 1M x 768 fp32 corpus, k=10, one B200 (HBM-bound scan).
   N > 1 (torchrun) workload c4 = BASELINE config 4: 100M x 768 bf16 corpus row-sharded over the N ranks, k=10,
-                   one NCCL all-gather of the [B, k] candidates per batch + merge kernel ("strong": the corpus is
+                   the [B, k] candidates exchanged + merged by ONE kernel over NVLink peer memory per batch (NCCL
+                   all-gathers + merge kernel when MQVS_XCHG=nccl or peer mapping fails) ("strong": the corpus is
                    fixed, each rank scans 1/N of it).  `--workload c4 --gpus 1` runs the same corpus on one GPU.
 `value` times K steps with the queries already in HBM (CUDA events, max over ranks); `e2e` times the public API
 with HOST query buffers (pinned) and host results, copies inside the timed region.  `roofline` is the scan
@@ -288,7 +289,7 @@ def main():
     ms_total, out = timed(lambda: step_device(q_dev), args.steps)
     clocks = sampler.stop() if sampler else None
     st1 = sh.index.stats()
-    launches = (st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if world > 1 else 0)  # + merge kernel
+    launches = (st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if world > 1 else 0)  # + exchange/merge kernel
     scan_launches = st1["scan_launches"] - st0["scan_launches"]
     scan_ms = st1["scan_ms"] - st0["scan_ms"]
     ms_per_step = ms_total / args.steps
@@ -397,7 +398,8 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch": B, "k": k, "rows": rows, "rows_per_gpu": sh.local_rows,
-                   "store_dtype": wl["dtype"], "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                   "store_dtype": wl["dtype"],
+                   "parallelism": (f"row-shard x{world}, candidate exchange: {sh.exchange}" if world > 1 else "single GPU"),
                    "l2": ("inputs larger than L2 (corpus per GPU %.2f GB vs 126 MB L2); no flush needed" % (algo_bytes / 1e9)
                           if algo_bytes > 126e6 else "corpus fits in L2 (%.1f KB): launch-latency-bound case, no flush" % (algo_bytes / 1e3)),
                    "ingest_s": round(ingest_s, 3), "scan_passes_per_step": scan_launches / args.steps},

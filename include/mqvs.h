@@ -106,6 +106,25 @@ MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, cons
 MQVS_API int mqvs_merge_candidates(int device, const float* scores_dev, const int64_t* ids_dev, int W, int B, int k,
                           float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 
+/* The same step fused with its transfer, for the ranks of one box (one process per GPU): instead of two NCCL
+ * all-gathers + mqvs_merge_candidates, ONE kernel stores this rank's [B, k] candidates into every peer's inbox over
+ * NVLink peer memory (CUDA IPC), signals, waits for the peers' signals and merges W*k -> k (same ordering rule).
+ * Setup: every rank creates its exchange, publishes its 64-byte handle to the others by any host channel
+ * (sharded.py uses torch.distributed.all_gather_object), then connects with the W handles in rank order.
+ * Every rank must call mqvs_xchg_merge the same number of times with the same (B, k); B * k <= max_entries. */
+typedef struct mqvs_xchg mqvs_xchg_t;
+MQVS_API int mqvs_xchg_create(int device, int rank, int world, uint64_t max_entries, mqvs_xchg_t** out);
+MQVS_API int mqvs_xchg_get_handle(mqvs_xchg_t* x, void* handle_out, int handle_bytes);
+MQVS_API int mqvs_xchg_connect(mqvs_xchg_t* x, const void* handles);
+/* Ranks that live in ONE process (one host thread per GPU, or several logical shards on one GPU in the tests) skip
+ * IPC: each publishes mqvs_xchg_base() and connects with the W base pointers (peer access is enabled as needed). */
+MQVS_API int mqvs_xchg_base(mqvs_xchg_t* x, void** base_out);
+MQVS_API int mqvs_xchg_connect_ptrs(mqvs_xchg_t* x, void* const* bases);
+MQVS_API int mqvs_xchg_max_entries(mqvs_xchg_t* x, uint64_t* out);
+MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k,
+                             float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
+MQVS_API void mqvs_xchg_destroy(mqvs_xchg_t* x);
+
 /* collection.get(ids, include=["embeddings"]): stored (normalised) rows as fp32, [n, dim] to host. */
 MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float* out_host);
 

@@ -58,6 +58,14 @@ SIGNATURES = {
     "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
+    "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
+    "mqvs_xchg_get_handle": (_i, [_vp, _vp, _i]),
+    "mqvs_xchg_connect": (_i, [_vp, _vp]),
+    "mqvs_xchg_base": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "mqvs_xchg_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "mqvs_xchg_max_entries": (_i, [_vp, ctypes.POINTER(_u64)]),
+    "mqvs_xchg_merge": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "mqvs_xchg_destroy": (None, [_vp]),
 }
 
 
@@ -204,3 +212,60 @@ def merge_candidates(device: int, scores, ids, out_scores, out_ids, stream: int 
     W, B, k = scores.shape
     check(load().mqvs_merge_candidates(int(device), _ptr(scores), _ptr(ids), W, B, k, _ptr(out_scores), _ptr(out_ids),
                                        _vp(stream)))
+
+
+class PeerExchange:
+    """Cross-shard candidate exchange + merge in one kernel over NVLink peer memory (include/mqvs.h, mqvs_xchg_*).
+    Create on every rank, publish `.handle` (64 bytes) to all ranks over any host channel, then `.connect(handles)`
+    with the handles in rank order."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, device: int, rank: int, world: int, max_entries: int = 1 << 18):
+        h = _vp()
+        check(load().mqvs_xchg_create(int(device), int(rank), int(world), int(max_entries), ctypes.byref(h)))
+        self._h, self.world = h, int(world)
+        try:
+            buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+            check(load().mqvs_xchg_get_handle(self._h, buf, self.HANDLE_BYTES))
+            self.handle = bytes(buf.raw)
+            cap = _u64(0)
+            check(load().mqvs_xchg_max_entries(self._h, ctypes.byref(cap)))
+            self.max_entries = cap.value
+        except Exception:
+            self.close()
+            raise
+
+    def connect(self, handles) -> None:
+        handles = [bytes(x) for x in handles]
+        if len(handles) != self.world or any(len(x) != self.HANDLE_BYTES for x in handles):
+            raise ValueError("expected one 64-byte handle per rank")
+        blob = ctypes.create_string_buffer(b"".join(handles), self.HANDLE_BYTES * self.world)
+        check(load().mqvs_xchg_connect(self._h, blob))
+
+    @property
+    def base(self) -> int:
+        p = _vp()
+        check(load().mqvs_xchg_base(self._h, ctypes.byref(p)))
+        return p.value
+
+    def connect_ptrs(self, bases) -> None:
+        """Same-process ranks: the W inbox base pointers (`.base` of every rank's exchange) in rank order."""
+        arr = (_vp * self.world)(*[_vp(int(b)) for b in bases])
+        check(load().mqvs_xchg_connect_ptrs(self._h, arr))
+
+    def merge(self, scores, ids, out_scores, out_ids, stream: int = 0) -> None:
+        """scores/ids [B, k] device tensors of this rank -> out [B, k]: best k of all ranks' candidates."""
+        B, k = scores.shape
+        check(load().mqvs_xchg_merge(self._h, _ptr(scores), _ptr(ids), B, k, _ptr(out_scores), _ptr(out_ids), _vp(stream)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load().mqvs_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

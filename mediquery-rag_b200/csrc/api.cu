@@ -64,6 +64,18 @@ size_t elem_size(int dtype) { return dtype == MQVS_F32 ? 4 : 2; }
 
 }  // namespace
 
+namespace mqvs {
+int mqvs_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace mqvs
+
 struct mqvs_store {
     std::mutex mu;
     int dev = 0;

@@ -6,6 +6,9 @@
 
 namespace mqvs {
 
+// sets the thread-local message mqvs_last_error() returns; returns `code` (api.cu)
+int mqvs_fail(int code, const char* fmt, ...);
+
 // K1: L2-normalise + pack.  x [n, dim] fp32 (device) -> out [n, 768] fp32 or bf16, zero-padded; counts
 // rows whose squared norm is not finite into *bad (and stores them as zeros).
 void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,

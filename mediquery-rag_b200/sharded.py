@@ -2,13 +2,19 @@
 
 SURVEY.md section 8e: rank r owns the contiguous global rows [r*S, min(N, (r+1)*S)) with S = ceil(N / W) rounded
 up to a multiple of 32 (so the packed filter mask splits on word boundaries); queries are replicated; each rank
-scans its shard and keeps its k best per query (exact fp32 scores, ids already global); ONE all-gather of the
-[B, k] candidates per batch -> [W, B, k] on every rank; a W*k -> k merge kernel (same ordering rule: score
-descending, ties -> lower global id) finishes the batch on every rank, so any rank can answer.
-torch is plumbing here (device buffers, streams, the process group); the scan and the merge are libmqvs kernels.
+scans its shard and keeps its k best per query (exact fp32 scores, ids already global); the [B, k] candidates of
+all ranks are exchanged and a W*k -> k merge (same ordering rule: score descending, ties -> lower global id)
+finishes the batch on every rank, so any rank can answer.
+Exchange, in order of preference:
+  "p2p"   ONE libmqvs kernel per batch (mqvs_xchg_merge): P2P stores into every peer's inbox over NVLink (CUDA IPC
+          mappings set up once; the 64-byte handles travel through the process group), flags, wait, merge.
+  "nccl"  all_gather_into_tensor of scores and ids + mqvs_merge_candidates -- when peer mappings cannot be set up
+          (MQVS_XCHG=nccl forces it), when B*k exceeds the inbox, and on CPU (gloo) in the tests.
+torch is plumbing here (device buffers, streams, the process group); the scan, exchange and merge are libmqvs kernels.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Callable, Optional, Tuple
 
 import numpy as np
@@ -48,6 +54,38 @@ class ShardedIndex:
         self.index = (index_factory or _native.Index)(dim, store_dtype, dev_index, self.hi - self.lo)
         self._merge = merge_fn or _native_merge
         self.dim = dim
+        self.exchange, self._xchg, self.exchange_error = "none" if self.world == 1 else "nccl", None, None
+        if (self.world > 1 and merge_fn is None and getattr(self.device, "type", "cpu") == "cuda"
+                and os.environ.get("MQVS_XCHG", "p2p") != "nccl"):
+            self._setup_peer_exchange(dev_index)
+
+    def _setup_peer_exchange(self, dev_index: int) -> None:
+        """Collective: every rank maps every other rank's inbox; all ranks agree on the outcome (else NCCL for all)."""
+        torch, dist = self._torch, self._dist
+        none = b"\0" * _native.PeerExchange.HANDLE_BYTES
+        xchg, handle, err = None, none, None
+        try:
+            xchg = _native.PeerExchange(dev_index, self.rank, self.world)
+            handle = xchg.handle
+        except Exception as exc:  # IPC disabled, out of memory, ...
+            err = str(exc)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.group)  # every rank takes part, whatever happened above
+        ok = 0
+        if xchg is not None and all(h != none for h in handles):
+            try:
+                xchg.connect(handles)
+                ok = 1
+            except Exception as exc:  # no peer access between two of the devices
+                err = str(exc)
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # also the barrier before the first exchange
+        if int(flag.item()) == 1:
+            self._xchg, self.exchange = xchg, "p2p"
+        else:
+            if xchg is not None:
+                xchg.close()
+            self.exchange_error = err or "a peer could not map the inboxes"
 
     @property
     def local_rows(self) -> int:
@@ -81,6 +119,10 @@ class ShardedIndex:
         self.index.search_device(q, k, loc_s, loc_i, mask=mask_local, id_base=self.lo, stream=stream)
         if self.world == 1:
             return loc_s, loc_i
+        if self._xchg is not None and B * k <= self._xchg.max_entries and q.is_cuda:
+            out_s, out_i = torch.empty_like(loc_s), torch.empty_like(loc_i)
+            self._xchg.merge(loc_s, loc_i, out_s, out_i, stream=stream)
+            return out_s, out_i
         all_s = torch.empty((self.world * B, k), dtype=torch.float32, device=q.device)
         all_i = torch.empty((self.world * B, k), dtype=torch.int64, device=q.device)
         dist.all_gather_into_tensor(all_s, loc_s, group=self.group)  # concatenated along dim 0: [W*B, k]

@@ -508,3 +508,42 @@ def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segment
         want = idx.search(q[:1].repeat(b, axis=0) + 0.01 * O.synth_rows(b, 0, b, 768), k)
         idx.set_path(0)
         assert_bit_equal(*got, *want)
+
+
+@pytest.mark.parametrize("W,B,k", [(2, 1, 10), (4, 37, 10), (8, 100, 10), (3, 5, 100)])
+def test_peer_exchange_kernel_equals_merge_of_gathered_candidates(gpu, W, B, k):
+    """mqvs_xchg_merge (candidate exchange through peer inboxes + merge, one kernel per rank) against
+    mqvs_merge_candidates on the gathered candidates and the oracle merge.  W logical ranks share this one GPU (one
+    stream each, inboxes connected by pointer), so the kernels really wait for each other's flags; ties across ranks
+    (equal scores) must resolve to the lower global id; repeated calls exercise the parity double-buffering."""
+    import torch
+    M = native()
+    ex = [M._native.PeerExchange(0, r, W, max_entries=4096) for r in range(W)]
+    try:
+        for e in ex:
+            e.connect_ptrs([x.base for x in ex])
+        streams = [torch.cuda.Stream() for _ in range(W)]
+        rng = np.random.default_rng(W * 1000 + B)
+        for call in range(3):
+            sc = np.sort(rng.integers(0, 50, size=(W, B, k)).astype(np.float32) / 7.0, axis=2)[:, :, ::-1].copy()  # many ties
+            ids = np.stack([rng.permutation(B * k * 4)[:B * k].reshape(B, k) * W + r for r in range(W)]).astype(np.int64)
+            ids[W - 1, :, k - 1] = -1                      # an empty slot (a shard with fewer than k rows)
+            sc[W - 1, :, k - 1] = -np.inf
+            d_s = [torch.from_numpy(sc[r]).cuda() for r in range(W)]
+            d_i = [torch.from_numpy(ids[r]).cuda() for r in range(W)]
+            o_s = [torch.empty((B, k), dtype=torch.float32, device="cuda") for _ in range(W)]
+            o_i = [torch.empty((B, k), dtype=torch.int64, device="cuda") for _ in range(W)]
+            torch.cuda.synchronize()
+            for r in range(W):
+                ex[r].merge(d_s[r], d_i[r], o_s[r], o_i[r], stream=streams[r].cuda_stream)
+            torch.cuda.synchronize()
+            es, ei = O.merge_topk(sc.transpose(1, 0, 2).reshape(B, W * k), ids.transpose(1, 0, 2).reshape(B, W * k), k)
+            g_s, g_i = torch.empty_like(o_s[0]), torch.empty_like(o_i[0])
+            M._native.merge_candidates(0, torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda(), g_s, g_i)
+            torch.cuda.synchronize()
+            for r in range(W):
+                assert_bit_equal(o_s[r].cpu().numpy(), o_i[r].cpu().numpy(), es, ei)
+            assert_bit_equal(g_s.cpu().numpy(), g_i.cpu().numpy(), es, ei)
+    finally:
+        for e in ex:
+            e.close()

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Real multi-GPU parity (run under torchrun on W GPUs): the row-sharded NCCL path == the CPU oracle, bit for bit.
+"""Real multi-GPU parity (run under torchrun on W GPUs): the row-sharded path (peer-memory exchange kernel by default,
+MQVS_XCHG=nccl for the all-gather form) == the CPU oracle, bit for bit.
 Covers N not divisible by W, a shard smaller than k, a where-mask, both store dtypes and both search paths."""
 import json, os, sys
 import numpy as np
@@ -32,7 +33,7 @@ for n, dtype, B, k, frac in [(200_003, "bf16", 1, 10, None), (200_003, "bf16", 3
         qn, _ = O.normalize_rows(q, "fp32", 768)
         es, ei = O.brute_force_topk(qn, st, k, mask)
         ok = bool(np.array_equal(i, ei) and np.array_equal(s.view(np.uint32), es.view(np.uint32)))
-        results.append(dict(world=W, n=n, dtype=dtype, B=B, k=k, mask=frac, bounds=sh.bounds[:3], path=sh.index.stats()["last_path"], bit_exact=ok))
+        results.append(dict(world=W, n=n, dtype=dtype, B=B, k=k, mask=frac, bounds=sh.bounds[:3], path=sh.index.stats()["last_path"], exchange=sh.exchange, exchange_error=sh.exchange_error, bit_exact=ok))
         print(results[-1], flush=True)
     # every rank must hold the same answer
     chk = torch.from_numpy(i.astype(np.int64)).to(dev)
@@ -42,6 +43,6 @@ for n, dtype, B, k, frac in [(200_003, "bf16", 1, 10, None), (200_003, "bf16", 3
     del sh
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(results, open(f"gpurun_out/multi_gpu_parity_w{W}.json", "w"), indent=1)
+    json.dump(results, open(f"gpurun_out/multi_gpu_parity_w{W}_{os.environ.get('MQVS_XCHG', 'p2p')}.json", "w"), indent=1)
     print("MULTI-GPU PARITY", "OK" if all(r["bit_exact"] for r in results) else "FAILED")
 dist.destroy_process_group()
