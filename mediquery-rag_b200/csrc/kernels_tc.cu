@@ -50,7 +50,7 @@ constexpr int kTmemCols = 512;    // two 128 x 256 fp32 accumulators
 constexpr int kStageChunkBytes = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32 scores x 32 lanes) staging for the hit path
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStageChunkBytes;
 constexpr int kMaxQueriesPerLaunch = 4096;
-constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thresholds on 16 CTAs
+constexpr uint32_t kFirstSegmentTiles = 256;  // first filtered segment; its thresholds come from the cold pass below
 // Corpus segments end at 16, 256, 4096, ... tiles: each is 16x everything before it.  What matters is hits per
 // warp-chunk (32 queries x 32 rows = 1024 scores against thresholds learnt on S rows: ~1024 k'/S), not appends per
 // list.  Measured alternatives on B200 (r01, 1M and 10M rows): growth 8 / 32 / 64, a two-segment schedule for a single
@@ -61,6 +61,10 @@ constexpr uint32_t kFirstSegmentTiles = 16;  // 4096 rows: learns the first thre
 constexpr uint32_t kSegmentGrowth = 16;
 __host__ inline uint64_t first_segment_end(uint32_t /*m_tiles*/, int /*grid*/) { return kFirstSegmentTiles; }
 __host__ inline uint64_t next_segment_end(uint64_t end, uint32_t /*m_tiles*/) { return end * kSegmentGrowth; }
+// a short remainder (< half of what is already scored) is not worth a launch + selection of its own
+__host__ inline uint64_t clamp_segment_end(uint64_t end, uint32_t n_tiles) {
+    return (end >= n_tiles || n_tiles - end < end / 2) ? n_tiles : end;
+}
 
 template <typename T>
 struct Kind;
@@ -239,11 +243,21 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
     for (int ch = 0; ch < BN / 32; ++ch) {
         const uint32_t row0 = tile_row0 + ch * 32;
         if (row0 >= n_rows) break;  // uniform
+        // allow-mask word of this chunk (uniform over the warp).  Masked and out-of-range rows become -inf BEFORE the
+        // fast-reject test: thresholds are learnt on allowed rows only, so at 10 % selectivity unmasked scores would send
+        // ten times as many chunks through the hit path only to be dropped there (measured: +17 % on config 5); chunks
+        // without any allowed row are not even read from TMEM.
+        uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
+        if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
+        if (mw == 0u) continue;
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(taddr + ch * 32, v);
-        // fast reject: one 3-input max tree per 32 scores, one compare.  (Masked / out-of-range rows are
-        // not excluded here -- that only makes the test conservative; the slow path applies the mask.)
+        if (mw != 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (mw >> j) & 1u ? v[j] : 0xff800000u;
+        }
+        // fast reject: one 3-input max tree per 32 scores, one compare
         float grp[11];
         const float mx = max32(v, grp);
         const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
@@ -258,18 +272,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
                 st[j * 32 + lane] = v[j];
                 pm |= __uint_as_float(v[j]) >= tau ? (1u << j) : 0u;
             }
-            uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
-            if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
-            pm &= mw;
+            pm &= mw;  // tau may still be -inf
             if constexpr (TRACK) {
                 if (pm != 0u && trk->on) {  // this chunk's best allowed row clears tau: is it among this thread's 8 best chunks?
-                    float m = mx;
-                    if (mw != 0xffffffffu) {
-                        m = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);
-                    }
-                    const uint32_t o = ord_u32(m);
+                    const uint32_t o = ord_u32(mx);
                     if (o > trk->mn) {
                         bool done = false;
                         uint32_t nm = 0xffffffffu;
@@ -322,6 +328,30 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
     }
 }
 
+// Maximum of each 32-row chunk of one accumulator tile for this thread's query, masked and out-of-range rows excluded,
+// as order-preserving bits (0 = the chunk has no allowed row).  Distinct chunks are distinct rows, so the k'-th largest
+// chunk maximum of a set of tiles is a valid shortlist threshold for them: at least k' rows score that much.
+__device__ __forceinline__ void tile_chunk_maxima(uint32_t taddr, uint32_t tile_row0, uint32_t n_rows,
+                                                  const uint32_t* __restrict__ mask, uint32_t (&out)[BN / 32]) {
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        const uint32_t row0 = tile_row0 + ch * 32;
+        uint32_t ord = 0u;
+        if (row0 < n_rows) {  // uniform
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(taddr + ch * 32, v);
+            uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
+            if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);
+            ord = mw ? ord_u32(m) : 0u;
+        }
+        out[ch] = ord;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 struct ScoreArgs {
     uint32_t n_rows;        // valid corpus rows
@@ -334,6 +364,8 @@ struct ScoreArgs {
     uint32_t* cnt;          // [grid][B_pad] list lengths
     uint64_t* lists;        // [grid][B_pad][CAP]
     uint32_t b_pad;
+    uint32_t* cmax;         // cold pass only (else nullptr): [B_pad][ncols] chunk maxima, no list appends
+    uint32_t ncols;         // 8 * CTAs of the cold pass
 };
 
 template <typename T, int CAP, int KPRIME>
@@ -436,6 +468,15 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+                if (a.cmax != nullptr) {  // cold pass (uniform): only the chunk maxima that seed the thresholds
+                    uint32_t cm[BN / 32];
+                    tile_chunk_maxima(taddr, nt * BN, a.n_rows, a.mask, cm);
+                    if (q_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.cmax + (size_t)q * a.ncols + (size_t)(nt - a.tile_begin) * 8);
+                        dst[0] = make_uint4(cm[0], cm[1], cm[2], cm[3]);
+                        dst[1] = make_uint4(cm[4], cm[5], cm[6], cm[7]);
+                    }
+                } else
                 epilogue_tile<CAP, KPRIME>(taddr, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024, a.tau + q, lane, tau, cnt, lst);
                 // accumulator fully read -> hand TMEM back to the MMA warp
                 tcgen05_fence_before();
@@ -488,13 +529,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_p
 // ------------------------------------------------------------------------------------------ select + rescore
 constexpr int kSelThreads = 256;
 
-// One CTA per query, run after every corpus segment: (running shortlist of earlier segments) U (this segment's
-// per-CTA lists) -> new running shortlist of the kp (= k') best approximate keys, and tau[q] raised to the k'-th
-// best score of everything seen so far -- the threshold the next segment's epilogue filters with.  Entries that
-// cannot beat the current k'-th key are dropped before they reach the sort buffer, and only the filled part of
-// the buffer is sorted, so after the first segment a call costs a few microseconds.
-// Body shared by select_lists_kernel (NT = 256, one CTA per query) and the tail of tc_fused_kernel (NT = 192).
-// Leaves the kp best keys, sorted descending, in buf[0, kp).  buf: 2048 keys; pre_s: NT + 1; warp_tot: NT / 32.
+// General streaming selection, correct for any number of candidates: (previous shortlist) U (per-CTA lists of query q)
+// -> the kp (= k') best keys, sorted descending, in buf[0, kp).  Streams the lists through a 2048-key buffer in batches
+// that fit even if every entry survives the filter, with a block bitonic sort per batch.  This is the FALLBACK of
+// select_lists_kernel (NT = 256) and of tc_fused_kernel's tail (NT = 192) when the candidates overflow their fast
+// paths (adversarial orderings, thousands of ties).  buf: 2048 keys; pre_s: NT + 1; warp_tot: NT / 32.
 template <int NT>
 __device__ __forceinline__ void select_lists_body(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt,
                                                   int grid_ctas, int b_pad, int cap, int kp, const uint64_t* __restrict__ prev_keys,
@@ -599,25 +638,193 @@ __device__ __forceinline__ void select_lists_body(const uint64_t* __restrict__ l
     }
 }
 
+// One CTA per query, run after every corpus segment: (running shortlist of earlier segments) U (this segment's per-CTA
+// lists) -> new running shortlist of the kp (= k') best approximate keys, and tau[q] raised to the k'-th best score of
+// everything seen so far -- the threshold the next segment's epilogue filters with.
+// Nobody needs the shortlist SORTED (the next call needs the set and its minimum, K4 rescoring the set), so this is a
+// selection: all candidates that beat the previous k'-th key go to shared memory and an MSB-first radix select (8-bit
+// digits, per-warp histograms, bytes every key shares skipped) finds the k'-th largest key in a few passes; the keys
+// above it are compacted into slots [0, k'-1) and the k'-th key itself is stored LAST, where the next call looks for the
+// floor.  At 4096 queries x k' = 256 this replaced bitonic sorts of 2048 keys: 650-820 us -> see DESIGN.md per call.
+// More candidates than fit in shared memory (adversarial orderings) take the general streaming selection instead.
+constexpr int kSelMaxKeys = 8192;  // 64 KB of keys
+
 __global__ void __launch_bounds__(kSelThreads)
 select_lists_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ tau,
                     int grid_ctas, int b_pad, int cap, int kp, int first_segment, uint64_t* __restrict__ short_keys,
                     float* __restrict__ tau_tilde) {
-    __shared__ uint64_t buf[2048];
-    __shared__ int pre_s[kSelThreads + 1];    // exclusive prefix sum of the list lengths (<= one list per thread)
+    extern __shared__ __align__(16) uint64_t keys[];  // kSelMaxKeys
+    __shared__ int pre_s[kSelThreads + 1];
     __shared__ int warp_tot[kSelThreads / 32];
     __shared__ int fill_s;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    select_lists_body<kSelThreads>(lists, cnt, grid_ctas, b_pad, cap, kp, first_segment ? nullptr : short_keys, q, buf, pre_s,
-                                   warp_tot, &fill_s);
-    for (int i = tid; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = buf[i];
+    __shared__ unsigned hist[kSelThreads / 32][256];
+    __shared__ unsigned long long red_s[kSelThreads / 32];
+    __shared__ unsigned sel_digit, sel_need, sel_count;
+    __shared__ unsigned long long kstar_s;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // list lengths -> exclusive prefix sum (one list per thread)
+    const int mine = tid < grid_ctas ? min((int)cnt[(size_t)tid * b_pad + q], cap) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    if (tid == 0) fill_s = 0;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    pre_s[tid + 1] = base + incl;
+    if (tid == 0) pre_s[0] = 0;
+    __syncthreads();
+    const int total = pre_s[grid_ctas];
+    const int n_prev = first_segment ? 0 : kp;
+    uint64_t kstar = 0ull;
+
+    if (n_prev + total > kSelMaxKeys) {
+        __syncthreads();
+        select_lists_body<kSelThreads>(lists, cnt, grid_ctas, b_pad, cap, kp, first_segment ? nullptr : short_keys, q, keys,
+                                       pre_s, warp_tot, &fill_s);
+        for (int i = tid; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = keys[i];  // sorted: the k'-th is last
+        kstar = keys[kp - 1];
+    } else {
+        // gather: previous shortlist + every candidate that beats its k'-th key (0 while the shortlist is not full)
+        const uint64_t floor_key = first_segment ? 0ull : short_keys[(size_t)q * kp + kp - 1];
+        for (int i = tid; i < n_prev; i += kSelThreads) {
+            const uint64_t key = short_keys[(size_t)q * kp + i];
+            if (key != 0ull) keys[atomicAdd(&fill_s, 1)] = key;
+        }
+        for (int idx = tid; idx < total; idx += kSelThreads) {
+            int lo = 0, hi = grid_ctas;  // list g with pre_s[g] <= idx < pre_s[g + 1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre_s[mid] <= idx) lo = mid; else hi = mid;
+            }
+            const uint64_t key = __ldcg(lists + ((size_t)lo * b_pad + q) * cap + (idx - pre_s[lo]));
+            if (key > floor_key) keys[atomicAdd(&fill_s, 1)] = key;
+        }
+        __syncthreads();
+        const int n = fill_s;
+        if (n < kp) {  // shortlist not full yet: keep everything, no floor
+            for (int i = tid; i < kp; i += kSelThreads) short_keys[(size_t)q * kp + i] = i < n ? keys[i] : 0ull;
+        } else {
+            // bytes shared by every key carry no information: start below the highest differing bit
+            uint64_t diff = 0ull;
+            const uint64_t k0 = keys[0];
+            for (int i = tid; i < n; i += kSelThreads) diff |= keys[i] ^ k0;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, m);
+            if (lane == 0) red_s[warp] = diff;
+            __syncthreads();
+            diff = 0ull;
+#pragma unroll
+            for (int w = 0; w < kSelThreads / 32; ++w) diff |= red_s[w];
+            int shift = diff ? ((63 - __clzll((long long)diff)) & ~7) : 0;
+            uint64_t prefix = (shift + 8 < 64) ? (k0 >> (shift + 8)) << (shift + 8) : 0ull;  // bits above the first digit
+            unsigned need = (unsigned)kp;
+            bool found = n == 1;
+            if (n == 1) kstar = k0;
+            while (!found) {
+                for (int i = tid; i < (kSelThreads / 32) * 256; i += kSelThreads) (&hist[0][0])[i] = 0u;
+                __syncthreads();
+                for (int i = tid; i < n; i += kSelThreads) {
+                    const uint64_t key = keys[i];
+                    const bool in = shift + 8 >= 64 || ((key ^ prefix) >> (shift + 8)) == 0ull;
+                    if (in) atomicAdd(&hist[warp][(unsigned)(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (warp == 0) {  // digits in descending order: lane l owns 255 - 8l .. 248 - 8l
+                    unsigned c[8], s = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int d = 255 - (8 * lane + j);
+                        unsigned v = 0;
+#pragma unroll
+                        for (int w = 0; w < kSelThreads / 32; ++w) v += hist[w][d];
+                        c[j] = v;
+                        s += v;
+                    }
+                    unsigned inc = s;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+                        if (lane >= off) inc += t;
+                    }
+                    unsigned run = inc - s;
+                    if (run < need && need <= inc) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (run < need && need <= run + c[j]) {
+                                sel_digit = (unsigned)(255 - (8 * lane + j));
+                                sel_need = need - run;
+                                sel_count = c[j];
+                            }
+                            run += c[j];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (uint64_t)sel_digit << shift;
+                need = sel_need;
+                const unsigned count = sel_count;
+                if (shift == 0) {
+                    kstar = prefix;  // all 64 bits fixed (keys are unique, so count == 1 here)
+                    found = true;
+                } else if (count == 1) {  // one key left in the bin: it is the k'-th
+                    for (int i = tid; i < n; i += kSelThreads)
+                        if (((keys[i] ^ prefix) >> shift) == 0ull) kstar_s = keys[i];
+                    __syncthreads();
+                    kstar = kstar_s;
+                    found = true;
+                } else {
+                    shift -= 8;
+                }
+                __syncthreads();
+            }
+            // keys above the k'-th -> slots [0, k'-1) in any order; the k'-th itself last
+            if (tid == 0) fill_s = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += kSelThreads) {
+                const uint64_t key = keys[i];
+                if (key > kstar) short_keys[(size_t)q * kp + atomicAdd(&fill_s, 1)] = key;
+            }
+            if (tid == 0) short_keys[(size_t)q * kp + kp - 1] = kstar;
+        }
+    }
     if (tid == 0) {
         // every row discarded so far (epilogue filter, list compaction, this selection) scored <= the k'-th best
         uint32_t t = tau[q];
-        if (buf[kp - 1]) t = max(t, (uint32_t)(buf[kp - 1] >> 32));
+        if (kstar) t = max(t, (uint32_t)(kstar >> 32));
         tau[q] = t;
         tau_tilde[q] = ord_to_float(t);
     }
+}
+
+// After the cold pass (tc_score_kernel with ScoreArgs::cmax set): tau[q] = k'-th largest chunk maximum of query q.
+__global__ void __launch_bounds__(128)
+tau_from_chunk_maxima_kernel(const uint32_t* __restrict__ cmax, int ncols, int kp, uint32_t* __restrict__ tau) {
+    __shared__ int s_cnt[8];
+    const uint32_t* vals = cmax + (size_t)blockIdx.x * ncols;
+    const int et = threadIdx.x;
+    uint32_t v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = i * 128 + et < ncols ? vals[i * 128 + et] : 0u;
+    uint32_t lo = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = lo | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) c += v[i] >= cand ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        int* sc = s_cnt + ((bit & 1) << 2);
+        if ((et & 31) == 0) sc[et >> 5] = c;
+        __syncthreads();
+        if (sc[0] + sc[1] + sc[2] + sc[3] >= kp) lo = cand;
+    }
+    if (et == 0) tau[blockIdx.x] = lo > kOrdNegInf ? lo : kOrdNegInf;
 }
 
 // K4: one warp per (query, shortlisted row): canonical fp32 dot -> exact key.
@@ -863,25 +1070,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             mbar_wait(bar_tfull, 0);
             tcgen05_fence_after();
             if (et == 0) MQVS_STAMP(1);
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                const uint32_t row0 = first_tile * BN + ch * 32;
-                uint32_t ord = 0u;
-                if (row0 < a.n_rows) {  // uniform
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld32(lane_taddr + ch * 32, v);
-                    uint32_t mw = a.mask ? __ldg(a.mask + (row0 >> 5)) : 0xffffffffu;
-                    if (a.n_rows - row0 < 32) mw &= (1u << (a.n_rows - row0)) - 1u;
-                    float m = -INFINITY;
+            tile_chunk_maxima(lane_taddr, first_tile * BN, a.n_rows, a.mask, trk.v);
+            if (q_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);
-                    ord = mw ? ord_u32(m) : 0u;
-                }
-                if (q_ok) my_cmax[ch] = ord;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i == ch) trk.v[i] = ord;
+                for (int ch = 0; ch < BN / 32; ++ch) my_cmax[ch] = trk.v[ch];
             }
         } else if (q_ok) {
 #pragma unroll
@@ -1202,9 +1394,9 @@ size_t cnt_bytes(const Plan& p) { return (size_t)p.grid * p.b_pad * sizeof(uint3
 int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
     uint32_t tiles = (n_rows + BN - 1) / BN, segs = 0;
     const uint32_t m_tiles = (uint32_t)((std::min(B, kMaxQueriesPerLaunch) + BM - 1) / BM);
-    for (uint64_t end = first_segment_end(m_tiles, p.grid); ; end = next_segment_end(end, m_tiles)) { ++segs; if (end >= tiles) break; }
+    for (uint64_t end = first_segment_end(m_tiles, p.grid); ; end = next_segment_end(end, m_tiles)) { ++segs; if (clamp_segment_end(end, tiles) >= tiles) break; }
     const int chunks = (B + kMaxQueriesPerLaunch - 1) / kMaxQueriesPerLaunch;
-    return chunks * (int)(1 + 2 * segs + 2);
+    return chunks * (int)(1 + 2 /* cold pass + thresholds */ + 2 * segs + 2);
 }
 
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn_all, int B_all,
@@ -1236,32 +1428,62 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.cnt = b.cnt;
         a.lists = b.lists;
         a.b_pad = (uint32_t)p.b_pad;
-        // Corpus segments of geometrically growing size.  After each one the per-query threshold becomes the k'-th
-        // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
-        // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
-        uint32_t begin = 0;
-        for (uint64_t end = first_segment_end(a.m_tiles, p.grid); begin < n_tiles; end = next_segment_end(end, a.m_tiles)) {
-            a.tile_begin = begin;
-            a.tile_end = (uint32_t)std::min<uint64_t>(end, n_tiles);
-            const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
-            if (cudaMemsetAsync(b.cnt, 0, (size_t)grid * p.b_pad * sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
-            cudaError_t e = cudaSuccess;
+        a.cmax = nullptr;
+        a.ncols = 0;
+        cudaError_t e = cudaSuccess;
 #define MQVS_TC(KP_)                                                                          \
     if (p.kprime == KP_)                                                                      \
         e = dtype == MQVS_F32 ? launch_score<float, 512, KP_>(mq, mx, a, grid, st)            \
                               : launch_score<__nv_bfloat16, 512, KP_>(mq, mx, a, grid, st);
+        // Cold pass: one tile per CTA, no list appends -- the epilogue only records the maximum of every 32-row chunk,
+        // and the k'-th largest of a query's G*8 chunk maxima becomes its first threshold (>= k' distinct rows score that
+        // much).  Costs one tile per CTA per query tile at tensor speed; the appending cold segment it replaces (4096 rows
+        // on 16 CTAs, every score written out, then a selection over 4096 keys per query) took 2.0 ms at config 3.
+        // The tiles of the cold pass are scored again by the first segment, now filtered.
+        {
+            const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, n_tiles);
+            a.tile_begin = 0;
+            a.tile_end = (uint32_t)grid;
+            a.cmax = b.cmax;
+            a.ncols = (uint32_t)grid * 8;
+            if (cudaMemsetAsync(b.cmax, 0, (size_t)p.b_pad * a.ncols * sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
             MQVS_TC(32)
             MQVS_TC(64)
             MQVS_TC(128)
             MQVS_TC(256)
-#undef MQVS_TC
+            if (e != cudaSuccess) return cudaGetErrorString(e);
+            g_trace.mark("cold score", st);
+            tau_from_chunk_maxima_kernel<<<B, 128, 0, st>>>(b.cmax, (int)a.ncols, p.kprime, b.tau);
+            g_trace.mark("thresholds", st);
+            a.cmax = nullptr;
+            a.ncols = 0;
+        }
+        // Corpus segments of geometrically growing size.  After each one the per-query threshold becomes the k'-th
+        // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
+        // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
+        static bool sel_attr = false;
+        if (!sel_attr) {
+            cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxKeys * (int)sizeof(uint64_t));
+            sel_attr = true;
+        }
+        uint32_t begin = 0;
+        for (uint64_t end = first_segment_end(a.m_tiles, p.grid); begin < n_tiles; end = next_segment_end(end, a.m_tiles)) {
+            a.tile_begin = begin;
+            a.tile_end = (uint32_t)clamp_segment_end(end, n_tiles);
+            const int grid = (int)std::min<uint32_t>((uint32_t)p.grid, a.tile_end - a.tile_begin);
+            if (cudaMemsetAsync(b.cnt, 0, (size_t)grid * p.b_pad * sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
+            MQVS_TC(32)
+            MQVS_TC(64)
+            MQVS_TC(128)
+            MQVS_TC(256)
             if (e != cudaSuccess) return cudaGetErrorString(e);
             g_trace.mark("score", st);
-            select_lists_kernel<<<B, kSelThreads, 0, st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap, p.kprime, begin == 0,
-                                                           b.short_keys, b.tau_tilde);
+            select_lists_kernel<<<B, kSelThreads, kSelMaxKeys * sizeof(uint64_t), st>>>(b.lists, b.cnt, b.tau, grid, p.b_pad, p.cap,
+                                                                                         p.kprime, begin == 0, b.short_keys, b.tau_tilde);
             g_trace.mark("select", st);
             begin = a.tile_end;
         }
+#undef MQVS_TC
 
         const size_t items = (size_t)B * p.kprime;
         const unsigned rs_grid = (unsigned)((items + 7) / 8);
@@ -1283,7 +1505,7 @@ bool fused_ok(int B, int k, int sm_count) {
     // CTA c finishes query c, so there must be at least B CTAs
     return B >= 1 && B <= BM && k <= 128 && sm_count >= BM && sm_count <= 160;
 }
-size_t cmax_bytes(const Plan& p) { return (size_t)BM * p.grid * 8 * sizeof(uint32_t); }
+size_t cmax_bytes(const Plan& p) { return (size_t)p.b_pad * p.grid * 8 * sizeof(uint32_t); }
 
 namespace {
 template <typename T, int KP>
