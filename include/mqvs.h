@@ -125,6 +125,31 @@ MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int6
                              float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 MQVS_API void mqvs_xchg_destroy(mqvs_xchg_t* x);
 
+/* Chroma `where` filters evaluated ON THE DEVICE (collection.query(where=...)): metadata
+ * columns are uploaded once as typed arrays (strings as dictionary codes the host assigns in string order), a filter is a
+ * postfix program of leaf comparisons and AND / OR, and mqvs_filter_build writes the packed allow-bitmask mqvs_search
+ * takes (mask_is_device = 1) without the mask ever visiting the host.  Semantics as Chroma's: a row whose field is
+ * missing matches only $ne / $nin.  live_words (host, ceil(rows/32) words, nullable) is AND-ed in (tombstones). */
+enum { MQVS_OP_EQ = 0, MQVS_OP_NE = 1, MQVS_OP_GT = 2, MQVS_OP_GTE = 3, MQVS_OP_LT = 4, MQVS_OP_LTE = 5, MQVS_OP_IN = 6,
+       MQVS_OP_NIN = 7, MQVS_OP_AND = 16, MQVS_OP_OR = 17 };
+enum { MQVS_COL_I64 = 0, MQVS_COL_F64 = 1 };
+typedef struct mqvs_filter_op {
+    int32_t op;        /* MQVS_OP_* */
+    int32_t col;       /* leaves: column id given to mqvs_column_set */
+    int64_t ival;      /* comparison constant for MQVS_COL_I64 columns */
+    double fval;       /* comparison constant for MQVS_COL_F64 columns */
+    uint32_t set_off;  /* $in / $nin: first element of the set in the constant pool */
+    uint32_t set_len;
+} mqvs_filter_op;
+/* values_host: n 8-byte values (int64 or float64); present_host: n bytes (0 = field missing) or NULL = all present.
+ * Replaces column col_id (0..63).  n may be smaller than the row count: later rows count as "field missing". */
+MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
+                             uint64_t n);
+/* prog: n_ops <= 64 operations in postfix order; pool: pool_len 8-byte constants (int64 or float64 bit patterns) the
+ * $in / $nin leaves point into.  *mask_dev_out is owned by the handle and valid until the next mqvs_filter_build. */
+MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
+                               const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
+
 /* collection.get(ids, include=["embeddings"]): stored (normalised) rows as fp32, [n, dim] to host. */
 MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float* out_host);
 

@@ -18,6 +18,26 @@ MAX_K = 1024
 DTYPES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16}
 
 
+class FilterOp(ctypes.Structure):
+    """mqvs_filter_op (include/mqvs.h): one operation of a postfix `where` program."""
+    _fields_ = [("op", ctypes.c_int32), ("col", ctypes.c_int32), ("ival", ctypes.c_int64), ("fval", ctypes.c_double),
+                ("set_off", ctypes.c_uint32), ("set_len", ctypes.c_uint32)]
+
+
+OP = {"$eq": 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5, "$in": 6, "$nin": 7, "$and": 16, "$or": 17}
+COL_I64, COL_F64 = 0, 1
+
+
+class DeviceMask:
+    """A packed allow-bitmask in device memory owned by the index (valid until its next filter_build)."""
+
+    def __init__(self, ptr: int, words: int):
+        self._ptr, self.words = int(ptr), int(words)
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+
 class MqvsError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"mqvs error {code}: {msg}")
@@ -58,6 +78,8 @@ SIGNATURES = {
     "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
+    "mqvs_column_set": (_i, [_vp, _i, _i, _vp, _vp, _u64]),
+    "mqvs_filter_build": (_i, [_vp, _vp, _i, _vp, _u64, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
     "mqvs_xchg_get_handle": (_i, [_vp, _vp, _i]),
     "mqvs_xchg_connect": (_i, [_vp, _vp]),
@@ -171,7 +193,7 @@ class Index:
         ids = np.empty((B, k), np.int64)
         mask_dev = 0
         if mask is not None:
-            if _is_torch(mask):
+            if _is_torch(mask) or isinstance(mask, DeviceMask):
                 mask_dev = 1
             else:
                 mask = np.ascontiguousarray(mask, dtype=np.uint32)
@@ -197,6 +219,30 @@ class Index:
 
     def load_file(self, path: str) -> None:
         check(load().mqvs_load(self._h, os.fsencode(path)))
+
+    def column_set(self, col_id: int, values: np.ndarray, present: Optional[np.ndarray] = None) -> None:
+        """Upload metadata column `col_id` (int64 or float64 values, optional presence flags) for filter_build."""
+        values = np.ascontiguousarray(values)
+        if values.dtype == np.int64:
+            ctype = COL_I64
+        elif values.dtype == np.float64:
+            ctype = COL_F64
+        else:
+            raise ValueError("device columns are int64 or float64")
+        pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+        check(load().mqvs_column_set(self._h, int(col_id), ctype, _ptr(values), _ptr(pres), values.shape[0]))
+
+    def filter_build(self, ops, pool: Optional[np.ndarray] = None, live_words: Optional[np.ndarray] = None):
+        """ops: list of FilterOp in postfix order -> (DeviceMask, number of allowed rows)."""
+        arr = (FilterOp * max(len(ops), 1))(*ops)
+        pool = np.zeros(0, np.int64) if pool is None else np.ascontiguousarray(pool)
+        if pool.dtype.itemsize != 8:
+            raise ValueError("the constant pool holds 8-byte values")
+        live = None if live_words is None else np.ascontiguousarray(live_words, dtype=np.uint32)
+        ptr, allowed = _vp(), _u64(0)
+        check(load().mqvs_filter_build(self._h, arr, len(ops), _ptr(pool), pool.shape[0], _ptr(live), ctypes.byref(ptr),
+                                       ctypes.byref(allowed)))
+        return DeviceMask(ptr.value or 0, (len(self) + 31) // 32), int(allowed.value)
 
     def stats(self) -> dict:
         st = Stats()

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/mqvs.h"
+#include "filter.h"
 #include "launch.h"
 #include "tc.h"
 
@@ -108,6 +109,17 @@ struct mqvs_store {
     bool last_fused = false;                 // the last search reported non-finite queries through the epoch word
     mqvs_stats stats{};
     uint64_t host_fallbacks = 0;
+    // device-side `where` evaluation
+    struct Column {
+        DevBuf values, present;
+        uint64_t n = 0;
+        int type = 0;
+        bool used = false, has_present = false;
+    } columns[mqvs::kFilterMaxCols];
+    DevBuf f_table, f_prog, f_pool, f_live, f_mask;
+    unsigned long long* f_count_dev = nullptr;
+    unsigned long long* f_count_host = nullptr;  // pinned
+    bool f_table_dirty = true;
 
     size_t row_bytes() const { return (size_t)MQVS_DIM_PAD * elem_size(dtype); }
 };
@@ -407,6 +419,13 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (!s) return;
     cudaSetDevice(s->dev);
     if (s->st) cudaStreamSynchronize(s->st);
+    for (auto& c : s->columns) {
+        c.values.release();
+        c.present.release();
+    }
+    for (DevBuf* b : {&s->f_table, &s->f_prog, &s->f_pool, &s->f_live, &s->f_mask}) b->release();
+    if (s->f_count_dev) cudaFree(s->f_count_dev);
+    if (s->f_count_host) cudaFreeHost(s->f_count_host);
     for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
                       &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand, &s->tc_cmax})
         b->release();
@@ -693,6 +712,109 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     fclose(f);
     s->n = h.rows;
     s->stats.rows = s->n;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
+                             uint64_t n) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
+    if (col_type != MQVS_COL_I64 && col_type != MQVS_COL_F64) return fail(MQVS_E_INVALID, "unknown column type %d", col_type);
+    if (n && !values_host) return fail(MQVS_E_INVALID, "values is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    auto& c = s->columns[col_id];
+    int rc;
+    if ((rc = c.values.ensure(std::max<uint64_t>(n, 1) * 8)) != MQVS_OK) return rc;
+    if (n) CU(cudaMemcpyAsync(c.values.p, values_host, n * 8, cudaMemcpyHostToDevice, s->st));
+    c.has_present = present_host != nullptr;
+    if (present_host) {
+        const uint64_t words = (n + 31) / 32;
+        std::vector<uint32_t> bits(std::max<uint64_t>(words, 1), 0u);
+        for (uint64_t r = 0; r < n; ++r)
+            if (present_host[r]) bits[r >> 5] |= 1u << (r & 31);
+        if ((rc = c.present.ensure(bits.size() * 4)) != MQVS_OK) return rc;
+        CU(cudaMemcpyAsync(c.present.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));  // `bits` goes out of scope
+    }
+    CU(cudaStreamSynchronize(s->st));
+    c.n = n;
+    c.type = col_type;
+    c.used = true;
+    s->f_table_dirty = true;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
+                               const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out) {
+    using namespace mqvs;
+    if (!s || !mask_dev_out || !allowed_out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (n_ops < 0 || n_ops > kFilterMaxOps) return fail(MQVS_E_INVALID, "a filter program holds at most %d operations", kFilterMaxOps);
+    if (n_ops && !prog) return fail(MQVS_E_INVALID, "prog is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    // validate: known columns, sets inside the pool, a well-formed postfix expression
+    int depth = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const mqvs_filter_op& o = prog[i];
+        if (o.op == MQVS_OP_AND || o.op == MQVS_OP_OR) {
+            if (depth < 2) return fail(MQVS_E_INVALID, "filter program: operator %d at %d lacks operands", o.op, i);
+            --depth;
+        } else if (o.op >= MQVS_OP_EQ && o.op <= MQVS_OP_NIN) {
+            if (o.col < 0 || o.col >= kFilterMaxCols || !s->columns[o.col].used)
+                return fail(MQVS_E_INVALID, "filter program: column %d was never set", o.col);
+            if ((o.op == MQVS_OP_IN || o.op == MQVS_OP_NIN) && (uint64_t)o.set_off + o.set_len > pool_len)
+                return fail(MQVS_E_INVALID, "filter program: set of operation %d leaves the constant pool", i);
+            if (++depth > 32) return fail(MQVS_E_INVALID, "filter program nests deeper than 32");
+        } else {
+            return fail(MQVS_E_INVALID, "filter program: unknown operation %d", o.op);
+        }
+    }
+    if (n_ops && depth != 1) return fail(MQVS_E_INVALID, "filter program leaves %d values on the stack", depth);
+    const uint64_t words = (s->n + 31) / 32;
+    int rc;
+    if (!s->f_count_dev) {
+        CU(cudaMalloc(&s->f_count_dev, sizeof(unsigned long long)));
+        CU(cudaMallocHost(&s->f_count_host, sizeof(unsigned long long)));
+    }
+    if (s->f_table_dirty) {
+        FilterColumn table[kFilterMaxCols];
+        for (int i = 0; i < kFilterMaxCols; ++i) {
+            const auto& c = s->columns[i];
+            table[i] = FilterColumn{c.values.p, c.has_present ? (const uint32_t*)c.present.p : nullptr, c.used ? c.n : 0, c.type};
+        }
+        if ((rc = s->f_table.ensure(sizeof(table))) != MQVS_OK) return rc;
+        CU(cudaMemcpyAsync(s->f_table.p, table, sizeof(table), cudaMemcpyHostToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));  // `table` is a stack array
+        s->f_table_dirty = false;
+    }
+    if ((rc = s->f_prog.ensure(std::max(n_ops, 1) * sizeof(mqvs_filter_op))) != MQVS_OK) return rc;
+    if ((rc = s->f_pool.ensure(std::max<uint64_t>(pool_len, 1) * 8)) != MQVS_OK) return rc;
+    if ((rc = s->f_mask.ensure(std::max<uint64_t>(words, 1) * 4)) != MQVS_OK) return rc;
+    if (n_ops) CU(cudaMemcpyAsync(s->f_prog.p, prog, n_ops * sizeof(mqvs_filter_op), cudaMemcpyHostToDevice, s->st));
+    if (pool_len) CU(cudaMemcpyAsync(s->f_pool.p, pool, pool_len * 8, cudaMemcpyHostToDevice, s->st));
+    if (live_words_host) {
+        if ((rc = s->f_live.ensure(std::max<uint64_t>(words, 1) * 4)) != MQVS_OK) return rc;
+        if (words) CU(cudaMemcpyAsync(s->f_live.p, live_words_host, words * 4, cudaMemcpyHostToDevice, s->st));
+    }
+    CU(cudaMemsetAsync(s->f_count_dev, 0, sizeof(unsigned long long), s->st));
+    FilterArgs a{};
+    a.prog = (const mqvs_filter_op*)s->f_prog.p;
+    a.n_ops = n_ops;
+    a.cols = (const FilterColumn*)s->f_table.p;
+    a.pool = s->f_pool.p;
+    a.live = live_words_host ? (const uint32_t*)s->f_live.p : nullptr;
+    a.n_rows = s->n;
+    a.n_words = words;
+    a.mask = (uint32_t*)s->f_mask.p;
+    a.allowed = s->f_count_dev;
+    launch_filter_eval(a, s->st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->f_count_host, s->f_count_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.kernel_launches += words ? 1 : 0;
+    *mask_dev_out = (const uint32_t*)s->f_mask.p;
+    *allowed_out = *s->f_count_host;
     return MQVS_OK;
 }
 

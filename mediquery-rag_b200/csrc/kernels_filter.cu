@@ -1,0 +1,97 @@
+// kernels_filter.cu -- K5: Chroma `where` predicates evaluated on the device into the packed allow-bitmask the scan
+// kernels consume.  Metadata columns live in HBM as typed arrays (int64 / float64; strings are
+// dictionary codes assigned by the host, ordered like the strings) with one presence bit per row; the filter arrives as
+// a postfix program of leaf comparisons and AND / OR.  One thread per row, one ballot per warp = one mask word.
+// HBM-bound: 8 bytes per row per referenced column (+ 1 bit presence, + 1 bit live) -> 4 bytes per 32 rows out.
+#include "common.cuh"
+#include "filter.h"
+#include "launch.h"
+
+namespace mqvs {
+namespace {
+
+constexpr int kFilterThreads = 256;
+
+__device__ __forceinline__ bool leaf_i64(int op, long long v, long long c) {
+    switch (op) {
+        case MQVS_OP_EQ: return v == c;
+        case MQVS_OP_NE: return v != c;
+        case MQVS_OP_GT: return v > c;
+        case MQVS_OP_GTE: return v >= c;
+        case MQVS_OP_LT: return v < c;
+        default: return v <= c;
+    }
+}
+__device__ __forceinline__ bool leaf_f64(int op, double v, double c) {
+    switch (op) {
+        case MQVS_OP_EQ: return v == c;
+        case MQVS_OP_NE: return v != c;
+        case MQVS_OP_GT: return v > c;
+        case MQVS_OP_GTE: return v >= c;
+        case MQVS_OP_LT: return v < c;
+        default: return v <= c;
+    }
+}
+
+__global__ void __launch_bounds__(kFilterThreads)
+filter_eval_kernel(const FilterArgs a) {
+    __shared__ mqvs_filter_op prog[kFilterMaxOps];
+    for (int i = threadIdx.x; i < a.n_ops; i += kFilterThreads) prog[i] = a.prog[i];
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * kFilterThreads + threadIdx.x;
+    const bool in_range = r < a.n_rows;
+    uint32_t stk = 0;  // bit stack, top = bit 0
+    for (int i = 0; i < a.n_ops; ++i) {
+        const mqvs_filter_op op = prog[i];
+        if (op.op == MQVS_OP_AND || op.op == MQVS_OP_OR) {
+            const uint32_t b2 = stk & 1u;
+            stk >>= 1;
+            const uint32_t b1 = stk & 1u;
+            stk = (stk & ~1u) | (op.op == MQVS_OP_AND ? (b1 & b2) : (b1 | b2));
+            continue;
+        }
+        bool hit = false;
+        if (in_range) {
+            const FilterColumn col = a.cols[op.col];
+            // rows beyond the column's length (added since it was uploaded) count as "field missing"
+            const bool present = r < col.n && (col.present == nullptr || ((col.present[r >> 5] >> (r & 31)) & 1u));
+            const bool negated = op.op == MQVS_OP_NE || op.op == MQVS_OP_NIN;
+            if (!present) {
+                hit = negated;  // a missing field matches only $ne / $nin
+            } else if (op.op == MQVS_OP_IN || op.op == MQVS_OP_NIN) {
+                bool found = false;
+                if (col.type == MQVS_COL_I64) {
+                    const long long v = reinterpret_cast<const long long*>(col.values)[r];
+                    for (uint32_t j = 0; j < op.set_len; ++j) found |= v == reinterpret_cast<const long long*>(a.pool)[op.set_off + j];
+                } else {
+                    const double v = reinterpret_cast<const double*>(col.values)[r];
+                    for (uint32_t j = 0; j < op.set_len; ++j) found |= v == reinterpret_cast<const double*>(a.pool)[op.set_off + j];
+                }
+                hit = found != negated;
+            } else if (col.type == MQVS_COL_I64) {
+                hit = leaf_i64(op.op, reinterpret_cast<const long long*>(col.values)[r], (long long)op.ival);
+            } else {
+                hit = leaf_f64(op.op, reinterpret_cast<const double*>(col.values)[r], op.fval);
+            }
+        }
+        stk = (stk << 1) | (hit ? 1u : 0u);
+    }
+    const bool allowed = in_range && (a.n_ops == 0 || (stk & 1u));
+    uint32_t word = __ballot_sync(0xffffffffu, allowed);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) < a.n_words) {
+        if (a.live != nullptr) word &= a.live[r >> 5];
+        a.mask[r >> 5] = word;
+        if (word) atomicAdd(a.allowed, (unsigned long long)__popc(word));
+    }
+}
+
+}  // namespace
+
+void launch_filter_eval(const FilterArgs& a, cudaStream_t st) {
+    const uint64_t rows_padded = a.n_words * 32ull;
+    if (rows_padded == 0) return;
+    const unsigned grid = (unsigned)((rows_padded + kFilterThreads - 1) / kFilterThreads);
+    filter_eval_kernel<<<grid, kFilterThreads, 0, st>>>(a);
+}
+
+}  // namespace mqvs

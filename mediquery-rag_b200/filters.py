@@ -29,6 +29,7 @@ class MetadataColumns:
         self._explicit: Dict[str, np.ndarray] = {}   # bulk columns supplied as arrays (no per-row dicts)
         self._cache: Dict[str, tuple] = {}           # field -> (n_rows_built, values object array, present bool array)
         self._dict_fields: set = set()               # fields that occur in per-row dicts
+        self.version = 0                             # bumped by every mutation (device copies of columns key on it)
 
     def __len__(self) -> int:
         return len(self._rows)
@@ -38,6 +39,7 @@ class MetadataColumns:
             md = md if md else _EMPTY
             self._dict_fields.update(md.keys())
             self._rows.append(md)
+        self.version += 1
 
     def extend_columns(self, n: int, columns: Mapping[str, np.ndarray]) -> None:
         """Append n rows whose metadata is given column-wise (bulk ingest of millions of rows)."""
@@ -63,6 +65,7 @@ class MetadataColumns:
                 self._explicit[name] = (np.concatenate([vals, np.zeros(pad, vals.dtype)]),
                                         np.concatenate([present, np.zeros(pad, bool)]))
         self._cache.clear()
+        self.version += 1
 
     def row(self, r: int) -> Dict[str, Any]:
         md = dict(self._rows[r])
@@ -75,6 +78,7 @@ class MetadataColumns:
         self._rows[r] = md if md else _EMPTY
         self._dict_fields.update(self._rows[r].keys())
         self._cache.clear()
+        self.version += 1
 
     def column(self, field: str):
         """-> (values, present): values is a typed array when the field is homogeneous, else object."""
@@ -222,3 +226,151 @@ def compile_mask(where: Optional[Mapping[str, Any]], cols: MetadataColumns, live
     if allowed is None:
         return None, n
     return pack_mask(allowed), int(allowed.sum())
+
+
+# ------------------------------------------------------------------------------------------ device-side evaluation
+class NotOnDevice(Exception):
+    """This filter (or one of its columns) needs the host evaluator: mixed-type field, bool/None constants, ..."""
+
+
+def _typed_column(vals: np.ndarray, present: np.ndarray):
+    """-> (kind, int64/float64 array, dictionary or None); kind in {"i", "f", "s", "n"}.  Raises NotOnDevice."""
+    if not present.any():
+        return "n", np.zeros(vals.shape[0], np.int64), None
+    if vals.dtype != object:
+        k = vals.dtype.kind
+        if k in "iu" and vals.dtype.itemsize <= 8 and vals.dtype != np.uint64:
+            return "i", vals.astype(np.int64), None
+        if k == "f":
+            return "f", vals.astype(np.float64), None
+        if k in "US":
+            uniq, codes = np.unique(vals[present], return_inverse=True)
+            out = np.zeros(vals.shape[0], np.int64)
+            out[present] = codes
+            return "s", out, uniq
+        raise NotOnDevice(f"column dtype {vals.dtype}")
+    have = [v for v, p in zip(vals, present) if p]
+    if not have:  # no row has the field: only the "missing" rule of each operator matters
+        return "n", np.zeros(vals.shape[0], np.int64), None
+    if all(isinstance(v, str) for v in have):
+        uniq = np.unique(np.asarray(have, dtype=str)) if have else np.zeros(0, dtype=str)
+        out = np.zeros(vals.shape[0], np.int64)
+        if have:
+            out[present] = np.searchsorted(uniq, np.asarray(have, dtype=str))
+        return "s", out, uniq
+    if all(isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)) for v in have):
+        if any(abs(int(v)) >= 2 ** 63 for v in have):
+            raise NotOnDevice("integer beyond int64")
+        out = np.zeros(vals.shape[0], np.int64)
+        out[present] = [int(v) for v in have]
+        return "i", out, None
+    if all(isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, (bool, np.bool_)) for v in have):
+        if any(isinstance(v, (int, np.integer)) and abs(int(v)) > 2 ** 53 for v in have):
+            raise NotOnDevice("integer not exact in float64")
+        out = np.zeros(vals.shape[0], np.float64)
+        out[present] = [float(v) for v in have]
+        return "f", out, None
+    raise NotOnDevice("mixed-type field")
+
+
+class DeviceFilter:
+    """Compiles Chroma `where` dicts to mqvs_filter_op programs and keeps the referenced metadata columns resident on
+    the device (re-uploaded when MetadataColumns.version moves).  `index` is a _native.Index."""
+
+    def __init__(self, index: Any, cols: MetadataColumns):
+        self.index, self.cols = index, cols
+        self._resident: Dict[str, tuple] = {}  # field -> (version, column id, kind, dictionary)
+
+    def _column(self, field: str):
+        hit = self._resident.get(field)
+        if hit is not None and hit[0] == self.cols.version:
+            return hit[1:]
+        vals, present = self.cols.column(field)
+        kind, typed, uniq = _typed_column(vals, present)
+        col_id = hit[1] if hit is not None else len(self._resident)
+        if col_id >= 64:
+            raise NotOnDevice("more than 64 filterable fields")
+        self.index.column_set(col_id, typed, None if present.all() else present)
+        self._resident[field] = (self.cols.version, col_id, kind, uniq)
+        return col_id, kind, uniq
+
+    def _const(self, kind: str, uniq, op: str, want: Any):
+        """-> (op, ival, fval) for a scalar leaf; raises NotOnDevice where host and device semantics could differ."""
+        if kind == "n":
+            return op, 0, 0.0
+        if isinstance(want, (bool, np.bool_)) or want is None:
+            raise NotOnDevice("bool / None constant")
+        if kind == "s":
+            if not isinstance(want, str):
+                raise NotOnDevice("non-string constant against a string field")
+            lo, hi = int(np.searchsorted(uniq, want, "left")), int(np.searchsorted(uniq, want, "right"))
+            if op in ("$eq", "$ne"):
+                return op, (lo if hi > lo else -1), 0.0
+            # codes are ranks in the sorted dictionary, so order comparisons carry over
+            return {"$gt": ("$gte", hi), "$gte": ("$gte", lo), "$lt": ("$lt", lo), "$lte": ("$lt", hi)}[op] + (0.0,)
+        if isinstance(want, str):
+            raise NotOnDevice("string constant against a numeric field")
+        if kind == "i":
+            if isinstance(want, (float, np.floating)):
+                if not float(want).is_integer():
+                    raise NotOnDevice("fractional constant against an integer field")
+                want = int(want)
+            if abs(int(want)) >= 2 ** 63:
+                raise NotOnDevice("constant beyond int64")
+            return op, int(want), 0.0
+        return op, 0, float(want)
+
+    def program(self, where: Mapping[str, Any]):
+        """-> (list of FilterOp, constant pool as uint64 bit patterns)."""
+        from ._native import OP, FilterOp
+
+        ops: List[Any] = []
+        pool: List[int] = []
+
+        def emit(w: Mapping[str, Any]) -> None:
+            if not isinstance(w, Mapping) or len(w) != 1:
+                raise FilterError("where expects a dict with exactly one key per level (use $and / $or to combine)")
+            (key, val), = w.items()
+            if key in ("$and", "$or"):
+                if not isinstance(val, (list, tuple)) or not val:
+                    raise FilterError(f"{key} expects a non-empty list of filters")
+                for i, part in enumerate(val):
+                    emit(part)
+                    if i:
+                        ops.append(FilterOp(OP[key], 0, 0, 0.0, 0, 0))
+                return
+            if key.startswith("$"):
+                raise FilterError(f"unknown logical operator {key}")
+            if isinstance(val, Mapping):
+                if len(val) != 1:
+                    raise FilterError("an operator expression takes exactly one operator")
+                (op, want), = val.items()
+                if op not in _LEAF_OPS:
+                    raise FilterError(f"unknown operator {op}")
+            else:
+                op, want = "$eq", val
+            col_id, kind, uniq = self._column(key)
+            if op in ("$in", "$nin"):
+                if not isinstance(want, (list, tuple, set, frozenset, np.ndarray)):
+                    raise FilterError(f"{op} expects a list, got {type(want).__name__}")
+                off = len(pool)
+                for w1 in list(want):
+                    _, iv, fv = self._const(kind, uniq, "$eq", w1)
+                    pool.append(int(np.float64(fv).view(np.uint64)) if kind == "f" else int(np.int64(iv).view(np.uint64)))
+                ops.append(FilterOp(OP[op], col_id, 0, 0.0, off, len(pool) - off))
+                return
+            if isinstance(want, (list, dict, tuple, set)):
+                raise FilterError(f"{op} expects a scalar, got {type(want).__name__}")
+            op2, iv, fv = self._const(kind, uniq, op, want)
+            ops.append(FilterOp(OP[op2], col_id, iv, fv, 0, 0))
+
+        emit(where)
+        if len(ops) > 64:
+            raise NotOnDevice("filter program longer than 64 operations")
+        return ops, np.asarray(pool, dtype=np.uint64)
+
+    def build(self, where: Mapping[str, Any], live: Optional[np.ndarray]):
+        """-> (DeviceMask, allowed rows).  Raises NotOnDevice when the host evaluator must be used."""
+        ops, pool = self.program(where)
+        live_words = None if live is None or live.all() else pack_mask(live)
+        return self.index.filter_build(ops, pool, live_words)

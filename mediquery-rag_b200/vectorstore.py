@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _native
 from .documents import HAVE_LANGCHAIN, Document, Embeddings
-from .filters import MetadataColumns, compile_mask
+from .filters import DeviceFilter, MetadataColumns, NotOnDevice, compile_mask
 
 if HAVE_LANGCHAIN:  # pragma: no cover
     from langchain_core.vectorstores import VectorStore as _Base  # type: ignore
@@ -105,6 +105,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._texts: List[Optional[str]] = []
         self._cols = MetadataColumns()
         self._live = np.zeros(0, dtype=bool)
+        self._device_filter: Optional[DeviceFilter] = None
         if persist_directory is not None:
             # the reference tests os.path.exists(DB_PATH) before opening (src/medical_engine.py:34-37)
             os.makedirs(persist_directory, exist_ok=True)
@@ -237,13 +238,26 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             raise ValueError("k must be >= 1")
         if self._index is None or len(self._ids) == 0:
             return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
-        mask, allowed = compile_mask(filter, self._cols, self._live, where_document, self._texts)
+        mask, allowed = self._allow_mask(filter, where_document)
         k_eff = min(k, allowed)  # Chroma clamps n_results to the collection size
         if k_eff == 0:
             return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
         if k_eff > _native.MAX_K:
             raise ValueError(f"k is limited to {_native.MAX_K}")
         return self._index.search(q, k_eff, mask)
+
+    def _allow_mask(self, filter: Optional[Mapping[str, Any]], where_document: Optional[Mapping[str, Any]]):
+        """-> (mask or None, allowed rows).  Metadata filters over typed fields are evaluated ON THE DEVICE (columns stay
+        resident in HBM, the bitmask never visits the host); where_document, mixed-type fields and bool / None constants
+        use the host evaluator.  Both produce the same bitmask (tests/test_gpu_parity.py)."""
+        if filter and not where_document and hasattr(self._index, "filter_build"):
+            if self._device_filter is None or self._device_filter.index is not self._index:
+                self._device_filter = DeviceFilter(self._index, self._cols)
+            try:
+                return self._device_filter.build(filter, self._live)
+            except NotOnDevice:
+                pass
+        return compile_mask(filter, self._cols, self._live, where_document, self._texts)
 
     def _docs(self, scores: np.ndarray, rows: np.ndarray) -> List[Tuple[Document, float]]:
         out = []
@@ -382,6 +396,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             self._index.close()
         self._index, self._ids, self._id2row, self._texts = None, [], {}, []
         self._cols, self._live = MetadataColumns(), np.zeros(0, dtype=bool)
+        self._device_filter = None
         if self._persist_directory is not None:
             for f in (_ROWS_FILE, _DOCS_FILE, _MANIFEST):
                 try:

@@ -1,0 +1,119 @@
+"""Host half of the device-side `where` evaluation (mediquery_rag_b200.filters.DeviceFilter): the Chroma filter ->
+postfix mqvs_filter_op program compiler, the typed / dictionary-coded columns it uploads, and its refusal (NotOnDevice)
+of the cases whose semantics only the host evaluator reproduces.  The index is a numpy interpreter of the program that
+mirrors kernels_filter.cu line by line, so compiler + program semantics are pinned against filters.evaluate on CPU;
+tests/test_gpu_parity.py runs the same filters through the real kernel."""
+import numpy as np
+import pytest
+
+from mediquery_rag_b200 import _native
+from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns, NotOnDevice, evaluate, pack_mask
+
+
+class ProgramInterpreter:
+    """Stands in for _native.Index: column_set / filter_build with the kernel's semantics, in numpy."""
+
+    def __init__(self, n):
+        self.n, self.cols = n, {}
+
+    def __len__(self):
+        return self.n
+
+    def column_set(self, col_id, values, present=None):
+        assert values.dtype in (np.int64, np.float64)
+        self.cols[col_id] = (values.copy(), None if present is None else np.asarray(present, bool).copy())
+
+    def filter_build(self, ops, pool=None, live_words=None):
+        n, stack = self.n, []
+        for o in ops:
+            if o.op in (_native.OP["$and"], _native.OP["$or"]):
+                b2, b1 = stack.pop(), stack.pop()
+                stack.append(b1 & b2 if o.op == _native.OP["$and"] else b1 | b2)
+                continue
+            vals, present = self.cols[o.col]
+            m = vals.shape[0]
+            v = np.zeros(n, vals.dtype)
+            v[:min(m, n)] = vals[:n]
+            pres = np.zeros(n, bool)
+            pres[:min(m, n)] = True if present is None else present[:n]
+            name = {c: k for k, c in _native.OP.items()}[o.op]
+            negated = name in ("$ne", "$nin")
+            if name in ("$in", "$nin"):
+                consts = pool[o.set_off:o.set_off + o.set_len].view(vals.dtype)
+                hit = np.isin(v, consts) != negated
+            else:
+                c = o.ival if vals.dtype == np.int64 else o.fval
+                hit = {"$eq": v == c, "$ne": v != c, "$gt": v > c, "$gte": v >= c, "$lt": v < c, "$lte": v <= c}[name]
+            stack.append(np.where(pres, hit, negated))
+        allowed = stack.pop() if ops else np.ones(n, bool)
+        assert not stack
+        words = pack_mask(allowed)
+        if live_words is not None:
+            words &= live_words
+        return words, int(sum(bin(int(w)).count("1") for w in words))
+
+
+def make_cols(n=300, seed=0):
+    rng = np.random.default_rng(seed)
+    cols = MetadataColumns()
+    rows = []
+    for r in range(n):
+        md = {"year": int(rng.integers(1990, 2025)), "title": f"t{int(rng.integers(0, 12))}"}
+        if rng.random() < 0.8:
+            md["score"] = float(np.round(rng.random() * 10, 1))
+        if rng.random() < 0.5:
+            md["tags"] = str(rng.choice(["sleep,diet", "diet", "exercise,sleep", ""]))
+        if rng.random() < 0.3:
+            md["mixed"] = rng.choice([1, "one", 2.5], p=[0.4, 0.3, 0.3]).item() if False else [1, "one", 2.5][int(rng.integers(0, 3))]
+        rows.append(md)
+    cols.extend(rows)
+    cols.extend_columns(50, {"source_id": rng.integers(0, 16, 50), "year": rng.integers(1990, 2025, 50)})
+    return cols
+
+
+FILTERS = [
+    {"year": 2001}, {"year": {"$ne": 2001}}, {"year": {"$gt": 2010}}, {"year": {"$lte": 1995}}, {"year": {"$gte": 2010.0}},
+    {"year": {"$in": [1999, 2003, 2020]}}, {"year": {"$nin": [1999, 2003, 2020]}}, {"year": {"$in": []}},
+    {"score": {"$gt": 5}}, {"score": {"$lt": 2.5}}, {"score": {"$eq": 3.3}}, {"score": {"$ne": 3.3}}, {"score": {"$in": [1.0, 2.5, 7]}},
+    {"title": "t3"}, {"title": {"$ne": "t3"}}, {"title": {"$in": ["t1", "t9", "nope"]}}, {"title": {"$nin": ["t1"]}},
+    {"title": {"$gt": "t5"}}, {"title": {"$gte": "t5"}}, {"title": {"$lt": "t10"}}, {"title": {"$lte": "t10"}}, {"title": {"$eq": "absent"}},
+    {"tags": "diet"}, {"tags": {"$ne": ""}}, {"source_id": {"$in": [0, 1, 2]}}, {"source_id": {"$lt": 8}}, {"source_id": {"$ne": 3}},
+    {"nosuchfield": 1}, {"nosuchfield": {"$ne": 1}},
+    {"$and": [{"year": {"$gte": 2000}}, {"score": {"$lt": 5}}]},
+    {"$or": [{"title": "t1"}, {"title": "t2"}, {"year": {"$lt": 1992}}]},
+    {"$and": [{"$or": [{"year": 1999}, {"score": {"$gte": 9}}]}, {"title": {"$nin": ["t0"]}}, {"source_id": {"$ne": 5}}]},
+]
+
+
+@pytest.mark.parametrize("where", FILTERS, ids=[str(f)[:50] for f in FILTERS])
+def test_compiled_program_equals_host_evaluator(where):
+    cols = make_cols()
+    idx = ProgramInterpreter(len(cols))
+    live = np.random.default_rng(1).random(len(cols)) > 0.1
+    words, allowed = DeviceFilter(idx, cols).build(where, live)
+    want = evaluate(where, cols) & live
+    assert np.array_equal(words, pack_mask(want)) and allowed == int(want.sum())
+
+
+@pytest.mark.parametrize("where", [{"mixed": 1}, {"year": True}, {"year": {"$gt": 2000.5}}, {"year": "1999"}, {"title": 3},
+                                   {"title": {"$in": ["t1", 2]}}, {"score": None}])
+def test_cases_only_the_host_evaluator_reproduces_are_refused(where):
+    cols = make_cols()
+    with pytest.raises(NotOnDevice):
+        DeviceFilter(ProgramInterpreter(len(cols)), cols).build(where, None)
+
+
+def test_columns_are_reuploaded_only_when_the_metadata_changed():
+    cols = make_cols()
+    idx = ProgramInterpreter(len(cols))
+    uploads = []
+    orig = idx.column_set
+    idx.column_set = lambda *a, **k: (uploads.append(a[0]), orig(*a, **k))[1]
+    f = DeviceFilter(idx, cols)
+    f.build({"year": 2001}, None)
+    f.build({"year": {"$gt": 2001}}, None)
+    assert uploads == [0]
+    cols.extend([{"year": 2001}])
+    idx.n = len(cols)
+    words, allowed = f.build({"year": 2001}, None)
+    assert uploads == [0, 0] and allowed == int(evaluate({"year": 2001}, cols).sum())

@@ -547,3 +547,47 @@ def test_peer_exchange_kernel_equals_merge_of_gathered_candidates(gpu, W, B, k):
     finally:
         for e in ex:
             e.close()
+
+
+def test_device_side_where_evaluation_equals_host_evaluator(gpu):
+    """K5 filter_eval_kernel: every filter of tests/test_device_filter_cpu.py compiled by DeviceFilter, evaluated on the
+    device into the packed bitmask and consumed by a search with k = number of allowed rows: the returned id SET must be
+    exactly the rows the host evaluator allows (and the count the kernel reports must match); then the same through
+    MediQueryVectorStore.similarity_search_by_vector(filter=...), where the device path is taken automatically."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_device_filter_cpu import FILTERS, make_cols
+    from mediquery_rag_b200 import MediQueryVectorStore
+    from mediquery_rag_b200._native import DeviceMask
+    from mediquery_rag_b200.filters import DeviceFilter, evaluate
+
+    cols = make_cols()
+    n = len(cols)
+    x = O.synth_rows(SEED, 0, n, 768)
+    idx = native().Index(768, "fp32")
+    idx.add(x)
+    live = np.random.default_rng(1).random(n) > 0.1
+    dev = DeviceFilter(idx, cols)
+    q = O.synth_rows(QSEED, 0, 1, 768)
+    for where in FILTERS:
+        want = evaluate(where, cols) & live
+        mask, allowed = dev.build(where, live)
+        assert isinstance(mask, DeviceMask) and allowed == int(want.sum()), where
+        if allowed:
+            s, i = idx.search(q, allowed, mask)
+            assert set(i[0].tolist()) == set(np.flatnonzero(want).tolist()), where
+    idx.close()
+
+    store = MediQueryVectorStore()
+    store.add_embeddings(([f"doc {r}" for r in range(n)], x), metadatas=[cols.row(r) for r in range(n)])
+    for where in FILTERS[::3]:
+        want = evaluate(where, store._cols)
+        mask, allowed = store._allow_mask(where, None)
+        assert isinstance(mask, DeviceMask) and allowed == int(want.sum())
+        docs = store.similarity_search_by_vector(q[0], k=7, filter=where)
+        es, ei = O.brute_force_topk(O.normalize_rows(q, "fp32", 768)[0], O.normalize_rows(x, "fp32", 768)[0], min(7, allowed),
+                                    O.mask_from_bool(want)) if allowed else (None, np.zeros((1, 0), np.int64))
+        assert [d.page_content for d in docs] == [f"doc {r}" for r in ei[0].tolist()]
+    # a where_document filter or a mixed-type field still goes through the host evaluator, same answers
+    mask, allowed = store._allow_mask({"mixed": 1}, None)
+    assert not isinstance(mask, DeviceMask) and allowed == int(evaluate({"mixed": 1}, store._cols).sum())
