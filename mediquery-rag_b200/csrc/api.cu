@@ -183,7 +183,13 @@ bool use_tensor_path(const mqvs_store* s, int B, int k) {
     if (s->path == 2 || s->path == 4) return true;
     // measured on B200 (profiles/r01_*): the register-resident SIMT scan holds the HBM roofline for 1 query (bf16 rows)
     // or 1-2 queries (fp32 rows); beyond that its multi-query variants fall to 2-3.4 TB/s while the tensor path streams
-    // the corpus once for up to 128 queries at 4.8-7 TB/s.
+    // the corpus once for up to 128 queries at 6.3-7.1 TB/s.
+    // From 1M rows on even single queries take the (single-launch) tensor pipeline: same bandwidth as the SIMT scan when
+    // the SM clock is at boost (0.471 vs 0.487 ms at 1M x 768 fp32, 2.67 vs 2.68 ms at 12.5M bf16), and it keeps it when
+    // the clock drops under a power cap -- on 8 power-capped GPUs the SIMT scan alternated between 2.72 and 3.17 ms per
+    // 12.5M-row shard while the TMA-fed pipeline stayed at 2.71-2.75 (profiles/r01_b1_paths_w8.json).  Below 1M rows the
+    // SIMT path's single launch wins on latency.
+    if (s->n >= 1000000ull) return true;
     const int simt_max = s->dtype == MQVS_F32 ? 2 : 1;
     return B > simt_max && s->n >= 65536;
 }

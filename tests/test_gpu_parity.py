@@ -591,3 +591,39 @@ def test_device_side_where_evaluation_equals_host_evaluator(gpu):
     # a where_document filter or a mixed-type field still goes through the host evaluator, same answers
     mask, allowed = store._allow_mask({"mixed": 1}, None)
     assert not isinstance(mask, DeviceMask) and allowed == int(evaluate({"mixed": 1}, store._cols).sum())
+
+
+def test_one_handle_from_several_host_threads_and_two_handles_at_once(gpu):
+    """LangGraph may call the retriever off the main thread (/root/reference/src/agents/graph.py:95 opens its sqlite
+    checkpointer with check_same_thread=False): a handle serialises its calls, so four threads searching one store get
+    the same answers as one thread.  Two different stores searched concurrently each launch the cooperative
+    single-launch kernel (grid barriers): cooperative launches are scheduled whole, so they must not deadlock."""
+    import threading
+    n, B, k = 200_000, 48, 10
+    a = native().Index(768, "bf16", capacity_rows=n)
+    a.add_synthetic(SEED, 0, n)
+    b = native().Index(768, "fp32", capacity_rows=n)
+    b.add_synthetic(SEED + 1, 0, n)
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    want_a, want_b = a.search(q, k), b.search(q, k)
+    assert a.stats()["last_pipeline"] == 3 and b.stats()["last_pipeline"] == 3
+    errors = []
+
+    def worker(idx, want, reps, lo):
+        try:
+            for r in range(reps):
+                sl = slice(lo, lo + 1 + (r % 40))          # batch sizes 1..40: SIMT, single-launch SIMT and tensor paths
+                s, i = idx.search(q[sl], k)
+                if not (np.array_equal(i, want[1][sl]) and np.array_equal(s.view(np.uint32), want[0][sl].view(np.uint32))):
+                    errors.append((lo, r))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(a, want_a, 40, t)) for t in range(4)]
+    threads += [threading.Thread(target=worker, args=(b, want_b, 40, t)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in threads), "searches did not finish (deadlock?)"
+    assert errors == []
