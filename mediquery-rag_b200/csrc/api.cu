@@ -83,6 +83,7 @@ struct mqvs_store {
     int dim = 0;
     int dtype = MQVS_F32;
     int sm_count = 148;
+    bool coop_ok = false;  // cooperative launches available (the single-launch tensor pipeline needs grid barriers)
     int path = 0;
     void* rows = nullptr;
     uint64_t n = 0, cap = 0;
@@ -106,6 +107,9 @@ struct mqvs_store {
     unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits)
     unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
     unsigned int epoch = 0;                  // id of the last fused search
+    // latency path with host outputs: the kernel writes results + status straight into this mapped pinned block
+    // (no device-to-host copies): [64 floats scores | 64 int64 ids | 2 uint32 status]
+    char* host_out = nullptr;
     bool last_fused = false;                 // the last search reported non-finite queries through the epoch word
     mqvs_stats stats{};
     uint64_t host_fallbacks = 0;
@@ -220,7 +224,7 @@ int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev,
 
 // Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
-                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st) {
+                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status = nullptr) {
     using namespace mqvs;
     const int slot = s->ev_cursor;
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
@@ -238,7 +242,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         CU(cudaEventRecord(ev[1], st));
         launch_scan_fused(s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, B, mask_dev, k, (uint64_t*)s->cand.p,
                           out_scores_dev, out_ids_dev, id_base, s->ticket_dev, (unsigned int*)(s->bad_dev + 1), ++s->epoch,
-                          s->sm_count, st);
+                          s->sm_count, st, host_status);
         CU(cudaEventRecord(ev[2], st));
         CU(cudaEventRecord(ev[3], st));
         CU(cudaGetLastError());
@@ -254,7 +258,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         return MQVS_OK;
     }
     // single-launch tensor pipeline for one query tile (B <= 128); path 4 = keep the segmented pipeline (tests compare)
-    const bool tc_one = tensor && s->path != 4 && tc::fused_ok(B, k, s->sm_count);
+    bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
         const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 32) * sizeof(uint32_t);
@@ -299,10 +303,21 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->last_fused = true;  // non-finite queries are reported through the epoch word, as on the latency path
         CU(cudaEventRecord(ev[0], st));
         CU(cudaEventRecord(ev[1], st));
+        bool coop_refused = false;
         const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
                                            mask_dev, id_base, out_scores_dev, out_ids_dev, (unsigned int*)(s->bad_dev + 1),
-                                           ++s->epoch, st);
-        if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
+                                           ++s->epoch, st, &coop_refused);
+        if (err && coop_refused) {
+            // the device cannot hold one CTA per SM right now (MPS with an SM limit, a partitioned GPU): this handle
+            // keeps to the segmented pipeline from here on
+            s->coop_ok = false;
+            tc_one = false;
+            s->last_fused = false;
+        } else if (err) {
+            return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
+        }
+    }
+    if (tc_one) {
         CU(cudaEventRecord(ev[2], st));  // brackets prep + the single scan/select/rescore launch
         enqueue_repair();
         CU(cudaEventRecord(ev[3], st));
@@ -395,6 +410,7 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     s->dim = dim;
     s->dtype = store_dtype;
     s->sm_count = prop.multiProcessorCount;
+    s->coop_ok = prop.cooperativeLaunch != 0;
     auto bail = [&](int rc) {
         mqvs_destroy(s);
         return rc;
@@ -409,6 +425,12 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
         cudaMemset(s->ticket_dev, 0, sizeof(unsigned int)) != cudaSuccess)
         return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (cudaMallocHost(&s->bad_host, 2 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
+    if (cudaHostAlloc((void**)&s->host_out, 64 * 4 + 64 * 8 + 16, cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        s->host_out = nullptr;  // not fatal: the latency path copies its results back instead
+    } else {
+        memset(s->host_out, 0, 64 * 4 + 64 * 8 + 16);
+    }
     if (cudaMalloc(&s->fix_dev, (mqvs_store::kMaxDeviceFix + 1) * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&s->fix_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(s->fix_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
@@ -442,6 +464,7 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->ticket_dev) cudaFree(s->ticket_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
+    if (s->host_out) cudaFreeHost(s->host_out);
     for (auto& set : s->evr)
         for (auto& e : set.e)
             if (e) cudaEventDestroy(e);
@@ -548,6 +571,22 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     }
     float* os = out_scores;
     int64_t* oi = out_ids;
+    // latency path (B <= 4, k <= 16, the reference's own regime) with host outputs: results and status are written by the
+    // kernel into mapped pinned memory -- the call is one H2D copy of the queries, one launch, one stream sync
+    const bool zero_copy = !out_is_device && s->host_out != nullptr && !use_tensor_path(s, B, k) && s->path != 3 &&
+                           mqvs::scan_fused_ok(B, k);
+    if (zero_copy) {
+        os = (float*)s->host_out;
+        oi = (int64_t*)(s->host_out + 64 * 4);
+        unsigned int* status = (unsigned int*)(s->host_out + 64 * 4 + 64 * 8);
+        if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, status)) != MQVS_OK) return rc;
+        CU(cudaStreamSynchronize(s->st));
+        if (status[0] != s->epoch) return fail(MQVS_E_CUDA, "latency path: the kernel did not report completion");
+        memcpy(out_scores, os, (size_t)B * k * sizeof(float));
+        memcpy(out_ids, oi, (size_t)B * k * sizeof(int64_t));
+        if (status[1]) return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
+        return MQVS_OK;
+    }
     if (!out_is_device) {
         if ((rc = s->out_s.ensure((size_t)B * k * sizeof(float))) != MQVS_OK) return rc;
         if ((rc = s->out_i.ensure((size_t)B * k * sizeof(int64_t))) != MQVS_OK) return rc;

@@ -150,6 +150,7 @@ struct FusedArgs {
     unsigned int* ticket;    // zero on entry; the last CTA leaves it zero again
     unsigned int* bad_epoch; // raised to `epoch` (atomicMax) when a query has a non-finite norm
     unsigned int epoch;
+    unsigned int* host_status;  // optional mapped host words: [0] <- epoch when the results are written, [1] <- 1 if a query was non-finite
 };
 
 template <typename T, int QB, int U>
@@ -186,7 +187,14 @@ scan_fused_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uin
     for (int b = 0; b < nq; ++b)
         block_select_small<24>(cand + (size_t)b * gridDim.x * k, (int)gridDim.x * k, k, a.id_base,
                                a.out_scores + (size_t)b * k, a.out_ids + (size_t)b * k, win);
-    if (threadIdx.x == 0) *a.ticket = 0u;
+    if (threadIdx.x == 0) {
+        *a.ticket = 0u;
+        if (a.host_status != nullptr) {  // results went straight to mapped host memory: report status the same way
+            a.host_status[1] = (*reinterpret_cast<volatile unsigned int*>(a.bad_epoch) == a.epoch) ? 1u : 0u;
+            __threadfence_system();
+            a.host_status[0] = a.epoch;
+        }
+    }
 }
 
 template <typename T, int QB, int KPL, int U>
@@ -264,7 +272,11 @@ int launch_fused_t(const void* rows, uint32_t n_rows, int nq, const uint32_t* ma
         cudaGetLastError();
         occ = 1;
     }
-    const int grid = sm_count * (occ < 2 ? occ : 2);  // <= 296 CTAs: grid * k <= 4736 keys for the in-kernel merge
+    int grid = sm_count * (occ < 2 ? occ : 2);  // <= 296 CTAs: grid * k <= 4736 keys for the in-kernel merge
+    // tiny stores (the reference ships 154 chunks): no more CTAs than there are row groups, so the last CTA merges
+    // a handful of candidate lists instead of 296 mostly empty ones
+    const uint32_t groups = (n_rows + kScanWarps * U - 1) / (kScanWarps * U);
+    if ((uint32_t)grid > groups) grid = groups > 0 ? (int)groups : 1;
     kern<<<grid, kScanThreads, 0, st>>>((const T*)rows, n_rows, nq, mask, k, cand, a);
     return grid;
 }
@@ -273,9 +285,10 @@ int scan_fused_max_grid(int sm_count) { return sm_count * 2; }
 
 void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float* q_raw, int dim, int nq,
                        const uint32_t* mask, int k, uint64_t* cand, float* out_scores, int64_t* out_ids, int64_t id_base,
-                       unsigned int* ticket, unsigned int* bad_epoch, unsigned int epoch, int sm_count, cudaStream_t st) {
+                       unsigned int* ticket, unsigned int* bad_epoch, unsigned int epoch, int sm_count, cudaStream_t st,
+                       unsigned int* host_status) {
     FusedArgs a{q_raw, dim, (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0,
-                out_scores, out_ids, id_base, ticket, bad_epoch, epoch};
+                out_scores, out_ids, id_base, ticket, bad_epoch, epoch, host_status};
     const int qb = nq >= 3 ? 4 : nq;  // 1, 2 or 4 register-resident queries
 #define MQVS_FUSED(T_, U_)                                                                                     \
     (qb == 1   ? launch_fused_t<T_, 1, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st)                     \

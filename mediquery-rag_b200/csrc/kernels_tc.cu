@@ -1521,8 +1521,9 @@ cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const Fus
 
 const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
                          int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
-                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st) {
+                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused) {
     CUtensorMap mq, mx;
+    *coop_refused = false;
     if (!make_map(&mq, b.q_op, (uint64_t)BM, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
     g_trace.mark("begin", st);
@@ -1566,6 +1567,10 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     MQVS_TCF(128)
     MQVS_TCF(256)
 #undef MQVS_TCF
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        *coop_refused = true;
+    }
     if (e != cudaSuccess) return cudaGetErrorString(e);
     g_trace.mark("fused", st);
     e = cudaGetLastError();

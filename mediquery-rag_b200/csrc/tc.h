@@ -40,11 +40,12 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
 
 // Single-launch pipeline for B <= 128 (one query tile): prep kernel + one cooperative persistent kernel that learns the
 // thresholds, scans, selects, rescores and finalizes.  Takes the RAW queries (normalises them into qn itself).
+// *coop_refused: the cooperative launch was rejected (not enough co-resident CTAs): use search() instead.
 bool fused_ok(int B, int k, int sm_count);
 size_t cmax_bytes(const Plan& p);
 const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
                          int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
-                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st);
+                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused);
 
 void trace_dump();  // MQVS_TRACE=1 developer aid: per-launch timings of the last searches to stderr
 int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize

@@ -627,3 +627,36 @@ def test_one_handle_from_several_host_threads_and_two_handles_at_once(gpu):
         t.join(timeout=120)
     assert not any(t.is_alive() for t in threads), "searches did not finish (deadlock?)"
     assert errors == []
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_single_launch_pipeline_on_a_corpus_made_of_ties(gpu, dtype):
+    """A corpus drawn from only 40 distinct vectors (every score value occurs ~2500 times): thresholds learnt from
+    chunk maxima tie with thousands of rows, candidate lists overflow and are compacted, the tail's shortlist overflows
+    into the streaming selection, margins cannot be proven and the repair scan must run -- and the answer must still
+    be the oracle's, i.e. the LOWEST row ids of each tie group, on the single-launch and the segmented pipeline."""
+    n, B, k = 100_000, 24, 10
+    rng = np.random.default_rng(7)
+    base = O.synth_rows(SEED, 0, 40, 768)
+    pick = rng.integers(0, 40, n)
+    x = base[pick]
+    q = base[rng.integers(0, 40, B)] + 0.05 * O.synth_rows(QSEED, 0, B, 768)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    idx = native().Index(768, dtype)
+    idx.add(x)
+    for path in (2, 4):
+        idx.set_path(path)
+        s, i = idx.search(q, k)
+        assert idx.stats()["last_path"] == 1
+        assert_bit_equal(s, i, es, ei)
+    # a mask that leaves exactly one row of every tie group (ids then are forced) and one that leaves nothing
+    keep = np.zeros(n, bool)
+    keep[[int(np.flatnonzero(pick == g)[-1]) for g in range(40)]] = True
+    for allowed in (keep, np.zeros(n, bool)):
+        mask = O.mask_from_bool(allowed)
+        want = O.brute_force_topk(qn, st, k, mask)
+        for path in (2, 4):
+            idx.set_path(path)
+            assert_bit_equal(*idx.search(q, k, mask), *want)
