@@ -110,6 +110,10 @@ struct mqvs_store {
     // latency path with host outputs: the kernel writes results + status straight into this mapped pinned block
     // (no device-to-host copies): [64 floats scores | 64 int64 ids | 2 uint32 status]
     char* host_out = nullptr;
+    // pinned staging for host outputs of every other path: D2H copies into pageable user memory are staged and
+    // synchronous inside the driver (~10 us each), copies into pinned memory are not
+    char* out_pinned = nullptr;
+    size_t out_pinned_bytes = 0;
     bool last_fused = false;                 // the last search reported non-finite queries through the epoch word
     mqvs_stats stats{};
     uint64_t host_fallbacks = 0;
@@ -465,6 +469,7 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     if (s->ticket_dev) cudaFree(s->ticket_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
     if (s->host_out) cudaFreeHost(s->host_out);
+    if (s->out_pinned) cudaFreeHost(s->out_pinned);
     for (auto& set : s->evr)
         for (auto& e : set.e)
             if (e) cudaEventDestroy(e);
@@ -587,16 +592,28 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         if (status[1]) return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
         return MQVS_OK;
     }
+    const size_t n_out = (size_t)B * k;
+    float* host_s = nullptr;
+    int64_t* host_i = nullptr;
     if (!out_is_device) {
-        if ((rc = s->out_s.ensure((size_t)B * k * sizeof(float))) != MQVS_OK) return rc;
-        if ((rc = s->out_i.ensure((size_t)B * k * sizeof(int64_t))) != MQVS_OK) return rc;
+        if ((rc = s->out_s.ensure(n_out * sizeof(float))) != MQVS_OK) return rc;
+        if ((rc = s->out_i.ensure(n_out * sizeof(int64_t))) != MQVS_OK) return rc;
         os = (float*)s->out_s.p;
         oi = (int64_t*)s->out_i.p;
+        if (s->out_pinned_bytes < n_out * 12) {
+            if (s->out_pinned) cudaFreeHost(s->out_pinned);
+            s->out_pinned = nullptr;
+            s->out_pinned_bytes = 0;
+            CU(cudaMallocHost((void**)&s->out_pinned, n_out * 12));
+            s->out_pinned_bytes = n_out * 12;
+        }
+        host_i = (int64_t*)s->out_pinned;
+        host_s = (float*)(s->out_pinned + n_out * sizeof(int64_t));
     }
     if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st)) != MQVS_OK) return rc;
     if (!out_is_device) {
-        CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(host_s, os, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpyAsync(host_i, oi, n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
     }
     CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
     const bool tensor = s->stats.last_path == 1;
@@ -623,10 +640,14 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
             s->host_fallbacks += 1;
         }
         if (!out_is_device) {
-            CU(cudaMemcpyAsync(out_scores, os, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-            CU(cudaMemcpyAsync(out_ids, oi, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
+            CU(cudaMemcpyAsync(host_s, os, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->st));
+            CU(cudaMemcpyAsync(host_i, oi, n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
         }
         CU(cudaStreamSynchronize(s->st));
+    }
+    if (!out_is_device) {
+        memcpy(out_scores, host_s, n_out * sizeof(float));
+        memcpy(out_ids, host_i, n_out * sizeof(int64_t));
     }
     settle_events(s);
     mqvs::tc::trace_dump();

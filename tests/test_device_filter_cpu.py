@@ -117,3 +117,41 @@ def test_columns_are_reuploaded_only_when_the_metadata_changed():
     idx.n = len(cols)
     words, allowed = f.build({"year": 2001}, None)
     assert uploads == [0, 0] and allowed == int(evaluate({"year": 2001}, cols).sum())
+
+
+def where_trees():
+    """hypothesis strategy: random Chroma `where` trees over the typed fields of make_cols()."""
+    from hypothesis import strategies as hs
+    ints = hs.integers(1985, 2030)
+    floats = hs.sampled_from([0.0, 1.0, 2.5, 3.3, 5.0, 7.7, 9.9, 10.0, -1.0])
+    titles = hs.sampled_from([f"t{i}" for i in range(14)] + ["", "t", "zz"])
+    cmp_ops = hs.sampled_from(["$eq", "$ne", "$gt", "$gte", "$lt", "$lte"])
+    set_ops = hs.sampled_from(["$in", "$nin"])
+
+    def leaf(field, consts):
+        return hs.one_of(hs.tuples(cmp_ops, consts).map(lambda t: {field: {t[0]: t[1]}}),
+                         hs.tuples(set_ops, hs.lists(consts, min_size=0, max_size=5)).map(lambda t: {field: {t[0]: t[1]}}),
+                         consts.map(lambda c: {field: c}))
+
+    leaves = hs.one_of(leaf("year", ints), leaf("score", floats), leaf("title", titles),
+                       leaf("source_id", hs.integers(-1, 17)), leaf("tags", hs.sampled_from(["diet", "sleep,diet", "", "x"])),
+                       leaf("nosuchfield", ints))
+    return hs.recursive(leaves, lambda kids: hs.tuples(hs.sampled_from(["$and", "$or"]), hs.lists(kids, min_size=1, max_size=3))
+                        .map(lambda t: {t[0]: t[1]}), max_leaves=8)
+
+
+def test_random_where_trees_compile_to_programs_that_equal_the_host_evaluator():
+    from hypothesis import given, settings
+
+    cols = make_cols(seed=3)
+    live = np.random.default_rng(2).random(len(cols)) > 0.2
+
+    @settings(max_examples=200, deadline=None, derandomize=True)
+    @given(where=where_trees())
+    def run(where):
+        idx = ProgramInterpreter(len(cols))
+        words, allowed = DeviceFilter(idx, cols).build(where, live)
+        want = evaluate(where, cols) & live
+        assert np.array_equal(words, pack_mask(want)) and allowed == int(want.sum())
+
+    run()

@@ -660,3 +660,33 @@ def test_single_launch_pipeline_on_a_corpus_made_of_ties(gpu, dtype):
         for path in (2, 4):
             idx.set_path(path)
             assert_bit_equal(*idx.search(q, k, mask), *want)
+
+
+def test_device_side_where_evaluation_random_trees(gpu):
+    """Random `where` trees (hypothesis, derandomised) through the real filter_eval_kernel: reported count and the id set
+    returned by a search with k = allowed rows must match the host evaluator."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from hypothesis import given, settings
+    from test_device_filter_cpu import make_cols, where_trees
+    from mediquery_rag_b200.filters import DeviceFilter, evaluate
+
+    cols = make_cols(seed=3)
+    n = len(cols)
+    idx = native().Index(768, "bf16")
+    idx.add(O.synth_rows(SEED, 0, n, 768))
+    live = np.random.default_rng(2).random(n) > 0.2
+    dev = DeviceFilter(idx, cols)
+    q = O.synth_rows(QSEED, 0, 1, 768)
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(where=where_trees())
+    def run(where):
+        want = evaluate(where, cols) & live
+        mask, allowed = dev.build(where, live)
+        assert allowed == int(want.sum()), where
+        if allowed:
+            _, i = idx.search(q, allowed, mask)
+            assert set(i[0].tolist()) == set(np.flatnonzero(want).tolist()), where
+
+    run()
