@@ -57,3 +57,25 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "liboracle" not in src, f
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/mqvs.h compiles as strict C99 and examples/mqvs_demo.c (the reference's three call sites from plain C)
+    links against libmqvs.so and runs: on a GPU box it must find its planted row, without one it must report the
+    library's error and exit 2 -- never crash."""
+    import shutil
+    import subprocess
+    from conftest import have_gpu
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "mqvs_demo")
+    lib_dir = os.path.join(ROOT, "mediquery-rag_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "mqvs_demo.c"), "-L" + lib_dir, "-lmqvs", "-Wl,-rpath," + lib_dir, "-lm",
+                    "-o", exe], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "libmqvs version 100" in run.stdout
+    if have_gpu():
+        assert run.returncode == 0 and "row 42" in run.stdout.splitlines()[2], run.stdout
+    else:
+        assert run.returncode == 2 and "no usable GPU" in run.stdout, run.stdout

@@ -690,3 +690,19 @@ def test_device_side_where_evaluation_random_trees(gpu):
             assert set(i[0].tolist()) == set(np.flatnonzero(want).tolist()), where
 
     run()
+
+
+def test_plain_c_host_program_through_the_c_abi(gpu, tmp_path):
+    """examples/mqvs_demo.c (no Python, no torch): create, add 154 rows, search k=5 from compiled C against libmqvs.so."""
+    import os, shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir, exe = os.path.join(root, "mediquery-rag_b200"), str(tmp_path / "mqvs_demo")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "mqvs_demo.c"), "-L" + lib_dir, "-lmqvs", "-Wl,-rpath," + lib_dir, "-lm",
+                    "-o", exe], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = run.stdout.splitlines()
+    assert "154 rows stored" in lines[1] and lines[2].split()[:2] == ["row", "42"]
