@@ -706,3 +706,44 @@ def test_plain_c_host_program_through_the_c_abi(gpu, tmp_path):
     assert run.returncode == 0, run.stdout + run.stderr
     lines = run.stdout.splitlines()
     assert "154 rows stored" in lines[1] and lines[2].split()[:2] == ["row", "42"]
+
+
+def test_full_size_config4_shard_and_config5_filter_properties(gpu):
+    """One rank's share of BASELINE config 4 (100M x 768 bf16 over 8 GPUs = 12.5M rows) and the config-5 filter on it,
+    through size-independent properties: planted neighbours first, scores sorted and equal to the canonical fp32 score of
+    the returned rows (rows regenerated on the CPU from the counter-based generator), the single-launch tensor pipeline
+    (B = 1 and B = 64) bit-identical to the exact SIMT scan, and with a device-built `where` mask every returned row
+    satisfies the predicate while the unfiltered winners that satisfy it are all still there."""
+    from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns
+    n, k = 12_500_000, 10
+    seed = 0x5EED0004
+    idx = native().Index(768, "bf16", capacity_rows=n)
+    idx.add_synthetic(seed, 0, n)
+    q, planted = O.planted_queries(QSEED, 64, seed, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    s64, i64 = idx.search(q, k)
+    assert idx.stats()["last_pipeline"] == 3 and idx.stats()["exact_fallbacks"] == 0
+    s1, i1 = idx.search(q[:1], k)
+    assert idx.stats()["last_pipeline"] == 3          # single queries take the tensor pipeline from 1M rows on
+    assert all(i64[b, 0] == planted[b] for b in range(0, 64, 2))
+    assert np.all(np.diff(s64, axis=1) <= 0) and (i64 >= 0).all()
+    for b in (0, 1, 37):
+        rows = np.concatenate([O.synth_rows(seed, int(r), 1, 768) for r in i64[b]])
+        st_b, _ = O.normalize_rows(rows, "bf16", 768)
+        assert np.array_equal(O.canonical_scores(qn[b:b + 1], st_b)[0].view(np.uint32), s64[b].view(np.uint32))
+    idx.set_path(1)
+    es, ei = idx.search(q[:3], k)
+    assert_bit_equal(s64[:3], i64[:3], es, ei)
+    assert_bit_equal(s1, i1, es[:1], ei[:1])
+    idx.set_path(0)
+    # config-5 style categorical filter, evaluated on the device
+    cols = MetadataColumns()
+    src = (np.arange(n, dtype=np.int64) * 2654435761 >> 7) % 100
+    cols.extend_columns(n, {"source_id": src})
+    mask, allowed = DeviceFilter(idx, cols).build({"source_id": {"$in": list(range(10))}}, None)
+    assert allowed == int((src < 10).sum())
+    fs, fi = idx.search(q, k, mask)
+    assert (src[fi] < 10).all() and np.all(np.diff(fs, axis=1) <= 0)
+    for b in range(64):
+        keep = i64[b][src[i64[b]] < 10]              # unfiltered winners that pass the filter stay, in the same order
+        assert np.array_equal(fi[b][:keep.shape[0]], keep)
