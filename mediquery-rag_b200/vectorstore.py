@@ -338,6 +338,47 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                                       **kwargs: Any) -> List[Document]:
         return self.max_marginal_relevance_search_by_vector(self._embed_query(query), k, fetch_k, lambda_mult, filter)
 
+    # ------------------------------------------------------------------------------------------- update / async
+    def update_document(self, document_id: str, document: Document) -> None:
+        """langchain_chroma's update_document: re-embed and replace the row behind `document_id` (upsert: the old row is
+        tombstoned, the new one appended -- ids stay stable for callers)."""
+        self.update_documents([document_id], [document])
+
+    def update_documents(self, ids: List[str], documents: List[Document]) -> None:
+        missing = [i for i in ids if str(i) not in self._id2row]
+        if missing:
+            raise ValueError(f"unknown document ids: {missing[:3]}")
+        self.add_texts([d.page_content for d in documents], [d.metadata for d in documents], ids=[str(i) for i in ids])
+
+    # LangChain's VectorStore exposes a-prefixed coroutines that run the blocking call in a worker thread; the handle is
+    # safe to use from any thread (tests/test_gpu_parity.py::test_one_handle_from_several_host_threads...).  With
+    # langchain_core installed the base class provides them; these are the stand-ins otherwise.
+    if not HAVE_LANGCHAIN:
+        async def asimilarity_search(self, query: str, k: int = DEFAULT_K, **kwargs: Any) -> List[Document]:
+            import asyncio
+            return await asyncio.to_thread(self.similarity_search, query, k, **kwargs)
+
+        async def asimilarity_search_with_score(self, query: str, k: int = DEFAULT_K, **kwargs: Any):
+            import asyncio
+            return await asyncio.to_thread(self.similarity_search_with_score, query, k, **kwargs)
+
+        async def asimilarity_search_by_vector(self, embedding: List[float], k: int = DEFAULT_K, **kwargs: Any) -> List[Document]:
+            import asyncio
+            return await asyncio.to_thread(self.similarity_search_by_vector, embedding, k, **kwargs)
+
+        async def amax_marginal_relevance_search(self, query: str, k: int = DEFAULT_K, fetch_k: int = 20,
+                                                 lambda_mult: float = 0.5, **kwargs: Any) -> List[Document]:
+            import asyncio
+            return await asyncio.to_thread(self.max_marginal_relevance_search, query, k, fetch_k, lambda_mult, **kwargs)
+
+        async def aadd_texts(self, texts: Iterable[str], metadatas: Optional[List[Optional[dict]]] = None, **kwargs: Any) -> List[str]:
+            import asyncio
+            return await asyncio.to_thread(self.add_texts, list(texts), metadatas, **kwargs)
+
+        async def aadd_documents(self, documents: List[Document], **kwargs: Any) -> List[str]:
+            import asyncio
+            return await asyncio.to_thread(self.add_documents, documents, **kwargs)
+
     def as_retriever(self, **kwargs: Any) -> Any:
         if HAVE_LANGCHAIN:  # pragma: no cover
             return super().as_retriever(**kwargs)

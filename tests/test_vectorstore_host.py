@@ -177,3 +177,31 @@ def test_where_document_contains(embedder):
     assert {d.page_content for d in got} == {"饮食", "睡眠 与 记忆"}
     with pytest.raises(FilterError):
         vs.similarity_search("q", where_document={"$regex": "x"})
+
+
+def test_update_documents_and_async_wrappers(medical_docs, embedder):
+    import asyncio
+    docs = make_docs(medical_docs, 30)
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    ids = vs.add_documents(docs)
+    new = Document(page_content="问题：更新后的文档\n答案：全新的内容", metadata={"title": "更新", "tags": "x", "source": "s"})
+    vs.update_document(ids[3], new)
+    assert len(vs) == 30                                  # the old row is tombstoned, not duplicated
+    got = vs.similarity_search(new.page_content, k=1)
+    assert got[0].page_content == new.page_content and got[0].id == ids[3]
+    assert docs[3].page_content not in [d.page_content for d in vs.similarity_search(docs[3].page_content, k=30)]
+    with pytest.raises(ValueError):
+        vs.update_document("no-such-id", new)
+
+    async def go():
+        a = await vs.asimilarity_search(docs[7].page_content, k=3)
+        b = await vs.asimilarity_search_with_score(docs[7].page_content, k=3)
+        c = await vs.asimilarity_search_by_vector(embedder.embed_query(docs[7].page_content), k=3)
+        more = await vs.aadd_documents(docs[:2])
+        return a, b, c, more
+
+    a, b, c, more = asyncio.run(go())
+    sync = vs.similarity_search(docs[7].page_content, k=3)
+    assert a[0].page_content == docs[7].page_content and [d.page_content for d, _ in b] == [d.page_content for d in a]
+    assert [d.page_content for d in c] == [d.page_content for d in a] and len(more) == 2 and len(vs) == 32
+    assert [d.page_content for d in sync][0] == docs[7].page_content
