@@ -50,7 +50,7 @@ class Stats(ctypes.Structure):
                 ("scan_bytes", ctypes.c_uint64), ("scan_ms", ctypes.c_double), ("last_search_ms", ctypes.c_double),
                 ("last_scan_ms", ctypes.c_double), ("last_scan_passes", ctypes.c_uint32),
                 ("last_path", ctypes.c_uint32), ("exact_fallbacks", ctypes.c_uint64), ("unrepaired", ctypes.c_uint64),
-                ("last_pipeline", ctypes.c_uint32), ("reserved_", ctypes.c_uint32)]
+                ("last_pipeline", ctypes.c_uint32), ("reserved_", ctypes.c_uint32), ("band_repairs", ctypes.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

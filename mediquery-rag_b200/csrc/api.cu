@@ -99,10 +99,12 @@ struct mqvs_store {
     DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
     static constexpr int kMaxDeviceFix = 64;             // flagged queries repaired on the device per search
     uint32_t* fix_dev = nullptr;                         // [kMaxDeviceFix] list + [1] count
-    unsigned long long* fix_counters = nullptr;          // device [2]: repaired on device, left to the host
+    unsigned long long* fix_counters = nullptr;          // device [4]: repaired by the exact scan on device, left to the host, repaired by the band pass
     uint32_t* flags_host = nullptr;                      // pinned [1 + max B]: flag_count, flags[B]
     size_t flags_host_n = 0;
     uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
+    mqvs::tc::Buffers last_b{};                          // scratch layout + plan of the last tensor-core search: the
+    mqvs::tc::Plan last_plan{};                          // blocking call enqueues its repair only after it has seen flags
     unsigned long long* bad_dev = nullptr;   // [0] = non-finite rows counted by K1, [1] = epoch of the last fused
     unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits)
     unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
@@ -226,9 +228,38 @@ int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev,
     return MQVS_OK;
 }
 
+// Repair of tensor-path queries whose shortlist was not proven exact: first the band pass (all flagged queries together
+// through the tensor pipeline once more, with given thresholds), then whatever it could not settle is re-scanned exactly.
+// Entirely device-driven (no host sync), so mqvs_search_async enqueues it unconditionally after every tensor search;
+// the blocking mqvs_search looks at the flag count first and skips it when nothing is flagged (the common case).
+void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
+                           int64_t* out_ids_dev, cudaStream_t st, int band_rounds) {
+    using namespace mqvs;
+    const tc::Buffers& b = s->last_b;
+    if (s->coop_ok && s->path != 4 && tc::fused_ok(1, k, s->sm_count)) {
+        for (int r = 0; r < band_rounds; ++r) {  // 128 flagged queries per round
+            const char* err = tc::search_band(b, s->last_plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k,
+                                              mask_dev, id_base, out_scores_dev, out_ids_dev, s->fix_counters, st);
+            if (err) {
+                cudaGetLastError();  // a refused cooperative launch: the exact scan below still repairs everything
+                break;
+            }
+            s->stats.kernel_launches += 2;
+        }
+    }
+    uint32_t* fix_list = s->fix_dev;
+    uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
+    launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n,
+                    s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st);
+    launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
+                     fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
+    s->stats.kernel_launches += 2;
+}
+
 // Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
-                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status = nullptr) {
+                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status = nullptr,
+                   bool defer_repair = false) {
     using namespace mqvs;
     const int slot = s->ev_cursor;
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
@@ -265,7 +296,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
-        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 2 + 32) * sizeof(uint32_t);
+        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 3 + 32 + 144) * sizeof(uint32_t);
         if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
         if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
@@ -285,7 +316,10 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.eps = (float*)(b.tau + plan.b_pad);    // [B]
         b.flag_count = (uint32_t*)(b.eps + B);   // flag_count immediately followed by flags[B]: one D2H copy
         b.flags = b.flag_count + 1;
-        b.gbar = (unsigned int*)(b.flags + B);
+        b.gbar = (unsigned int*)(b.flags + B);  // [4]
+        b.band = (uint32_t*)(b.gbar + 8);        // [B]
+        b.band_list = b.band + B;               // [128]
+        b.band_n = b.band_list + 128;           // [1]
         b.cnt = (uint32_t*)s->tc_cnt.p;
         b.lists = (uint64_t*)s->tc_lists.p;
         b.short_keys = (uint64_t*)s->tc_keys.p;
@@ -293,15 +327,13 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.cmax = (uint32_t*)s->tc_cmax.p;
         s->last_flags_dev = b.flag_count;
     }
-    // queries whose shortlist was not proven exact are re-scanned exactly, driven from the device (no host sync)
+    if (tensor) {
+        s->last_b = b;
+        s->last_plan = plan;
+    }
     auto enqueue_repair = [&]() {
-        uint32_t* fix_list = s->fix_dev;
-        uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
-        launch_compact_flags(b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n, s->fix_counters, st);
-        launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, fix_list, fix_n, mask_dev, k,
-                        (uint64_t*)s->tc_fixcand.p, s->sm_count, st);
-        launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
-                         fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
+        // nobody can look at the flags here: one band round per 128 queries of the batch, at most two
+        if (!defer_repair) enqueue_tensor_repair(s, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, B > 128 ? 2 : 1);
     };
     if (tc_one) {
         s->last_fused = true;  // non-finite queries are reported through the epoch word, as on the latency path
@@ -327,7 +359,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         CU(cudaEventRecord(ev[3], st));
         CU(cudaGetLastError());
         s->evr[slot].pending = true;
-        s->stats.kernel_launches += 2 + 3;
+        s->stats.kernel_launches += 2;
         s->stats.scan_launches += 1;
         s->stats.scan_bytes += s->n * s->row_bytes();
         s->stats.last_scan_passes = 1;
@@ -351,7 +383,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
         enqueue_repair();
         passes = 1;
-        s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B) + 3;
+        s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B);
         s->stats.last_path = 1;
         s->stats.last_pipeline = 2;
     } else {
@@ -436,8 +468,8 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
         memset(s->host_out, 0, 64 * 4 + 64 * 8 + 16);
     }
     if (cudaMalloc(&s->fix_dev, (mqvs_store::kMaxDeviceFix + 1) * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&s->fix_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(s->fix_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+        cudaMalloc(&s->fix_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->fix_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
         return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (capacity_rows) {
         int rc = grow(s, capacity_rows);
@@ -610,7 +642,7 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
         host_i = (int64_t*)s->out_pinned;
         host_s = (float*)(s->out_pinned + n_out * sizeof(int64_t));
     }
-    if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st)) != MQVS_OK) return rc;
+    if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, nullptr, /*defer_repair=*/true)) != MQVS_OK) return rc;
     if (!out_is_device) {
         CU(cudaMemcpyAsync(host_s, os, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->st));
         CU(cudaMemcpyAsync(host_i, oi, n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
@@ -630,8 +662,12 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     CU(cudaStreamSynchronize(s->st));
     if (s->last_fused ? (unsigned int)s->bad_host[1] == s->epoch : s->bad_host[0] != 0)
         return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
-    if (tensor && s->flags_host[0] > (uint32_t)mqvs_store::kMaxDeviceFix) {
-        // more flagged queries than the device repair pass takes: re-run the rest on the exact scan from here
+    if (tensor && s->flags_host[0] > 0) {
+        // some shortlists were not proven exact: band pass + exact scan of up to 64 queries on the device, then look again
+        enqueue_tensor_repair(s, B, k, mask_dev, 0, os, oi, s->st, (int)((s->flags_host[0] + 127) / 128));
+        CU(cudaMemcpyAsync(s->flags_host, s->last_flags_dev, ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        // more flagged queries than the device repair takes: re-run the rest on the exact scan from here
         for (int b = 0; b < B; ++b) {
             if (!s->flags_host[1 + b]) continue;  // flags of device-repaired queries were cleared
             uint32_t passes = 0;
@@ -890,8 +926,9 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
     cudaSetDevice(s->dev);
     settle_events(s);
     s->stats.rows = s->n;
-    unsigned long long c[2] = {0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     if (s->fix_counters && cudaMemcpy(c, s->fix_counters, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
+    s->stats.band_repairs = c[2];
     s->stats.exact_fallbacks = c[0] + s->host_fallbacks;  // async callers: c[1] - host_fallbacks queries stayed unrepaired
     s->stats.unrepaired = c[1] > s->host_fallbacks ? c[1] - s->host_fallbacks : 0;
     *out = s->stats;

@@ -206,17 +206,48 @@ scan_simt_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __res
 }
 
 // Device-driven repair pass of the tensor-core path: re-scans the corpus exactly for the (few) queries whose
-// shortlist could not be proven exact.  The list lives in device memory, so no host round trip is needed; with an
-// empty list every CTA returns at once.
+// shortlist could not be proven exact.  Every CTA derives the list of flagged queries itself (one warp, ballot +
+// popcount over flags[B], first max_fix in index order), so no separate compaction launch is needed and no host round
+// trip; block 0 publishes the list for merge_fix_kernel and updates the repair counters.  With no flag set every CTA
+// returns at once.
 template <typename T, int KPL, int U>
 __global__ void __launch_bounds__(kScanThreads)
 scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn_all,
-                const uint32_t* __restrict__ fix_list, const uint32_t* __restrict__ fix_n,
+                const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
+                uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters,
                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride) {
     extern __shared__ __align__(16) uint64_t smem_keys[];
-    const uint32_t n = *fix_n;
+    __shared__ uint32_t list_s[64];
+    __shared__ uint32_t n_s, total_s;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        uint32_t base = 0;
+        for (int c = 0; c < B; c += 32) {
+            const bool f = c + lane < B && flags[c + lane] != 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (f && pos < (uint32_t)max_fix) list_s[pos] = (uint32_t)(c + lane);
+            base += __popc(m);
+        }
+        if (lane == 0) {
+            total_s = base;
+            n_s = base < (uint32_t)max_fix ? base : (uint32_t)max_fix;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = n_s;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            *fix_n = n;
+            if (total_s) {
+                atomicAdd(counters + 0, (unsigned long long)n);              // repaired on the device
+                atomicAdd(counters + 1, (unsigned long long)(total_s - n));  // left flagged (the blocking call repairs them)
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fix_list[i] = list_s[i];
+    }
     for (uint32_t f = 0; f < n; ++f) {
-        scan_body<T, 1, KPL, U>(rows, n_rows, qn_all + (size_t)fix_list[f] * kDim, 1, mask, k,
+        scan_body<T, 1, KPL, U>(rows, n_rows, qn_all + (size_t)list_s[f] * kDim, 1, mask, k,
                                 cand + (size_t)f * cand_stride * k, cand_stride, smem_keys);
         __syncthreads();
     }
@@ -303,14 +334,16 @@ void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float
 
 int scan_fix_grid(int sm_count) { return sm_count * 2; }
 
-void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* fix_list,
-                     const uint32_t* fix_n, const uint32_t* mask, int k, uint64_t* cand, int sm_count, cudaStream_t st) {
+void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
+                     uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
+                     int sm_count, cudaStream_t st) {
     const int kpl = k <= 32 ? 1 : 4;  // the tensor path serves k <= 128
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
-#define MQVS_FIX(T_, KPL_, U_)                                                                                   \
-    scan_fix_kernel<T_, KPL_, U_><<<grid, kScanThreads, smem, st>>>((const T_*)rows, n_rows, qn_all, fix_list, fix_n, \
-                                                                     mask, k, cand, stride)
+    if (max_fix > 64) max_fix = 64;
+#define MQVS_FIX(T_, KPL_, U_)                                                                                                \
+    scan_fix_kernel<T_, KPL_, U_><<<grid, kScanThreads, smem, st>>>((const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, \
+                                                                     fix_n, counters, mask, k, cand, stride)
     if (dtype == MQVS_F32) {
         if (kpl == 1) MQVS_FIX(float, 1, 2); else MQVS_FIX(float, 4, 2);
     } else {

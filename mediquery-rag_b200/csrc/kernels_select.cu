@@ -69,28 +69,6 @@ merge_fix_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, int
     if (threadIdx.x == 0) flags[q] = 0u;
 }
 
-// flags[B] -> fix_list (first `max_fix` flagged queries), *fix_n, and the running repair counters
-__global__ void compact_flags_kernel(const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
-                                     uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t n_s;
-    if (threadIdx.x == 0) n_s = 0;
-    __syncthreads();
-    uint32_t flagged = 0;
-    for (int q = threadIdx.x; q < B; q += blockDim.x)
-        if (flags[q]) {
-            ++flagged;
-            uint32_t slot = atomicAdd(&n_s, 1u);
-            if (slot < (uint32_t)max_fix) fix_list[slot] = (uint32_t)q;
-        }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t n = n_s < (uint32_t)max_fix ? n_s : (uint32_t)max_fix;
-        *fix_n = n;
-        atomicAdd(counters + 0, (unsigned long long)n);          // repaired on the device
-        atomicAdd(counters + 1, (unsigned long long)(n_s - n));  // left flagged (host repairs them in the blocking call)
-    }
-}
-
 // Cross-shard merge with 64-bit ids: entries are (order-preserving score bits, id); sorted by score desc, id asc.
 struct Cand {
     uint32_t ord;  // 0 == empty
@@ -163,11 +141,6 @@ void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_
     if (next_pow2(kp + m) < buf_n) buf_n = next_pow2(kp + m) > 2 * kp ? next_pow2(kp + m) : 2 * kp;
     size_t smem = (size_t)buf_n * sizeof(uint64_t);
     merge_keys_kernel<<<B, kSelThreads, smem, st>>>(keys_in, m, k, kp, buf_n, id_base, out_scores, out_ids);
-}
-
-void launch_compact_flags(const uint32_t* flags, int B, int max_fix, uint32_t* fix_list, uint32_t* fix_n,
-                          unsigned long long* counters, cudaStream_t st) {
-    compact_flags_kernel<<<1, 256, 0, st>>>(flags, B, max_fix, fix_list, fix_n, counters);
 }
 
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,

@@ -433,7 +433,7 @@ rescore_kernel(const T* __restrict__ rows, const float* __restrict__ qn, const u
 __global__ void __launch_bounds__(kSelThreads)
 finalize_kernel(const uint64_t* __restrict__ exact_keys, const float* __restrict__ tau_tilde, const float* __restrict__ eps,
                 int kp, int k, int64_t id_base, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                uint32_t* __restrict__ flags, uint32_t* __restrict__ flag_count) {
+                uint32_t* __restrict__ flags, uint32_t* __restrict__ flag_count, uint32_t* __restrict__ band) {
     __shared__ uint64_t buf[256];
     const int q = blockIdx.x;
     for (int i = threadIdx.x; i < kp; i += kSelThreads) buf[i] = exact_keys[(size_t)q * kp + i];
@@ -446,12 +446,15 @@ finalize_kernel(const uint64_t* __restrict__ exact_keys, const float* __restrict
     if (threadIdx.x == 0) {
         const float tt = tau_tilde[q];
         bool ok = true;
-        if (tt != -INFINITY) {  // something was discarded: the k-th exact score must clear every discarded row's bound
-            const uint64_t kth = (k <= kp) ? buf[k - 1] : 0ull;
+        const uint64_t kth = (k <= kp) ? buf[k - 1] : 0ull;
+        if (tt != -INFINITY)  // something was discarded: the k-th exact score must clear every discarded row's bound
             ok = kth != 0ull && key_score(kth) > tt + eps[q];
-        }
         flags[q] = ok ? 0u : 1u;
-        if (!ok) atomicAdd(flag_count, 1u);
+        if (!ok) {
+            atomicAdd(flag_count, 1u);
+            // threshold of the band pass (tc.h search_band): whatever can beat the k-th exact score scores at least this
+            band[q] = kth ? ord_u32(__fsub_rd(key_score(kth), eps[q])) : kOrdNegInf;
+        }
     }
 }
 
@@ -523,6 +526,8 @@ cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const Sco
 Plan plan(int k, int B, int sm_count) {
     Plan p{};
     p.kprime = k <= 10 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : 256));
+    static const int kp_min = getenv("MQVS_KP_MIN") ? atoi(getenv("MQVS_KP_MIN")) : 0;  // developer knob: wider shortlists
+    if (kp_min == 64 || kp_min == 128 || kp_min == 256) p.kprime = std::max(p.kprime, kp_min);
     p.cap = 512;  // per-(CTA, query) list capacity; a list is compacted to its k' best once it passes cap - 32 entries
     const int chunk = B < kMaxQueriesPerLaunch ? B : kMaxQueriesPerLaunch;
     p.b_pad = (chunk + BM - 1) / BM * BM;
@@ -636,7 +641,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
             rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
         finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps + q0, p.kprime, k, id_base,
                                                    out_scores_all + (size_t)q0 * k, out_ids_all + (size_t)q0 * k,
-                                                   b.flags + q0, b.flag_count);
+                                                   b.flags + q0, b.flag_count, b.band + q0);
         g_trace.mark("rescore+finalize", st);
     }
     cudaError_t e = cudaGetLastError();

@@ -27,13 +27,14 @@ int scan_max_grid(int sm_count);
 void launch_scan_simt(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
                       int k, uint64_t* cand, int cand_stride, int grid, cudaStream_t st);
 
-// Device-driven repair of tensor-path queries flagged "not proven exact": compact the flags into a list, re-scan the
-// corpus exactly for the listed queries (cand [max_fix][scan_fix_grid][k]), merge into the outputs.
-void launch_compact_flags(const uint32_t* flags, int B, int max_fix, uint32_t* fix_list, uint32_t* fix_n,
-                          unsigned long long* counters, cudaStream_t st);
+// Device-driven repair of tensor-path queries flagged "not proven exact": scan_fix compacts the flags into a list itself
+// (first max_fix <= 64 flagged queries, published in fix_list / fix_n; counters[0] += listed, [1] += left over), re-scans
+// the corpus exactly for the listed queries (cand [max_fix][scan_fix_grid][k]); merge_fix merges into the outputs and
+// clears their flags.
 int scan_fix_grid(int sm_count);  // CTAs (= candidate stride per listed query) of the repair scan
-void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* fix_list,
-                     const uint32_t* fix_n, const uint32_t* mask, int k, uint64_t* cand, int sm_count, cudaStream_t st);
+void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
+                     uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
+                     int sm_count, cudaStream_t st);
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
                       const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st);
 

@@ -27,6 +27,9 @@ struct Buffers {       // all device memory, owned by the store handle
     uint32_t* flag_count;
     uint32_t* cmax;    // single-launch pipeline: [128][grid * 8] chunk maxima of every CTA's first tile
     unsigned int* gbar;  // single-launch pipeline: [3] grid barrier counters
+    uint32_t* band;       // [B] band-pass threshold of every flagged query: ord(k-th exact score - eps)
+    uint32_t* band_list;  // [128] flagged queries, compacted
+    uint32_t* band_n;     // [1]
 };
 
 Plan plan(int k, int B, int sm_count);
@@ -46,6 +49,12 @@ size_t cmax_bytes(const Plan& p);
 const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
                          int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
                          int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused);
+
+// Repair of flagged queries by a second single-launch pass with given thresholds (kernels_tc_fused.cu); enqueue after
+// search() / search_fused() and before the exact-scan repair.  counters[2] counts the queries it repaired.
+const char* search_band(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
+                        int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids,
+                        unsigned long long* counters, cudaStream_t st);
 
 void trace_dump();  // MQVS_TRACE=1 developer aid: per-launch timings of the last searches to stderr
 int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize

@@ -474,7 +474,8 @@ def test_tensor_path_adversarial_order_forces_list_compaction(gpu, dtype, k, pat
 
 def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segmented_one(gpu):
     """B <= 128 on the tensor path: prep kernel + ONE cooperative persistent kernel (threshold learning through grid
-    barriers, scan, selection, fp32 rescoring, margin check) + the three device-driven repair launches.  Must agree bit
+    barriers, scan, selection, fp32 rescoring, margin check); the blocking call enqueues the repair launches only when a
+    query was flagged, so a clean search is exactly two launches.  Must agree bit
     for bit with the segmented pipeline (path 4), the exact SIMT scan (path 1) and the oracle; repeated calls on one
     handle reuse the barrier counters; a non-finite query still raises and leaves the handle usable."""
     n, B, k = 300_000, 64, 10
@@ -485,7 +486,7 @@ def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segment
     l0 = idx.stats()["kernel_launches"]
     one = idx.search(q, k)
     st = idx.stats()
-    assert st["last_path"] == 1 and st["kernel_launches"] - l0 == 5 and st["exact_fallbacks"] == 0
+    assert st["last_path"] == 1 and st["kernel_launches"] - l0 == 2 and st["exact_fallbacks"] == 0
     again = idx.search(q, k)
     assert all(one[1][b, 0] == planted[b] for b in range(0, B, 2))
     idx.set_path(4)
@@ -747,3 +748,33 @@ def test_full_size_config4_shard_and_config5_filter_properties(gpu):
     for b in range(64):
         keep = i64[b][src[i64[b]] < 10]              # unfiltered winners that pass the filter stay, in the same order
         assert np.array_equal(fi[b][:keep.shape[0]], keep)
+
+
+@pytest.mark.parametrize("dtype,B", [("bf16", 64), ("fp32", 20), ("bf16", 300)])
+def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, B):
+    """Clustered corpus (2000-member clusters at cosine 0.98 to their centre): the scores around rank k are closer
+    together than the tensor-core error bound, so the margin check flags (nearly) every query.  The band pass -- one more
+    tensor-core pass that collects and rescoring every row within eps of the k-th exact score -- must settle them all:
+    bit-identical to the oracle, band_repairs > 0, and no query left for the exact scan.  B = 300 goes through the
+    segmented pipeline first (3 query tiles), B <= 128 through the single-launch one."""
+    n, members, k = 200_000, 2000, 10
+    rng = np.random.default_rng(0)
+    sigma = np.sqrt((1.0 / 0.98 ** 2 - 1.0) / 256.0)
+    centres = rng.standard_normal((n // members, 768)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    x = np.repeat(centres, members, axis=0) + sigma * rng.uniform(-1, 1, (n, 768)).astype(np.float32)
+    q = x[rng.integers(0, n, B)] + 0.5 * sigma * rng.uniform(-1, 1, (B, 768)).astype(np.float32)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    idx = native().Index(768, dtype)
+    idx.add(x)
+    idx.set_path(2)
+    s, i = idx.search(q, k)
+    stats = idx.stats()
+    assert_bit_equal(s, i, es, ei)
+    assert stats["band_repairs"] >= min(B, 128) // 2 and stats["exact_fallbacks"] == 0, stats
+    idx.set_path(4)                                # without the band pass the same queries need exact scans
+    s4, i4 = idx.search(q[:16], k)
+    assert_bit_equal(s4, i4, es[:16], ei[:16])
+    assert idx.stats()["exact_fallbacks"] > 0
