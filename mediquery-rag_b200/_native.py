@@ -203,8 +203,13 @@ class Index:
         return scores, ids
 
     def search_device(self, q, k: int, out_scores, out_ids, mask=None, id_base: int = 0, stream: int = 0) -> None:
-        """All-device variant on a caller stream (torch tensors; plumbing only)."""
+        """All-device variant on a caller stream (torch tensors; plumbing only).  The C ABI takes raw pointers, so the
+        layout is checked here: q [B, dim] float32, out_scores [B, k] float32, out_ids [B, k] int64, all contiguous."""
         B = q.shape[0]
+        for name, t, want, shape in (("q", q, "float32", (B, self.dim)), ("out_scores", out_scores, "float32", (B, int(k))),
+                                     ("out_ids", out_ids, "int64", (B, int(k)))):
+            if not str(t.dtype).endswith(want) or tuple(t.shape) != shape or not t.is_contiguous():
+                raise TypeError(f"{name} must be a contiguous {want} tensor of shape {shape}, got {t.dtype} {tuple(t.shape)}")
         check(load().mqvs_search_async(self._h, _ptr(q), B, int(k), _ptr(mask), int(id_base), _ptr(out_scores),
                                        _ptr(out_ids), _vp(stream)))
 

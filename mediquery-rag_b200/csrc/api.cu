@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -236,7 +237,8 @@ void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev
                            int64_t* out_ids_dev, cudaStream_t st, int band_rounds) {
     using namespace mqvs;
     const tc::Buffers& b = s->last_b;
-    if (s->coop_ok && s->path != 4 && tc::fused_ok(1, k, s->sm_count)) {
+    static const bool no_band = getenv("MQVS_NO_BAND") != nullptr;  // developer knob: measure what the band pass costs
+    if (!no_band && s->coop_ok && s->path != 4 && tc::fused_ok(1, k, s->sm_count)) {
         for (int r = 0; r < band_rounds; ++r) {  // 128 flagged queries per round
             const char* err = tc::search_band(b, s->last_plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k,
                                               mask_dev, id_base, out_scores_dev, out_ids_dev, s->fix_counters, st);

@@ -762,8 +762,8 @@ def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, 
     sigma = np.sqrt((1.0 / 0.98 ** 2 - 1.0) / 256.0)
     centres = rng.standard_normal((n // members, 768)).astype(np.float32)
     centres /= np.linalg.norm(centres, axis=1, keepdims=True)
-    x = np.repeat(centres, members, axis=0) + sigma * rng.uniform(-1, 1, (n, 768)).astype(np.float32)
-    q = x[rng.integers(0, n, B)] + 0.5 * sigma * rng.uniform(-1, 1, (B, 768)).astype(np.float32)
+    x = (np.repeat(centres, members, axis=0) + sigma * rng.uniform(-1, 1, (n, 768))).astype(np.float32)
+    q = (x[rng.integers(0, n, B)] + 0.5 * sigma * rng.uniform(-1, 1, (B, 768))).astype(np.float32)
     st, _ = O.normalize_rows(x, dtype, 768)
     qn, _ = O.normalize_rows(q, "fp32", 768)
     es, ei = O.brute_force_topk(qn, st, k)
@@ -774,6 +774,18 @@ def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, 
     stats = idx.stats()
     assert_bit_equal(s, i, es, ei)
     assert stats["band_repairs"] >= min(B, 128) // 2 and stats["exact_fallbacks"] == 0, stats
+    if B <= 128:                                   # the same through the all-device call (what the sharded path uses)
+        import torch
+        idx.set_path(2)
+        before = idx.stats()["band_repairs"]
+        out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+        idx.search_device(torch.from_numpy(q).cuda(), k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+        assert idx.stats()["band_repairs"] > before and idx.stats()["exact_fallbacks"] == 0
+        with pytest.raises(TypeError):             # raw pointers cross the ABI: the binding refuses a float64 tensor
+            idx.search_device(torch.from_numpy(q.astype(np.float64)).cuda(), k, out_s, out_i)
     idx.set_path(4)                                # without the band pass the same queries need exact scans
     s4, i4 = idx.search(q[:16], k)
     assert_bit_equal(s4, i4, es[:16], ei[:16])
