@@ -157,6 +157,9 @@ MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float*
 
 /* persist_directory -- src/ingest_medical.py:109, src/medical_engine.py:32-37,52: raw row file + header. */
 MQVS_API int mqvs_save(mqvs_t* s, const char* path);
+/* Append rows [first_row, count) to a file written earlier by mqvs_save / mqvs_save_append that holds exactly first_row
+ * rows (re-running ingest appends -- src/ingest_medical.py:106 on an existing ./medical_db); first_row = 0 rewrites. */
+MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row);
 MQVS_API int mqvs_load(mqvs_t* s, const char* path);
 
 MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "mqvs_merge_candidates": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "mqvs_get_rows": (_i, [_vp, _vp, _u64, _vp]),
     "mqvs_save": (_i, [_vp, ctypes.c_char_p]),
+    "mqvs_save_append": (_i, [_vp, ctypes.c_char_p, _u64]),
     "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
@@ -221,6 +222,10 @@ class Index:
 
     def save(self, path: str) -> None:
         check(load().mqvs_save(self._h, os.fsencode(path)))
+
+    def save_append(self, path: str, first_row: int) -> None:
+        """Append rows [first_row, len) to a row file that holds exactly first_row rows (0 = rewrite everything)."""
+        check(load().mqvs_save_append(self._h, os.fsencode(path), int(first_row)))
 
     def load_file(self, path: str) -> None:
         check(load().mqvs_load(self._h, os.fsencode(path)))

@@ -778,6 +778,44 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
     return MQVS_OK;
 }
 
+MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
+    if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
+    if (first_row == 0) return mqvs_save(s, path);
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    if (first_row > s->n) return fail(MQVS_E_INVALID, "first_row %llu beyond the %llu stored rows", (unsigned long long)first_row, (unsigned long long)s->n);
+    FILE* f = fopen(path, "r+b");
+    if (!f) return fail(MQVS_E_IO, "cannot open %s for appending", path);
+    FileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MQVSROW1", 8) != 0) {
+        fclose(f);
+        return fail(MQVS_E_IO, "%s is not an mqvs row file", path);
+    }
+    if ((int)h.dim != s->dim || (int)h.dtype != s->dtype || h.dim_pad != MQVS_DIM_PAD || h.rows != first_row) {
+        fclose(f);
+        return fail(MQVS_E_INVALID, "%s holds %llu rows (dim=%u dtype=%u); cannot append from row %llu", path,
+                    (unsigned long long)h.rows, h.dim, h.dtype, (unsigned long long)first_row);
+    }
+    bool ok = fseek(f, (long)(sizeof(h) + first_row * s->row_bytes()), SEEK_SET) == 0;
+    const uint64_t chunk = 65536;
+    std::vector<char> host((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(s->n - first_row, 1)) * s->row_bytes());
+    for (uint64_t r = first_row; ok && r < s->n; r += chunk) {
+        uint64_t m = std::min(chunk, s->n - r);
+        cudaError_t e = cudaMemcpy(host.data(), (char*)s->rows + r * s->row_bytes(), m * s->row_bytes(), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            fclose(f);
+            return fail(MQVS_E_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+        }
+        ok = fwrite(host.data(), s->row_bytes(), m, f) == m;
+    }
+    // the row count in the header moves last: a crash before this leaves the old, consistent file (plus ignored bytes)
+    h.rows = s->n;
+    ok = ok && fflush(f) == 0 && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof(h), 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(MQVS_E_IO, "appending to %s failed", path);
+    return MQVS_OK;
+}
+
 MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(s->mu);

@@ -35,7 +35,7 @@ else:
 
 DEFAULT_K = 4  # langchain_chroma's default
 _SPACES = ("l2", "cosine", "ip")
-_ROWS_FILE, _DOCS_FILE, _MANIFEST = "rows.mqvs", "docs.jsonl", "manifest.json"
+_ROWS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE = "rows.mqvs", "docs.jsonl", "manifest.json", "dead.json"
 
 
 def _distance(space: str, sim: float) -> float:
@@ -106,6 +106,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._cols = MetadataColumns()
         self._live = np.zeros(0, dtype=bool)
         self._device_filter: Optional[DeviceFilter] = None
+        self._persisted_rows = 0            # rows already in rows.mqvs / docs.jsonl (appends start here)
+        self._persisted_dead: Optional[List[int]] = None
         if persist_directory is not None:
             # the reference tests os.path.exists(DB_PATH) before opening (src/medical_engine.py:34-37)
             os.makedirs(persist_directory, exist_ok=True)
@@ -439,7 +441,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._cols, self._live = MetadataColumns(), np.zeros(0, dtype=bool)
         self._device_filter = None
         if self._persist_directory is not None:
-            for f in (_ROWS_FILE, _DOCS_FILE, _MANIFEST):
+            self._persisted_rows, self._persisted_dead = 0, None
+            for f in (_ROWS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE):
                 try:
                     os.remove(os.path.join(self._persist_directory, f))
                 except FileNotFoundError:
@@ -447,26 +450,54 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
 
     # ------------------------------------------------------------------------------------------- persistence
     def persist(self) -> None:
-        """rows.mqvs (raw normalised rows, written by mqvs_save) + docs.jsonl + manifest.json."""
+        """rows.mqvs (raw normalised rows, mqvs_save / mqvs_save_append) + docs.jsonl (id, text, metadata per row) +
+        dead.json (tombstoned rows) + manifest.json.  APPEND-ONLY for rows and documents: adding to a store of N rows
+        writes only the new rows (re-running the reference's ingest on an existing ./medical_db appends,
+        src/ingest_medical.py:106-110), so the cost of `auto_persist` does not grow with the store.  Order of writes:
+        documents, rows (their count in the file header moves last), tombstones, manifest -- a crash in between leaves a
+        directory that still opens (surplus document lines are ignored)."""
         d = self._persist_directory
         if d is None:
             raise ValueError("no persist_directory")
         os.makedirs(d, exist_ok=True)
-        if self._index is not None:
-            self._index.save(os.path.join(d, _ROWS_FILE))
-        tmp = os.path.join(d, _DOCS_FILE + ".tmp")
-        with open(tmp, "w", encoding="utf-8") as f:
-            for r, doc_id in enumerate(self._ids):
-                f.write(json.dumps({"id": doc_id, "text": self._texts[r], "metadata": self._cols.row(r),
-                                    "live": bool(self._live[r])}, ensure_ascii=False) + "\n")
-        os.replace(tmp, os.path.join(d, _DOCS_FILE))
-        manifest = {"format": 1, "collection_name": self._collection_name, "dim": self._dim,
-                    "store_dtype": self._store_dtype, "rows": len(self._ids), "space": self._space,
+        n, done = len(self._ids), self._persisted_rows
+        rows_path, docs_path = os.path.join(d, _ROWS_FILE), os.path.join(d, _DOCS_FILE)
+        append = 0 < done <= n and os.path.exists(rows_path) and os.path.exists(docs_path)
+
+        def record(r: int) -> str:
+            return json.dumps({"id": self._ids[r], "text": self._texts[r], "metadata": self._cols.row(r)}, ensure_ascii=False) + "\n"
+
+        if append:
+            if n > done:
+                with open(docs_path, "a", encoding="utf-8") as f:
+                    for r in range(done, n):
+                        f.write(record(r))
+                    f.flush()
+                    os.fsync(f.fileno())
+                self._index.save_append(rows_path, done)
+        else:
+            tmp = docs_path + ".tmp"
+            with open(tmp, "w", encoding="utf-8") as f:
+                for r in range(n):
+                    f.write(record(r))
+            os.replace(tmp, docs_path)
+            if self._index is not None:
+                self._index.save(rows_path)
+        dead = np.flatnonzero(~self._live).tolist()
+        if dead != self._persisted_dead:
+            tmp = os.path.join(d, _DEAD_FILE + ".tmp")
+            with open(tmp, "w", encoding="utf-8") as f:
+                json.dump(dead, f)
+            os.replace(tmp, os.path.join(d, _DEAD_FILE))
+            self._persisted_dead = dead
+        manifest = {"format": 2, "collection_name": self._collection_name, "dim": self._dim,
+                    "store_dtype": self._store_dtype, "rows": n, "space": self._space,
                     "collection_metadata": self._collection_metadata}
         tmp = os.path.join(d, _MANIFEST + ".tmp")
         with open(tmp, "w", encoding="utf-8") as f:
             json.dump(manifest, f, ensure_ascii=False, indent=1)
         os.replace(tmp, os.path.join(d, _MANIFEST))
+        self._persisted_rows = n
 
     def _load(self) -> None:
         d = self._persist_directory
@@ -477,21 +508,35 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._store_dtype = manifest["store_dtype"]
         if "hnsw:space" not in self._collection_metadata:
             self._space = manifest.get("space", self._space)
+        if manifest.get("dim") is None:
+            return
+        self._ensure_index(manifest["dim"])
+        if manifest["rows"]:
+            self._index.load_file(os.path.join(d, _ROWS_FILE))
+        n = len(self._index)  # the row file is the authority: its header moves only after the rows are on disk
         metas: List[dict] = []
         live: List[bool] = []
+        lines = 0
         with open(os.path.join(d, _DOCS_FILE), "r", encoding="utf-8") as f:
             for line in f:
+                lines += 1
+                if len(self._ids) == n:
+                    continue  # document lines of an append whose rows never made it to disk
                 rec = json.loads(line)
                 self._ids.append(rec["id"])
                 self._texts.append(rec["text"])
                 metas.append(rec["metadata"])
-                live.append(bool(rec["live"]))
+                live.append(bool(rec.get("live", True)))  # format 1 kept the tombstone in the record
+        if len(self._ids) != n:
+            raise RuntimeError(f"{d}: {n} stored rows but {len(self._ids)} documents")
         self._cols.extend(metas)
         self._live = np.asarray(live, dtype=bool)
+        dead_path = os.path.join(d, _DEAD_FILE)
+        if os.path.exists(dead_path):
+            with open(dead_path, "r", encoding="utf-8") as f:
+                dead = [r for r in json.load(f) if r < n]
+            self._live[dead] = False
+            self._persisted_dead = dead
         self._id2row = {i: r for r, i in enumerate(self._ids) if self._live[r]}
-        if manifest.get("dim") is not None:
-            self._ensure_index(manifest["dim"])
-            if manifest["rows"]:
-                self._index.load_file(os.path.join(d, _ROWS_FILE))
-            if len(self._index) != len(self._ids):
-                raise RuntimeError(f"{d}: {len(self._index)} stored rows but {len(self._ids)} documents")
+        # appends continue from here unless the directory needs a clean rewrite (older format, surplus document lines)
+        self._persisted_rows = n if manifest.get("format", 1) >= 2 and lines == n else 0

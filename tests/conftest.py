@@ -76,6 +76,10 @@ class OracleIndex:
     def get_rows(self, ids):
         return O.stored_as_f32(self.rows)[np.asarray(ids, np.int64), : self.dim]
 
+    def save_append(self, path, first_row):
+        assert first_row <= len(self)
+        self.save(path)
+
     def save(self, path):
         np.save(path + ".npy", self.rows)
         os.replace(path + ".npy", path)

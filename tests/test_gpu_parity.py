@@ -156,6 +156,30 @@ def test_save_load_round_trip(gpu, tmp_path):
     wrong = native().Index(768, "fp32")
     with pytest.raises(native().MqvsError):
         wrong.load_file(path)
+    # append-only persistence: only the new rows are written; a file that does not hold exactly first_row rows is refused
+    import os
+    size0 = os.path.getsize(path)
+    extra = O.synth_rows(SEED + 9, 0, 700, 768)
+    idx.add(extra)
+    idx.save_append(path, 2500)
+    assert os.path.getsize(path) == size0 + 700 * 768 * 2
+    again = native().Index(768, "bf16")
+    again.load_file(path)
+    assert len(again) == 3200
+    assert_bit_equal(*again.search(q, 7), *idx.search(q, 7))
+    assert np.array_equal(again.get_rows(np.arange(2490, 2510)), idx.get_rows(np.arange(2490, 2510)))
+    with pytest.raises(native().MqvsError):
+        idx.save_append(path, 2500)              # the file holds 3200 rows now
+    # the vector store on top: re-running the reference's ingest on an existing directory appends
+    from mediquery_rag_b200 import MediQueryVectorStore
+    db = str(tmp_path / "medical_db")
+    vs = MediQueryVectorStore(persist_directory=db)
+    vs.add_embeddings(([f"a{r}" for r in range(300)], x[:300]))
+    rows_size = os.path.getsize(os.path.join(db, "rows.mqvs"))
+    vs.add_embeddings(([f"b{r}" for r in range(50)], x[300:350]))
+    assert os.path.getsize(os.path.join(db, "rows.mqvs")) == rows_size + 50 * 768 * 4
+    vs2 = MediQueryVectorStore(persist_directory=db)
+    assert len(vs2) == 350 and vs2.similarity_search_by_vector(x[320], k=1)[0].page_content == "b20"
 
 
 def test_cross_shard_merge_equals_unsharded(gpu):

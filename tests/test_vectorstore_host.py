@@ -205,3 +205,48 @@ def test_update_documents_and_async_wrappers(medical_docs, embedder):
     assert a[0].page_content == docs[7].page_content and [d.page_content for d, _ in b] == [d.page_content for d in a]
     assert [d.page_content for d in c] == [d.page_content for d in a] and len(more) == 2 and len(vs) == 32
     assert [d.page_content for d in sync][0] == docs[7].page_content
+
+
+def test_persistence_is_append_only_and_survives_reopen_delete_and_old_format(tmp_path, medical_docs, embedder):
+    import json, os
+    db = str(tmp_path / "db")
+    docs = make_docs(medical_docs, 40)
+    vs = MediQueryVectorStore.from_documents(docs[:20], embedder, persist_directory=db, index_factory=OracleIndex)
+    size0 = os.path.getsize(os.path.join(db, "docs.jsonl"))
+    first_line = open(os.path.join(db, "docs.jsonl"), encoding="utf-8").readline()
+    ids2 = vs.add_documents(docs[20:30])                      # appends 10 records, rewrites nothing
+    assert os.path.getsize(os.path.join(db, "docs.jsonl")) > size0
+    assert open(os.path.join(db, "docs.jsonl"), encoding="utf-8").readline() == first_line
+    assert sum(1 for _ in open(os.path.join(db, "docs.jsonl"), encoding="utf-8")) == 30
+    vs.delete(ids2[:3])
+    assert json.load(open(os.path.join(db, "dead.json"))) == [20, 21, 22]
+    assert json.load(open(os.path.join(db, "manifest.json")))["format"] == 2
+    # reopen (src/medical_engine.py:52), keep appending (src/ingest_medical.py:106 re-run), reopen again
+    vs2 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(vs2) == 27 and vs2.similarity_search(docs[25].page_content, k=1)[0].page_content == docs[25].page_content
+    assert docs[21].page_content not in [d.page_content for d in vs2.similarity_search(docs[21].page_content, k=27)]
+    vs2.add_documents(docs[30:40])
+    vs3 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(vs3) == 37 and [d.page_content for d in vs3.similarity_search(docs[35].page_content, k=3)] == \
+        [d.page_content for d in vs2.similarity_search(docs[35].page_content, k=3)]
+    # surplus document lines (a crash after the documents of an append were written but before its rows): ignored, and
+    # the next persist rewrites the directory cleanly
+    with open(os.path.join(db, "docs.jsonl"), "a", encoding="utf-8") as f:
+        f.write(json.dumps({"id": "ghost", "text": "never stored", "metadata": {}}) + "\n")
+    vs4 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(vs4) == 37 and "ghost" not in vs4.get()["ids"]
+    vs4.add_documents(docs[:1])
+    assert sum(1 for _ in open(os.path.join(db, "docs.jsonl"), encoding="utf-8")) == 41
+    assert len(MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)) == 38
+    # a format-1 directory (tombstones inside the records) still opens
+    old = str(tmp_path / "old")
+    os.makedirs(old)
+    v = MediQueryVectorStore.from_documents(docs[:5], embedder, persist_directory=str(tmp_path / "scratch"), index_factory=OracleIndex)
+    v._index.save(os.path.join(old, "rows.mqvs"))
+    with open(os.path.join(old, "docs.jsonl"), "w", encoding="utf-8") as f:
+        for r in range(5):
+            f.write(json.dumps({"id": v._ids[r], "text": v._texts[r], "metadata": v._cols.row(r), "live": r != 2}, ensure_ascii=False) + "\n")
+    json.dump({"format": 1, "collection_name": "langchain", "dim": v._dim, "store_dtype": "fp32", "rows": 5, "space": "l2",
+               "collection_metadata": {}}, open(os.path.join(old, "manifest.json"), "w"))
+    vo = MediQueryVectorStore(persist_directory=old, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(vo) == 4 and docs[2].page_content not in [d.page_content for d in vo.similarity_search(docs[2].page_content, k=4)]
