@@ -57,7 +57,7 @@ typedef struct mqvs_stats {
                                     (their results are approximate; the blocking mqvs_search repairs every one) */
     uint32_t last_pipeline;      /* how the last search ran: 0 = SIMT scan, normalise + scan(s) + merge launches; 1 = SIMT scan, one
                                     launch (B <= 4, k <= 16); 2 = tensor cores, corpus segments + selection launches;
-                                    3 = tensor cores, one cooperative launch (B <= 128) */
+                                    3 = tensor cores, one cooperative launch (B <= 256) */
     uint32_t reserved_;
     uint64_t band_repairs;       /* flagged queries settled by the band pass (a second tensor-core pass that collects and rescoring every
                                     row within eps of the k-th exact score) instead of an exact scan */
@@ -165,7 +165,7 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path);
 MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);
 /* 0 = choose by batch size, 1 = force the SIMT fp32 scan, 2 = force the tensor-core path,
  * 3 = SIMT scan without the single-launch latency kernel, 4 = tensor-core path without the single-launch pipeline
- * for B <= 128 and without the band pass (tests compare the variants) */
+ * for B <= 256 and without the band pass (tests compare the variants) */
 MQVS_API int mqvs_set_path(mqvs_t* s, int path);
 
 #ifdef __cplusplus

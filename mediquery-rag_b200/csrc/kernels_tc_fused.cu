@@ -18,7 +18,7 @@ Trace& g_trace = trace();
 // ------------------------------------------------------------------------------------------ single-launch pipeline
 struct FusedArgs;
 template <typename T, int CAP, int KPRIME>
-__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al);
+__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al, int slot, int b_pad);
 
 // Batches of up to 128 queries (one query tile) are HBM-bound: the corpus is streamed once and the tensor pipe idles
 // most of the time, so what the segmented pipeline above pays for -- two short cold segments and three selection
@@ -105,9 +105,20 @@ __device__ __forceinline__ uint32_t kth_largest_u32(const uint32_t* __restrict__
     return lo;
 }
 
-template <typename T, int CAP, int KPRIME>
+// MT = query tiles per launch: 1 (B <= 128) or 2 (B <= 256; the two TMEM accumulators then hold the first corpus tile of both
+// query tiles through the cold phase, and alternate between the query tiles afterwards).
+template <typename T, int CAP, int KPRIME, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const FusedArgs a) {
+    static_assert(MT == 1 || MT == 2, "two accumulators: at most two query tiles");
+    constexpr int kQ = MT * BM;  // query slots per CTA (stride of the per-CTA list / count arrays)
+    // Two query tiles over fp32 rows share every staged corpus chunk ([A0 | A1 | B] stages): the tf32 chunks are twice as
+    // many bytes per flop, staging them once instead of twice is worth more than overlapping one query tile's epilogue
+    // with the other's MMAs (measured at 1M x 768, B = 256: 0.95 -> 0.70 ms).  Over bf16 rows it is the other way round
+    // (0.38 -> 0.43 ms), so there each query tile streams the chunk itself and the accumulators alternate.
+    constexpr bool kShareB = MT == 2 && sizeof(T) == 4;
+    constexpr int kStage2Bytes = 2 * kABytes + kBBytes, kStages2 = 3;
+    static_assert(kStages2 * kStage2Bytes <= kStages * kStageBytes, "the two-tile ring must fit the one-tile ring's shared memory");
     using K = Kind<T>;
     constexpr int kChunks768 = kDim / K::kElemsPerChunk;
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
@@ -116,7 +127,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // Band pass (second launch, see search_band): thresholds are GIVEN (k-th exact score of the first launch minus eps),
     // every row above them is collected and rescored, nothing is learnt.  No flagged query -> nothing to do.
     const bool band = a.band_list != nullptr;
-    const uint32_t n_queries = band ? min(__ldcg(a.band_n), (uint32_t)BM) : a.n_queries;
+    const uint32_t n_queries = band ? min(__ldcg(a.band_n), (uint32_t)kQ) : a.n_queries;
     if (band && n_queries == 0) return;  // uniform over the grid, before any barrier or TMEM allocation
 
     extern __shared__ uint8_t smem_raw[];
@@ -161,117 +172,183 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G)
-                for (int kc = 0; kc < kChunks768; ++kc) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-                    tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, 0);
-                    tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
+            if constexpr (!kShareB) {
+                for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G)
+                    for (int mt = 0; mt < MT; ++mt)
+                        for (int kc = 0; kc < kChunks768; ++kc) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                            mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, mt * BM);
+                            tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+            } else {
+                // two query tiles share every corpus chunk: a stage is [A0 | A1 | B] (64 KB, three stages in the same
+                // 192 KB), so the corpus is staged once per chunk, not once per query tile
+                for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G)
+                    for (int kc = 0; kc < kChunks768; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * kStage2Bytes, sb = sa + 2 * kABytes;
+                        mbar_expect_tx(bar_full + 8 * stage, kStage2Bytes);
+                        tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, 0);
+                        tma_load_2d(sa + kABytes, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, BM);
+                        tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
+                        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+                    }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t w = 0; w < n_my; ++w) {
-                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kc = 0; kc < kChunks768; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
+            if constexpr (!kShareB) {
+                for (uint32_t w = 0; w < n_my * MT; ++w) {  // w = tile * MT + query tile
+                    const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    for (int kc = 0; kc < kChunks768; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                        const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma<K::kTf32>(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
-                    tcgen05_commit(bar_empty + 8 * stage);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        for (int kk = 0; kk < 4; ++kk)
+                            tcgen05_mma<K::kTf32>(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                        tcgen05_commit(bar_empty + 8 * stage);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    tcgen05_commit(bar_tfull + 8 * acc);
                 }
-                tcgen05_commit(bar_tfull + 8 * acc);
+            } else {
+                // accumulator mt belongs to query tile mt; both are filled from the same staged corpus chunk and complete
+                // together, once per corpus tile (the epilogue's w = 2 t + mt sees accumulator mt in phase t & 1)
+                for (uint32_t t = 0; t < n_my; ++t) {
+                    mbar_wait(bar_tempty + 0, (t & 1) ^ 1);
+                    mbar_wait(bar_tempty + 8, (t & 1) ^ 1);
+                    tcgen05_fence_after();
+                    for (int kc = 0; kc < kChunks768; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_base + stage * kStage2Bytes;
+                        const uint64_t a0 = smem_desc(sa), a1 = smem_desc(sa + kABytes), bdesc = smem_desc(sa + 2 * kABytes);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            tcgen05_mma<K::kTf32>(tmem_base, a0 + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                            tcgen05_mma<K::kTf32>(tmem_base + BN, a1 + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                        }
+                        tcgen05_commit(bar_empty + 8 * stage);
+                        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+                    }
+                    tcgen05_commit(bar_tfull + 0);
+                    tcgen05_commit(bar_tfull + 8);
+                }
             }
         }
     } else {
         // ===================== epilogue =====================
         const int quad = warp & 3;
         const int et = (int)threadIdx.x - 64;  // 0..127
-        const uint32_t q = quad * 32 + lane;
-        const bool q_ok = q < n_queries;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint64_t* lst = a.lists + ((size_t)blockIdx.x * BM + q) * CAP;
-        uint32_t cnt = 0;
+        // this thread's query of every query tile: TMEM lane quad*32 + lane of accumulator mt
+        uint32_t q[MT], cnt[MT];
+        bool q_ok[MT];
+        uint64_t* lst[MT];
+        float tau[MT];
+        ChunkTop trk[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            q[mt] = mt * BM + quad * 32 + lane;
+            q_ok[mt] = q[mt] < n_queries;
+            lst[mt] = a.lists + ((size_t)blockIdx.x * kQ + q[mt]) * CAP;
+            cnt[mt] = 0;
+            trk[mt].out = a.cmax + (size_t)(q_ok[mt] ? q[mt] : 0) * a.ncols + blockIdx.x * 8;
+            trk[mt].on = false;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) trk[mt].v[i] = 0u;
+        }
 
-        // ---- 1. chunk maxima of the first tile
-        uint32_t* my_cmax = a.cmax + (size_t)(q_ok ? q : 0) * a.ncols + blockIdx.x * 8;
-        ChunkTop trk;
-        trk.out = my_cmax;
-        trk.on = false;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) trk.v[i] = 0u;
         if (!band) {
+            // ---- 1. chunk maxima of the first tile (of every query tile: accumulator mt holds it)
             if (et == 0) MQVS_STAMP(0);
-            if (n_my > 0) {
-                mbar_wait(bar_tfull, 0);
-                tcgen05_fence_after();
-                if (et == 0) MQVS_STAMP(1);
-                tile_chunk_maxima(lane_taddr, first_tile * BN, a.n_rows, a.mask, trk.v);
-                if (q_ok) {
 #pragma unroll
-                    for (int ch = 0; ch < BN / 32; ++ch) my_cmax[ch] = trk.v[ch];
+            for (int mt = 0; mt < MT; ++mt) {
+                if (n_my > 0) {
+                    mbar_wait(bar_tfull + 8 * mt, 0);
+                    tcgen05_fence_after();
+                    if (et == 0 && mt == 0) MQVS_STAMP(1);
+                    tile_chunk_maxima(lane_taddr + mt * BN, first_tile * BN, a.n_rows, a.mask, trk[mt].v);
                 }
-            } else if (q_ok) {
+                if (q_ok[mt]) {
 #pragma unroll
-                for (int ch = 0; ch < BN / 32; ++ch) my_cmax[ch] = 0u;
+                    for (int ch = 0; ch < BN / 32; ++ch) trk[mt].out[ch] = trk[mt].v[ch];  // zeros when this CTA has no tile
+                }
             }
             __threadfence();
             epi_bar_sync();
             if (et == 0) { MQVS_STAMP(2); grid_arrive_and_wait(a.gbar + 0, G); MQVS_STAMP(3); }
             epi_bar_sync();
 
-            // ---- 2. CTA c: tau[c] = k'-th largest chunk maximum of query c
-            if (blockIdx.x < n_queries) {
-                const uint32_t t = kth_largest_u32(a.cmax + (size_t)blockIdx.x * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
-                if (et == 0) a.tau[blockIdx.x] = t > kOrdNegInf ? t : kOrdNegInf;
+            // ---- 2. CTA c: tau = k'-th largest chunk maximum, for its queries c (and c + G)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const uint32_t qo = blockIdx.x + j * G;
+                if (qo < n_queries) {
+                    const uint32_t t = kth_largest_u32(a.cmax + (size_t)qo * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
+                    if (et == 0) a.tau[qo] = t > kOrdNegInf ? t : kOrdNegInf;
+                }
             }
             __threadfence();
             epi_bar_sync();
             if (et == 0) { MQVS_STAMP(4); grid_arrive_and_wait(a.gbar + 1, G); MQVS_STAMP(5); }
             epi_bar_sync();
         }
-        float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
-        trk.mn = trk.v[0];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) trk.mn = min(trk.mn, trk.v[i]);
+        for (int mt = 0; mt < MT; ++mt) {
+            tau[mt] = q_ok[mt] ? ord_to_float(__ldcg(a.tau + q[mt])) : INFINITY;
+            trk[mt].mn = trk[mt].v[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) trk[mt].mn = min(trk[mt].mn, trk[mt].v[i]);
+        }
 
         // ---- 3. first tile again, now against tau, then the rest of this CTA's tiles
-        uint32_t w = 0;
-        for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G, ++w) {
-            const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
-            if (w > 0 || band) {  // (the first launch already waited for its first tile in step 1)
-                if (q_ok) tau = fmaxf(tau, ord_to_float(__ldcg(a.tau + q)));  // raised by list compactions anywhere
-                mbar_wait(bar_tfull + 8 * acc, acc_phase);
-                tcgen05_fence_after();
+        uint32_t w = 0, t_idx = 0;
+        for (uint32_t nt = first_tile; nt < a.n_tiles; nt += G, ++t_idx) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt, ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                if (t_idx > 0 || band) {  // (the first launch already waited for its first tile in step 1)
+                    if (q_ok[mt]) tau[mt] = fmaxf(tau[mt], ord_to_float(__ldcg(a.tau + q[mt])));  // raised by refreshes / compactions
+                    mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                    tcgen05_fence_after();
+                }
+                trk[mt].on = !band && t_idx > 0 && q_ok[mt];  // the first tile's chunks are already in trk
+                epilogue_tile<CAP, KPRIME, true>(lane_taddr + acc * BN, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024,
+                                                 a.tau + q[mt], lane, tau[mt], cnt[mt], lst[mt], &trk[mt]);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             }
-            trk.on = !band && w > 0 && q_ok;  // the first tile's chunks are already in trk
-            epilogue_tile<CAP, KPRIME, true>(lane_taddr + acc * BN, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024,
-                                             a.tau + q, lane, tau, cnt, lst, &trk);
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            // Threshold refresh after 2, 4, 8, ... tiles and after the last one: every (CTA, query) mirrors its 8 largest chunk maxima so far in
-            // cmax, so the k'-th largest of a query's G*8 slots is a valid threshold that tightens as the scan proceeds
-            // (a query then collects ~k' candidates per doubling of the rows scanned instead of k' N / (256 G)).  Slots are
-            // replaced one word at a time and a chunk is only ever written to one slot, so whatever mix of old and new
-            // values the reader sees, distinct slots are distinct chunks, i.e. distinct rows scoring at least that much.
-            if (!band && blockIdx.x < n_queries && w >= 1 && (((w + 1) & w) == 0 || w + 1 == n_my)) {
-                const uint32_t t = kth_largest_u32(a.cmax + (size_t)blockIdx.x * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
-                if (et == 0 && t > kOrdNegInf) atomicMax(a.tau + blockIdx.x, t);
+            // Threshold refresh after 2, 4, 8, ... tiles and after the last one: every (CTA, query) mirrors its 8 largest chunk
+            // maxima so far in cmax, so the k'-th largest of a query's G*8 slots is a valid threshold that tightens as the scan
+            // proceeds (a query then collects ~k' candidates per doubling of the rows scanned instead of k' N / (256 G)).
+            // Slots are replaced one word at a time and a chunk is only ever written to one slot, so whatever mix of old and
+            // new values the reader sees, distinct slots are distinct chunks, i.e. distinct rows scoring at least that much.
+            if (!band && t_idx >= 1 && (((t_idx + 1) & t_idx) == 0 || t_idx + 1 == n_my)) {
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    const uint32_t qo = blockIdx.x + j * G;
+                    if (qo < n_queries) {
+                        const uint32_t t = kth_largest_u32(a.cmax + (size_t)qo * a.ncols, (int)a.ncols, KPRIME, et, s_cnt);
+                        if (et == 0 && t > kOrdNegInf) atomicMax(a.tau + qo, t);
+                    }
+                }
             }
         }
-        if (q_ok) a.cnt[(size_t)blockIdx.x * BM + q] = cnt;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            if (q_ok[mt]) a.cnt[(size_t)blockIdx.x * kQ + q[mt]] = cnt[mt];
     }
 
     tcgen05_fence_before();
@@ -285,8 +362,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __threadfence();
     if (threadIdx.x == 0) { MQVS_STAMP(6); grid_arrive_and_wait(a.gbar + 2, G); MQVS_STAMP(7); }
     __syncthreads();
-    if (blockIdx.x >= n_queries) return;
-    fused_tail<T, CAP, KPRIME>(a, (int)G, smem_al);
+#pragma unroll 1
+    for (int j = 0; j < MT; ++j) {
+        const uint32_t slot = blockIdx.x + j * G;
+        if (slot < n_queries) fused_tail<T, CAP, KPRIME>(a, (int)G, smem_al, (int)slot, kQ);
+        __syncthreads();
+    }
 }
 
 // ---- tail of tc_fused_kernel: CTA c turns the G per-CTA lists of query c into the final top-k.
@@ -295,7 +376,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // order comes from ranking each exact key against the others (keys are unique: they embed the row id).  A sorting
 // network on one warp costs 10+ us here (single-warp issue latency); this tail is ~6 us at k = 10.
 template <typename T, int CAP, int KPRIME>
-__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al) {
+__device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al, const int slot, const int b_pad) {
     constexpr int NW = kThreads / 32;
     constexpr int kCcap = 1024;  // shortlist capacity of the direct path (>= 2 k' with room for ties)
     // the operand ring is idle now (every TMA load was consumed by an MMA that has retired): reuse it
@@ -306,12 +387,12 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
     int* fill_s = warp_tot + NW;
     int* valid_s = fill_s + 1;
     const bool band = a.band_list != nullptr;
-    const int slot = blockIdx.x;                                  // operand row / TMEM lane of this CTA's query
+    // slot = operand row / (query tile, TMEM lane) of the query this call finishes; b_pad = slots per CTA in lists / cnt
     const int qf = band ? (int)__ldcg(a.band_list + slot) : slot;   // the query it is
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // list lengths -> exclusive prefix sum (one list per thread)
-    const int mine = tid < G ? min((int)__ldcg(a.cnt + (size_t)tid * BM + slot), CAP) : 0;
+    const int mine = tid < G ? min((int)__ldcg(a.cnt + (size_t)tid * b_pad + slot), CAP) : 0;
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -340,7 +421,7 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
             const int mid = (lo + hi) >> 1;
             if (pre_s[mid] <= idx) lo = mid; else hi = mid;
         }
-        const uint64_t key = __ldcg(a.lists + ((size_t)lo * BM + slot) * CAP + (idx - pre_s[lo]));
+        const uint64_t key = __ldcg(a.lists + ((size_t)lo * b_pad + slot) * CAP + (idx - pre_s[lo]));
         if ((uint32_t)(key >> 32) >= tq) {
             const int slot = atomicAdd(fill_s, 1);
             if (slot < kCcap) C[slot] = key;
@@ -353,7 +434,7 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
         // far more survivors than k' (hundreds of exact ties, adversarial orderings): the general streaming selection
         // picks the k' best approximate keys; its k'-th key then bounds everything it left out
         __syncthreads();
-        select_lists_body<kThreads>(a.lists, a.cnt, G, BM, CAP, KPRIME, nullptr, slot, C, pre_s, warp_tot, fill_s);
+        select_lists_body<kThreads>(a.lists, a.cnt, G, b_pad, CAP, KPRIME, nullptr, slot, C, pre_s, warp_tot, fill_s);
         if (C[KPRIME - 1]) tq = max(tq, (uint32_t)(C[KPRIME - 1] >> 32));
         nC = KPRIME;
     }
@@ -545,16 +626,16 @@ prep_band_kernel(const float* __restrict__ qn, const uint32_t* __restrict__ flag
 }
 
 bool fused_ok(int B, int k, int sm_count) {
-    // one query tile; one list / 8 chunk maxima per CTA must fit select_lists_body<192> and kth_largest_u32 (1280 values);
-    // CTA c finishes query c, so there must be at least B CTAs
-    return B >= 1 && B <= BM && k <= 128 && sm_count >= BM && sm_count <= 160;
+    // one or two query tiles (the two TMEM accumulators); one list / 8 chunk maxima per CTA must fit
+    // select_lists_body<192> and kth_largest_u32 (1280 values); CTA c finishes queries c and c + G, so 2 G >= B
+    return B >= 1 && B <= 2 * BM && k <= 128 && sm_count >= BM && sm_count <= 160;
 }
 size_t cmax_bytes(const Plan& p) { return (size_t)p.b_pad * p.grid * 8 * sizeof(uint32_t); }
 
 namespace {
-template <typename T, int KP>
+template <typename T, int KP, int MT>
 cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const FusedArgs& a, int grid, cudaStream_t st) {
-    auto kern = tc_fused_kernel<T, 512, KP>;
+    auto kern = tc_fused_kernel<T, 512, KP, MT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&mq, (void*)&mx, (void*)&a};
@@ -568,15 +649,16 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
                          int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused) {
     CUtensorMap mq, mx;
     *coop_refused = false;
-    if (!make_map(&mq, b.q_op, (uint64_t)BM, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
+    const int rows_q = p.b_pad;  // 128 or 256 operand rows
+    if (!make_map(&mq, b.q_op, (uint64_t)rows_q, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
     g_trace.mark("begin", st);
     const int vec4 = (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0;
     if (dtype == MQVS_F32)
-        prep_fused_kernel<float><<<BM / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (float*)b.q_op, b.eps, b.tau, b.gbar,
+        prep_fused_kernel<float><<<rows_q / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (float*)b.q_op, b.eps, b.tau, b.gbar,
                                                          b.flag_count, bad_epoch, epoch);
     else
-        prep_fused_kernel<__nv_bfloat16><<<BM / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (__nv_bfloat16*)b.q_op, b.eps, b.tau,
+        prep_fused_kernel<__nv_bfloat16><<<rows_q / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (__nv_bfloat16*)b.q_op, b.eps, b.tau,
                                                                  b.gbar, b.flag_count, bad_epoch, epoch);
     g_trace.mark("prep", st);
     FusedArgs a{};
@@ -606,10 +688,15 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     a.dbg = g_trace.on ? g_trace.fused_dbg(p.grid) : nullptr;
     if (a.dbg) cudaMemsetAsync(a.dbg, 0, 256 * 16 * sizeof(unsigned long long), st);
     cudaError_t e = cudaSuccess;
-#define MQVS_TCF(KP_)                                                                          \
-    if (p.kprime == KP_)                                                                       \
-        e = dtype == MQVS_F32 ? launch_fused<float, KP_>(mq, mx, a, p.grid, st)                \
-                              : launch_fused<__nv_bfloat16, KP_>(mq, mx, a, p.grid, st);
+#define MQVS_TCF(KP_)                                                                                                  \
+    if (p.kprime == KP_) {                                                                                             \
+        if (rows_q <= BM)                                                                                              \
+            e = dtype == MQVS_F32 ? launch_fused<float, KP_, 1>(mq, mx, a, p.grid, st)                                 \
+                                  : launch_fused<__nv_bfloat16, KP_, 1>(mq, mx, a, p.grid, st);                        \
+        else                                                                                                           \
+            e = dtype == MQVS_F32 ? launch_fused<float, KP_, 2>(mq, mx, a, p.grid, st)                                 \
+                                  : launch_fused<__nv_bfloat16, KP_, 2>(mq, mx, a, p.grid, st);                        \
+    }
     MQVS_TCF(32)
     MQVS_TCF(64)
     MQVS_TCF(128)
@@ -672,8 +759,8 @@ const char* search_band(const Buffers& b, const Plan& p, const void* rows, int d
     cudaError_t e = cudaSuccess;
 #define MQVS_TCF(KP_)                                                                          \
     if (p.kprime == KP_)                                                                       \
-        e = dtype == MQVS_F32 ? launch_fused<float, KP_>(mq, mx, a, p.grid, st)                \
-                              : launch_fused<__nv_bfloat16, KP_>(mq, mx, a, p.grid, st);
+        e = dtype == MQVS_F32 ? launch_fused<float, KP_, 1>(mq, mx, a, p.grid, st)             \
+                              : launch_fused<__nv_bfloat16, KP_, 1>(mq, mx, a, p.grid, st);
     MQVS_TCF(32)
     MQVS_TCF(64)
     MQVS_TCF(128)

@@ -296,11 +296,15 @@ TC_CASES = [
     (37000, "bf16", 128, 10, None),       # fewer corpus tiles (145) than CTAs: some CTAs own no tile at all
     (200001, "fp32", 7, 1, 0.02),         # k = 1, ragged tail, sparse mask
     (151552, "bf16", 96, 100, None),      # exactly 4 tiles per CTA (148 x 4 x 256 rows), k' = 256
+    (100003, "bf16", 256, 100, None),     # two query tiles in the single-launch kernel, both full
+    (70000, "fp32", 200, 10, 0.3),        # two query tiles, the second ragged, with a mask
+    (300000, "bf16", 129, 10, None),      # one query in the second tile
+    (20000, "fp32", 160, 32, None),       # fewer corpus tiles (79) than CTAs, two query tiles
 ]
 
 
-# path 2 = tensor-core path (single cooperative launch for B <= 128, segmented pipeline above); 4 = always segmented
-TC_CASES_PATHS = [c + (2,) for c in TC_CASES] + [c + (4,) for c in TC_CASES if c[2] <= 128]
+# path 2 = tensor-core path (single cooperative launch for B <= 256, segmented pipeline above); 4 = always segmented
+TC_CASES_PATHS = [c + (2,) for c in TC_CASES] + [c + (4,) for c in TC_CASES if c[2] <= 256]
 
 
 @pytest.mark.parametrize("n,dtype,B,k,frac,path", TC_CASES_PATHS)
@@ -774,13 +778,13 @@ def test_full_size_config4_shard_and_config5_filter_properties(gpu):
         assert np.array_equal(fi[b][:keep.shape[0]], keep)
 
 
-@pytest.mark.parametrize("dtype,B", [("bf16", 64), ("fp32", 20), ("bf16", 300)])
+@pytest.mark.parametrize("dtype,B", [("bf16", 64), ("fp32", 20), ("bf16", 200), ("bf16", 300)])
 def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, B):
     """Clustered corpus (2000-member clusters at cosine 0.98 to their centre): the scores around rank k are closer
     together than the tensor-core error bound, so the margin check flags (nearly) every query.  The band pass -- one more
     tensor-core pass that collects and rescoring every row within eps of the k-th exact score -- must settle them all:
     bit-identical to the oracle, band_repairs > 0, and no query left for the exact scan.  B = 300 goes through the
-    segmented pipeline first (3 query tiles), B <= 128 through the single-launch one."""
+    segmented pipeline first (3 query tiles), B <= 256 through the single-launch one (one or two query tiles)."""
     n, members, k = 200_000, 2000, 10
     rng = np.random.default_rng(0)
     sigma = np.sqrt((1.0 / 0.98 ** 2 - 1.0) / 256.0)
@@ -798,7 +802,7 @@ def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, 
     stats = idx.stats()
     assert_bit_equal(s, i, es, ei)
     assert stats["band_repairs"] >= min(B, 128) // 2 and stats["exact_fallbacks"] == 0, stats
-    if B <= 128:                                   # the same through the all-device call (what the sharded path uses)
+    if B <= 256:                                   # the same through the all-device call (what the sharded path uses)
         import torch
         idx.set_path(2)
         before = idx.stats()["band_repairs"]
