@@ -33,6 +33,9 @@ extern "C" {
 enum { MQVS_OK = 0, MQVS_E_INVALID = -1, MQVS_E_CUDA = -2, MQVS_E_NCCL = -3, MQVS_E_OOM = -4, MQVS_E_IO = -5 };
 enum { MQVS_F32 = 0, MQVS_BF16 = 1 };
 
+/* Chroma's `hnsw:space` (collection_metadata; the reference passes none, so upstream it is "l2" -- src/medical_engine.py:52) */
+enum { MQVS_METRIC_COSINE = 0, MQVS_METRIC_L2 = 1, MQVS_METRIC_IP = 2 };
+
 /* widest embedding the kernels are built for; rows are zero-padded to MQVS_DIM_PAD elements in HBM
  * (768 = width of shaw/dmeta-embedding-zh, src/medical_engine.py:43) */
 #define MQVS_DIM_PAD 768
@@ -161,6 +164,23 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path);
  * rows (re-running ingest appends -- src/ingest_medical.py:106 on an existing ./medical_db); first_row = 0 rewrites. */
 MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row);
 MQVS_API int mqvs_load(mqvs_t* s, const char* path);
+
+/* collection_metadata={"hnsw:space": ...} -- the space rows are RANKED in when the raw vectors given to mqvs_add are not
+ * unit vectors (on unit vectors the three spaces order rows identically and MQVS_METRIC_COSINE, the default, serves all
+ * of them).  Rows are always stored normalised; with MQVS_METRIC_L2 / MQVS_METRIC_IP the store also keeps ||x|| of every
+ * raw row (4 bytes per row, written by K1, saved to `<path>.norms` by mqvs_save) and the scan maps the cosine s of the
+ * normalised pair to the space's ranking score before top-k (larger = better in every space):
+ *     cosine: s            ip: ||x|| s = <q, x> / ||q||            l2: ||x|| s - ||x||^2 / (2 ||q||) = (||q||^2 - ||q - x||^2) / (2 ||q||)
+ * out_scores of mqvs_search hold that ranking score; the caller converts to Chroma's distances with its ||q||
+ * (ip: 1 - ||q|| t; l2: ||q||^2 - 2 ||q|| t).  Norms are kept from the first call with a non-cosine metric on, so that
+ * call must come while the store is empty; afterwards the metric may be switched freely (e.g. back to
+ * MQVS_METRIC_COSINE while every row is a unit vector, see mqvs_norm_deviation).  Non-cosine metrics run on the exact
+ * SIMT scan (one corpus pass per 1-4 queries). */
+MQVS_API int mqvs_set_metric(mqvs_t* s, int metric);
+/* largest | ||x|| - 1 | over the raw rows added (or loaded with their norms) so far: 0 for a collection of exact unit vectors */
+MQVS_API int mqvs_norm_deviation(mqvs_t* s, float* out);
+/* ||x|| of raw rows [first_row, first_row + n) as stored by K1 (needs a non-cosine metric set before the rows were added) */
+MQVS_API int mqvs_get_norms(mqvs_t* s, uint64_t first_row, uint64_t n, float* out_host);
 
 MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);
 /* 0 = choose by batch size, 1 = force the SIMT fp32 scan, 2 = force the tensor-core path,

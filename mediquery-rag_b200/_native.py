@@ -16,6 +16,7 @@ F32, BF16 = 0, 1
 DIM_PAD = 768
 MAX_K = 1024
 DTYPES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16}
+METRICS = {"cosine": 0, "l2": 1, "ip": 2}  # Chroma's hnsw:space -> MQVS_METRIC_*
 
 
 class FilterOp(ctypes.Structure):
@@ -79,6 +80,9 @@ SIGNATURES = {
     "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
+    "mqvs_set_metric": (_i, [_vp, _i]),
+    "mqvs_norm_deviation": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "mqvs_get_norms": (_i, [_vp, _u64, _u64, _vp]),
     "mqvs_column_set": (_i, [_vp, _i, _i, _vp, _vp, _u64]),
     "mqvs_filter_build": (_i, [_vp, _vp, _i, _vp, _u64, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
@@ -138,6 +142,7 @@ class Index:
         self.dim = int(dim)
         self.store_dtype = store_dtype
         self.device = int(device)
+        self.metric = "cosine"
         dev = (_i * 1)(self.device)
         check(load().mqvs_create(1, dev, self.dim, DTYPES[store_dtype], int(capacity_rows), ctypes.byref(self._h)))
 
@@ -261,6 +266,24 @@ class Index:
 
     def set_path(self, path: int) -> None:
         check(load().mqvs_set_path(self._h, int(path)))
+
+    def set_metric(self, space: str) -> None:
+        """Space the rows are ranked in ("cosine" | "l2" | "ip"); a non-cosine space must first be chosen while the
+        index is empty (row norms are kept from then on).  Scores of later searches are that space's ranking score."""
+        check(load().mqvs_set_metric(self._h, METRICS[space]))
+        self.metric = space
+
+    def norm_deviation(self) -> float:
+        """Largest | ||x|| - 1 | over the raw rows added so far (0: every row was a unit vector)."""
+        d = ctypes.c_float(0.0)
+        check(load().mqvs_norm_deviation(self._h, ctypes.byref(d)))
+        return float(d.value)
+
+    def get_norms(self, first_row: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = len(self) - int(first_row) if n is None else int(n)
+        out = np.empty(max(n, 0), np.float32)
+        check(load().mqvs_get_norms(self._h, int(first_row), n, _ptr(out)))
+        return out
 
 
 def merge_candidates(device: int, scores, ids, out_scores, out_ids, stream: int = 0) -> None:

@@ -88,6 +88,11 @@ struct mqvs_store {
     int path = 0;
     void* rows = nullptr;
     uint64_t n = 0, cap = 0;
+    // l2 / ip spaces over raw vectors (mqvs_set_metric): ||x|| per row, kept from the first non-cosine metric on
+    int metric = MQVS_METRIC_COSINE;
+    bool keep_norms = false;
+    float* norms = nullptr;   // [cap] when keep_norms
+    float norm_dev = 0.0f;    // largest | ||x|| - 1 | over the rows accepted so far
     cudaStream_t st = nullptr;
     // ring of event quads so that back-to-back async searches never wait on each other's timing
     static constexpr int kEvRing = 32;
@@ -96,7 +101,7 @@ struct mqvs_store {
         bool pending = false;
     } evr[kEvRing];
     int ev_cursor = 0;
-    DevBuf stage, qraw, qn, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
+    DevBuf stage, qraw, qn, qnorm, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
     DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
     static constexpr int kMaxDeviceFix = 64;             // flagged queries repaired on the device per search
     uint32_t* fix_dev = nullptr;                         // [kMaxDeviceFix] list + [1] count
@@ -107,7 +112,8 @@ struct mqvs_store {
     mqvs::tc::Buffers last_b{};                          // scratch layout + plan of the last tensor-core search: the
     mqvs::tc::Plan last_plan{};                          // blocking call enqueues its repair only after it has seen flags
     unsigned long long* bad_dev = nullptr;   // [0] = non-finite rows counted by K1, [1] = epoch of the last fused
-    unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits)
+    unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits),
+                                             // [2] = bits of the largest | ||x|| - 1 | of the current mqvs_add (low 32 bits)
     unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
     unsigned int epoch = 0;                  // id of the last fused search
     // latency path with host outputs: the kernel writes results + status straight into this mapped pinned block
@@ -153,16 +159,29 @@ int grow(mqvs_store* s, uint64_t need_rows) {
         return fail(MQVS_E_OOM, "cudaMalloc of %llu rows (%.2f GB) failed: %s", (unsigned long long)want,
                     want * s->row_bytes() / 1e9, cudaGetErrorString(e));
     }
+    float* fresh_norms = nullptr;
+    if (s->keep_norms && cudaMalloc(&fresh_norms, want * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(fresh);
+        return fail(MQVS_E_OOM, "cudaMalloc of %llu row norms failed", (unsigned long long)want);
+    }
     cudaError_t ce = cudaSuccess;
     if (s->n) ce = cudaMemcpyAsync(fresh, s->rows, s->n * s->row_bytes(), cudaMemcpyDeviceToDevice, s->st);
+    if (ce == cudaSuccess && s->n && fresh_norms)
+        ce = cudaMemcpyAsync(fresh_norms, s->norms, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->st);
     if (ce != cudaSuccess) {
         cudaGetLastError();
         cudaFree(fresh);
+        if (fresh_norms) cudaFree(fresh_norms);
         return fail(MQVS_E_CUDA, "moving %llu rows to the larger allocation failed: %s", (unsigned long long)s->n, cudaGetErrorString(ce));
     }
     if (s->rows) cudaFree(s->rows);
     s->rows = fresh;
+    if (fresh_norms) {
+        if (s->norms) cudaFree(s->norms);
+        s->norms = fresh_norms;
+    }
     s->cap = want;
     return MQVS_OK;
 }
@@ -189,6 +208,7 @@ void settle_events(mqvs_store* s) {
 
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
 bool use_tensor_path(const mqvs_store* s, int B, int k) {
+    if (s->metric != MQVS_METRIC_COSINE) return false;  // l2 / ip over raw vectors: exact SIMT scan (kernels_scan.cu)
     if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2 || s->path == 4) return true;
@@ -217,8 +237,13 @@ int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev,
     for (int b = 0; b < nb;) {
         int nq = 0, grid = 0;
         scan_plan(s->dtype, nb - b, k, s->sm_count, &nq, &grid);
-        launch_scan_simt(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)(b0 + b) * MQVS_DIM_PAD, nq,
-                         mask_dev, k, (uint64_t*)s->cand.p + (size_t)b * gmax * k, gmax, grid, st);
+        if (s->metric != MQVS_METRIC_COSINE)
+            launch_scan_simt_metric(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)(b0 + b) * MQVS_DIM_PAD, nq,
+                                    mask_dev, k, (uint64_t*)s->cand.p + (size_t)b * gmax * k, gmax, grid, s->metric, s->norms,
+                                    (const float*)s->qnorm.p + (b0 + b), st);
+        else
+            launch_scan_simt(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p + (size_t)(b0 + b) * MQVS_DIM_PAD, nq,
+                             mask_dev, k, (uint64_t*)s->cand.p + (size_t)b * gmax * k, gmax, grid, st);
         b += nq;
         ++passes;
     }
@@ -268,7 +293,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
     const bool tensor = use_tensor_path(s, B, k);
-    const bool fused = !tensor && s->path != 3 && scan_fused_ok(B, k);
+    const bool fused = !tensor && s->path != 3 && s->metric == MQVS_METRIC_COSINE && scan_fused_ok(B, k);
     s->last_fused = fused;
     tc::Plan plan{};
     int rc;
@@ -308,6 +333,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if ((rc = s->tc_cmax.ensure(tc::cmax_bytes(plan))) != MQVS_OK) return rc;
     }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
+    if (s->metric != MQVS_METRIC_COSINE && (rc = s->qnorm.ensure((size_t)B * sizeof(float))) != MQVS_OK) return rc;
 
     tc::Buffers b{};
     if (tensor) {
@@ -374,7 +400,8 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
 
     CU(cudaEventRecord(ev[0], st));
     CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
-    launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st);
+    launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st,
+                     s->metric != MQVS_METRIC_COSINE ? (float*)s->qnorm.p : nullptr);
     s->stats.kernel_launches += 1;
     uint32_t passes = 0;
     if (tensor) {
@@ -457,12 +484,12 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     for (auto& set : s->evr)
         for (auto& e : set.e)
             if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "event creation failed"));
-    if (cudaMalloc(&s->bad_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(s->bad_dev, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc(&s->bad_dev, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->bad_dev, 0, 3 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&s->ticket_dev, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(s->ticket_dev, 0, sizeof(unsigned int)) != cudaSuccess)
         return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
-    if (cudaMallocHost(&s->bad_host, 2 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
+    if (cudaMallocHost(&s->bad_host, 3 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
     if (cudaHostAlloc((void**)&s->host_out, 64 * 4 + 64 * 8 + 16, cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         s->host_out = nullptr;  // not fatal: the latency path copies its results back instead
@@ -492,13 +519,14 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     for (DevBuf* b : {&s->f_table, &s->f_prog, &s->f_pool, &s->f_live, &s->f_mask}) b->release();
     if (s->f_count_dev) cudaFree(s->f_count_dev);
     if (s->f_count_host) cudaFreeHost(s->f_count_host);
-    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
+    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->qnorm, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
                       &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand, &s->tc_cmax})
         b->release();
     if (s->fix_dev) cudaFree(s->fix_dev);
     if (s->fix_counters) cudaFree(s->fix_counters);
     if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->rows) cudaFree(s->rows);
+    if (s->norms) cudaFree(s->norms);
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->ticket_dev) cudaFree(s->ticket_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
@@ -536,13 +564,16 @@ static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uin
     int rc = grow(s, s->n + n);
     if (rc != MQVS_OK) return rc;
     char* dst = (char*)s->rows + s->n * s->row_bytes();
+    float* norms_dst = s->keep_norms ? s->norms + s->n : nullptr;
+    unsigned int* dev_word = (unsigned int*)(s->bad_dev + 2);
     CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), s->st));
+    CU(cudaMemsetAsync(s->bad_dev + 2, 0, sizeof(unsigned long long), s->st));
     uint64_t launches = 0;
     if (synth) {
-        launch_synth_normalize(seed, first_index, n, s->dim, s->dtype, dst, s->bad_dev, s->st);
+        launch_synth_normalize(seed, first_index, n, s->dim, s->dtype, dst, s->bad_dev, s->st, norms_dst, dev_word);
         launches = 1;
     } else if (x_is_device) {
-        launch_normalize((const float*)x, n, s->dim, s->dtype, dst, s->bad_dev, s->st);
+        launch_normalize((const float*)x, n, s->dim, s->dtype, dst, s->bad_dev, s->st, norms_dst, dev_word);
         launches = 1;
     } else {
         const uint64_t chunk = 65536;
@@ -551,18 +582,25 @@ static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uin
             uint64_t m = std::min(chunk, n - r);
             CU(cudaMemcpyAsync(s->stage.p, (const float*)x + r * s->dim, (size_t)m * s->dim * sizeof(float),
                                cudaMemcpyHostToDevice, s->st));
-            launch_normalize((const float*)s->stage.p, m, s->dim, s->dtype, dst + r * s->row_bytes(), s->bad_dev, s->st);
+            launch_normalize((const float*)s->stage.p, m, s->dim, s->dtype, dst + r * s->row_bytes(), s->bad_dev, s->st,
+                             norms_dst ? norms_dst + r : nullptr, dev_word);
             CU(cudaStreamSynchronize(s->st));  // staging buffer is reused
             ++launches;
         }
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     s->stats.kernel_launches += launches;
     if (*s->bad_host)
         return fail(MQVS_E_INVALID, "%llu of %llu embeddings have a non-finite norm; nothing was added",
                     *s->bad_host, (unsigned long long)n);
+    {
+        const uint32_t bits = (uint32_t)s->bad_host[2];
+        float dev;
+        memcpy(&dev, &bits, 4);
+        s->norm_dev = std::max(s->norm_dev, dev);
+    }
     s->n += n;
     s->stats.rows = s->n;
     return MQVS_OK;
@@ -613,7 +651,7 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     // latency path (B <= 4, k <= 16, the reference's own regime) with host outputs: results and status are written by the
     // kernel into mapped pinned memory -- the call is one H2D copy of the queries, one launch, one stream sync
     const bool zero_copy = !out_is_device && s->host_out != nullptr && !use_tensor_path(s, B, k) && s->path != 3 &&
-                           mqvs::scan_fused_ok(B, k);
+                           s->metric == MQVS_METRIC_COSINE && mqvs::scan_fused_ok(B, k);
     if (zero_copy) {
         os = (float*)s->host_out;
         oi = (int64_t*)(s->host_out + 64 * 4);
@@ -741,6 +779,51 @@ struct FileHeader {
     uint32_t version, dim, dtype, dim_pad;
     uint64_t rows;
 };
+struct NormsHeader {
+    char magic[8];
+    uint64_t rows;
+};
+
+// `<path>.norms`: ||x|| of every raw row, rewritten whole (4 bytes per row) through a temporary + rename
+int save_norms(mqvs_store* s, const char* path) {
+    if (!s->keep_norms) return MQVS_OK;
+    std::vector<float> host((size_t)std::max<uint64_t>(s->n, 1));
+    if (s->n) CU(cudaMemcpy(host.data(), s->norms, s->n * sizeof(float), cudaMemcpyDeviceToHost));
+    const std::string dst = std::string(path) + ".norms", tmp = dst + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(MQVS_E_IO, "cannot open %s for writing", tmp.c_str());
+    NormsHeader h{};
+    memcpy(h.magic, "MQVSNRM1", 8);
+    h.rows = s->n;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(host.data(), sizeof(float), (size_t)s->n, f) == (size_t)s->n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), dst.c_str()) != 0) {
+        remove(tmp.c_str());
+        return fail(MQVS_E_IO, "writing %s failed", dst.c_str());
+    }
+    return MQVS_OK;
+}
+
+// after the rows: norms of rows [0, rows) back into HBM, deviation recomputed
+int load_norms(mqvs_store* s, const char* path, uint64_t rows) {
+    if (!s->keep_norms) return MQVS_OK;
+    const std::string src = std::string(path) + ".norms";
+    FILE* f = fopen(src.c_str(), "rb");
+    if (!f)
+        return fail(MQVS_E_IO, "%s is missing: the collection was saved without row norms (cosine space) and cannot be "
+                               "opened in the l2 / ip space", src.c_str());
+    NormsHeader h{};
+    std::vector<float> host((size_t)std::max<uint64_t>(rows, 1));
+    const bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "MQVSNRM1", 8) == 0 && h.rows >= rows &&
+                    fread(host.data(), sizeof(float), (size_t)rows, f) == (size_t)rows;
+    fclose(f);
+    if (!ok) return fail(MQVS_E_IO, "%s does not hold the norms of %llu rows", src.c_str(), (unsigned long long)rows);
+    if (rows) CU(cudaMemcpy(s->norms, host.data(), rows * sizeof(float), cudaMemcpyHostToDevice));
+    float dev = 0.0f;
+    for (uint64_t r = 0; r < rows; ++r) dev = std::max(dev, fabsf(host[r] - 1.0f));
+    s->norm_dev = dev;
+    return MQVS_OK;
+}
 }  // namespace
 
 MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
@@ -771,6 +854,13 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
         ok = fwrite(host.data(), s->row_bytes(), m, f) == m;
     }
     ok = (fclose(f) == 0) && ok;
+    if (ok) {  // norms first: a row file is never newer than its norms
+        int rc = save_norms(s, path);
+        if (rc != MQVS_OK) {
+            remove(tmp.c_str());
+            return rc;
+        }
+    }
     if (!ok || rename(tmp.c_str(), path) != 0) {
         remove(tmp.c_str());
         return fail(MQVS_E_IO, "writing %s failed", path);
@@ -807,6 +897,13 @@ MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
             return fail(MQVS_E_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
         }
         ok = fwrite(host.data(), s->row_bytes(), m, f) == m;
+    }
+    if (ok) {  // holds the norms of MORE rows than the header claims until the count below moves: load accepts that
+        int rc = save_norms(s, path);
+        if (rc != MQVS_OK) {
+            fclose(f);
+            return rc;
+        }
     }
     // the row count in the header moves last: a crash before this leaves the old, consistent file (plus ignored bytes)
     h.rows = s->n;
@@ -852,6 +949,7 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
         }
     }
     fclose(f);
+    if ((rc = load_norms(s, path, h.rows)) != MQVS_OK) return rc;
     s->n = h.rows;
     s->stats.rows = s->n;
     return MQVS_OK;
@@ -972,6 +1070,49 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
     s->stats.exact_fallbacks = c[0] + s->host_fallbacks;  // async callers: c[1] - host_fallbacks queries stayed unrepaired
     s->stats.unrepaired = c[1] > s->host_fallbacks ? c[1] - s->host_fallbacks : 0;
     *out = s->stats;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_set_metric(mqvs_t* s, int metric) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (metric != MQVS_METRIC_COSINE && metric != MQVS_METRIC_L2 && metric != MQVS_METRIC_IP)
+        return fail(MQVS_E_INVALID, "unknown metric %d", metric);
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (metric != MQVS_METRIC_COSINE && !s->keep_norms) {
+        if (s->n)
+            return fail(MQVS_E_INVALID, "the %llu rows already stored were added without their norms: choose the l2 / ip "
+                                        "metric while the store is empty", (unsigned long long)s->n);
+        CU(cudaSetDevice(s->dev));
+        if (s->cap && cudaMalloc(&s->norms, s->cap * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            s->norms = nullptr;
+            return fail(MQVS_E_OOM, "cudaMalloc of %llu row norms failed", (unsigned long long)s->cap);
+        }
+        s->keep_norms = true;
+    }
+    s->metric = metric;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_norm_deviation(mqvs_t* s, float* out) {
+    if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    *out = s->norm_dev;
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_get_norms(mqvs_t* s, uint64_t first_row, uint64_t n, float* out_host) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (n == 0) return MQVS_OK;
+    if (!out_host) return fail(MQVS_E_INVALID, "NULL buffer");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->keep_norms) return fail(MQVS_E_INVALID, "norms are kept only for the l2 / ip metrics (mqvs_set_metric)");
+    if (first_row > s->n || n > s->n - first_row)
+        return fail(MQVS_E_INVALID, "rows [%llu, %llu) out of range [0, %llu)", (unsigned long long)first_row,
+                    (unsigned long long)(first_row + n), (unsigned long long)s->n);
+    CU(cudaSetDevice(s->dev));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemcpy(out_host, s->norms + first_row, n * sizeof(float), cudaMemcpyDeviceToHost));
     return MQVS_OK;
 }
 

@@ -131,10 +131,13 @@ __device__ __forceinline__ void load_lane_share(const float* p, int dim, bool ve
 }
 // K1's arithmetic on a lane share (whole warp participates): v <- v / max(||v||, eps) in the canonical order.
 // Returns false (and zeroes v) when the squared norm is not finite.
-__device__ __forceinline__ bool normalize_lane_share(float4 (&v)[kChunks]) {
+// *norm_out (optional) receives ||v|| as K1 computed it (0 for a non-finite row).
+__device__ __forceinline__ bool normalize_lane_share(float4 (&v)[kChunks], float* norm_out = nullptr) {
     const float ss = warp_butterfly_sum(lane_dot(v, v));
     const bool ok = isfinite(ss);
-    const float inv = ok ? __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ss), kEps)) : 0.0f;
+    const float nrm = ok ? __fsqrt_rn(ss) : 0.0f;
+    if (norm_out != nullptr) *norm_out = nrm;
+    const float inv = ok ? __fdiv_rn(1.0f, fmaxf(nrm, kEps)) : 0.0f;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         v[c].x = ok ? __fmul_rn(v[c].x, inv) : 0.0f;
@@ -143,6 +146,18 @@ __device__ __forceinline__ bool normalize_lane_share(float4 (&v)[kChunks]) {
         v[c].w = ok ? __fmul_rn(v[c].w, inv) : 0.0f;
     }
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------------- metrics
+// Ranking score of a stored row under the collection's space (mqvs_set_metric; oracle/canonical.c:orc_rank_score
+// restates it operation by operation).  s = canonical cosine of the normalised query and the normalised row,
+// a = ||x|| of the raw row as K1 measured it, h = 0.5 / max(||q||, eps):
+//   cosine: s          ip: a*s  (= <q, x> / ||q||)          l2: a*s - a*a*h  (= (||q||^2 - ||q - x||^2) / (2 ||q||))
+// Larger is better in every space, so the top-k machinery is the same.
+__device__ __forceinline__ float rank_score(int metric, float s, float a, float h) {
+    if (metric == MQVS_METRIC_IP) return __fmul_rn(a, s);
+    if (metric == MQVS_METRIC_L2) return __fmaf_rn(a, s, -__fmul_rn(__fmul_rn(a, a), h));
+    return s;
 }
 
 // ---------------------------------------------------------------------------------------------- sort

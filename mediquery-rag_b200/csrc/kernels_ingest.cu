@@ -49,14 +49,19 @@ struct SynthSource {
 
 template <typename Source, typename OutT>
 __global__ void __launch_bounds__(kIngestWarps * 32)
-normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned long long* __restrict__ bad) {
+normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned long long* __restrict__ bad,
+                      float* __restrict__ norms, unsigned int* __restrict__ max_dev) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps_total = (uint64_t)gridDim.x * kIngestWarps;
+    float dev_max = 0.0f;  // largest | ||x|| - 1 | this warp has seen
     for (uint64_t row = (uint64_t)blockIdx.x * kIngestWarps + (threadIdx.x >> 5); row < n; row += warps_total) {
         float4 v[kChunks];
         src.load(row, lane, v);
-        const bool ok = normalize_lane_share(v);
+        float nrm;
+        const bool ok = normalize_lane_share(v, &nrm);
         if (!ok && lane == 0) atomicAdd(bad, 1ull);
+        if (norms != nullptr && lane == 0) norms[row] = nrm;
+        dev_max = fmaxf(dev_max, fabsf(nrm - 1.0f));
         OutT* o = out + row * (uint64_t)kDim;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
@@ -73,17 +78,21 @@ normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned l
             }
         }
     }
+    // non-negative floats order like their bit patterns: one atomicMax per warp per launch
+    if (max_dev != nullptr && lane == 0 && dev_max > 0.0f) atomicMax(max_dev, __float_as_uint(dev_max));
 }
 
 template <typename Source>
-void launch_k1(Source src, uint64_t n, int out_dtype, void* out, unsigned long long* bad, cudaStream_t st) {
+void launch_k1(Source src, uint64_t n, int out_dtype, void* out, unsigned long long* bad, float* norms,
+               unsigned int* max_dev, cudaStream_t st) {
     if (n == 0) return;
     uint64_t blocks = (n + kIngestWarps - 1) / kIngestWarps;
     int grid = (int)(blocks < 148ull * 16 ? blocks : 148ull * 16);
     if (out_dtype == MQVS_F32)
-        normalize_pack_kernel<Source, float><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (float*)out, bad);
+        normalize_pack_kernel<Source, float><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (float*)out, bad, norms, max_dev);
     else
-        normalize_pack_kernel<Source, __nv_bfloat16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (__nv_bfloat16*)out, bad);
+        normalize_pack_kernel<Source, __nv_bfloat16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, (__nv_bfloat16*)out, bad,
+                                                                                         norms, max_dev);
 }
 
 template <typename T>
@@ -98,15 +107,15 @@ __global__ void gather_rows_kernel(const T* __restrict__ rows, const int64_t* __
 }  // namespace
 
 void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* norms, unsigned int* max_dev) {
     MemSource src{x, dim, (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)};
-    launch_k1(src, n, out_dtype, out, bad, st);
+    launch_k1(src, n, out_dtype, out, bad, norms, max_dev, st);
 }
 
 void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int dim, int out_dtype, void* out,
-                            unsigned long long* bad, cudaStream_t st) {
+                            unsigned long long* bad, cudaStream_t st, float* norms, unsigned int* max_dev) {
     SynthSource src{seed, first_index, dim};
-    launch_k1(src, n, out_dtype, out, bad, st);
+    launch_k1(src, n, out_dtype, out, bad, norms, max_dev, st);
 }
 
 void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,

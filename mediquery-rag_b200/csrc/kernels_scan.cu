@@ -59,9 +59,19 @@ struct TopK {
 
 // The row walk shared by every SIMT kernel: warp `gw` of `warps_total` visits groups of U consecutive rows in
 // ascending order, scores them against the QB register-resident queries and offers them to the warp's top-k lists.
-template <typename T, int QB, int KPL, int U>
+// l2 / ip spaces over the raw vectors (mqvs_set_metric): the cosine of the normalised pair is mapped to the space's
+// ranking score with the row's stored norm (common.cuh:rank_score) before it meets the top-k list.
+template <int QB>
+struct SpaceXf {
+    int metric;
+    const float* __restrict__ norms;  // [n_rows] ||x|| of the raw rows (K1)
+    float h[QB];                      // 0.5 / max(||q||, eps) per register-resident query
+};
+
+template <typename T, int QB, int KPL, int U, bool XF = false>
 __device__ __forceinline__ void scan_rows(const T* __restrict__ rows, uint32_t n_rows, const float4 (&q)[QB][kChunks],
-                                          const uint32_t* __restrict__ mask, TopK<QB, KPL>& top, int lane) {
+                                          const uint32_t* __restrict__ mask, TopK<QB, KPL>& top, int lane,
+                                          const SpaceXf<QB>* xf = nullptr) {
     const uint32_t warps_total = gridDim.x * kScanWarps;
     const uint32_t gw = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
     for (uint64_t r0 = (uint64_t)gw * U; r0 < n_rows; r0 += (uint64_t)warps_total * U) {
@@ -74,6 +84,11 @@ __device__ __forceinline__ void scan_rows(const T* __restrict__ rows, uint32_t n
             live[u] = (r0 + u < n_rows) && ((mw >> u) & 1u);
             if (live[u]) x[u].load(rows + (r0 + u) * (uint64_t)kDim, lane);
         }
+        float nrm[U];
+        if constexpr (XF) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) nrm[u] = live[u] ? __ldg(xf->norms + r0 + u) : 0.0f;
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!live[u]) continue;
@@ -83,6 +98,7 @@ __device__ __forceinline__ void scan_rows(const T* __restrict__ rows, uint32_t n
 #pragma unroll
             for (int b = 0; b < QB; ++b) {
                 float s = warp_butterfly_sum(lane_dot(q[b], xv));
+                if constexpr (XF) s = rank_score(xf->metric, s, nrm[u], xf->h[b]);
                 if (s >= top.thr[b]) {
                     uint64_t key = pack_key(s, (uint32_t)(r0 + u));
                     if (key > top.minkey[b]) top.insert(b, key, lane);
@@ -115,10 +131,10 @@ __device__ __forceinline__ void cta_reduce(const TopK<QB, KPL>& top, int nq, int
     }
 }
 
-template <typename T, int QB, int KPL, int U>
+template <typename T, int QB, int KPL, int U, bool XF = false>
 __device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
                                           const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand,
-                                          int cand_stride, uint64_t* smem_keys) {
+                                          int cand_stride, uint64_t* smem_keys, const SpaceXf<QB>* xf = nullptr) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // queries -> registers (lane's canonical share); missing queries are zero and never written out
@@ -131,7 +147,7 @@ __device__ __forceinline__ void scan_body(const T* __restrict__ rows, uint32_t n
                              : make_float4(0.f, 0.f, 0.f, 0.f);
     TopK<QB, KPL> top;
     top.init(k, lane);
-    scan_rows<T, QB, KPL, U>(rows, n_rows, q, mask, top, lane);
+    scan_rows<T, QB, KPL, U, XF>(rows, n_rows, q, mask, top, lane, xf);
     cta_reduce<QB, KPL>(top, nq, k, cand, cand_stride, smem_keys, lane, warp);
 }
 
@@ -205,6 +221,20 @@ scan_simt_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __res
     scan_body<T, QB, KPL, U>(rows, n_rows, qn, nq, mask, k, cand, cand_stride, smem_keys);
 }
 
+template <typename T, int QB, int KPL, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_simt_metric_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn, int nq,
+                        const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride, int metric,
+                        const float* __restrict__ row_norms, const float* __restrict__ q_norms) {
+    extern __shared__ __align__(16) uint64_t smem_keys[];  // [QB][sort_n]
+    SpaceXf<QB> xf;
+    xf.metric = metric;
+    xf.norms = row_norms;
+#pragma unroll
+    for (int b = 0; b < QB; ++b) xf.h[b] = b < nq ? __fdiv_rn(0.5f, fmaxf(__ldg(q_norms + b), kEps)) : 0.0f;
+    scan_body<T, QB, KPL, U, true>(rows, n_rows, qn, nq, mask, k, cand, cand_stride, smem_keys, &xf);
+}
+
 // Device-driven repair pass of the tensor-core path: re-scans the corpus exactly for the (few) queries whose
 // shortlist could not be proven exact.  Every CTA derives the list of flagged queries itself (one warp, ballot +
 // popcount over flags[B], first max_fix in index order), so no separate compaction launch is needed and no host round
@@ -272,10 +302,19 @@ const void* kernel_ptr() {
     return reinterpret_cast<const void*>(&scan_simt_kernel<T, QB, KPL, U>);
 }
 
-const void* find_kernel(int dtype, const ScanCfg& c) {
-#define MQVS_CASE(QB_, KPL_)                                                                    \
-    if (c.qb == QB_ && c.kpl == KPL_)                                                           \
-        return dtype == MQVS_F32 ? kernel_ptr<float, QB_, KPL_, 2>() : kernel_ptr<__nv_bfloat16, QB_, KPL_, 4>();
+template <typename T, int QB, int KPL, int U>
+const void* metric_kernel_ptr() {
+    return reinterpret_cast<const void*>(&scan_simt_metric_kernel<T, QB, KPL, U>);
+}
+
+const void* find_kernel(int dtype, const ScanCfg& c, bool metric = false) {
+#define MQVS_CASE(QB_, KPL_)                                                                                  \
+    if (c.qb == QB_ && c.kpl == KPL_) {                                                                       \
+        if (metric)                                                                                           \
+            return dtype == MQVS_F32 ? metric_kernel_ptr<float, QB_, KPL_, 2>()                               \
+                                     : metric_kernel_ptr<__nv_bfloat16, QB_, KPL_, 4>();                      \
+        return dtype == MQVS_F32 ? kernel_ptr<float, QB_, KPL_, 2>() : kernel_ptr<__nv_bfloat16, QB_, KPL_, 4>(); \
+    }
     MQVS_CASE(1, 1)
     MQVS_CASE(2, 1)
     MQVS_CASE(4, 1)
@@ -367,6 +406,18 @@ void scan_plan(int dtype, int nq_remaining, int k, int sm_count, int* nq_pass, i
 }
 
 int scan_max_grid(int sm_count) { return sm_count * kMaxCtasPerSm; }
+
+void launch_scan_simt_metric(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
+                             int k, uint64_t* cand, int cand_stride, int grid, int metric, const float* row_norms,
+                             const float* q_norms, cudaStream_t st) {
+    ScanCfg c = pick_cfg(nq, k);
+    const void* kern = find_kernel(dtype, c, true);
+    const size_t smem = scan_smem(c, k);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void* args[] = {(void*)&rows, (void*)&n_rows, (void*)&qn, (void*)&nq, (void*)&mask, (void*)&k, (void*)&cand,
+                    (void*)&cand_stride, (void*)&metric, (void*)&row_norms, (void*)&q_norms};
+    cudaLaunchKernel(kern, dim3(grid), dim3(kScanThreads), args, smem, st);
+}
 
 void launch_scan_simt(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
                       int k, uint64_t* cand, int cand_stride, int grid, cudaStream_t st) {

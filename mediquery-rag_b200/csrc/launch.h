@@ -10,12 +10,15 @@ namespace mqvs {
 int mqvs_fail(int code, const char* fmt, ...);
 
 // K1: L2-normalise + pack.  x [n, dim] fp32 (device) -> out [n, 768] fp32 or bf16, zero-padded; counts
-// rows whose squared norm is not finite into *bad (and stores them as zeros).
+// rows whose squared norm is not finite into *bad (and stores them as zeros).  norms (optional, [n]) receives ||x|| of
+// every raw row (what the l2 / ip spaces rank with); max_dev (optional) is raised to the bit pattern of the largest
+// | ||x|| - 1 | seen (atomicMax), which tells the host whether the collection consists of unit vectors.
 void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
-                      cudaStream_t st);
+                      cudaStream_t st, float* norms = nullptr, unsigned int* max_dev = nullptr);
 // Same K1 fed by the counter-based generator instead of memory.
 void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int dim, int out_dtype, void* out,
-                            unsigned long long* bad, cudaStream_t st);
+                            unsigned long long* bad, cudaStream_t st, float* norms = nullptr,
+                            unsigned int* max_dev = nullptr);
 
 // K2 (SIMT) + K3: exact fp32 scan of `n_rows` stored rows against nq (<= scan_max_queries_per_pass) normalised
 // queries, fused per-warp top-k with optional allow-mask; writes per-CTA sorted candidate keys
@@ -26,6 +29,11 @@ void scan_plan(int dtype, int nq_remaining, int k, int sm_count, int* nq_pass, i
 int scan_max_grid(int sm_count);
 void launch_scan_simt(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
                       int k, uint64_t* cand, int cand_stride, int grid, cudaStream_t st);
+// The same scan ranking by the l2 / ip space of the RAW vectors (mqvs_set_metric): row_norms [n_rows] as K1 stored them,
+// q_norms [nq] = ||q|| of the raw queries (K1 again); scores are common.cuh:rank_score.
+void launch_scan_simt_metric(const void* rows, int dtype, uint32_t n_rows, const float* qn, int nq, const uint32_t* mask,
+                             int k, uint64_t* cand, int cand_stride, int grid, int metric, const float* row_norms,
+                             const float* q_norms, cudaStream_t st);
 
 // Device-driven repair of tensor-path queries flagged "not proven exact": scan_fix compacts the flags into a list itself
 // (first max_fix <= 64 flagged queries, published in fix_list / fix_n; counters[0] += listed, [1] += left over), re-scans

@@ -38,7 +38,8 @@ def _native_merge(all_scores, all_ids, out_scores, out_ids) -> None:
 
 class ShardedIndex:
     def __init__(self, dim: int, store_dtype: str, n_total: int, *, group: Any = None, device: Any = None,
-                 index_factory: Optional[Callable[..., Any]] = None, merge_fn: Optional[Callable[..., None]] = None):
+                 index_factory: Optional[Callable[..., Any]] = None, merge_fn: Optional[Callable[..., None]] = None,
+                 metric: str = "cosine"):
         import torch
         import torch.distributed as dist
 
@@ -52,6 +53,10 @@ class ShardedIndex:
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         dev_index = self.device.index if hasattr(self.device, "index") and self.device.index is not None else 0
         self.index = (index_factory or _native.Index)(dim, store_dtype, dev_index, self.hi - self.lo)
+        if metric != "cosine":
+            # l2 / ip over raw (non-unit) vectors: every shard keeps its rows' norms; the ranking score of a query is
+            # comparable across shards (include/mqvs.h, mqvs_set_metric), so the exchange + merge are unchanged
+            self.index.set_metric(metric)
         self._merge = merge_fn or _native_merge
         self.dim = dim
         self.exchange, self._xchg, self.exchange_error = "none" if self.world == 1 else "nccl", None, None

@@ -13,7 +13,10 @@ vectors live in HBM behind libmqvs.so and every search is an EXACT scan there (n
 Scores come back as cosine similarity; `*_with_score` converts to the distance Chroma would report for the
 collection's `hnsw:space` (default "l2", as in the reference, which passes no collection_metadata):
 l2 -> 2 - 2s (= ||a-b||^2 on unit vectors), cosine / ip -> 1 - s.  Rows are stored L2-normalised (Ollama's
-embedder already returns unit vectors), so for non-unit inputs l2/ip distances are those of the normalised rows.
+embedder already returns unit vectors).  In the l2 / ip spaces the device also keeps ||x|| of every raw row; as
+long as every row is a unit vector (| ||x|| - 1 | <= 1e-5, the reference's case) the three spaces order rows
+identically and the cosine kernels serve all of them; once a non-unit row is stored, searches rank by the space's
+own score over the RAW vectors (mqvs_set_metric) and distances are ||q - x||^2 / 1 - <q, x> of the raw vectors.
 """
 from __future__ import annotations
 
@@ -36,10 +39,19 @@ else:
 DEFAULT_K = 4  # langchain_chroma's default
 _SPACES = ("l2", "cosine", "ip")
 _ROWS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE = "rows.mqvs", "docs.jsonl", "manifest.json", "dead.json"
+_NORMS_FILE = _ROWS_FILE + ".norms"  # written by mqvs_save next to the rows in the l2 / ip spaces
+_UNIT_TOL = 1e-5  # a collection whose raw rows all satisfy | ||x|| - 1 | <= this is ranked as unit vectors
 
 
 def _distance(space: str, sim: float) -> float:
     return 2.0 - 2.0 * sim if space == "l2" else 1.0 - sim
+
+
+def _raw_distance(space: str, t: float, q_norm: float) -> float:
+    """Chroma's distance over the RAW vectors from the backend's ranking score t (include/mqvs.h, mqvs_set_metric):
+    ip: t = <q,x> / ||q|| -> 1 - <q,x>;  l2: t = (||q||^2 - ||q-x||^2) / (2 ||q||) -> ||q-x||^2."""
+    qc = max(q_norm, 1e-12)
+    return q_norm * q_norm - 2.0 * qc * t if space == "l2" else 1.0 - qc * t
 
 
 def _relevance(space: str, sim: float) -> float:
@@ -106,6 +118,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._cols = MetadataColumns()
         self._live = np.zeros(0, dtype=bool)
         self._device_filter: Optional[DeviceFilter] = None
+        self._raw_space = space != "cosine"  # keep ||x|| on the device so l2 / ip can rank non-unit vectors
         self._persisted_rows = 0            # rows already in rows.mqvs / docs.jsonl (appends start here)
         self._persisted_dead: Optional[List[int]] = None
         if persist_directory is not None:
@@ -128,6 +141,10 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if self._index is None:
             self._dim = int(dim)
             self._index = self._index_factory(self._dim, self._store_dtype, self._device, self._capacity)
+            if self._raw_space and self._space != "cosine" and hasattr(self._index, "set_metric"):
+                self._index.set_metric(self._space)  # while empty: row norms are kept from here on
+            else:
+                self._raw_space = False
         elif dim != self._dim:
             raise ValueError(f"embedding dimension {dim} does not match the collection's {self._dim}")
 
@@ -229,10 +246,21 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                               collection_name, persist_directory, collection_metadata, **kwargs)
 
     # ------------------------------------------------------------------------------------------- search
+    def rank_space(self) -> str:
+        """The space the next search ranks in: "cosine" while every stored raw row is a unit vector (all spaces agree
+        there and every kernel path is available), else the collection's hnsw:space over the raw vectors."""
+        if not self._raw_space or self._index is None:
+            return "cosine"
+        want = self._space if self._index.norm_deviation() > _UNIT_TOL else "cosine"
+        if self._index.metric != want:
+            self._index.set_metric(want)
+        return want
+
     def search_batch(self, queries: Any, k: int = DEFAULT_K, filter: Optional[Mapping[str, Any]] = None,
                      where_document: Optional[Mapping[str, Any]] = None) -> Tuple[np.ndarray, np.ndarray]:
-        """Batch extension used by the benchmark configs: queries [B, dim] -> (cosine scores [B, k'], row ids
-        [B, k']) with k' = min(k, allowed rows); rows best-first, ties -> lower row id."""
+        """Batch extension used by the benchmark configs: queries [B, dim] -> (scores [B, k'], row ids [B, k']) with
+        k' = min(k, allowed rows); rows best-first, ties -> lower row id.  Scores are cosine similarities, or the
+        ranking score of `rank_space()` when that is "l2" / "ip" (non-unit rows; include/mqvs.h)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -246,6 +274,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
         if k_eff > _native.MAX_K:
             raise ValueError(f"k is limited to {_native.MAX_K}")
+        self.rank_space()
         return self._index.search(q, k_eff, mask)
 
     def _allow_mask(self, filter: Optional[Mapping[str, Any]], where_document: Optional[Mapping[str, Any]]):
@@ -271,8 +300,14 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
 
     def _similar(self, vector: Any, k: int, filter: Optional[Mapping[str, Any]],
                  where_document: Optional[Mapping[str, Any]] = None) -> List[Tuple[Document, float]]:
-        scores, rows = self.search_batch(np.asarray(vector, dtype=np.float32)[None, :], k, filter, where_document)
-        return self._docs(scores[0], rows[0])
+        """(Document, distance in the collection's hnsw:space) pairs, best (smallest distance) first."""
+        q = np.asarray(vector, dtype=np.float32)
+        scores, rows = self.search_batch(q[None, :], k, filter, where_document)
+        ranked = self.rank_space()
+        if ranked == "cosine":
+            return [(d, _distance(self._space, s)) for d, s in self._docs(scores[0], rows[0])]
+        q_norm = float(np.linalg.norm(q.astype(np.float64)))
+        return [(d, _raw_distance(ranked, t, q_norm)) for d, t in self._docs(scores[0], rows[0])]
 
     def similarity_search(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
                           **kwargs: Any) -> List[Document]:
@@ -282,8 +317,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                                      where_document: Optional[Dict[str, Any]] = None, **kwargs: Any
                                      ) -> List[Tuple[Document, float]]:
         """(Document, distance) pairs, LOWER is better, in the collection's hnsw:space."""
-        return [(d, _distance(self._space, s))
-                for d, s in self._similar(self._embed_query(query), k, filter, where_document)]
+        return self._similar(self._embed_query(query), k, filter, where_document)
 
     def similarity_search_by_vector(self, embedding: List[float], k: int = DEFAULT_K,
                                     filter: Optional[Dict[str, Any]] = None, **kwargs: Any) -> List[Document]:
@@ -293,7 +327,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                                                           filter: Optional[Dict[str, Any]] = None, **kwargs: Any
                                                           ) -> List[Tuple[Document, float]]:
         # langchain_chroma returns the raw distance here despite the name; kept for compatibility
-        return [(d, _distance(self._space, s)) for d, s in self._similar(embedding, k, filter)]
+        return self._similar(embedding, k, filter)
 
     def _select_relevance_score_fn(self) -> Callable[[float], float]:
         if self._relevance_fn is not None:
@@ -413,8 +447,12 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if "documents" in include:
             out["documents"] = [self._texts[r] for r in rows]
         if "embeddings" in include:
-            out["embeddings"] = (self._index.get_rows(np.asarray(rows, np.int64)) if rows
-                                 else np.zeros((0, self._dim or 0), np.float32))
+            emb = (self._index.get_rows(np.asarray(rows, np.int64)) if rows
+                   else np.zeros((0, self._dim or 0), np.float32))
+            if rows and self._raw_space:  # l2 / ip collections hand back the raw vectors: unit row x stored norm
+                lo, hi = min(rows), max(rows) + 1
+                emb = emb * self._index.get_norms(lo, hi - lo)[np.asarray(rows) - lo, None]
+            out["embeddings"] = emb
         return out
 
     def get_by_ids(self, ids: Sequence[str]) -> List[Document]:
@@ -442,7 +480,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._device_filter = None
         if self._persist_directory is not None:
             self._persisted_rows, self._persisted_dead = 0, None
-            for f in (_ROWS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE):
+            for f in (_ROWS_FILE, _NORMS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE):
                 try:
                     os.remove(os.path.join(self._persist_directory, f))
                 except FileNotFoundError:
@@ -510,6 +548,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             self._space = manifest.get("space", self._space)
         if manifest.get("dim") is None:
             return
+        # a directory written before row norms were kept (or in the cosine space) opens with unit-vector semantics
+        self._raw_space = self._space != "cosine" and (not manifest["rows"] or os.path.exists(os.path.join(d, _NORMS_FILE)))
         self._ensure_index(manifest["dim"])
         if manifest["rows"]:
             self._index.load_file(os.path.join(d, _ROWS_FILE))

@@ -14,6 +14,7 @@ from .oracle import (  # noqa: F401
     DIM_ALIGN,
     brute_force_topk,
     canonical_scores,
+    distances_from_rank_scores,
     eval_where,
     f64_scores,
     lib,
@@ -23,6 +24,7 @@ from .oracle import (  # noqa: F401
     pad_dim,
     planted_queries,
     referee_topk_f64,
+    row_norms,
     sgemm_topk,
     stored_as_f32,
     synth_rows,

@@ -136,6 +136,34 @@ int64_t orc_normalize_bf16(const float* x, int64_t n, int dim, int dim_pad, uint
     return bad;
 }
 
+/* ||x|| of the raw rows as K1 measures it: sqrtf of the canonical sum of squares (0 for a non-finite row).
+ * Needed by Chroma's "l2" / "ip" spaces when the raw vectors are not unit vectors (langchain_chroma passes
+ * collection_metadata={"hnsw:space": ...} through; the reference passes none -> "l2", src/medical_engine.py:52). */
+void orc_norms_f32(const float* x, int64_t n, int dim, int dim_pad, float* norms) {
+    float tmp[4096];
+    for (int64_t r = 0; r < n; ++r) {
+        memcpy(tmp, x + r * (int64_t)dim, sizeof(float) * (size_t)dim);
+        for (int j = dim; j < dim_pad; ++j) tmp[j] = 0.0f;
+        float ss = canonical_dot_f32(tmp, tmp, dim_pad);
+        norms[r] = isfinite(ss) ? sqrtf(ss) : 0.0f;
+    }
+}
+
+/* Ranking score of a row in the collection's space (metric 0 = cosine, 1 = l2, 2 = ip), larger = better:
+ * s = canonical cosine of the normalised pair, a = ||x|| (raw row), h = 0.5 / max(||q||, eps):
+ *   cosine s;   ip a*s = <q,x>/||q||;   l2 a*s - (a*a)*h = (||q||^2 - ||q-x||^2) / (2||q||)   -- chromadb's
+ * "l2" is the squared distance, "ip" is 1 - <q,x>; both are monotone in these scores for a fixed query.
+ * Every product is rounded to fp32 on its own and the last step is one fused multiply-add (the kernels' order). */
+float orc_rank_score(int metric, float s, float a, float h) {
+    if (metric == 2) return a * s;
+    if (metric == 1) {
+        float aa = a * a;
+        float w = aa * h;
+        return fmaf(a, s, -w);
+    }
+    return s;
+}
+
 /* scores[b, r] = canonical <q_b, x_r>; store_dtype 0 = fp32 rows, 1 = bf16 rows */
 void orc_scores(const float* q, int B, const void* rows, int store_dtype, int64_t n, int dim_pad,
                 float* scores) {
@@ -159,10 +187,23 @@ static int cmp_key_desc(const void* a, const void* b) {
  * Exact brute-force top-k: out_scores/out_ids [B, k], best first, ties -> lower id, rows whose mask bit
  * is 0 are skipped (mask == NULL: all allowed), missing slots = (-inf, -1).  id_base is added to ids.
  */
+void orc_topk_metric(const float* q, int B, const void* rows, int store_dtype, int64_t n, int dim_pad,
+                     const uint32_t* mask, int k, int64_t id_base, int metric, const float* row_norms,
+                     const float* q_norms, float* out_scores, int64_t* out_ids);
+
 void orc_topk(const float* q, int B, const void* rows, int store_dtype, int64_t n, int dim_pad,
               const uint32_t* mask, int k, int64_t id_base, float* out_scores, int64_t* out_ids) {
+    orc_topk_metric(q, B, rows, store_dtype, n, dim_pad, mask, k, id_base, 0, NULL, NULL, out_scores, out_ids);
+}
+
+/* The same in the collection's space: q = NORMALISED queries, q_norms [B] = ||q|| of the raw queries, row_norms [n] =
+ * ||x|| of the raw rows (both NULL for cosine); scores out are orc_rank_score. */
+void orc_topk_metric(const float* q, int B, const void* rows, int store_dtype, int64_t n, int dim_pad,
+                     const uint32_t* mask, int k, int64_t id_base, int metric, const float* row_norms,
+                     const float* q_norms, float* out_scores, int64_t* out_ids) {
     for (int b = 0; b < B; ++b) {
         const float* qb = q + (int64_t)b * dim_pad;
+        const float h = metric ? 0.5f / fmaxf(q_norms[b], ORC_EPS) : 0.0f;
         uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
         int64_t m = 0;
         for (int64_t r = 0; r < n; ++r) {
@@ -170,6 +211,7 @@ void orc_topk(const float* q, int B, const void* rows, int store_dtype, int64_t 
             float s = store_dtype == 0
                           ? canonical_dot_f32(qb, (const float*)rows + r * (int64_t)dim_pad, dim_pad)
                           : canonical_dot_f32_bf16(qb, (const uint16_t*)rows + r * (int64_t)dim_pad, dim_pad);
+            if (metric) s = orc_rank_score(metric, s, row_norms[r], h);
             keys[m++] = pack_key(s, (uint32_t)r);
         }
         qsort(keys, (size_t)m, sizeof(uint64_t), cmp_key_desc);

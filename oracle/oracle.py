@@ -47,6 +47,10 @@ def lib() -> ctypes.CDLL:
     L.orc_scores.restype = None
     L.orc_topk.argtypes = [vp, i32, vp, i32, i64, i32, vp, i32, i64, vp, vp]
     L.orc_topk.restype = None
+    L.orc_topk_metric.argtypes = [vp, i32, vp, i32, i64, i32, vp, i32, i64, i32, vp, vp, vp, vp]
+    L.orc_topk_metric.restype = None
+    L.orc_norms_f32.argtypes = [vp, i64, i32, i32, vp]
+    L.orc_norms_f32.restype = None
     L.orc_synth_rows.argtypes = [u64, i64, i64, i32, vp]
     L.orc_synth_rows.restype = None
     _LIB = L
@@ -137,8 +141,45 @@ def mask_from_bool(allowed: np.ndarray) -> np.ndarray:
     return np.packbits(padded.reshape(words, 32), axis=1, bitorder="little").view(np.uint32).reshape(words).copy()
 
 
-def brute_force_topk(qn, stored, k: int, mask: np.ndarray | None = None, id_base: int = 0):
-    """Exact canonical-fp32 top-k.  mask: packed uint32 words (mask_from_bool) or bool[n] or None."""
+METRICS = {"cosine": 0, "l2": 1, "ip": 2}
+
+
+def row_norms(x: np.ndarray, dim_pad: int | None = None) -> np.ndarray:
+    """||x|| of raw rows as K1 measures it (canonical fp32 sum of squares, sqrtf); what the l2 / ip spaces rank with."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    n, dim = x.shape
+    out = np.empty(n, np.float32)
+    lib().orc_norms_f32(_p(x), n, dim, dim_pad or pad_dim(dim), _p(out))
+    return out
+
+
+def distances_from_rank_scores(space: str, t: np.ndarray, q_norm: np.ndarray) -> np.ndarray:
+    """Chroma's distance (lower = better) from the backend's ranking score t (orc_rank_score) and ||q||, float64:
+    cosine 1 - t; ip 1 - ||q|| t = 1 - <q,x>; l2 ||q||^2 - 2 ||q|| t = ||q - x||^2."""
+    t = np.asarray(t, np.float64)
+    qn = np.asarray(q_norm, np.float64).reshape(-1, *([1] * (t.ndim - 1)))
+    qc = np.maximum(qn, 1e-12)
+    if space == "cosine":
+        return 1.0 - t
+    if space == "ip":
+        return 1.0 - qc * t
+    if space == "l2":
+        return qn * qn - 2.0 * qc * t
+    raise ValueError(space)
+
+
+def brute_force_topk(qn, stored, k: int, mask: np.ndarray | None = None, id_base: int = 0, metric: str = "cosine",
+                     norms: np.ndarray | None = None, q_norms: np.ndarray | None = None):
+    """Exact canonical-fp32 top-k.  mask: packed uint32 words (mask_from_bool) or bool[n] or None.
+    metric "l2" / "ip": ranking in that space over the RAW vectors: norms [n] = row_norms(raw rows), q_norms [B] =
+    row_norms(raw queries), qn / stored the normalised forms as always; scores out are the ranking scores."""
+    code_m = METRICS[metric]
+    if code_m:
+        norms = np.ascontiguousarray(norms, np.float32)
+        q_norms = np.ascontiguousarray(q_norms, np.float32)
+        assert norms.shape[0] == stored.shape[0] and q_norms.shape[0] == qn.shape[0]
     qn = np.ascontiguousarray(qn, np.float32)
     stored = np.ascontiguousarray(stored)
     B, dp = qn.shape
@@ -154,8 +195,9 @@ def brute_force_topk(qn, stored, k: int, mask: np.ndarray | None = None, id_base
         a, b = ab
         s = np.empty((B, k), np.float32)
         i = np.empty((B, k), np.int64)
-        lib().orc_topk(_p(qn), B, _p(stored[a:b]), code, b - a, dp,
-                       _p(mask[a // 32:]) if mask is not None else None, k, id_base + a, _p(s), _p(i))
+        lib().orc_topk_metric(_p(qn), B, _p(stored[a:b]), code, b - a, dp,
+                              _p(mask[a // 32:]) if mask is not None else None, k, id_base + a, code_m,
+                              _p(norms[a:b]) if code_m else None, _p(q_norms) if code_m else None, _p(s), _p(i))
         return s, i
 
     parts = _pmap(part, _row_chunks(n, 32))

@@ -45,6 +45,7 @@ class OracleIndex:
     def __init__(self, dim, store_dtype="fp32", device=0, capacity_rows=0):
         self.dim, self.store_dtype = dim, store_dtype
         self.rows = np.zeros((0, 768), np.float32 if store_dtype == "fp32" else np.uint16)
+        self.metric, self.norms, self._dev = "cosine", None, 0.0
 
     def __len__(self):
         return self.rows.shape[0]
@@ -56,11 +57,33 @@ class OracleIndex:
             raise RuntimeError("non-finite")
         first = len(self)
         self.rows = np.concatenate([self.rows, st])
+        nr = O.row_norms(x, 768)
+        self._dev = max(self._dev, float(np.abs(nr - np.float32(1.0)).max())) if len(nr) else self._dev
+        if self.norms is not None:
+            self.norms = np.concatenate([self.norms, nr])
         return first
 
     def search(self, q, k, mask=None):
-        qn, _ = O.normalize_rows(np.ascontiguousarray(q, np.float32), "fp32", 768)
+        q = np.ascontiguousarray(q, np.float32)
+        qn, _ = O.normalize_rows(q, "fp32", 768)
+        if self.metric != "cosine":
+            return O.brute_force_topk(qn, self.rows, k, mask, metric=self.metric, norms=self.norms,
+                                      q_norms=O.row_norms(q, 768))
         return O.brute_force_topk(qn, self.rows, k, mask)
+
+    def set_metric(self, space):
+        if space != "cosine" and self.norms is None:
+            if len(self):
+                raise RuntimeError("rows were added without their norms")
+            self.norms = np.zeros(0, np.float32)
+        self.metric = space
+
+    def norm_deviation(self):
+        return self._dev
+
+    def get_norms(self, first_row=0, n=None):
+        n = len(self) - first_row if n is None else n
+        return self.norms[first_row:first_row + n].copy()
 
     def add_synthetic(self, seed, first_index, n):
         return self.add(O.synth_rows(seed, first_index, n, self.dim))
@@ -83,24 +106,33 @@ class OracleIndex:
     def save(self, path):
         np.save(path + ".npy", self.rows)
         os.replace(path + ".npy", path)
+        if self.norms is not None:
+            np.save(path + ".norms.npy", self.norms)
+            os.replace(path + ".norms.npy", path + ".norms")
 
     def load_file(self, path):
         with open(path, "rb") as f:
             self.rows = np.load(f)
+        if self.norms is not None:
+            with open(path + ".norms", "rb") as f:
+                self.norms = np.load(f)[: len(self)]
+            self._dev = float(np.abs(self.norms - np.float32(1.0)).max()) if len(self.norms) else 0.0
 
     def close(self):
         pass
 
 
 class HashEmbedder:
-    """Deterministic stand-in for OllamaEmbeddings (no daemon here): text -> 768-d vector from its sha256."""
+    """Deterministic stand-in for OllamaEmbeddings (no daemon here): text -> 768-d UNIT vector from its sha256
+    (Ollama's /api/embed returns L2-normalised rows; `unit=False` gives raw vectors of norm ~16 instead)."""
 
-    def __init__(self, dim=768):
-        self.dim = dim
+    def __init__(self, dim=768, unit=True):
+        self.dim, self.unit = dim, unit
 
     def _one(self, text):
         seed = int.from_bytes(hashlib.sha256(text.encode("utf-8")).digest()[:8], "little")
-        return O.synth_rows(seed, 0, 1, self.dim)[0]
+        v = O.synth_rows(seed, 0, 1, self.dim)[0]
+        return (v / np.float32(np.linalg.norm(v.astype(np.float64)))).astype(np.float32) if self.unit else v
 
     def embed_documents(self, texts):
         return [self._one(t).tolist() for t in texts]

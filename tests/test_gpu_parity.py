@@ -607,7 +607,7 @@ def test_device_side_where_evaluation_equals_host_evaluator(gpu):
             assert set(i[0].tolist()) == set(np.flatnonzero(want).tolist()), where
     idx.close()
 
-    store = MediQueryVectorStore()
+    store = MediQueryVectorStore(collection_metadata={"hnsw:space": "cosine"})  # x holds raw (non-unit) vectors
     store.add_embeddings(([f"doc {r}" for r in range(n)], x), metadatas=[cols.row(r) for r in range(n)])
     for where in FILTERS[::3]:
         want = evaluate(where, store._cols)
@@ -818,3 +818,110 @@ def test_band_pass_repairs_dense_neighbourhoods_without_exact_scans(gpu, dtype, 
     s4, i4 = idx.search(q[:16], k)
     assert_bit_equal(s4, i4, es[:16], ei[:16])
     assert idx.stats()["exact_fallbacks"] > 0
+
+
+def _raw_rows(n, seed=SEED, lo=0.25, hi=4.0):
+    """non-unit vectors: synthetic rows (norm ~16) rescaled to lengths spread over [lo, hi]"""
+    x = O.synth_rows(seed, 0, n, 768)
+    scale = np.random.default_rng(11).uniform(lo, hi, (n, 1)).astype(np.float32) / np.float32(16.0)
+    return (x * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("space", ["l2", "ip"])
+def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_path):
+    """Chroma's hnsw:space on NON-unit vectors: K1 keeps ||x|| per row, the exact scan maps the
+    cosine of the normalised pair to the space's ranking score (common.cuh:rank_score) before top-k.  Bit-identical
+    to oracle/canonical.c:orc_topk_metric, which tests/test_spaces.py ties to a float64 brute force over raw vectors."""
+    import torch
+    M = native()
+    n = 70_001  # large enough that the cosine space would take the tensor-core path for B >= 2
+    x = _raw_rows(n)
+    idx = M.Index(768, dtype)
+    idx.set_metric(space)
+    idx.add(x[:30_000])
+    idx.add(x[30_000:])  # regrowth moves the norms with the rows
+    nr = O.row_norms(x, 768)
+    assert np.array_equal(idx.get_norms().view(np.uint32), nr.view(np.uint32))
+    assert idx.norm_deviation() == float(np.abs(nr - np.float32(1.0)).max())
+    st, _ = O.normalize_rows(x, dtype, 768)
+    rng = np.random.default_rng(2)
+    for B, k, frac in ((1, 10, None), (3, 5, None), (9, 10, 0.3), (2, 40, None), (1, 200, 0.5), (64, 10, None)):
+        q = (_raw_rows(B, seed=QSEED) * np.float32(3.0) + 0.5 * x[rng.integers(0, n, B)]).astype(np.float32)
+        qn, _ = O.normalize_rows(q, "fp32", 768)
+        mask = None if frac is None else O.mask_from_bool(rng.random(n) < frac)
+        s, i = idx.search(q, k, mask)
+        es, ei = O.brute_force_topk(qn, st, k, mask, metric=space, norms=nr, q_norms=O.row_norms(q, 768))
+        assert_bit_equal(s, i, es, ei)
+        stats = idx.stats()
+        assert stats["last_path"] == 0 and stats["last_pipeline"] == 0
+    assert not np.array_equal(O.brute_force_topk(qn, st, k)[1], ei)  # the space matters on these rows
+    # all-device call on a caller stream, with an id base (the sharded path)
+    qd = torch.from_numpy(q).cuda()
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    idx.search_device(qd, k, out_s, out_i, id_base=1000, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei + 1000)
+    # the metric can be switched once the norms are kept: cosine ranks the normalised rows (tensor path for B = 64)
+    idx.set_metric("cosine")
+    s, i = idx.search(q, k)
+    assert_bit_equal(s, i, *O.brute_force_topk(qn, st, k))
+    assert idx.stats()["last_path"] == 1
+    idx.set_metric(space)
+    # persistence: the norms travel next to the rows (rows.mqvs.norms), appends included
+    path = str(tmp_path / "rows.mqvs")
+    idx.save(path)
+    extra = _raw_rows(500, seed=SEED + 7)
+    idx.add(extra)
+    idx.save_append(path, n)
+    again = M.Index(768, dtype)
+    again.set_metric(space)
+    again.load_file(path)
+    assert len(again) == n + 500 and again.norm_deviation() == idx.norm_deviation()
+    assert np.array_equal(again.get_norms(), np.concatenate([nr, O.row_norms(extra, 768)]))
+    assert_bit_equal(*again.search(q[:5], 10), *idx.search(q[:5], 10))
+    # rows stored without their norms cannot be ranked in l2 / ip afterwards, and a row file without norms does not open
+    plain = M.Index(768, dtype)
+    plain.add(x[:100])
+    with pytest.raises(M.MqvsError):
+        plain.set_metric(space)
+    plain.save(str(tmp_path / "plain.mqvs"))
+    fresh = M.Index(768, dtype)
+    fresh.set_metric(space)
+    with pytest.raises(M.MqvsError):
+        fresh.load_file(str(tmp_path / "plain.mqvs"))
+    with pytest.raises(M.MqvsError):
+        plain.get_norms()
+
+
+def test_vectorstore_default_space_on_raw_vectors_ranks_by_squared_l2(gpu, tmp_path):
+    """The reference opens Chroma without collection_metadata (src/medical_engine.py:52), i.e. in chromadb's default "l2"
+    space.  With an embedder that does NOT normalise, the drop-in must rank by the squared L2 distance of the raw vectors
+    and report it; with unit vectors (Ollama) it stays on the cosine kernels and reports 2 - 2s."""
+    from conftest import HashEmbedder
+    from mediquery_rag_b200 import MediQueryVectorStore
+    texts = [f"text {r}" for r in range(3000)]
+    raw, unit = HashEmbedder(unit=False), HashEmbedder()
+    db = str(tmp_path / "db")
+    vs = MediQueryVectorStore(embedding_function=raw, persist_directory=db)
+    x = np.asarray(raw.embed_documents(texts), np.float32)
+    x *= np.random.default_rng(5).uniform(0.5, 1.5, (len(texts), 1)).astype(np.float32)
+    vs.add_embeddings((texts, x))
+    assert vs.rank_space() == "l2"
+    for store in (vs, MediQueryVectorStore(embedding_function=raw, persist_directory=db)):
+        for query in ("text 5 again", "anything"):
+            qv = np.asarray(raw.embed_query(query), np.float64)
+            d = ((qv[None, :] - x.astype(np.float64)) ** 2).sum(1)
+            got = store.similarity_search_with_score(query, k=6)
+            assert [doc.page_content for doc, _ in got] == [texts[r] for r in np.argsort(d, kind="stable")[:6]]
+            assert np.allclose([dist for _, dist in got], np.sort(d)[:6], rtol=1e-5)
+    vu = MediQueryVectorStore(embedding_function=unit)
+    vu.add_texts(texts)
+    assert vu.rank_space() == "cosine" and vu._index.norm_deviation() <= 1e-6
+    xu = np.asarray(unit.embed_documents(texts), np.float64)
+    d = ((np.asarray(unit.embed_query("text 5 again"), np.float64)[None, :] - xu) ** 2).sum(1)
+    got = vu.similarity_search_with_score("text 5 again", k=6)
+    assert [doc.page_content for doc, _ in got] == [texts[r] for r in np.argsort(d, kind="stable")[:6]]
+    assert np.allclose([dist for _, dist in got], np.sort(d)[:6], atol=2e-6)
+    assert vu._index.stats()["last_pipeline"] == 1  # the single-launch latency kernel, as before

@@ -34,13 +34,14 @@ def _oracle_merge(all_s, all_i, out_s, out_i):
     out_i.copy_(torch.from_numpy(i))
 
 
-def _worker(rank, world, port, n, B, k, frac, ret):
+def _worker(rank, world, port, n, B, k, frac, ret, metric="cosine"):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from conftest import OracleIndex
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        sh = ShardedIndex(768, "fp32", n, device=torch.device("cpu"), index_factory=OracleIndex, merge_fn=_oracle_merge)
+        sh = ShardedIndex(768, "fp32", n, device=torch.device("cpu"), index_factory=OracleIndex, merge_fn=_oracle_merge,
+                          metric=metric)
         sh.add_synthetic(SEED)
         q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
         mask = None if frac is None else O.mask_from_bool(np.random.default_rng(5).random(n) < frac)
@@ -70,3 +71,23 @@ def test_sharded_search_equals_unsharded_oracle(world, n, B, k, frac):
         s, i, bounds = ret[rank]
         assert np.array_equal(i, ei) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
         assert bounds == shard_bounds(n, world)
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_sharded_search_in_the_l2_and_ip_spaces_over_raw_vectors(metric):
+    """Chroma's l2 / ip spaces on non-unit vectors: every shard ranks with its rows' norms; the ranking score of a query
+    is comparable across shards, so the merged result equals the unsharded oracle in that space."""
+    world, n, B, k = 2, 3001, 4, 10
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, B, k, None, ret, metric), nprocs=world, join=True)
+    x = O.synth_rows(SEED, 0, n, 768)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    es, ei = O.brute_force_topk(qn, st, k, metric=metric, norms=O.row_norms(x, 768), q_norms=O.row_norms(q, 768))
+    cs, ci = O.brute_force_topk(qn, st, k)
+    assert not np.array_equal(ei, ci)  # the space matters on these rows (norms 15.5 - 16.5)
+    for rank in range(world):
+        s, i, _ = ret[rank]
+        assert np.array_equal(i, ei) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
