@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=str, default=None, help="comma-separated extra batch sizes to report")
     ap.add_argument("--selectivity", type=float, default=0.1, help="c5: fraction of rows the where-filter allows")
+    ap.add_argument("--space", choices=["cosine", "l2", "ip"], default="cosine",
+                    help="hnsw:space the rows are ranked in; l2 / ip rank the RAW synthetic vectors (norms 15.5-16.5) with the "
+                         "stored row norms on the exact SIMT scan (SURVEY.md section 8 f3); the default is the headline config")
     ap.add_argument("--no-scaling-base", action="store_true",
                     help="N=1 default run: skip the extra config-4 (100M x 768 bf16) measurement on this one GPU")
     args = ap.parse_args()
@@ -232,7 +235,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     k, B, rows = wl["k"], args.batch, wl["rows"]
 
-    sh = ShardedIndex(768, wl["dtype"], rows)
+    sh = ShardedIndex(768, wl["dtype"], rows, metric=args.space)
     t0 = time.perf_counter()
     sh.add_synthetic(CORPUS_SEED[args.workload])
     torch.cuda.synchronize()
@@ -307,7 +310,10 @@ def main():
 
     # correctness guard on the timed configuration: planted neighbours must come first
     ids = out[1].cpu().numpy()
-    if mask_dev is None:
+    if args.space != "cosine":  # unit queries against rows of norm ~16: the planted row is not the l2 / ip neighbour
+        sc = out[0].cpu().numpy()
+        assert (ids >= 0).all() and (np.diff(sc, axis=1) <= 0).all(), "results are not sorted best-first"
+    elif mask_dev is None:
         assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
     else:  # every returned row must carry an allowed source_id
         got = ids[ids >= 0].astype(np.uint64)
@@ -375,7 +381,8 @@ def main():
     pk = peaks()
     algo_bytes = sh.local_rows * 768 * ELEM[wl["dtype"]]  # corpus bytes one scan streams on this rank
     avg_launch_ms = scan_ms / max(1, scan_launches)
-    kernel = {0: "scan_simt_kernel (+ candidate memset, bracketed together)",
+    kernel = {0: ("scan_simt_kernel" if args.space == "cosine" else f"scan_simt_metric_kernel ({args.space} space, row norms)")
+                 + " (+ candidate memset, bracketed together)",
               1: "scan_fused_kernel (single-launch SIMT search)",
               2: "tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, bracketed together)",
               3: "prep_fused_kernel + tc_fused_kernel (one cooperative launch: tcgen05 scoring of the whole corpus, in-kernel "
@@ -384,7 +391,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.workload}_b{B}")
+            traffic = json.load(f).get(f"{args.workload}_b{B}" + ("" if args.space == "cosine" else f"_{args.space}"))
     # intensity = B flop per corpus byte (bf16) or B/2 (fp32): above the ridge the tensor pipe bounds the search
     ridge = pk["tf_burst"] * 1e3 / pk["hbm"] * (1 if wl["dtype"] == "bf16" else 2)
     if B >= ridge:
@@ -408,7 +415,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch": B, "k": k, "rows": rows, "rows_per_gpu": sh.local_rows,
-                   "store_dtype": wl["dtype"],
+                   "store_dtype": wl["dtype"], "space": args.space,
                    "parallelism": (f"row-shard x{world}, candidate exchange: {sh.exchange}" if world > 1 else "single GPU"),
                    "l2": ("inputs larger than L2 (corpus per GPU %.2f GB vs 126 MB L2); no flush needed" % (algo_bytes / 1e9)
                           if algo_bytes > 126e6 else "corpus fits in L2 (%.1f KB): launch-latency-bound case, no flush" % (algo_bytes / 1e3)),
@@ -424,7 +431,7 @@ def main():
         line["selectivity_sweep"] = sel_sweep
     # N=1 default run only: the multi-GPU runs use config 4 (strong scaling over a fixed 100M-row corpus), so the
     # same corpus is also measured here on ONE GPU (153.6 GB of the 180 GB) -- the base point of that scaling curve.
-    if world == 1 and args.workload == "c2" and not args.rows and not args.no_scaling_base:
+    if world == 1 and args.workload == "c2" and not args.rows and not args.no_scaling_base and args.space == "cosine":
         try:
             del sh
             torch.cuda.empty_cache()

@@ -17,9 +17,13 @@ dist.init_process_group("nccl", device_id=dev)
 W = dist.get_world_size()
 SEED, QSEED = 0x5EED0004, 0x0BADC0DE
 results = []
-for n, dtype, B, k, frac in [(200_003, "bf16", 1, 10, None), (200_003, "bf16", 37, 10, None), (200_003, "fp32", 64, 100, 0.2),
-                             (70, "fp32", 3, 40, None), (300_000, "bf16", 300, 10, 0.01), (131_072 * W + 5, "bf16", 16, 10, None)]:
-    sh = ShardedIndex(768, dtype, n)
+# last column: the space rows are ranked in (l2 / ip: over the raw, non-unit synthetic vectors -- norms 15.5-16.5)
+for n, dtype, B, k, frac, space in [(200_003, "bf16", 1, 10, None, "cosine"), (200_003, "bf16", 37, 10, None, "cosine"),
+                                    (200_003, "fp32", 64, 100, 0.2, "cosine"), (70, "fp32", 3, 40, None, "cosine"),
+                                    (300_000, "bf16", 300, 10, 0.01, "cosine"), (131_072 * W + 5, "bf16", 16, 10, None, "cosine"),
+                                    (250_000, "bf16", 200, 10, None, "cosine"), (250_000, "fp32", 256, 10, 0.5, "cosine"),
+                                    (100_003, "fp32", 5, 10, None, "l2"), (100_003, "bf16", 9, 10, 0.3, "ip")]:
+    sh = ShardedIndex(768, dtype, n, metric=space)
     sh.add_synthetic(SEED)
     q, planted = O.planted_queries(QSEED, B, SEED, n, 768)
     mask = None if frac is None else O.mask_from_bool(np.random.default_rng(3).random(n) < frac)
@@ -31,9 +35,15 @@ for n, dtype, B, k, frac in [(200_003, "bf16", 1, 10, None), (200_003, "bf16", 3
     if rank == 0:
         st, _ = O.normalize_rows(O.synth_rows(SEED, 0, n, 768), dtype, 768)
         qn, _ = O.normalize_rows(q, "fp32", 768)
-        es, ei = O.brute_force_topk(qn, st, k, mask)
+        if space == "cosine":
+            es, ei = O.brute_force_topk(qn, st, k, mask)
+        else:
+            es, ei = O.brute_force_topk(qn, st, k, mask, metric=space, norms=O.row_norms(O.synth_rows(SEED, 0, n, 768), 768),
+                                        q_norms=O.row_norms(q, 768))
         ok = bool(np.array_equal(i, ei) and np.array_equal(s.view(np.uint32), es.view(np.uint32)))
-        results.append(dict(world=W, n=n, dtype=dtype, B=B, k=k, mask=frac, bounds=sh.bounds[:3], path=sh.index.stats()["last_path"], exchange=sh.exchange, exchange_error=sh.exchange_error, bit_exact=ok))
+        st_ = sh.index.stats()
+        results.append(dict(world=W, n=n, dtype=dtype, B=B, k=k, mask=frac, space=space, bounds=sh.bounds[:3], path=st_["last_path"],
+                            pipeline=st_["last_pipeline"], exchange=sh.exchange, exchange_error=sh.exchange_error, bit_exact=ok))
         print(results[-1], flush=True)
     # every rank must hold the same answer
     chk = torch.from_numpy(i.astype(np.int64)).to(dev)
