@@ -93,6 +93,7 @@ struct mqvs_store {
     bool keep_norms = false;
     float* norms = nullptr;   // [cap] when keep_norms
     float norm_dev = 0.0f;    // largest | ||x|| - 1 | over the rows accepted so far
+    float norm_max = 0.0f;    // largest ||x|| over the rows accepted so far
     cudaStream_t st = nullptr;
     // ring of event quads so that back-to-back async searches never wait on each other's timing
     static constexpr int kEvRing = 32;
@@ -111,6 +112,7 @@ struct mqvs_store {
     uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
     mqvs::tc::Buffers last_b{};                          // scratch layout + plan of the last tensor-core search: the
     mqvs::tc::Plan last_plan{};                          // blocking call enqueues its repair only after it has seen flags
+    mqvs::tc::Space last_space{};                        // and the space it ranked in
     unsigned long long* bad_dev = nullptr;   // [0] = non-finite rows counted by K1, [1] = epoch of the last fused
     unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits),
                                              // [2] = bits of the largest | ||x|| - 1 | of the current mqvs_add (low 32 bits)
@@ -208,7 +210,10 @@ void settle_events(mqvs_store* s) {
 
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
 bool use_tensor_path(const mqvs_store* s, int B, int k) {
-    if (s->metric != MQVS_METRIC_COSINE) return false;  // l2 / ip over raw vectors: exact SIMT scan (kernels_scan.cu)
+    // l2 / ip over raw vectors: only the single-launch pipeline carries the space transform (B <= 256 per launch; larger
+    // batches are split by the callers), everything else is the exact SIMT scan (kernels_scan.cu)
+    if (s->metric != MQVS_METRIC_COSINE &&
+        (s->path == 4 || !s->coop_ok || !mqvs::tc::fused_ok(B, k, s->sm_count))) return false;
     if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2 || s->path == 4) return true;
@@ -220,8 +225,10 @@ bool use_tensor_path(const mqvs_store* s, int B, int k) {
     // the clock drops under a power cap -- on 8 power-capped GPUs the SIMT scan alternated between 2.72 and 3.17 ms per
     // 12.5M-row shard while the TMA-fed pipeline stayed at 2.71-2.75 (profiles/r01_b1_paths_w8.json).  Below 1M rows the
     // SIMT path's single launch wins on latency.
-    if (s->n >= 1000000ull) return true;
     const int simt_max = s->dtype == MQVS_F32 ? 2 : 1;
+    // (l2 / ip spaces: the transform makes the tensor epilogue ~4 % slower than the SIMT scan for the 1-2 queries that scan
+    // holds the roofline for -- 0.508 vs 0.489 ms at 1M x 768 fp32, B=1 -- so those stay on the SIMT scan at every size)
+    if (s->n >= 1000000ull && (s->metric == MQVS_METRIC_COSINE || B > simt_max)) return true;
     return B > simt_max && s->n >= 65536;
 }
 
@@ -266,7 +273,7 @@ void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev
     if (!no_band && s->coop_ok && s->path != 4 && tc::fused_ok(1, k, s->sm_count)) {
         for (int r = 0; r < band_rounds; ++r) {  // 128 flagged queries per round
             const char* err = tc::search_band(b, s->last_plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k,
-                                              mask_dev, id_base, out_scores_dev, out_ids_dev, s->fix_counters, st);
+                                              mask_dev, id_base, out_scores_dev, out_ids_dev, s->fix_counters, st, s->last_space);
             if (err) {
                 cudaGetLastError();  // a refused cooperative launch: the exact scan below still repairs everything
                 break;
@@ -277,7 +284,8 @@ void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev
     uint32_t* fix_list = s->fix_dev;
     uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
     launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n,
-                    s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st);
+                    s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st, s->last_space.metric,
+                    s->last_space.norms, s->last_space.qnorm);
     launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
                      fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
     s->stats.kernel_launches += 2;
@@ -292,7 +300,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
-    const bool tensor = use_tensor_path(s, B, k);
+    bool tensor = use_tensor_path(s, B, k);
     const bool fused = !tensor && s->path != 3 && s->metric == MQVS_METRIC_COSINE && scan_fused_ok(B, k);
     s->last_fused = fused;
     tc::Plan plan{};
@@ -323,7 +331,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
-        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 3 + 32 + 144) * sizeof(uint32_t);
+        const size_t small = ((size_t)plan.b_pad * 4 + (size_t)B * 3 + 32 + 144) * sizeof(uint32_t);
         if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
         if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
@@ -348,6 +356,8 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.band = (uint32_t*)(b.gbar + 8);        // [B]
         b.band_list = b.band + B;               // [128]
         b.band_n = b.band_list + 128;           // [1]
+        b.hq = (float*)(b.band_n + 8);          // [b_pad]
+        b.h_op = b.hq + plan.b_pad;             // [b_pad]
         b.cnt = (uint32_t*)s->tc_cnt.p;
         b.lists = (uint64_t*)s->tc_lists.p;
         b.short_keys = (uint64_t*)s->tc_keys.p;
@@ -355,9 +365,17 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.cmax = (uint32_t*)s->tc_cmax.p;
         s->last_flags_dev = b.flag_count;
     }
+    tc::Space space{};
     if (tensor) {
+        if (s->metric != MQVS_METRIC_COSINE) {
+            space.metric = s->metric;
+            space.norms = s->norms;
+            space.amax = s->norm_max;
+            space.qnorm = (float*)s->qnorm.p;
+        }
         s->last_b = b;
         s->last_plan = plan;
+        s->last_space = space;
     }
     auto enqueue_repair = [&]() {
         // nobody can look at the flags here: one band round per 128 queries of the batch, at most two
@@ -370,13 +388,14 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         bool coop_refused = false;
         const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
                                            mask_dev, id_base, out_scores_dev, out_ids_dev, (unsigned int*)(s->bad_dev + 1),
-                                           ++s->epoch, st, &coop_refused);
+                                           ++s->epoch, st, &coop_refused, space);
         if (err && coop_refused) {
             // the device cannot hold one CTA per SM right now (MPS with an SM limit, a partitioned GPU): this handle
-            // keeps to the segmented pipeline from here on
+            // keeps to the segmented pipeline from here on (l2 / ip spaces: to the exact scan)
             s->coop_ok = false;
             tc_one = false;
             s->last_fused = false;
+            if (s->metric != MQVS_METRIC_COSINE) tensor = false;
         } else if (err) {
             return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         }
@@ -596,10 +615,12 @@ static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uin
         return fail(MQVS_E_INVALID, "%llu of %llu embeddings have a non-finite norm; nothing was added",
                     *s->bad_host, (unsigned long long)n);
     {
-        const uint32_t bits = (uint32_t)s->bad_host[2];
-        float dev;
+        const uint32_t bits = (uint32_t)s->bad_host[2], bits_max = (uint32_t)(s->bad_host[2] >> 32);
+        float dev, mx;
         memcpy(&dev, &bits, 4);
+        memcpy(&mx, &bits_max, 4);
         s->norm_dev = std::max(s->norm_dev, dev);
+        s->norm_max = std::max(s->norm_max, mx);
     }
     s->n += n;
     s->stats.rows = s->n;
@@ -626,6 +647,16 @@ static int check_search_args(mqvs_t* s, const float* q, int B, int k, const void
     return MQVS_OK;
 }
 
+// l2 / ip spaces: the single-launch tensor pipeline takes at most 256 queries, so larger batches go through it in slices
+// (the segmented pipeline does not carry the space transform); 0 = no slicing
+static int metric_slice(const mqvs_store* s, int B, int k) {
+    const int slice = 2 * 128;
+    return s->metric != MQVS_METRIC_COSINE && B > slice && use_tensor_path(s, slice, k) ? slice : 0;
+}
+
+static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
+                         float* out_scores, int64_t* out_ids, int out_is_device);
+
 MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
                 float* out_scores, int64_t* out_ids, int out_is_device) {
     int rc = check_search_args(s, q, B, k, out_scores, out_ids);
@@ -633,6 +664,28 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     if (B == 0) return MQVS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
+    if (const int slice = metric_slice(s, B, k)) {
+        if (mask && !mask_is_device) {  // upload the filter once, not per slice
+            const size_t bytes = (size_t)((s->n + 31) / 32) * sizeof(uint32_t);
+            if ((rc = s->maskbuf.ensure(bytes)) != MQVS_OK) return rc;
+            CU(cudaMemcpyAsync(s->maskbuf.p, mask, bytes, cudaMemcpyHostToDevice, s->st));
+            mask = (const uint32_t*)s->maskbuf.p;
+            mask_is_device = 1;
+        }
+        for (int b0 = 0; b0 < B; b0 += slice) {
+            const int nb = std::min(slice, B - b0);
+            if ((rc = search_locked(s, q + (size_t)b0 * s->dim, q_is_device, nb, k, mask, mask_is_device,
+                                    out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, out_is_device)) != MQVS_OK)
+                return rc;
+        }
+        return MQVS_OK;
+    }
+    return search_locked(s, q, q_is_device, B, k, mask, mask_is_device, out_scores, out_ids, out_is_device);
+}
+
+static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
+                         float* out_scores, int64_t* out_ids, int out_is_device) {
+    int rc;
     const float* q_dev = q;
     if (!q_is_device) {
         if ((rc = s->qraw.ensure((size_t)B * s->dim * sizeof(float))) != MQVS_OK) return rc;
@@ -737,6 +790,15 @@ MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, cons
     if (B == 0) return MQVS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
+    if (const int slice = metric_slice(s, B, k)) {  // stream-ordered: the slices reuse the handle's scratch one after another
+        for (int b0 = 0; b0 < B; b0 += slice) {
+            const int nb = std::min(slice, B - b0);
+            if ((rc = enqueue_search(s, q_dev + (size_t)b0 * s->dim, nb, k, mask_dev, id_base, out_scores_dev + (size_t)b0 * k,
+                                     out_ids_dev + (size_t)b0 * k, (cudaStream_t)cuda_stream)) != MQVS_OK)
+                return rc;
+        }
+        return MQVS_OK;
+    }
     return enqueue_search(s, q_dev, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, (cudaStream_t)cuda_stream);
 }
 
@@ -819,9 +881,13 @@ int load_norms(mqvs_store* s, const char* path, uint64_t rows) {
     fclose(f);
     if (!ok) return fail(MQVS_E_IO, "%s does not hold the norms of %llu rows", src.c_str(), (unsigned long long)rows);
     if (rows) CU(cudaMemcpy(s->norms, host.data(), rows * sizeof(float), cudaMemcpyHostToDevice));
-    float dev = 0.0f;
-    for (uint64_t r = 0; r < rows; ++r) dev = std::max(dev, fabsf(host[r] - 1.0f));
+    float dev = 0.0f, mx = 0.0f;
+    for (uint64_t r = 0; r < rows; ++r) {
+        dev = std::max(dev, fabsf(host[r] - 1.0f));
+        mx = std::max(mx, host[r]);
+    }
     s->norm_dev = dev;
+    s->norm_max = mx;
     return MQVS_OK;
 }
 }  // namespace

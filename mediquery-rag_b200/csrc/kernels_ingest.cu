@@ -53,7 +53,7 @@ normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned l
                       float* __restrict__ norms, unsigned int* __restrict__ max_dev) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps_total = (uint64_t)gridDim.x * kIngestWarps;
-    float dev_max = 0.0f;  // largest | ||x|| - 1 | this warp has seen
+    float dev_max = 0.0f, nrm_max = 0.0f;  // largest | ||x|| - 1 | and largest ||x|| this warp has seen
     for (uint64_t row = (uint64_t)blockIdx.x * kIngestWarps + (threadIdx.x >> 5); row < n; row += warps_total) {
         float4 v[kChunks];
         src.load(row, lane, v);
@@ -62,6 +62,7 @@ normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned l
         if (!ok && lane == 0) atomicAdd(bad, 1ull);
         if (norms != nullptr && lane == 0) norms[row] = nrm;
         dev_max = fmaxf(dev_max, fabsf(nrm - 1.0f));
+        nrm_max = fmaxf(nrm_max, nrm);
         OutT* o = out + row * (uint64_t)kDim;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
@@ -79,7 +80,10 @@ normalize_pack_kernel(Source src, uint64_t n, OutT* __restrict__ out, unsigned l
         }
     }
     // non-negative floats order like their bit patterns: one atomicMax per warp per launch
-    if (max_dev != nullptr && lane == 0 && dev_max > 0.0f) atomicMax(max_dev, __float_as_uint(dev_max));
+    if (max_dev != nullptr && lane == 0) {
+        if (dev_max > 0.0f) atomicMax(max_dev, __float_as_uint(dev_max));
+        if (nrm_max > 0.0f) atomicMax(max_dev + 1, __float_as_uint(nrm_max));  // [1]: largest ||x||
+    }
 }
 
 template <typename Source>

@@ -240,12 +240,13 @@ scan_simt_metric_kernel(const T* __restrict__ rows, uint32_t n_rows, const float
 // popcount over flags[B], first max_fix in index order), so no separate compaction launch is needed and no host round
 // trip; block 0 publishes the list for merge_fix_kernel and updates the repair counters.  With no flag set every CTA
 // returns at once.
-template <typename T, int KPL, int U>
+template <typename T, int KPL, int U, bool XF>
 __global__ void __launch_bounds__(kScanThreads)
 scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __restrict__ qn_all,
                 const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
                 uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters,
-                const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride) {
+                const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride, int metric,
+                const float* __restrict__ row_norms, const float* __restrict__ q_norms_all) {
     extern __shared__ __align__(16) uint64_t smem_keys[];
     __shared__ uint32_t list_s[64];
     __shared__ uint32_t n_s, total_s;
@@ -277,8 +278,17 @@ scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __rest
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fix_list[i] = list_s[i];
     }
     for (uint32_t f = 0; f < n; ++f) {
-        scan_body<T, 1, KPL, U>(rows, n_rows, qn_all + (size_t)list_s[f] * kDim, 1, mask, k,
-                                cand + (size_t)f * cand_stride * k, cand_stride, smem_keys);
+        if constexpr (XF) {  // l2 / ip spaces: the same ranking score as scan_simt_metric_kernel
+            SpaceXf<1> xf;
+            xf.metric = metric;
+            xf.norms = row_norms;
+            xf.h[0] = __fdiv_rn(0.5f, fmaxf(__ldg(q_norms_all + list_s[f]), kEps));
+            scan_body<T, 1, KPL, U, true>(rows, n_rows, qn_all + (size_t)list_s[f] * kDim, 1, mask, k,
+                                          cand + (size_t)f * cand_stride * k, cand_stride, smem_keys, &xf);
+        } else {
+            scan_body<T, 1, KPL, U>(rows, n_rows, qn_all + (size_t)list_s[f] * kDim, 1, mask, k,
+                                    cand + (size_t)f * cand_stride * k, cand_stride, smem_keys);
+        }
         __syncthreads();
     }
 }
@@ -375,14 +385,22 @@ int scan_fix_grid(int sm_count) { return sm_count * 2; }
 
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
-                     int sm_count, cudaStream_t st) {
+                     int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all) {
     const int kpl = k <= 32 ? 1 : 4;  // the tensor path serves k <= 128
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
     if (max_fix > 64) max_fix = 64;
-#define MQVS_FIX(T_, KPL_, U_)                                                                                                \
-    scan_fix_kernel<T_, KPL_, U_><<<grid, kScanThreads, smem, st>>>((const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, \
-                                                                     fix_n, counters, mask, k, cand, stride)
+#define MQVS_FIX(T_, KPL_, U_)                                                                                                     \
+    do {                                                                                                                           \
+        if (metric != MQVS_METRIC_COSINE)                                                                                          \
+            scan_fix_kernel<T_, KPL_, U_, true><<<grid, kScanThreads, smem, st>>>(                                                 \
+                (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, metric,      \
+                row_norms, q_norms_all);                                                                                           \
+        else                                                                                                                       \
+            scan_fix_kernel<T_, KPL_, U_, false><<<grid, kScanThreads, smem, st>>>(                                                \
+                (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, 0, nullptr,  \
+                nullptr);                                                                                                          \
+    } while (0)
     if (dtype == MQVS_F32) {
         if (kpl == 1) MQVS_FIX(float, 1, 2); else MQVS_FIX(float, 4, 2);
     } else {

@@ -11,8 +11,9 @@ int mqvs_fail(int code, const char* fmt, ...);
 
 // K1: L2-normalise + pack.  x [n, dim] fp32 (device) -> out [n, 768] fp32 or bf16, zero-padded; counts
 // rows whose squared norm is not finite into *bad (and stores them as zeros).  norms (optional, [n]) receives ||x|| of
-// every raw row (what the l2 / ip spaces rank with); max_dev (optional) is raised to the bit pattern of the largest
-// | ||x|| - 1 | seen (atomicMax), which tells the host whether the collection consists of unit vectors.
+// every raw row (what the l2 / ip spaces rank with); max_dev (optional, two words) is raised to the bit patterns of the
+// largest | ||x|| - 1 | seen ([0], atomicMax: tells the host whether the collection consists of unit vectors) and of the
+// largest ||x|| ([1]: scales the tensor-core error bound in those spaces).
 void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
                       cudaStream_t st, float* norms = nullptr, unsigned int* max_dev = nullptr);
 // Same K1 fed by the counter-based generator instead of memory.
@@ -42,7 +43,8 @@ void launch_scan_simt_metric(const void* rows, int dtype, uint32_t n_rows, const
 int scan_fix_grid(int sm_count);  // CTAs (= candidate stride per listed query) of the repair scan
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
-                     int sm_count, cudaStream_t st);
+                     int sm_count, cudaStream_t st, int metric = 0, const float* row_norms = nullptr,
+                     const float* q_norms_all = nullptr);
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
                       const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st);
 

@@ -30,6 +30,16 @@ struct Buffers {       // all device memory, owned by the store handle
     uint32_t* band;       // [B] band-pass threshold of every flagged query: ord(k-th exact score - eps)
     uint32_t* band_list;  // [128] flagged queries, compacted
     uint32_t* band_n;     // [1]
+    float* hq;            // l2 / ip spaces: [b_pad] 0.5 / max(||q||, eps) per query (0 in the ip space)
+    float* h_op;          // the same per operand row of the band pass (compacted queries)
+};
+
+// Chroma's l2 / ip spaces over raw (non-unit) vectors, single-launch pipeline only (common.cuh:rank_score; mqvs_set_metric)
+struct Space {
+    int metric = 0;                // MQVS_METRIC_*; 0 = cosine: the other fields are unused
+    const float* norms = nullptr;  // [n_rows] ||x|| of the raw rows (K1)
+    float amax = 1.0f;             // largest ||x||: the tensor-core error bound of a ranking score is amax * eps
+    float* qnorm = nullptr;        // [B] out: ||q|| of the raw queries (the exact-scan repair ranks with them)
 };
 
 Plan plan(int k, int B, int sm_count);
@@ -48,13 +58,14 @@ bool fused_ok(int B, int k, int sm_count);
 size_t cmax_bytes(const Plan& p);
 const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* q_raw,
                          int dim, float* qn, int B, int k, const uint32_t* mask, int64_t id_base, float* out_scores,
-                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused);
+                         int64_t* out_ids, unsigned int* bad_epoch, unsigned int epoch, cudaStream_t st, bool* coop_refused,
+                         const Space& space = Space());
 
 // Repair of flagged queries by a second single-launch pass with given thresholds (kernels_tc_fused.cu); enqueue after
 // search() / search_fused() and before the exact-scan repair.  counters[2] counts the queries it repaired.
 const char* search_band(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
                         int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids,
-                        unsigned long long* counters, cudaStream_t st);
+                        unsigned long long* counters, cudaStream_t st, const Space& space = Space());
 
 void trace_dump();  // MQVS_TRACE=1 developer aid: per-launch timings of the last searches to stderr
 int launches_per_search(const Plan& p, uint32_t n_rows, int B);  // prep + (score, select) per segment + rescore + finalize

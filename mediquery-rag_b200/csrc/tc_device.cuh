@@ -206,6 +206,23 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
 // test of this query's 256 scores, survivors appended to the thread's private list, lists about to overflow compacted.
 // The 8 largest chunk maxima (order-preserving bits; one chunk = 32 consecutive rows, masked rows excluded) this
 // (CTA, query) has seen, unsorted, mirrored in global memory slot by slot: tc_fused_kernel's threshold refresh reads them.
+// l2 / ip spaces over raw vectors (common.cuh:rank_score): what an epilogue thread needs to turn the approximate cosines
+// of a chunk into approximate ranking scores t = a s - a^2 h (ip: h = 0).  The exact scores come from the rescoring,
+// which uses rank_score itself; here only |t~ - t| <= a_max eps matters.
+struct TileSpace {
+    const float* norms = nullptr;  // [n_rows] ||x|| of the raw rows; nullptr = cosine (scores used as they are)
+    float h = 0.0f;                // this thread's query: 0.5 / max(||q||, eps) for l2, 0 for ip
+};
+__device__ __forceinline__ void apply_space(uint32_t (&v)[32], const TileSpace& sp, uint32_t row0, uint32_t n_rows, int lane) {
+    const float a_l = __ldg(sp.norms + min(row0 + (uint32_t)lane, n_rows - 1u));  // one coalesced load per chunk and warp
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float a = __shfl_sync(0xffffffffu, a_l, j);
+        const float t = __fmaf_rn(a, __uint_as_float(v[j]), -__fmul_rn(__fmul_rn(a, a), sp.h));
+        v[j] = v[j] == 0xff800000u ? v[j] : __float_as_uint(t);  // masked / out-of-range rows stay -inf (a may be 0)
+    }
+}
+
 struct ChunkTop {
     uint32_t v[8];
     uint32_t mn;     // min of v
@@ -216,7 +233,8 @@ struct ChunkTop {
 template <int CAP, int KPRIME, bool TRACK = false>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0, uint32_t n_rows,
                                               const uint32_t* __restrict__ mask, uint32_t* st, uint32_t* tau_glob_q, int lane,
-                                              float& tau, uint32_t& cnt, uint64_t* lst, ChunkTop* trk = nullptr) {
+                                              float& tau, uint32_t& cnt, uint64_t* lst, ChunkTop* trk = nullptr,
+                                              const TileSpace sp = TileSpace()) {
     constexpr int KPL = CAP / 32;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
@@ -236,6 +254,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (mw >> j) & 1u ? v[j] : 0xff800000u;
         }
+        if (sp.norms != nullptr) apply_space(v, sp, row0, n_rows, lane);  // uniform
         // fast reject: one 3-input max tree per 32 scores, one compare
         float grp[11];
         const float mx = max32(v, grp);
@@ -311,7 +330,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
 // as order-preserving bits (0 = the chunk has no allowed row).  Distinct chunks are distinct rows, so the k'-th largest
 // chunk maximum of a set of tiles is a valid shortlist threshold for them: at least k' rows score that much.
 __device__ __forceinline__ void tile_chunk_maxima(uint32_t taddr, uint32_t tile_row0, uint32_t n_rows,
-                                                  const uint32_t* __restrict__ mask, uint32_t (&out)[BN / 32]) {
+                                                  const uint32_t* __restrict__ mask, uint32_t (&out)[BN / 32],
+                                                  const TileSpace sp = TileSpace(), int lane = 0) {
 #pragma unroll
     for (int ch = 0; ch < BN / 32; ++ch) {
         const uint32_t row0 = tile_row0 + ch * 32;
@@ -322,6 +342,11 @@ __device__ __forceinline__ void tile_chunk_maxima(uint32_t taddr, uint32_t tile_
             tmem_ld32(taddr + ch * 32, v);
             uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
             if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
+            if (sp.norms != nullptr) {  // uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (mw >> j) & 1u ? v[j] : 0xff800000u;
+                apply_space(v, sp, row0, n_rows, lane);
+            }
             float m = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY);

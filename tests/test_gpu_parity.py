@@ -830,9 +830,10 @@ def _raw_rows(n, seed=SEED, lo=0.25, hi=4.0):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("space", ["l2", "ip"])
 def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_path):
-    """Chroma's hnsw:space on NON-unit vectors: K1 keeps ||x|| per row, the exact scan maps the
-    cosine of the normalised pair to the space's ranking score (common.cuh:rank_score) before top-k.  Bit-identical
-    to oracle/canonical.c:orc_topk_metric, which tests/test_spaces.py ties to a float64 brute force over raw vectors."""
+    """Chroma's hnsw:space on NON-unit vectors: K1 keeps ||x|| per row; the exact scan and the
+    single-launch tensor pipeline (epilogue transform + exact rescoring, batches above 256 in slices) map the cosine of the
+    normalised pair to the space's ranking score (common.cuh:rank_score) before top-k.  Bit-identical on every path to
+    oracle/canonical.c:orc_topk_metric, which tests/test_spaces.py ties to a float64 brute force over raw vectors."""
     import torch
     M = native()
     n = 70_001  # large enough that the cosine space would take the tensor-core path for B >= 2
@@ -846,7 +847,9 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
     assert idx.norm_deviation() == float(np.abs(nr - np.float32(1.0)).max())
     st, _ = O.normalize_rows(x, dtype, 768)
     rng = np.random.default_rng(2)
-    for B, k, frac in ((1, 10, None), (3, 5, None), (9, 10, 0.3), (2, 40, None), (1, 200, 0.5), (64, 10, None)):
+    simt_max = 2 if dtype == "fp32" else 1  # api.cu:use_tensor_path below 1M rows
+    for B, k, frac in ((1, 10, None), (3, 5, None), (9, 10, 0.3), (2, 40, None), (1, 200, 0.5), (200, 100, 0.5), (300, 10, None),
+                       (64, 10, None)):
         q = (_raw_rows(B, seed=QSEED) * np.float32(3.0) + 0.5 * x[rng.integers(0, n, B)]).astype(np.float32)
         qn, _ = O.normalize_rows(q, "fp32", 768)
         mask = None if frac is None else O.mask_from_bool(rng.random(n) < frac)
@@ -854,8 +857,14 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
         es, ei = O.brute_force_topk(qn, st, k, mask, metric=space, norms=nr, q_norms=O.row_norms(q, 768))
         assert_bit_equal(s, i, es, ei)
         stats = idx.stats()
-        assert stats["last_path"] == 0 and stats["last_pipeline"] == 0
+        tensor = B > simt_max and k <= 128
+        assert stats["last_path"] == int(tensor) and stats["last_pipeline"] == (3 if tensor else 0), stats
+        assert stats["exact_fallbacks"] == 0
     assert not np.array_equal(O.brute_force_topk(qn, st, k)[1], ei)  # the space matters on these rows
+    idx.set_path(1)                                                  # the exact scan alone gives the same answer
+    assert_bit_equal(*idx.search(q, k), es, ei)
+    assert idx.stats()["last_path"] == 0
+    idx.set_path(0)
     # all-device call on a caller stream, with an id base (the sharded path)
     qd = torch.from_numpy(q).cuda()
     out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
@@ -863,6 +872,7 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
     idx.search_device(qd, k, out_s, out_i, id_base=1000, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei + 1000)
+    assert idx.stats()["last_pipeline"] == 3
     # the metric can be switched once the norms are kept: cosine ranks the normalised rows (tensor path for B = 64)
     idx.set_metric("cosine")
     s, i = idx.search(q, k)
@@ -925,3 +935,48 @@ def test_vectorstore_default_space_on_raw_vectors_ranks_by_squared_l2(gpu, tmp_p
     assert [doc.page_content for doc, _ in got] == [texts[r] for r in np.argsort(d, kind="stable")[:6]]
     assert np.allclose([dist for _, dist in got], np.sort(d)[:6], atol=2e-6)
     assert vu._index.stats()["last_pipeline"] == 1  # the single-launch latency kernel, as before
+
+
+@pytest.mark.parametrize("space,dtype,B", [("l2", "bf16", 64), ("ip", "fp32", 20), ("l2", "fp32", 200), ("ip", "bf16", 300)])
+def test_spaces_on_the_tensor_pipeline_band_pass_and_exact_repair(gpu, space, dtype, B):
+    """The hard cases of the tensor path in the l2 / ip spaces: a clustered corpus of NON-unit rows (members of a cluster
+    share a direction within cosine 0.98 and a length within 2 %), where ranking scores around rank k are closer together
+    than amax * eps, so queries are flagged and the band pass must settle them in the transformed space; plus hundreds of
+    exact duplicates of one row, which overflow the shortlist and force the exact-scan repair (scan_fix_kernel with the
+    space transform).  Bit-identical to the oracle in every case."""
+    n, members, k = 120_000, 1500, 10
+    rng = np.random.default_rng(1)
+    sigma = np.sqrt((1.0 / 0.98 ** 2 - 1.0) / 256.0)
+    centres = rng.standard_normal((n // members, 768)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    length = np.repeat(rng.uniform(0.5, 3.0, n // members), members) * rng.uniform(0.98, 1.02, n)
+    x = ((np.repeat(centres, members, axis=0) + sigma * rng.uniform(-1, 1, (n, 768))) * length[:, None]).astype(np.float32)
+    x[60_000:61_500] = x[777]                        # 1500 exact copies: more than the direct shortlist holds
+    picks = rng.integers(0, n, B)
+    picks[0] = 777
+    q = (x[picks] * rng.uniform(0.8, 1.2, (B, 1)) + 0.5 * sigma * rng.uniform(-1, 1, (B, 768))).astype(np.float32)
+    q[0] = x[777]
+    st, _ = O.normalize_rows(x, dtype, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    nr = O.row_norms(x, 768)
+    es, ei = O.brute_force_topk(qn, st, k, metric=space, norms=nr, q_norms=O.row_norms(q, 768))
+    idx = native().Index(768, dtype)
+    idx.set_metric(space)
+    idx.add(x)
+    idx.set_path(2)
+    s, i = idx.search(q, k)
+    stats = idx.stats()
+    assert_bit_equal(s, i, es, ei)
+    assert stats["last_path"] == 1 and stats["last_pipeline"] == 3, stats
+    assert stats["band_repairs"] > 0, stats
+    # the all-device call (band pass + device-driven exact repair enqueued blindly) gives the same answer
+    import torch
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    idx.search_device(torch.from_numpy(q).cuda(), k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert idx.stats()["unrepaired"] == 0
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    # the duplicates: query 0 is (a multiple of) row 777; in the l2 space its copies tie at the top, lowest row ids first
+    if space == "l2":
+        assert i[0, 0] == 777 and list(i[0, 1:4]) == [60_000, 60_001, 60_002]
