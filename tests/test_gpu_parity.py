@@ -980,3 +980,36 @@ def test_spaces_on_the_tensor_pipeline_band_pass_and_exact_repair(gpu, space, dt
     # the duplicates: query 0 is (a multiple of) row 777; in the l2 space its copies tie at the top, lowest row ids first
     if space == "l2":
         assert i[0, 0] == 777 and list(i[0, 1:4]) == [60_000, 60_001, 60_002]
+
+
+@pytest.mark.parametrize("space", ["l2", "ip"])
+def test_full_size_config2_in_the_l2_and_ip_spaces_properties(gpu, space):
+    """BASELINE config 2 size (1M x 768 fp32) in Chroma's l2 / ip spaces over the raw synthetic rows (norms 15.5-16.5),
+    through size-independent properties: both kernel families agree bit for bit (single-launch tensor pipeline for the batch,
+    exact SIMT scan for one query), results are sorted and duplicate-free, the returned scores are the oracle's ranking
+    scores of the returned rows (rows regenerated from the hash), and no row of a 100k-row sample beats the k-th result."""
+    n, B, k = 1_000_000, 16, 10
+    idx = native().Index(768, "fp32", capacity_rows=n)
+    idx.set_metric(space)
+    idx.add_synthetic(SEED, 0, n)
+    q = (O.synth_rows(QSEED, 0, B, 768) * np.float32(0.9) + 0.3 * O.synth_rows(SEED, 4242, B, 768)).astype(np.float32)
+    s, i = idx.search(q, k)
+    assert idx.stats()["last_pipeline"] == 3
+    assert np.all(np.diff(s, axis=1) <= 0) and (i >= 0).all() and all(len(set(r)) == k for r in i.tolist())
+    s1, i1 = idx.search(q[3:4], k)
+    assert idx.stats()["last_pipeline"] == 0
+    assert np.array_equal(i1[0], i[3]) and np.array_equal(s1[0].view(np.uint32), s[3].view(np.uint32))
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    qnorm = O.row_norms(q, 768)
+    for b in range(0, B, 3):
+        rows = np.concatenate([O.synth_rows(SEED, int(r), 1, 768) for r in i[b]])
+        st_b, _ = O.normalize_rows(rows, "fp32", 768)
+        es, ei = O.brute_force_topk(qn[b:b + 1], st_b, k, metric=space, norms=O.row_norms(rows, 768), q_norms=qnorm[b:b + 1])
+        assert np.array_equal(ei[0], np.arange(k)) and np.array_equal(es[0].view(np.uint32), s[b].view(np.uint32))
+    lo = 300_000
+    sample = O.synth_rows(SEED, lo, 100_000, 768)
+    st_s, _ = O.normalize_rows(sample, "fp32", 768)
+    ss, si = O.brute_force_topk(qn, st_s, 1, metric=space, norms=O.row_norms(sample, 768), q_norms=qnorm, id_base=lo)
+    for b in range(B):  # the sample's best row is either in the result or no better than its k-th entry
+        assert si[b, 0] in i[b] or ss[b, 0] <= s[b, k - 1]
+    assert np.array_equal(idx.get_norms(lo, 1000).view(np.uint32), O.row_norms(sample[:1000], 768).view(np.uint32))

@@ -24,6 +24,15 @@ for dt in ("bf16", "fp32"):
     s, i = idx.search(q[:16], 10, mask)
     print(dt, "filtered", allowed, i[0, :3], flush=True)
     idx.close()
+    # Chroma's l2 / ip spaces over the raw rows (norms ~16): K1 with norms, the SIMT scan and the single-launch tensor
+    # pipeline with the space transform (one and two query tiles, a filter, n not a multiple of the tile)
+    for space in ("l2", "ip"):
+        idx = M.Index(768, dt); idx.set_metric(space); idx.add(x[: n - 77])
+        for path, B, k in ((1, 3, 5), (2, 2, 10), (2, 100, 10), (2, 200, 100)):
+            idx.set_path(path)
+            s, i = idx.search(q[:B] * np.float32(0.1), k)
+            print(dt, space, path, B, k, i[0, :3], idx.stats()["last_pipeline"], flush=True)
+        idx.close()
 import torch
 W, B, k = 3, 20, 10
 ex = [M._native.PeerExchange(0, r, W, max_entries=1024) for r in range(W)]
