@@ -175,7 +175,7 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path);
  * (ip: 1 - ||q|| t; l2: ||q||^2 - 2 ||q|| t).  Norms are kept from the first call with a non-cosine metric on, so that
  * call must come while the store is empty; afterwards the metric may be switched freely (e.g. back to
  * MQVS_METRIC_COSINE while every row is a unit vector, see mqvs_norm_deviation).  Non-cosine metrics run on the exact
- * SIMT scan (1-2 queries, small stores, k > 128) or the single-launch tensor pipeline (batches above 256 in slices). */
+ * SIMT scan (1-2 queries, small stores, k > 128) or the tensor pipelines, chosen by batch size as for cosine. */
 MQVS_API int mqvs_set_metric(mqvs_t* s, int metric);
 /* largest | ||x|| - 1 | over the raw rows added (or loaded with their norms) so far: 0 for a collection of exact unit vectors */
 MQVS_API int mqvs_norm_deviation(mqvs_t* s, float* out);

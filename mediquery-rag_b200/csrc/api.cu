@@ -210,10 +210,6 @@ void settle_events(mqvs_store* s) {
 
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
 bool use_tensor_path(const mqvs_store* s, int B, int k) {
-    // l2 / ip over raw vectors: only the single-launch pipeline carries the space transform (B <= 256 per launch; larger
-    // batches are split by the callers), everything else is the exact SIMT scan (kernels_scan.cu)
-    if (s->metric != MQVS_METRIC_COSINE &&
-        (s->path == 4 || !s->coop_ok || !mqvs::tc::fused_ok(B, k, s->sm_count))) return false;
     if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2 || s->path == 4) return true;
@@ -331,7 +327,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
-        const size_t small = ((size_t)plan.b_pad * 4 + (size_t)B * 3 + 32 + 144) * sizeof(uint32_t);
+        const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 4 + 128 + 256 + 32 + 144) * sizeof(uint32_t);
         if ((rc = s->tc_qop.ensure(tc::op_bytes(plan, s->dtype))) != MQVS_OK) return rc;
         if ((rc = s->tc_small.ensure(small)) != MQVS_OK) return rc;
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
@@ -356,8 +352,8 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.band = (uint32_t*)(b.gbar + 8);        // [B]
         b.band_list = b.band + B;               // [128]
         b.band_n = b.band_list + 128;           // [1]
-        b.hq = (float*)(b.band_n + 8);          // [b_pad]
-        b.h_op = b.hq + plan.b_pad;             // [b_pad]
+        b.h_op = (float*)(b.band_n + 8);        // [256]
+        b.hq = b.h_op + 256;                    // [B rounded up to 128]: every chunk of the segmented pipeline keeps its slice
         b.cnt = (uint32_t*)s->tc_cnt.p;
         b.lists = (uint64_t*)s->tc_lists.p;
         b.short_keys = (uint64_t*)s->tc_keys.p;
@@ -395,7 +391,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
             s->coop_ok = false;
             tc_one = false;
             s->last_fused = false;
-            if (s->metric != MQVS_METRIC_COSINE) tensor = false;
+
         } else if (err) {
             return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         }
@@ -426,7 +422,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     if (tensor) {
         CU(cudaEventRecord(ev[1], st));
         const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
-                                     id_base, out_scores_dev, out_ids_dev, st);
+                                     id_base, out_scores_dev, out_ids_dev, st, space);
         if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
         enqueue_repair();
@@ -647,13 +643,6 @@ static int check_search_args(mqvs_t* s, const float* q, int B, int k, const void
     return MQVS_OK;
 }
 
-// l2 / ip spaces: the single-launch tensor pipeline takes at most 256 queries, so larger batches go through it in slices
-// (the segmented pipeline does not carry the space transform); 0 = no slicing
-static int metric_slice(const mqvs_store* s, int B, int k) {
-    const int slice = 2 * 128;
-    return s->metric != MQVS_METRIC_COSINE && B > slice && use_tensor_path(s, slice, k) ? slice : 0;
-}
-
 static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
                          float* out_scores, int64_t* out_ids, int out_is_device);
 
@@ -664,22 +653,6 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     if (B == 0) return MQVS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
-    if (const int slice = metric_slice(s, B, k)) {
-        if (mask && !mask_is_device) {  // upload the filter once, not per slice
-            const size_t bytes = (size_t)((s->n + 31) / 32) * sizeof(uint32_t);
-            if ((rc = s->maskbuf.ensure(bytes)) != MQVS_OK) return rc;
-            CU(cudaMemcpyAsync(s->maskbuf.p, mask, bytes, cudaMemcpyHostToDevice, s->st));
-            mask = (const uint32_t*)s->maskbuf.p;
-            mask_is_device = 1;
-        }
-        for (int b0 = 0; b0 < B; b0 += slice) {
-            const int nb = std::min(slice, B - b0);
-            if ((rc = search_locked(s, q + (size_t)b0 * s->dim, q_is_device, nb, k, mask, mask_is_device,
-                                    out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, out_is_device)) != MQVS_OK)
-                return rc;
-        }
-        return MQVS_OK;
-    }
     return search_locked(s, q, q_is_device, B, k, mask, mask_is_device, out_scores, out_ids, out_is_device);
 }
 
@@ -790,15 +763,6 @@ MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, cons
     if (B == 0) return MQVS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
-    if (const int slice = metric_slice(s, B, k)) {  // stream-ordered: the slices reuse the handle's scratch one after another
-        for (int b0 = 0; b0 < B; b0 += slice) {
-            const int nb = std::min(slice, B - b0);
-            if ((rc = enqueue_search(s, q_dev + (size_t)b0 * s->dim, nb, k, mask_dev, id_base, out_scores_dev + (size_t)b0 * k,
-                                     out_ids_dev + (size_t)b0 * k, (cudaStream_t)cuda_stream)) != MQVS_OK)
-                return rc;
-        }
-        return MQVS_OK;
-    }
     return enqueue_search(s, q_dev, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, (cudaStream_t)cuda_stream);
 }
 

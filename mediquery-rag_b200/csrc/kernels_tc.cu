@@ -50,9 +50,14 @@ struct ScoreArgs {
     uint32_t b_pad;
     uint32_t* cmax;         // cold pass only (else nullptr): [B_pad][ncols] chunk maxima, no list appends
     uint32_t ncols;         // 8 * CTAs of the cold pass
+    // l2 / ip spaces over raw vectors (XF instantiations only; tc.h:Space)
+    const float* norms;     // [n_rows] ||x||
+    const float* hq;        // [B_pad] 0.5 / max(||q||, eps) (l2), 0 (ip)
 };
 
-template <typename T, int CAP, int KPRIME>
+// XF = the l2 / ip spaces: the epilogue maps each chunk's cosines to ranking scores (tc_device.cuh:apply_space) before the
+// thresholds see them; a separate instantiation, so the cosine kernels are unchanged.
+template <typename T, int CAP, int KPRIME, bool XF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScoreArgs a) {
     using K = Kind<T>;
@@ -148,20 +153,26 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 uint64_t* lst = a.lists + slot * CAP;
                 uint32_t cnt = q_ok ? a.cnt[slot] : 0;
                 float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
+                TileSpace sp;
+                if constexpr (XF) {
+                    sp.norms = a.norms;
+                    sp.h = q_ok ? __ldg(a.hq + q) : 0.0f;
+                }
 
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
                 if (a.cmax != nullptr) {  // cold pass (uniform): only the chunk maxima that seed the thresholds
                     uint32_t cm[BN / 32];
-                    tile_chunk_maxima(taddr, nt * BN, a.n_rows, a.mask, cm);
+                    tile_chunk_maxima(taddr, nt * BN, a.n_rows, a.mask, cm, sp, lane);
                     if (q_ok) {
                         uint4* dst = reinterpret_cast<uint4*>(a.cmax + (size_t)q * a.ncols + (size_t)(nt - a.tile_begin) * 8);
                         dst[0] = make_uint4(cm[0], cm[1], cm[2], cm[3]);
                         dst[1] = make_uint4(cm[4], cm[5], cm[6], cm[7]);
                     }
                 } else
-                epilogue_tile<CAP, KPRIME>(taddr, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024, a.tau + q, lane, tau, cnt, lst);
+                epilogue_tile<CAP, KPRIME>(taddr, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024, a.tau + q, lane, tau, cnt, lst,
+                                           nullptr, sp);
                 // accumulator fully read -> hand TMEM back to the MMA warp
                 tcgen05_fence_before();
                 __syncwarp();
@@ -183,7 +194,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // and eps[q], the rigorous bound on |tensor-core score - exact fp32 score| for unit-norm rows.
 template <typename T>
 __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_pad, T* __restrict__ q_op,
-                                    float* __restrict__ eps, uint32_t* __restrict__ tau) {
+                                    float* __restrict__ eps, uint32_t* __restrict__ tau, int metric, float amax,
+                                    const float* __restrict__ qnorm, float* __restrict__ hq) {
     const int q = blockIdx.x, lane = threadIdx.x;  // one warp per query row
     float err2 = 0.f;
     for (int j = lane; j < kDim; j += 32) {
@@ -205,6 +217,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_p
         // error < 2^-10 each): |err| <= 2^-9 * sum|q_i x_i| <= 2^-9 * 1.001.  Both get 1e-4 for the tensor core's fp32
         // accumulation (768 additions, each off by at most 2^-23 of a partial sum bounded by ||q|| ||x||).
         float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 1e-4f : 2.0f * 0.0009765625f * 1.001f + 1e-4f;
+        if (metric != MQVS_METRIC_COSINE) {  // l2 / ip ranking scores t = a s - a^2 h: same bound as prep_fused_kernel
+            const float h = metric == MQVS_METRIC_L2 && q < B ? __fdiv_rn(0.5f, fmaxf(qnorm[q], kEps)) : 0.0f;
+            if (q < B) hq[q] = h;  // (padding rows never read theirs)
+            e = amax * e * 1.0001f + 1e-6f * (amax + amax * amax * h);
+        }
         if (q < B) eps[q] = e;
         tau[q] = kOrdNegInf;
     }
@@ -406,7 +423,8 @@ tau_from_chunk_maxima_kernel(const uint32_t* __restrict__ cmax, int ncols, int k
 template <typename T>
 __global__ void __launch_bounds__(256)
 rescore_kernel(const T* __restrict__ rows, const float* __restrict__ qn, const uint64_t* __restrict__ short_keys,
-               int B, int kp, uint64_t* __restrict__ exact_keys) {
+               int B, int kp, uint64_t* __restrict__ exact_keys, int metric, const float* __restrict__ norms,
+               const float* __restrict__ hq) {
     const int lane = threadIdx.x & 31;
     const size_t item = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (item >= (size_t)B * kp) return;
@@ -425,7 +443,8 @@ rescore_kernel(const T* __restrict__ rows, const float* __restrict__ qn, const u
         qv[c] = *reinterpret_cast<const float4*>(qn + (size_t)q * kDim + c * 128 + lane * 4);
         xv[c] = x.get(c);
     }
-    const float s = warp_butterfly_sum(lane_dot(qv, xv));
+    float s = warp_butterfly_sum(lane_dot(qv, xv));
+    if (metric != MQVS_METRIC_COSINE) s = rank_score(metric, s, __ldg(norms + id), __ldg(hq + q));  // exact, as the SIMT scan
     if (lane == 0) exact_keys[item] = pack_key(s, id);
 }
 
@@ -514,7 +533,7 @@ Trace& g_trace = trace();
 
 template <typename T, int CAP, int KPRIME>
 cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a, int grid, cudaStream_t st) {
-    auto kern = tc_score_kernel<T, CAP, KPRIME>;
+    auto kern = a.norms != nullptr ? tc_score_kernel<T, CAP, KPRIME, true> : tc_score_kernel<T, CAP, KPRIME, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, kThreads, kSmemBytes, st>>>(mq, mx, a);
@@ -548,8 +567,10 @@ int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
 }
 
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn_all, int B_all,
-                   int k, const uint32_t* mask, int64_t id_base, float* out_scores_all, int64_t* out_ids_all, cudaStream_t st) {
+                   int k, const uint32_t* mask, int64_t id_base, float* out_scores_all, int64_t* out_ids_all, cudaStream_t st,
+                   const Space& space) {
     CUtensorMap mq, mx;
+    const bool xf = space.metric != MQVS_METRIC_COSINE;
     if (!make_map(&mq, b.q_op, (uint64_t)p.b_pad, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
     const uint32_t n_tiles = (n_rows + BN - 1) / BN;
@@ -562,9 +583,12 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         const int b_pad = (B + BM - 1) / BM * BM;
         const float* qn = qn_all + (size_t)q0 * kDim;
         if (dtype == MQVS_F32)
-            prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps + q0, b.tau);
+            prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps + q0, b.tau, space.metric,
+                                                               space.amax, xf ? space.qnorm + q0 : nullptr, xf ? b.hq + q0 : nullptr);
         else
-            prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps + q0, b.tau);
+            prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps + q0, b.tau,
+                                                                       space.metric, space.amax, xf ? space.qnorm + q0 : nullptr,
+                                                                       xf ? b.hq + q0 : nullptr);
 
         g_trace.mark("prep", st);
         ScoreArgs a{};
@@ -578,6 +602,8 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.b_pad = (uint32_t)p.b_pad;
         a.cmax = nullptr;
         a.ncols = 0;
+        a.norms = xf ? space.norms : nullptr;
+        a.hq = xf ? b.hq + q0 : nullptr;
         cudaError_t e = cudaSuccess;
 #define MQVS_TC(KP_)                                                                          \
     if (p.kprime == KP_)                                                                      \
@@ -636,9 +662,11 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         const size_t items = (size_t)B * p.kprime;
         const unsigned rs_grid = (unsigned)((items + 7) / 8);
         if (dtype == MQVS_F32)
-            rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+            rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys, space.metric,
+                                                           space.norms, b.hq + q0);
         else
-            rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys);
+            rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime,
+                                                                   b.exact_keys, space.metric, space.norms, b.hq + q0);
         finalize_kernel<<<B, kSelThreads, 0, st>>>(b.exact_keys, b.tau_tilde, b.eps + q0, p.kprime, k, id_base,
                                                    out_scores_all + (size_t)q0 * k, out_ids_all + (size_t)q0 * k,
                                                    b.flags + q0, b.flag_count, b.band + q0);

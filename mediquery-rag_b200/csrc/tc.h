@@ -30,11 +30,11 @@ struct Buffers {       // all device memory, owned by the store handle
     uint32_t* band;       // [B] band-pass threshold of every flagged query: ord(k-th exact score - eps)
     uint32_t* band_list;  // [128] flagged queries, compacted
     uint32_t* band_n;     // [1]
-    float* hq;            // l2 / ip spaces: [b_pad] 0.5 / max(||q||, eps) per query (0 in the ip space)
-    float* h_op;          // the same per operand row of the band pass (compacted queries)
+    float* hq;            // l2 / ip spaces: [B padded to 128] 0.5 / max(||q||, eps) per query (0 in the ip space)
+    float* h_op;          // [256] the same per operand row of the band pass (compacted queries)
 };
 
-// Chroma's l2 / ip spaces over raw (non-unit) vectors, single-launch pipeline only (common.cuh:rank_score; mqvs_set_metric)
+// Chroma's l2 / ip spaces over raw (non-unit) vectors on the tensor pipelines (common.cuh:rank_score; mqvs_set_metric)
 struct Space {
     int metric = 0;                // MQVS_METRIC_*; 0 = cosine: the other fields are unused
     const float* norms = nullptr;  // [n_rows] ||x|| of the raw rows (K1)
@@ -49,7 +49,8 @@ size_t cnt_bytes(const Plan& p);
 
 // Enqueue the whole tensor-core search on `st`.  Returns nullptr or an error message.
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn, int B,
-                   int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st);
+                   int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                   const Space& space = Space());
 
 // Single-launch pipeline for B <= 128 (one query tile): prep kernel + one cooperative persistent kernel that learns the
 // thresholds, scans, selects, rescores and finalizes.  Takes the RAW queries (normalises them into qn itself).

@@ -831,7 +831,7 @@ def _raw_rows(n, seed=SEED, lo=0.25, hi=4.0):
 @pytest.mark.parametrize("space", ["l2", "ip"])
 def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_path):
     """Chroma's hnsw:space on NON-unit vectors: K1 keeps ||x|| per row; the exact scan and the
-    single-launch tensor pipeline (epilogue transform + exact rescoring, batches above 256 in slices) map the cosine of the
+    tensor pipelines (epilogue transform + exact rescoring; single-launch up to 256 queries, segmented above) map the cosine of the
     normalised pair to the space's ranking score (common.cuh:rank_score) before top-k.  Bit-identical on every path to
     oracle/canonical.c:orc_topk_metric, which tests/test_spaces.py ties to a float64 brute force over raw vectors."""
     import torch
@@ -858,12 +858,15 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
         assert_bit_equal(s, i, es, ei)
         stats = idx.stats()
         tensor = B > simt_max and k <= 128
-        assert stats["last_path"] == int(tensor) and stats["last_pipeline"] == (3 if tensor else 0), stats
+        assert stats["last_path"] == int(tensor) and stats["last_pipeline"] == ((3 if B <= 256 else 2) if tensor else 0), stats
         assert stats["exact_fallbacks"] == 0
     assert not np.array_equal(O.brute_force_topk(qn, st, k)[1], ei)  # the space matters on these rows
     idx.set_path(1)                                                  # the exact scan alone gives the same answer
     assert_bit_equal(*idx.search(q, k), es, ei)
     assert idx.stats()["last_path"] == 0
+    idx.set_path(4)                                                  # and so does the segmented tensor pipeline
+    assert_bit_equal(*idx.search(q, k), es, ei)
+    assert idx.stats()["last_pipeline"] == 2
     idx.set_path(0)
     # all-device call on a caller stream, with an id base (the sharded path)
     qd = torch.from_numpy(q).cuda()
@@ -967,7 +970,7 @@ def test_spaces_on_the_tensor_pipeline_band_pass_and_exact_repair(gpu, space, dt
     s, i = idx.search(q, k)
     stats = idx.stats()
     assert_bit_equal(s, i, es, ei)
-    assert stats["last_path"] == 1 and stats["last_pipeline"] == 3, stats
+    assert stats["last_path"] == 1 and stats["last_pipeline"] == (3 if B <= 256 else 2), stats
     assert stats["band_repairs"] > 0, stats
     # the all-device call (band pass + device-driven exact repair enqueued blindly) gives the same answer
     import torch
@@ -980,6 +983,10 @@ def test_spaces_on_the_tensor_pipeline_band_pass_and_exact_repair(gpu, space, dt
     # the duplicates: query 0 is (a multiple of) row 777; in the l2 space its copies tie at the top, lowest row ids first
     if space == "l2":
         assert i[0, 0] == 777 and list(i[0, 1:4]) == [60_000, 60_001, 60_002]
+    idx.set_path(4)                                  # segmented pipeline without the band pass: exact scans repair instead
+    s4, i4 = idx.search(q[:12], k)
+    assert_bit_equal(s4, i4, es[:12], ei[:12])
+    assert idx.stats()["last_pipeline"] == 2 and idx.stats()["exact_fallbacks"] > 0
 
 
 @pytest.mark.parametrize("space", ["l2", "ip"])
