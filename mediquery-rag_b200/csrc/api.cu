@@ -323,7 +323,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->stats.queries += (uint64_t)B;
         return MQVS_OK;
     }
-    // single-launch tensor pipeline for one query tile (B <= 128); path 4 = keep the segmented pipeline (tests compare)
+    // single-launch tensor pipeline for one or two query tiles (B <= 256); path 4 = keep the segmented pipeline (tests compare)
     bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);

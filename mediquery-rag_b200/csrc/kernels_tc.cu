@@ -1,6 +1,6 @@
 // kernels_tc.cu -- K2' (tensor-core scoring) + K3 (fused shortlist epilogue) + K4 (exact fp32 rescoring): the SEGMENTED
-// pipeline that serves batches of more than 128 queries (cold pass, corpus segments of growing size with a selection
-// after each, rescoring, margin check).  Batches of up to 128 queries run the same building blocks as one cooperative
+// pipeline that serves batches of more than 256 queries (cold pass, corpus segments of growing size with a selection
+// after each, rescoring, margin check).  Batches of up to 256 queries run the same building blocks as one cooperative
 // launch: kernels_tc_fused.cu.  Shared device code: tc_device.cuh.
 //
 // For query batches where the contraction [B, 768] x [768, N] is real GEMM work, scoring runs on the 5th-gen

@@ -1,6 +1,8 @@
-// kernels_tc_fused.cu -- the tensor-core search as ONE cooperative launch, for batches of up to 128 queries (one query tile):
+// kernels_tc_fused.cu -- the tensor-core search as ONE cooperative launch, for batches of up to 256 queries (one or two query tiles):
 // in-kernel threshold learning through grid barriers, the corpus scan, selection, exact fp32 rescoring and the margin check.
-// Device building blocks (tile epilogue, chunk maxima, PTX wrappers) are shared with kernels_tc.cu through tc_device.cuh.
+// This file: the prep kernels, the host side (search_fused, search_band) and the cosine instantiations; the kernel itself and
+// its tail live in tc_fused_device.cuh (also instantiated for the l2 / ip spaces by kernels_tc_fused_space.cu), the device
+// building blocks (tile epilogue, chunk maxima, PTX wrappers) shared with kernels_tc.cu in tc_device.cuh.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -52,7 +52,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
                    int k, const uint32_t* mask, int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st,
                    const Space& space = Space());
 
-// Single-launch pipeline for B <= 128 (one query tile): prep kernel + one cooperative persistent kernel that learns the
+// Single-launch pipeline for B <= 256 (one or two query tiles): prep kernel + one cooperative persistent kernel that learns the
 // thresholds, scans, selects, rescores and finalizes.  Takes the RAW queries (normalises them into qn itself).
 // *coop_refused: the cooperative launch was rejected (not enough co-resident CTAs): use search() instead.
 bool fused_ok(int B, int k, int sm_count);

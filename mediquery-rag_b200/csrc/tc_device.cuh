@@ -1,5 +1,5 @@
 // tc_device.cuh -- device code shared by the two tensor-core pipelines (kernels_tc.cu: segmented, large batches;
-// kernels_tc_fused.cu: single cooperative launch, B <= 128): tile geometry, tcgen05 / TMA / mbarrier PTX wrappers,
+// kernels_tc_fused.cu: single cooperative launch, B <= 256): tile geometry, tcgen05 / TMA / mbarrier PTX wrappers,
 // the per-tile shortlist epilogue, chunk maxima, the warp bitonic sort and the general streaming selection; plus the
 // small host helpers both launchers use (tensor maps, the MQVS_TRACE event trace).
 #pragma once

@@ -14,7 +14,7 @@ struct FusedArgs;
 template <typename T, int CAP, int KPRIME, bool XF>
 __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al, int slot, int b_pad);
 
-// Batches of up to 128 queries (one query tile) are HBM-bound: the corpus is streamed once and the tensor pipe idles
+// Batches of one or two query tiles (up to 256 queries) are HBM-bound: the corpus is streamed once and the tensor pipe idles
 // most of the time, so what the segmented pipeline above pays for -- two short cold segments and three selection
 // launches, ~200 us next to a 425 us scan at 1M x 768 fp32 -- is pure latency.  tc_fused_kernel does the whole search
 // in ONE cooperative launch of one persistent CTA per SM:
