@@ -424,6 +424,14 @@ def main():
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 768 * 4, "d2h_bytes_per_step": B * k * 12},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    # what the N = 1, 2, 4, 8 lines of one scaling run have in common (the driver compares their `value`s)
+    line["scaling_note"] = (
+        "value is config 2 (the metric's single-GPU configuration); the 1-GPU point of the config-4 strong-scaling curve "
+        "that --gpus 2/4/8 measure is scaling_base_config4_n1.points[batch=64].qps in this line"
+        if world == 1 and args.workload == "c2" else
+        "strong scaling over the FIXED 100M x 768 bf16 corpus of config 4 (each rank scans 1/N of it); its 1-GPU point is "
+        "scaling_base_config4_n1 in the --gpus 1 line (that line's `value` is config 2, a different workload)"
+        if args.workload == "c4" else "single workload, no scaling curve")
     if sweep:
         line["sweep"] = sweep
     if mask_info:
