@@ -296,7 +296,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
-    bool tensor = use_tensor_path(s, B, k);
+    const bool tensor = use_tensor_path(s, B, k);
     const bool fused = !tensor && s->path != 3 && s->metric == MQVS_METRIC_COSINE && scan_fused_ok(B, k);
     s->last_fused = fused;
     tc::Plan plan{};
@@ -387,11 +387,10 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
                                            ++s->epoch, st, &coop_refused, space);
         if (err && coop_refused) {
             // the device cannot hold one CTA per SM right now (MPS with an SM limit, a partitioned GPU): this handle
-            // keeps to the segmented pipeline from here on (l2 / ip spaces: to the exact scan)
+            // keeps to the segmented pipeline from here on
             s->coop_ok = false;
             tc_one = false;
             s->last_fused = false;
-
         } else if (err) {
             return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         }
