@@ -94,6 +94,8 @@ struct mqvs_store {
     float* norms = nullptr;   // [cap] when keep_norms
     float norm_dev = 0.0f;    // largest | ||x|| - 1 | over the rows accepted so far
     float norm_max = 0.0f;    // largest ||x|| over the rows accepted so far
+    DevBuf norm_bounds;       // [ceil(n / 32)][2] (max, min) norm per 32-row chunk, brought up to date before a tensor search
+    uint64_t bounds_rows = 0; // rows the bounds cover
     cudaStream_t st = nullptr;
     // ring of event quads so that back-to-back async searches never wait on each other's timing
     static constexpr int kEvRing = 32;
@@ -368,6 +370,19 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
             space.norms = s->norms;
             space.amax = s->norm_max;
             space.qnorm = (float*)s->qnorm.p;
+            if (s->bounds_rows != s->n) {  // rows were added (or loaded): redo the chunks they touched
+                const size_t had = s->norm_bounds.bytes;
+                const size_t need = (size_t)((s->n + 31) / 32) * 2 * sizeof(float);
+                uint64_t first_chunk = s->bounds_rows / 32;
+                if (need > had) {  // grows: keep a 1.5x margin, recompute everything (4 bytes per row read, once per growth)
+                    if ((rc = s->norm_bounds.ensure(need + need / 2)) != MQVS_OK) return rc;
+                    first_chunk = 0;
+                }
+                launch_norm_bounds(s->norms, s->n, first_chunk, (float*)s->norm_bounds.p, st);
+                s->stats.kernel_launches += 1;
+                s->bounds_rows = s->n;
+            }
+            space.norm_bounds = (const float*)s->norm_bounds.p;
         }
         s->last_b = b;
         s->last_plan = plan;
@@ -533,7 +548,7 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     for (DevBuf* b : {&s->f_table, &s->f_prog, &s->f_pool, &s->f_live, &s->f_mask}) b->release();
     if (s->f_count_dev) cudaFree(s->f_count_dev);
     if (s->f_count_host) cudaFreeHost(s->f_count_host);
-    for (DevBuf* b : {&s->stage, &s->qraw, &s->qn, &s->qnorm, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
+    for (DevBuf* b : {&s->norm_bounds, &s->stage, &s->qraw, &s->qn, &s->qnorm, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
                       &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand, &s->tc_cmax})
         b->release();
     if (s->fix_dev) cudaFree(s->fix_dev);
@@ -851,6 +866,7 @@ int load_norms(mqvs_store* s, const char* path, uint64_t rows) {
     }
     s->norm_dev = dev;
     s->norm_max = mx;
+    s->bounds_rows = 0;  // other rows than the chunk bounds were computed from
     return MQVS_OK;
 }
 }  // namespace

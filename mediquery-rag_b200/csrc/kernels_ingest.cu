@@ -99,6 +99,23 @@ void launch_k1(Source src, uint64_t n, int out_dtype, void* out, unsigned long l
                                                                                          norms, max_dev);
 }
 
+// one warp per 32-row chunk: (max, min) of its rows' norms
+__global__ void norm_bounds_kernel(const float* __restrict__ norms, uint64_t n_rows, uint64_t first_chunk, uint64_t n_chunks,
+                                   float2* __restrict__ bounds) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t chunk = first_chunk + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chunk >= n_chunks) return;
+    const uint64_t r = chunk * 32 + lane;
+    const bool in = r < n_rows;
+    float hi = in ? norms[r] : 0.0f, lo = in ? norms[r] : INFINITY;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, m));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, m));
+    }
+    if (lane == 0) bounds[chunk] = make_float2(hi, lo);
+}
+
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ rows, const int64_t* __restrict__ ids, uint64_t n, int dim,
                                    float* __restrict__ out) {
@@ -120,6 +137,13 @@ void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int
                             unsigned long long* bad, cudaStream_t st, float* norms, unsigned int* max_dev) {
     SynthSource src{seed, first_index, dim};
     launch_k1(src, n, out_dtype, out, bad, norms, max_dev, st);
+}
+
+void launch_norm_bounds(const float* norms, uint64_t n_rows, uint64_t first_chunk, float* bounds, cudaStream_t st) {
+    const uint64_t n_chunks = (n_rows + 31) / 32;
+    if (first_chunk >= n_chunks) return;
+    const uint64_t blocks = (n_chunks - first_chunk + 7) / 8;
+    norm_bounds_kernel<<<(unsigned)blocks, 256, 0, st>>>(norms, n_rows, first_chunk, n_chunks, reinterpret_cast<float2*>(bounds));
 }
 
 void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,

@@ -52,6 +52,7 @@ struct ScoreArgs {
     uint32_t ncols;         // 8 * CTAs of the cold pass
     // l2 / ip spaces over raw vectors (XF instantiations only; tc.h:Space)
     const float* norms;     // [n_rows] ||x||
+    const float2* nbounds;  // [ceil(n_rows / 32)] (max, min) norm per 32-row chunk
     const float* hq;        // [B_pad] 0.5 / max(||q||, eps) (l2), 0 (ip)
 };
 
@@ -156,6 +157,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 TileSpace sp;
                 if constexpr (XF) {
                     sp.norms = a.norms;
+                    sp.bounds = a.nbounds;
                     sp.h = q_ok ? __ldg(a.hq + q) : 0.0f;
                 }
 
@@ -603,6 +605,7 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.cmax = nullptr;
         a.ncols = 0;
         a.norms = xf ? space.norms : nullptr;
+        a.nbounds = xf ? reinterpret_cast<const float2*>(space.norm_bounds) : nullptr;
         a.hq = xf ? b.hq + q0 : nullptr;
         cudaError_t e = cudaSuccess;
 #define MQVS_TC(KP_)                                                                          \

@@ -198,6 +198,7 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     a.counters = nullptr;
     a.metric = space.metric;
     a.norms = space.metric != MQVS_METRIC_COSINE ? space.norms : nullptr;
+    a.nbounds = reinterpret_cast<const float2*>(space.norm_bounds);
     a.hq = b.hq;
     a.h_op = b.hq;  // operand row q is query q
     a.dbg = g_trace.on ? g_trace.fused_dbg(p.grid) : nullptr;
@@ -261,6 +262,7 @@ const char* search_band(const Buffers& b, const Plan& p, const void* rows, int d
     a.counters = counters;
     a.metric = space.metric;
     a.norms = space.metric != MQVS_METRIC_COSINE ? space.norms : nullptr;
+    a.nbounds = reinterpret_cast<const float2*>(space.norm_bounds);
     a.hq = b.hq;
     a.h_op = b.h_op;
     cudaError_t e = launch_fused_space(dtype, p.kprime, 1, mq, mx, a, p.grid, st);

@@ -21,6 +21,10 @@ void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int
                             unsigned long long* bad, cudaStream_t st, float* norms = nullptr,
                             unsigned int* max_dev = nullptr);
 
+// (largest, smallest) ||x|| of the 32-row chunks [first_chunk, ceil(n_rows / 32)): what lets the tensor epilogue of the
+// l2 / ip spaces reject a chunk without transforming its scores (tc_device.cuh:chunk_score_bound).
+void launch_norm_bounds(const float* norms, uint64_t n_rows, uint64_t first_chunk, float* bounds, cudaStream_t st);
+
 // K2 (SIMT) + K3: exact fp32 scan of `n_rows` stored rows against nq (<= scan_max_queries_per_pass) normalised
 // queries, fused per-warp top-k with optional allow-mask; writes per-CTA sorted candidate keys
 // cand[q][cta][k].  Returns the grid size used (number of CTAs) so the merge knows the layout.

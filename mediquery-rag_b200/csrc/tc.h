@@ -38,6 +38,7 @@ struct Buffers {       // all device memory, owned by the store handle
 struct Space {
     int metric = 0;                // MQVS_METRIC_*; 0 = cosine: the other fields are unused
     const float* norms = nullptr;  // [n_rows] ||x|| of the raw rows (K1)
+    const float* norm_bounds = nullptr;  // [ceil(n_rows / 32)][2] largest and smallest norm of every 32-row chunk
     float amax = 1.0f;             // largest ||x||: the tensor-core error bound of a ranking score is amax * eps
     float* qnorm = nullptr;        // [B] out: ||q|| of the raw queries (the exact-scan repair ranks with them)
 };

@@ -210,9 +210,19 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
 // of a chunk into approximate ranking scores t = a s - a^2 h (ip: h = 0).  The exact scores come from the rescoring,
 // which uses rank_score itself; here only |t~ - t| <= a_max eps matters.
 struct TileSpace {
-    const float* norms = nullptr;  // [n_rows] ||x|| of the raw rows; nullptr = cosine (scores used as they are)
-    float h = 0.0f;                // this thread's query: 0.5 / max(||q||, eps) for l2, 0 for ip
+    const float* norms = nullptr;   // [n_rows] ||x|| of the raw rows; nullptr = cosine (scores used as they are)
+    const float2* bounds = nullptr; // [ceil(n_rows / 32)] (largest, smallest) norm of every 32-row chunk (norm_bounds_kernel)
+    float h = 0.0f;                 // this thread's query: 0.5 / max(||q||, eps) for l2, 0 for ip
 };
+// Upper bound of every ranking score t = a s - a^2 h of a chunk whose largest cosine is `smax` (this thread's query) and
+// whose norms lie in [b.y, b.x]: a s <= b.x smax for smax >= 0, <= b.y smax below; a^2 h >= b.y^2 h.  Rounded UP with slack
+// for the fp32 roundings of both sides, so a chunk rejected by it holds no score the exact transform would have kept.
+__device__ __forceinline__ float chunk_score_bound(float smax, float2 b, float h) {
+    if (!(smax > -INFINITY)) return -INFINITY;  // nothing allowed in the chunk
+    const float lin = smax >= 0.0f ? __fmul_ru(b.x, smax) : __fmul_ru(b.y, smax);
+    const float quad = __fmul_rd(__fmul_rd(b.y, b.y), h);
+    return __fadd_ru(__fsub_ru(lin, quad), 1e-6f * (fabsf(lin) + quad));
+}
 __device__ __forceinline__ void apply_space(uint32_t (&v)[32], const TileSpace& sp, uint32_t row0, uint32_t n_rows, int lane) {
     const float a_l = __ldg(sp.norms + min(row0 + (uint32_t)lane, n_rows - 1u));  // one coalesced load per chunk and warp
 #pragma unroll
@@ -254,10 +264,16 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (mw >> j) & 1u ? v[j] : 0xff800000u;
         }
-        if (sp.norms != nullptr) apply_space(v, sp, row0, n_rows, lane);  // uniform
         // fast reject: one 3-input max tree per 32 scores, one compare
         float grp[11];
-        const float mx = max32(v, grp);
+        float mx = max32(v, grp);
+        if (sp.norms != nullptr) {  // uniform: l2 / ip spaces
+            // most chunks hold nothing near the threshold: reject them with a bound on their ranking scores (two floats
+            // per chunk) before paying for the transform of all 32 x 32 scores
+            if (__ballot_sync(0xffffffffu, chunk_score_bound(mx, __ldg(sp.bounds + (row0 >> 5)), sp.h) >= tau) == 0u) continue;
+            apply_space(v, sp, row0, n_rows, lane);
+            mx = max32(v, grp);
+        }
         const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
         if (hit == 0u) continue;
         {

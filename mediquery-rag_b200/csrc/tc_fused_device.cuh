@@ -52,6 +52,7 @@ struct FusedArgs {
     unsigned long long* counters;  // [2] += queries the band pass repaired
     // l2 / ip spaces over raw vectors (tc.h:Space); norms == nullptr: cosine
     const float* norms;    // [n_rows] ||x||
+    const float2* nbounds; // [ceil(n_rows / 32)] (max, min) norm per 32-row chunk
     const float* hq;       // [B] by query: 0.5 / max(||q||, eps) (l2), 0 (ip)
     const float* h_op;     // the same by operand row (= hq in the first launch, the compacted queries in the band pass)
     int metric;
@@ -274,6 +275,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 sp[mt].norms = a.norms;
+                sp[mt].bounds = a.nbounds;
                 sp[mt].h = q_ok[mt] ? __ldg(a.h_op + q[mt]) : 0.0f;
             }
         }
