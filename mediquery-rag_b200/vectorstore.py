@@ -329,6 +329,18 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         # langchain_chroma returns the raw distance here despite the name; kept for compatibility
         return self._similar(embedding, k, filter)
 
+    def similarity_search_with_vectors(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
+                                       where_document: Optional[Dict[str, Any]] = None, **kwargs: Any
+                                       ) -> List[Tuple[Document, np.ndarray]]:
+        """langchain_chroma's (Document, stored embedding) pairs, best first: the vectors as the collection returns them for
+        `get(include=["embeddings"])` (raw vectors in an l2 / ip collection, unit rows otherwise)."""
+        hits = self._similar(self._embed_query(query), k, filter, where_document)
+        if not hits:
+            return []
+        emb = self.get(ids=[d.id for d, _ in hits], include=["embeddings"])
+        by_id = dict(zip(emb["ids"], emb["embeddings"]))
+        return [(d, np.asarray(by_id[d.id])) for d, _ in hits]
+
     def _select_relevance_score_fn(self) -> Callable[[float], float]:
         if self._relevance_fn is not None:
             return self._relevance_fn
@@ -485,6 +497,14 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                     os.remove(os.path.join(self._persist_directory, f))
                 except FileNotFoundError:
                     pass
+
+    def reset_collection(self) -> None:
+        """langchain_chroma's reset_collection: drop every row and start again with an empty collection of the same name,
+        space and storage type."""
+        self.delete_collection()
+        self._raw_space = self._space != "cosine"
+        if self._dim is not None:
+            self._ensure_index(self._dim)
 
     # ------------------------------------------------------------------------------------------- persistence
     def persist(self) -> None:

@@ -250,3 +250,22 @@ def test_persistence_is_append_only_and_survives_reopen_delete_and_old_format(tm
                "collection_metadata": {}}, open(os.path.join(old, "manifest.json"), "w"))
     vo = MediQueryVectorStore(persist_directory=old, embedding_function=embedder, index_factory=OracleIndex)
     assert len(vo) == 4 and docs[2].page_content not in [d.page_content for d in vo.similarity_search(docs[2].page_content, k=4)]
+
+
+def test_similarity_search_with_vectors_and_reset_collection(embedder, tmp_path):
+    """Two more calls of langchain_chroma's surface: (Document, embedding) pairs, and reset_collection (same name, space
+    and storage, no rows -- also on disk)."""
+    db = str(tmp_path / "db")
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex, persist_directory=db)
+    texts = [f"text {r}" for r in range(40)]
+    vs.add_texts(texts, ids=[str(r) for r in range(40)])
+    pairs = vs.similarity_search_with_vectors("text 7", k=3)
+    assert [d.page_content for d, _ in pairs] == [d.page_content for d in vs.similarity_search("text 7", k=3)]
+    want = np.asarray(embedder.embed_documents([d.page_content for d, _ in pairs]), np.float32)
+    assert np.allclose(np.stack([v for _, v in pairs]), want, atol=1e-6)
+    vs.reset_collection()
+    assert len(vs) == 0 and vs.similarity_search("text 7", k=3) == [] and vs.get()["ids"] == []
+    assert len(MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex, persist_directory=db)) == 0
+    vs.add_texts(["again"], ids=["0"])
+    assert [d.page_content for d in vs.similarity_search("again", k=2)] == ["again"]
+    assert len(MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex, persist_directory=db)) == 1
