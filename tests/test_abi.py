@@ -79,3 +79,29 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
         assert run.returncode == 0 and "row 42" in run.stdout.splitlines()[2], run.stdout
     else:
         assert run.returncode == 2 and "no usable GPU" in run.stdout, run.stdout
+
+
+def _sass_mnemonics(obj, pattern):
+    import shutil
+    import subprocess
+    path = os.path.join(ROOT, "mediquery-rag_b200", "csrc", "build", obj)
+    if shutil.which("cuobjdump") is None or not os.path.exists(path):
+        pytest.skip("cuobjdump or the build directory is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    return set(re.findall(pattern, sass))
+
+
+def test_the_hot_kernels_are_blackwell_native_sass():
+    """What the built objects contain (cuobjdump -sass, sm_100a): the tensor path really issues tcgen05.mma from TMA-staged
+    shared memory with TMEM accumulators (SASS names: UTCHMMA, UTMALDG, LDTM -- /opt/skills/guides/B200_PROFILING.md), the
+    SIMT scan really streams rows with 128-bit no-allocate loads, and the cross-GPU exchange uses system-scope stores, loads
+    and fences on peer memory."""
+    tc = _sass_mnemonics("kernels_tc.o", r"\b(UTCHMMA|UTMALDG|LDTM|UTCBAR)\b")
+    assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= tc
+    fused = _sass_mnemonics("kernels_tc_fused_space.o", r"\b(UTCHMMA|UTMALDG|LDTM)\b")
+    assert {"UTCHMMA", "UTMALDG", "LDTM"} <= fused
+    scan = _sass_mnemonics("kernels_scan.o", r"\bLDG\.E\.NA\.128\.CONSTANT\b|\bLDG\.E\.NA\.64\.CONSTANT\b")
+    assert "LDG.E.NA.128.CONSTANT" in scan and "LDG.E.NA.64.CONSTANT" in scan
+    xchg = _sass_mnemonics("kernels_xchg.o", r"\b(STG\.E\.STRONG\.SYS|LDG\.E\.STRONG\.SYS|MEMBAR\.\w+\.SYS)\b")
+    assert {"STG.E.STRONG.SYS", "LDG.E.STRONG.SYS"} <= xchg and any(m.startswith("MEMBAR") for m in xchg)
