@@ -146,3 +146,31 @@ def test_directories_written_without_norms_open_with_unit_semantics(tmp_path):
     d = f64_distances("cosine", x[7:8], x)[0]
     assert [doc.page_content for doc in old.similarity_search_by_vector(x[7].tolist(), k=3)] == \
         [f"d{r}" for r in np.argsort(d, kind="stable")[:3]]
+
+
+@pytest.mark.parametrize("space", ["cosine", "l2"])
+def test_oracle_agrees_with_scikit_learn_brute_force_neighbours(space):
+    """An independent, published implementation of exact k-nearest neighbours (scikit-learn's brute-force NearestNeighbors,
+    float64) returns the same rows as the oracle: cosine on the normalised rows, (squared) euclidean on the raw vectors.
+    chromadb itself is not installable here; this is the closest third-party referee in the image."""
+    from sklearn.neighbors import NearestNeighbors
+    n, B, k = 5000, 12, 10
+    x = raw_vectors(n)
+    q = (raw_vectors(B, lo=0.5, hi=2.0, seed=8) + 0.4 * x[100:100 + B]).astype(np.float32)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    if space == "cosine":
+        s, i = O.brute_force_topk(qn, st, k)
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(x.astype(np.float64))
+        dist, ref = nn.kneighbors(q.astype(np.float64))
+        got = 1.0 - s.astype(np.float64)
+        tol = 2e-6
+    else:
+        s, i = O.brute_force_topk(qn, st, k, metric="l2", norms=O.row_norms(x, 768), q_norms=O.row_norms(q, 768))
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="euclidean").fit(x.astype(np.float64))
+        dist, ref = nn.kneighbors(q.astype(np.float64))
+        dist = dist ** 2
+        got = O.distances_from_rank_scores("l2", s, O.row_norms(q, 768))
+        tol = 1e-5 * float((q.astype(np.float64) ** 2).sum(1).max() + 9.0)
+    assert np.all(np.abs(got - dist) <= tol)
+    assert (i == ref).mean() > 0.97  # same rows, same order: positions may differ only where fp32 cannot separate two neighbours
