@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MQVS_VERSION 100
+#define MQVS_VERSION 200
 
 #if defined(__GNUC__)
 #define MQVS_API __attribute__((visibility("default")))
@@ -40,6 +40,8 @@ enum { MQVS_METRIC_COSINE = 0, MQVS_METRIC_L2 = 1, MQVS_METRIC_IP = 2 };
  * (768 = width of shaw/dmeta-embedding-zh, src/medical_engine.py:43) */
 #define MQVS_DIM_PAD 768
 #define MQVS_MAX_K 1024
+#define MQVS_MAX_DEVICES 16      /* row shards one handle can drive (one B200 box has 8) */
+#define MQVS_SHARD_BLOCK 4096    /* rows per block of the block-cyclic placement of a multi-device handle */
 
 typedef struct mqvs_store mqvs_t;
 
@@ -56,8 +58,8 @@ typedef struct mqvs_stats {
     uint32_t last_scan_passes;   /* corpus passes the last search needed */
     uint32_t last_path;          /* 0 = SIMT fp32 scan, 1 = tensor-core shortlist + fp32 rescoring */
     uint64_t exact_fallbacks;    /* queries whose tensor-core shortlist could not be proven exact and were re-run on the SIMT scan */
-    uint64_t unrepaired;         /* mqvs_search_async only: flagged queries beyond the 64 the device repair pass takes per call
-                                    (their results are approximate; the blocking mqvs_search repairs every one) */
+    uint64_t unrepaired;         /* flagged queries the device-side repair rounds of a search left flagged.  mqvs_search_async sizes its
+                                    rounds to the batch, so this stays 0 there; the blocking mqvs_search repairs any rest from the host */
     uint32_t last_pipeline;      /* how the last search ran: 0 = SIMT scan, normalise + scan(s) + merge launches; 1 = SIMT scan, one
                                     launch (B <= 4, k <= 16); 2 = tensor cores, corpus segments + selection launches;
                                     3 = tensor cores, one cooperative launch (B <= 256) */
@@ -72,10 +74,19 @@ MQVS_API int mqvs_device_count(int* out);
 
 /* Chroma(persist_directory=..., embedding_function=...) -- src/medical_engine.py:52 -- and the collection
  * Chroma.from_documents creates -- src/ingest_medical.py:106-110.  dim <= MQVS_DIM_PAD.
- * One handle owns one row shard on ONE device: n_dev must be 1 and dev_ids[0] names the device (NULL = device 0).
- * A corpus spread over several GPUs is one handle per process/GPU plus mqvs_merge_candidates after the all-gather
- * (mediquery-rag_b200/sharded.py); the (n_dev, dev_ids) form is kept so a single-process variant can be added
- * without changing the ABI. */
+ * n_dev = 1: one row shard on device dev_ids[0] (NULL = device 0).
+ * n_dev > 1: ONE handle, in ONE process, over n_dev row shards on the devices dev_ids[0 .. n_dev) -- what the reference
+ * needs, since its `vectorstore` is one module-global object in one process (src/medical_engine.py:52, main.py:42-48) while
+ * 100M x 768 rows need the HBM of a whole box.  Rows are placed block-cyclically (global block r / MQVS_SHARD_BLOCK lives
+ * on shard block % n_dev, see mqvs_shard_of_row), so shards stay balanced under appends and every row keeps its GLOBAL id
+ * through every entry point below: searches scan all shards concurrently (one stream per device), each shard writes its
+ * exact top-k straight into the first device's memory over NVLink peer access (a peer copy where that is unavailable), and
+ * one merge kernel there finishes the batch (same ordering rule).  Results are bit-identical to a single-shard handle
+ * holding the same rows.  A device may be named more than once (several shards on one GPU: how the single-GPU tests
+ * exercise this path).  dev_ids[0] is the "home" device: device pointers passed to such a handle (x / q / outputs with
+ * *_is_device = 1, mqvs_search_async) must be memory of that device.
+ * The alternative layout -- one process per GPU, one single-shard handle each, candidates exchanged with mqvs_xchg_merge or
+ * NCCL + mqvs_merge_candidates -- is mediquery-rag_b200/sharded.py. */
 MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out);
 MQVS_API void mqvs_destroy(mqvs_t* s);
 MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out);
@@ -99,10 +110,17 @@ MQVS_API int mqvs_add_synthetic(mqvs_t* s, uint64_t seed, uint64_t first_index, 
 MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
                 float* out_scores, int64_t* out_ids, int out_is_device);
 
+/* Pure host arithmetic of the block-cyclic placement (no device needed): global row -> (shard, local row) for a handle of
+ * n_dev shards; the inverse is global = ((local / BLOCK) * n_dev + shard) * BLOCK + local % BLOCK. */
+MQVS_API int mqvs_shard_of_row(int n_dev, uint64_t row, int* shard_out, uint64_t* local_row_out);
+
 /* Same, enqueued on `cuda_stream` (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) with all
  * buffers on the device; returns after enqueueing.  id_base is added to every returned id (row-sharded
  * stores: the rank's first global row).  Scratch belongs to the handle: enqueue the next call on the same stream
- * (or after this one has finished).  Non-finite queries are not reported here (use mqvs_search to validate). */
+ * (or after this one has finished).  Exact on its own: the device-side repair (band pass, then exact-scan rounds sized to
+ * B) settles every query the tensor pipeline could not prove.  Non-finite queries are not reported here (their rows come
+ * back as scores of a zero query; use mqvs_search to validate).  On a multi-device handle the buffers and the stream
+ * belong to the home device and mask_dev must be the pointer mqvs_filter_build returned (or NULL). */
 MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                       float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 
@@ -151,7 +169,9 @@ typedef struct mqvs_filter_op {
 MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
                              uint64_t n);
 /* prog: n_ops <= 64 operations in postfix order; pool: pool_len 8-byte constants (int64 or float64 bit patterns) the
- * $in / $nin leaves point into.  *mask_dev_out is owned by the handle and valid until the next mqvs_filter_build. */
+ * $in / $nin leaves point into.  *mask_dev_out is owned by the handle and valid until the next mqvs_filter_build.
+ * Multi-device handles evaluate every shard's slice on its own device; *mask_dev_out is then an opaque token for
+ * mqvs_search / mqvs_search_async of the same handle (mask_is_device = 1), not a pointer to read through. */
 MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                                const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 
@@ -164,6 +184,12 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path);
  * rows (re-running ingest appends -- src/ingest_medical.py:106 on an existing ./medical_db); first_row = 0 rewrites. */
 MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row);
 MQVS_API int mqvs_load(mqvs_t* s, const char* path);
+
+/* Tombstone compaction (collection.delete / upsert leave dead rows that every scan still streams): keep only the rows whose
+ * bit is set in keep_words_host (bit r & 31 of word r >> 5, ceil(rows / 32) words), gathered bit-for-bit on the device in
+ * ascending order, so surviving row r becomes row popcount(keep[0 .. r)).  Stored norms follow; device-resident metadata
+ * columns are dropped.  Single-device handles only (rows of a multi-device handle would have to change devices). */
+MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out);
 
 /* collection_metadata={"hnsw:space": ...} -- the space rows are RANKED in when the raw vectors given to mqvs_add are not
  * unit vectors (on unit vectors the three spaces order rows identically and MQVS_METRIC_COSINE, the default, serves all

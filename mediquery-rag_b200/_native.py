@@ -15,6 +15,8 @@ OK, E_INVALID, E_CUDA, E_NCCL, E_OOM, E_IO = 0, -1, -2, -3, -4, -5
 F32, BF16 = 0, 1
 DIM_PAD = 768
 MAX_K = 1024
+MAX_DEVICES = 16
+SHARD_BLOCK = 4096  # rows per block of a multi-device handle's block-cyclic placement (include/mqvs.h)
 DTYPES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16}
 METRICS = {"cosine": 0, "l2": 1, "ip": 2}  # Chroma's hnsw:space -> MQVS_METRIC_*
 
@@ -78,6 +80,7 @@ SIGNATURES = {
     "mqvs_save": (_i, [_vp, ctypes.c_char_p]),
     "mqvs_save_append": (_i, [_vp, ctypes.c_char_p, _u64]),
     "mqvs_load": (_i, [_vp, ctypes.c_char_p]),
+    "mqvs_compact": (_i, [_vp, _vp, ctypes.POINTER(_u64)]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
     "mqvs_set_metric": (_i, [_vp, _i]),
@@ -85,6 +88,7 @@ SIGNATURES = {
     "mqvs_get_norms": (_i, [_vp, _u64, _u64, _vp]),
     "mqvs_column_set": (_i, [_vp, _i, _i, _vp, _vp, _u64]),
     "mqvs_filter_build": (_i, [_vp, _vp, _i, _vp, _u64, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
+    "mqvs_shard_of_row": (_i, [_i, _u64, ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
     "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
     "mqvs_xchg_get_handle": (_i, [_vp, _vp, _i]),
     "mqvs_xchg_connect": (_i, [_vp, _vp]),
@@ -134,17 +138,30 @@ def _is_torch(a) -> bool:
     return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
 
 
-class Index:
-    """One row shard on one B200: thin owner of an mqvs_t handle."""
+def shard_of_row(n_dev: int, row: int):
+    """(shard, local row) of a global row on a handle of n_dev shards -- libmqvs's own host arithmetic (no GPU needed)."""
+    shard, local = _i(0), _u64(0)
+    check(load().mqvs_shard_of_row(int(n_dev), int(row), ctypes.byref(shard), ctypes.byref(local)))
+    return shard.value, local.value
 
-    def __init__(self, dim: int, store_dtype: str = "fp32", device: int = 0, capacity_rows: int = 0):
+
+class Index:
+    """Thin owner of an mqvs_t handle: one row shard on one B200 (`device` = an int), or ONE handle over several shards
+    in this process (`device` = a sequence of device ids, e.g. range(8); a device may repeat -- several shards on one GPU).
+    Row ids are global in both cases; device tensors handed to a multi-device index live on its first device."""
+
+    def __init__(self, dim: int, store_dtype: str = "fp32", device=0, capacity_rows: int = 0):
         self._h = _vp(None)
         self.dim = int(dim)
         self.store_dtype = store_dtype
-        self.device = int(device)
+        self.devices = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
+        if not 1 <= len(self.devices) <= MAX_DEVICES:
+            raise ValueError(f"an index drives 1..{MAX_DEVICES} devices, got {len(self.devices)}")
+        self.device = self.devices[0]
         self.metric = "cosine"
-        dev = (_i * 1)(self.device)
-        check(load().mqvs_create(1, dev, self.dim, DTYPES[store_dtype], int(capacity_rows), ctypes.byref(self._h)))
+        dev = (_i * len(self.devices))(*self.devices)
+        check(load().mqvs_create(len(self.devices), dev, self.dim, DTYPES[store_dtype], int(capacity_rows),
+                                 ctypes.byref(self._h)))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -234,6 +251,16 @@ class Index:
 
     def load_file(self, path: str) -> None:
         check(load().mqvs_load(self._h, os.fsencode(path)))
+
+    def compact(self, keep_words: np.ndarray) -> int:
+        """Keep only the rows whose bit is set in the packed bitmap (bit r & 31 of word r >> 5), bit-for-bit, renumbered
+        in order.  -> new row count.  Device-resident metadata columns are dropped (upload them again)."""
+        words = np.ascontiguousarray(keep_words, dtype=np.uint32)
+        if words.shape[0] < (len(self) + 31) // 32:
+            raise ValueError("bitmap has fewer than ceil(rows/32) words")
+        n = _u64(0)
+        check(load().mqvs_compact(self._h, _ptr(words), ctypes.byref(n)))
+        return n.value
 
     def column_set(self, col_id: int, values: np.ndarray, present: Optional[np.ndarray] = None) -> None:
         """Upload metadata column `col_id` (int64 or float64 values, optional presence flags) for filter_build."""

@@ -1,68 +1,15 @@
 // api.cu -- the C ABI of libmqvs.so (include/mqvs.h): store lifetime, ingest, search orchestration, persistence.
 // No torch types, no exceptions across the boundary; CUDA errors become MQVS_E_CUDA with a thread-local message.
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
-#include <algorithm>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <vector>
+#include <thread>
 
-#include "../../include/mqvs.h"
-#include "filter.h"
-#include "launch.h"
-#include "tc.h"
+#include "store.h"
 
 namespace {
 
 thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
-
-#define CU(expr)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess) {                                                                         \
-            int code_ = (e_ == cudaErrorMemoryAllocation) ? MQVS_E_OOM : MQVS_E_CUDA;                    \
-            cudaGetLastError();                                                                          \
-            return fail(code_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-        }                                                                                                \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need) {
-        if (need <= bytes) return MQVS_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        size_t want = std::max(need, (size_t)4096);
-        CU(cudaMalloc(&p, want));
-        bytes = want;
-        return MQVS_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-size_t elem_size(int dtype) { return dtype == MQVS_F32 ? 4 : 2; }
 
 }  // namespace
 
@@ -78,74 +25,15 @@ int mqvs_fail(int code, const char* fmt, ...) {
 }
 }  // namespace mqvs
 
-struct mqvs_store {
-    std::mutex mu;
-    int dev = 0;
-    int dim = 0;
-    int dtype = MQVS_F32;
-    int sm_count = 148;
-    bool coop_ok = false;  // cooperative launches available (the single-launch tensor pipeline needs grid barriers)
-    int path = 0;
-    void* rows = nullptr;
-    uint64_t n = 0, cap = 0;
-    // l2 / ip spaces over raw vectors (mqvs_set_metric): ||x|| per row, kept from the first non-cosine metric on
-    int metric = MQVS_METRIC_COSINE;
-    bool keep_norms = false;
-    float* norms = nullptr;   // [cap] when keep_norms
-    float norm_dev = 0.0f;    // largest | ||x|| - 1 | over the rows accepted so far
-    float norm_max = 0.0f;    // largest ||x|| over the rows accepted so far
-    DevBuf norm_bounds;       // [ceil(n / 32)][2] (max, min) norm per 32-row chunk, brought up to date before a tensor search
-    uint64_t bounds_rows = 0; // rows the bounds cover
-    cudaStream_t st = nullptr;
-    // ring of event quads so that back-to-back async searches never wait on each other's timing
-    static constexpr int kEvRing = 32;
-    struct EvSet {
-        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
-        bool pending = false;
-    } evr[kEvRing];
-    int ev_cursor = 0;
-    DevBuf stage, qraw, qn, qnorm, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
-    DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
-    static constexpr int kMaxDeviceFix = 64;             // flagged queries repaired on the device per search
-    uint32_t* fix_dev = nullptr;                         // [kMaxDeviceFix] list + [1] count
-    unsigned long long* fix_counters = nullptr;          // device [4]: repaired by the exact scan on device, left to the host, repaired by the band pass
-    uint32_t* flags_host = nullptr;                      // pinned [1 + max B]: flag_count, flags[B]
-    size_t flags_host_n = 0;
-    uint32_t* last_flags_dev = nullptr;                  // device [1 + B] of the last tensor-core search
-    mqvs::tc::Buffers last_b{};                          // scratch layout + plan of the last tensor-core search: the
-    mqvs::tc::Plan last_plan{};                          // blocking call enqueues its repair only after it has seen flags
-    mqvs::tc::Space last_space{};                        // and the space it ranked in
-    unsigned long long* bad_dev = nullptr;   // [0] = non-finite rows counted by K1, [1] = epoch of the last fused
-    unsigned long long* bad_host = nullptr;  // pinned mirror     search that saw a non-finite query (low 32 bits),
-                                             // [2] = bits of the largest | ||x|| - 1 | of the current mqvs_add (low 32 bits)
-    unsigned int* ticket_dev = nullptr;      // CTA ticket of the fused latency kernel (zero between launches)
-    unsigned int epoch = 0;                  // id of the last fused search
-    // latency path with host outputs: the kernel writes results + status straight into this mapped pinned block
-    // (no device-to-host copies): [64 floats scores | 64 int64 ids | 2 uint32 status]
-    char* host_out = nullptr;
-    // pinned staging for host outputs of every other path: D2H copies into pageable user memory are staged and
-    // synchronous inside the driver (~10 us each), copies into pinned memory are not
-    char* out_pinned = nullptr;
-    size_t out_pinned_bytes = 0;
-    bool last_fused = false;                 // the last search reported non-finite queries through the epoch word
-    mqvs_stats stats{};
-    uint64_t host_fallbacks = 0;
-    // device-side `where` evaluation
-    struct Column {
-        DevBuf values, present;
-        uint64_t n = 0;
-        int type = 0;
-        bool used = false, has_present = false;
-    } columns[mqvs::kFilterMaxCols];
-    DevBuf f_table, f_prog, f_pool, f_live, f_mask;
-    unsigned long long* f_count_dev = nullptr;
-    unsigned long long* f_count_host = nullptr;  // pinned
-    bool f_table_dirty = true;
+#define CU MQVS_CU
+#define fail ::mqvs::mqvs_fail
+using mqvs::DevBuf;
+using mqvs::elem_size;
 
-    size_t row_bytes() const { return (size_t)MQVS_DIM_PAD * elem_size(dtype); }
-};
+namespace mqvs {
+namespace api {
 
-namespace {
+constexpr int kMaxFixRound = 256;  // capacity of the device-side repair list (flagged queries per exact-scan round)
 
 int grow(mqvs_store* s, uint64_t need_rows) {
     if (need_rows <= s->cap) return MQVS_OK;
@@ -191,7 +79,7 @@ int grow(mqvs_store* s, uint64_t need_rows) {
 }
 
 // fold one finished search's CUDA-event timings into the stats (waits for that search if still running)
-void settle_slot(mqvs_store* s, int slot) {
+static void settle_slot(mqvs_store* s, int slot) {
     auto& ev = s->evr[slot];
     if (!ev.pending) return;
     if (cudaEventSynchronize(ev.e[3]) == cudaSuccess) {
@@ -211,7 +99,7 @@ void settle_events(mqvs_store* s) {
 }
 
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
-bool use_tensor_path(const mqvs_store* s, int B, int k) {
+static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     if (s->path == 1 || s->path == 3) return false;
     if (k > 128 || s->n < 4096) return false;
     if (s->path == 2 || s->path == 4) return true;
@@ -231,7 +119,7 @@ bool use_tensor_path(const mqvs_store* s, int B, int k) {
 }
 
 // Exact SIMT scan of queries [b0, b0 + nb) of s->qn into out rows [b0, ...).  Returns passes launched.
-int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
+static int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
                  int64_t* out_ids_dev, cudaStream_t st, uint32_t* passes_out) {
     using namespace mqvs;
     const int gmax = scan_max_grid(s->sm_count);
@@ -263,8 +151,10 @@ int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev,
 // through the tensor pipeline once more, with given thresholds), then whatever it could not settle is re-scanned exactly.
 // Entirely device-driven (no host sync), so mqvs_search_async enqueues it unconditionally after every tensor search;
 // the blocking mqvs_search looks at the flag count first and skips it when nothing is flagged (the common case).
-void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
-                           int64_t* out_ids_dev, cudaStream_t st, int band_rounds) {
+// Exact-scan rounds take s->max_device_fix flagged queries each; a caller that cannot look at the flags (mqvs_search_async)
+// asks for ceil(B / max_device_fix) rounds so that EVERY flagged query is repaired whatever happens (idle rounds exit at once).
+static void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
+                                  int64_t* out_ids_dev, cudaStream_t st, int band_rounds, int fix_rounds) {
     using namespace mqvs;
     const tc::Buffers& b = s->last_b;
     static const bool no_band = getenv("MQVS_NO_BAND") != nullptr;  // developer knob: measure what the band pass costs
@@ -280,19 +170,24 @@ void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* mask_dev
         }
     }
     uint32_t* fix_list = s->fix_dev;
-    uint32_t* fix_n = s->fix_dev + mqvs_store::kMaxDeviceFix;
-    launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, b.flags, B, mqvs_store::kMaxDeviceFix, fix_list, fix_n,
-                    s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st, s->last_space.metric,
-                    s->last_space.norms, s->last_space.qnorm);
-    launch_merge_fix((const uint64_t*)s->tc_fixcand.p, mqvs_store::kMaxDeviceFix, scan_fix_grid(s->sm_count) * k, k, id_base,
-                     fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
-    s->stats.kernel_launches += 2;
+    uint32_t* fix_n = s->fix_dev + kMaxFixRound;
+    for (int r = 0; r < fix_rounds; ++r) {
+        launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, b.flags, B, s->max_device_fix, fix_list, fix_n,
+                        s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st, s->last_space.metric,
+                        s->last_space.norms, s->last_space.qnorm, /*count_leftover=*/r + 1 == fix_rounds);
+        launch_merge_fix((const uint64_t*)s->tc_fixcand.p, s->max_device_fix, scan_fix_grid(s->sm_count) * k, k, id_base,
+                         fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
+        s->stats.kernel_launches += 2;
+    }
 }
 
 // Enqueue one search on `st`; every pointer is device memory.  q_raw [B, dim] is normalised into s->qn first.
+// report_to_host: the caller will synchronise and read the outcome on the host -- the tensor pipelines then keep their
+// flag words in mapped pinned memory (s->flags_map) and the fused kernels report non-finite queries there too
+// (flags_map word [1 + B]), so the blocking call needs no device-to-host copy at all.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
-                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status = nullptr,
-                   bool defer_repair = false) {
+                   float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status,
+                   bool defer_repair, bool report_to_host) {
     using namespace mqvs;
     const int slot = s->ev_cursor;
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
@@ -335,7 +230,13 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if ((rc = s->tc_cnt.ensure(tc::cnt_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_keys.ensure((size_t)plan.b_pad * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
-        if ((rc = s->tc_fixcand.ensure((size_t)mqvs_store::kMaxDeviceFix * scan_fix_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+        // exact-scan repair rounds: 64 flagged queries each for small batches, up to 256 for large ones (fewer idle rounds)
+        s->max_device_fix = B <= 64 ? 64 : (B <= 1024 ? 128 : kMaxFixRound);
+        if ((rc = s->tc_fixcand.ensure((size_t)s->max_device_fix * scan_fix_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
+        if (report_to_host && ((size_t)B + 4) * sizeof(uint32_t) > s->flags_map.bytes) {
+            if ((rc = s->flags_map.ensure(((size_t)B + 4) * sizeof(uint32_t) * 2)) != MQVS_OK) return rc;
+            memset(s->flags_map.p, 0, s->flags_map.bytes);
+        }
         if ((rc = s->tc_cmax.ensure(tc::cmax_bytes(plan))) != MQVS_OK) return rc;
     }
     if ((rc = s->qn.ensure((size_t)B * MQVS_DIM_PAD * sizeof(float))) != MQVS_OK) return rc;
@@ -348,9 +249,13 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         b.tau_tilde = (float*)sm;
         b.tau = (uint32_t*)(b.tau_tilde + plan.b_pad);
         b.eps = (float*)(b.tau + plan.b_pad);    // [B]
-        b.flag_count = (uint32_t*)(b.eps + B);   // flag_count immediately followed by flags[B]: one D2H copy
+        b.flag_count = (uint32_t*)(b.eps + B);   // flag_count immediately followed by flags[B]
         b.flags = b.flag_count + 1;
         b.gbar = (unsigned int*)(b.flags + B);  // [4]
+        if (report_to_host) {  // the host reads them after its stream sync: mapped pinned words instead (written rarely)
+            b.flag_count = (uint32_t*)s->flags_map.p;  // [0] flag count, [1] non-finite-query epoch, [2 ..] flags[B]
+            b.flags = b.flag_count + 2;
+        }
         b.band = (uint32_t*)(b.gbar + 8);        // [B]
         b.band_list = b.band + B;               // [128]
         b.band_n = b.band_list + 128;           // [1]
@@ -389,16 +294,22 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->last_space = space;
     }
     auto enqueue_repair = [&]() {
-        // nobody can look at the flags here: one band round per 128 queries of the batch, at most two
-        if (!defer_repair) enqueue_tensor_repair(s, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, B > 128 ? 2 : 1);
+        // nobody can look at the flags here: one band round per 128 queries of the batch, at most two, then as many exact-scan
+        // rounds as it takes to cover all B queries -- the asynchronous search is exact on its own, whatever gets flagged
+        if (!defer_repair)
+            enqueue_tensor_repair(s, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, B > 128 ? 2 : 1,
+                                  (B + s->max_device_fix - 1) / s->max_device_fix);
     };
+    // where the fused kernels raise the epoch when a query is not finite
+    unsigned int* bad_epoch = (unsigned int*)(s->bad_dev + 1);
+    if (report_to_host && tc_one) bad_epoch = (unsigned int*)s->flags_map.p + 1;
     if (tc_one) {
         s->last_fused = true;  // non-finite queries are reported through the epoch word, as on the latency path
         CU(cudaEventRecord(ev[0], st));
         CU(cudaEventRecord(ev[1], st));
         bool coop_refused = false;
         const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
-                                           mask_dev, id_base, out_scores_dev, out_ids_dev, (unsigned int*)(s->bad_dev + 1),
+                                           mask_dev, id_base, out_scores_dev, out_ids_dev, bad_epoch,
                                            ++s->epoch, st, &coop_refused, space);
         if (err && coop_refused) {
             // the device cannot hold one CTA per SM right now (MPS with an SM limit, a partitioned GPU): this handle
@@ -465,7 +376,10 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     return MQVS_OK;
 }
 
-}  // namespace
+}  // namespace api
+}  // namespace mqvs
+
+using namespace mqvs::api;
 
 extern "C" {
 
@@ -484,12 +398,22 @@ MQVS_API int mqvs_device_count(int* out) {
 MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out) {
     if (!out) return fail(MQVS_E_INVALID, "out is NULL");
     *out = nullptr;
-    if (n_dev != 1)
-        return fail(MQVS_E_INVALID, "one device per handle: shard rows across ranks (one process per GPU) and merge "
-                                    "with mqvs_merge_candidates; got n_dev=%d", n_dev);
+    if (n_dev < 1 || n_dev > MQVS_MAX_DEVICES)
+        return fail(MQVS_E_INVALID, "n_dev must be in [1, %d], got %d", MQVS_MAX_DEVICES, n_dev);
+    if (n_dev > 1 && !dev_ids) return fail(MQVS_E_INVALID, "dev_ids is NULL with n_dev=%d", n_dev);
     if (dim < 1 || dim > MQVS_DIM_PAD) return fail(MQVS_E_INVALID, "dim must be in [1, %d], got %d", MQVS_DIM_PAD, dim);
     if (store_dtype != MQVS_F32 && store_dtype != MQVS_BF16) return fail(MQVS_E_INVALID, "unknown store_dtype %d", store_dtype);
-    int dev = dev_ids ? dev_ids[0] : 0;
+    if (n_dev > 1) return multi_create(n_dev, dev_ids, dim, store_dtype, capacity_rows, out);
+    return create_single(dev_ids ? dev_ids[0] : 0, dim, store_dtype, capacity_rows, out);
+}
+
+}  // extern "C"
+
+namespace mqvs {
+namespace api {
+
+int create_single(int dev, int dim, int store_dtype, uint64_t capacity_rows, mqvs_store** out) {
+    *out = nullptr;
     int count = 0;
     CU(cudaGetDeviceCount(&count));
     if (dev < 0 || dev >= count) return fail(MQVS_E_INVALID, "device %d not present (%d visible)", dev, count);
@@ -506,7 +430,7 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     s->sm_count = prop.multiProcessorCount;
     s->coop_ok = prop.cooperativeLaunch != 0;
     auto bail = [&](int rc) {
-        mqvs_destroy(s);
+        destroy_single(s);
         return rc;
     };
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(MQVS_E_CUDA, "stream creation failed"));
@@ -519,13 +443,9 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
         cudaMemset(s->ticket_dev, 0, sizeof(unsigned int)) != cudaSuccess)
         return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
     if (cudaMallocHost(&s->bad_host, 3 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(MQVS_E_OOM, "cudaMallocHost failed"));
-    if (cudaHostAlloc((void**)&s->host_out, 64 * 4 + 64 * 8 + 16, cudaHostAllocMapped) != cudaSuccess) {
-        cudaGetLastError();
-        s->host_out = nullptr;  // not fatal: the latency path copies its results back instead
-    } else {
-        memset(s->host_out, 0, 64 * 4 + 64 * 8 + 16);
-    }
-    if (cudaMalloc(&s->fix_dev, (mqvs_store::kMaxDeviceFix + 1) * sizeof(uint32_t)) != cudaSuccess ||
+    if (s->host_out.ensure(4096) != MQVS_OK) return bail(MQVS_E_OOM);
+    memset(s->host_out.p, 0, s->host_out.bytes);
+    if (cudaMalloc(&s->fix_dev, (kMaxFixRound + 1) * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&s->fix_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(s->fix_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
         return bail(fail(MQVS_E_OOM, "cudaMalloc failed"));
@@ -537,10 +457,11 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     return MQVS_OK;
 }
 
-MQVS_API void mqvs_destroy(mqvs_t* s) {
+void destroy_single(mqvs_store* s) {
     if (!s) return;
     cudaSetDevice(s->dev);
     if (s->st) cudaStreamSynchronize(s->st);
+    if (s->copy_st) cudaStreamSynchronize(s->copy_st);
     for (auto& c : s->columns) {
         c.values.release();
         c.present.release();
@@ -548,29 +469,174 @@ MQVS_API void mqvs_destroy(mqvs_t* s) {
     for (DevBuf* b : {&s->f_table, &s->f_prog, &s->f_pool, &s->f_live, &s->f_mask}) b->release();
     if (s->f_count_dev) cudaFree(s->f_count_dev);
     if (s->f_count_host) cudaFreeHost(s->f_count_host);
-    for (DevBuf* b : {&s->norm_bounds, &s->stage, &s->qraw, &s->qn, &s->qnorm, &s->cand, &s->out_s, &s->out_i, &s->maskbuf, &s->idbuf, &s->gatherbuf,
-                      &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys, &s->tc_fixcand, &s->tc_cmax})
+    for (DevBuf* b : {&s->norm_bounds, &s->stage[0], &s->stage[1], &s->qraw, &s->qn, &s->qnorm, &s->cand, &s->out_s, &s->out_i,
+                      &s->maskbuf, &s->idbuf, &s->gatherbuf, &s->tc_qop, &s->tc_small, &s->tc_cnt, &s->tc_lists, &s->tc_keys,
+                      &s->tc_fixcand, &s->tc_cmax})
         b->release();
+    for (PinBuf* b : {&s->bounce[0], &s->bounce[1], &s->host_out, &s->flags_map}) b->release();
     if (s->fix_dev) cudaFree(s->fix_dev);
     if (s->fix_counters) cudaFree(s->fix_counters);
-    if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->rows) cudaFree(s->rows);
     if (s->norms) cudaFree(s->norms);
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->ticket_dev) cudaFree(s->ticket_dev);
     if (s->bad_host) cudaFreeHost(s->bad_host);
-    if (s->host_out) cudaFreeHost(s->host_out);
-    if (s->out_pinned) cudaFreeHost(s->out_pinned);
     for (auto& set : s->evr)
         for (auto& e : set.e)
             if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+        if (s->ev_k1[i]) cudaEventDestroy(s->ev_k1[i]);
+    }
+    if (s->copy_st) cudaStreamDestroy(s->copy_st);
     if (s->st) cudaStreamDestroy(s->st);
     cudaGetLastError();
     delete s;
 }
 
+// ---- ingest
+namespace {
+
+// pageable host memory -> pinned bounce buffer with a few host threads (one core copies ~10 GB/s, PCIe Gen5 takes 50+)
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kPerThread = 4u << 20;
+    int nt = (int)std::min<size_t>(4, bytes / kPerThread);
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t part = (bytes / nt + 63) & ~(size_t)63;
+    for (int t = 1; t < nt; ++t) {
+        const size_t off = (size_t)t * part, len = off >= bytes ? 0 : std::min(part, bytes - off);
+        if (len) th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto& t : th) t.join();
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// Host rows -> K1 through a two-slot pipeline: the H2D copy of chunk i + 1 (copy stream) overlaps K1 of chunk i (the
+// store's stream); pageable sources are bounced through pinned buffers by a few host threads while the previous chunk is
+// in flight, pinned sources (cudaHostAlloc / cudaHostRegister by the caller) are copied from where they lie.
+static int ingest_host(mqvs_store* s, const AddSeg* segs, size_t n_segs, char* dst, float* norms_dst, unsigned int* dev_word,
+                       uint64_t* launches) {
+    const uint64_t chunk = 8192;  // rows per slot: 25 MB at 768 columns
+    const size_t slot_bytes = (size_t)chunk * s->dim * sizeof(float);
+    int rc;
+    if (!s->copy_st) {
+        CU(cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_k1[i], cudaEventDisableTiming));
+        }
+    }
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_segs; ++i) total += segs[i].n;
+    const size_t need = std::min<size_t>(slot_bytes, (size_t)total * s->dim * sizeof(float));
+    for (int i = 0; i < 2; ++i)
+        if ((rc = s->stage[i].ensure(need)) != MQVS_OK) return rc;
+    bool used[2] = {false, false};
+    uint64_t done = 0, c = 0;
+    for (size_t g = 0; g < n_segs; ++g) {
+        const bool pinned = is_pinned_host(segs[g].src);
+        for (uint64_t r = 0; r < segs[g].n; r += chunk, ++c) {
+            const int slot = (int)(c & 1);
+            const uint64_t m = std::min(chunk, segs[g].n - r);
+            const size_t bytes = (size_t)m * s->dim * sizeof(float);
+            if (used[slot]) CU(cudaEventSynchronize(s->ev_k1[slot]));  // K1 has consumed this slot (so its H2D is long done)
+            const void* src = segs[g].src + r * s->dim;
+            if (!pinned) {
+                if ((rc = s->bounce[slot].ensure(need)) != MQVS_OK) return rc;
+                parallel_memcpy(s->bounce[slot].p, src, bytes);
+                src = s->bounce[slot].p;
+            }
+            CU(cudaMemcpyAsync(s->stage[slot].p, src, bytes, cudaMemcpyHostToDevice, s->copy_st));
+            CU(cudaEventRecord(s->ev_h2d[slot], s->copy_st));
+            CU(cudaStreamWaitEvent(s->st, s->ev_h2d[slot], 0));
+            launch_normalize((const float*)s->stage[slot].p, m, s->dim, s->dtype, dst + done * s->row_bytes(), s->bad_dev, s->st,
+                             norms_dst ? norms_dst + done : nullptr, dev_word);
+            CU(cudaEventRecord(s->ev_k1[slot], s->st));
+            used[slot] = true;
+            done += m;
+            ++*launches;
+        }
+    }
+    return MQVS_OK;
+}
+
+int add_stage(mqvs_store* s, const AddSeg* segs, size_t n_segs, int x_is_device, bool synth, uint64_t seed, AddReport* rep) {
+    *rep = AddReport();
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_segs; ++i) total += segs[i].n;
+    rep->rows = total;
+    if (total == 0) return MQVS_OK;
+    int rc = grow(s, s->n + total);
+    if (rc != MQVS_OK) return rc;
+    char* dst = (char*)s->rows + s->n * s->row_bytes();
+    float* norms_dst = s->keep_norms ? s->norms + s->n : nullptr;
+    unsigned int* dev_word = (unsigned int*)(s->bad_dev + 2);
+    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), s->st));
+    CU(cudaMemsetAsync(s->bad_dev + 2, 0, sizeof(unsigned long long), s->st));
+    if (synth || x_is_device) {
+        uint64_t done = 0;
+        for (size_t i = 0; i < n_segs; ++i) {
+            if (segs[i].n == 0) continue;
+            if (synth)
+                launch_synth_normalize(seed, segs[i].first_index, segs[i].n, s->dim, s->dtype, dst + done * s->row_bytes(), s->bad_dev,
+                                       s->st, norms_dst ? norms_dst + done : nullptr, dev_word);
+            else
+                launch_normalize(segs[i].src, segs[i].n, s->dim, s->dtype, dst + done * s->row_bytes(), s->bad_dev, s->st,
+                                 norms_dst ? norms_dst + done : nullptr, dev_word);
+            done += segs[i].n;
+            ++rep->launches;
+        }
+    } else if ((rc = ingest_host(s, segs, n_segs, dst, norms_dst, dev_word, &rep->launches)) != MQVS_OK) {
+        cudaStreamSynchronize(s->st);
+        return rc;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->stats.kernel_launches += rep->launches;
+    rep->bad = *s->bad_host;
+    const uint32_t bits = (uint32_t)s->bad_host[2], bits_max = (uint32_t)(s->bad_host[2] >> 32);
+    memcpy(&rep->norm_dev, &bits, 4);
+    memcpy(&rep->norm_max, &bits_max, 4);
+    return MQVS_OK;
+}
+
+void add_commit(mqvs_store* s, const AddReport& rep) {
+    s->norm_dev = std::max(s->norm_dev, rep.norm_dev);
+    s->norm_max = std::max(s->norm_max, rep.norm_max);
+    s->n += rep.rows;
+    s->stats.rows = s->n;
+}
+
+}  // namespace api
+}  // namespace mqvs
+
+extern "C" {
+
+MQVS_API void mqvs_destroy(mqvs_t* s) {
+    if (!s) return;
+    if (s->multi) return multi_destroy(s);
+    destroy_single(s);
+}
+
 MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out) {
     if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_count(s, out);
     std::lock_guard<std::mutex> lk(s->mu);
     *out = s->n;
     return MQVS_OK;
@@ -578,6 +644,7 @@ MQVS_API int mqvs_count(mqvs_t* s, uint64_t* out) {
 
 MQVS_API int mqvs_reserve(mqvs_t* s, uint64_t capacity_rows) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (s->multi) return multi_reserve(s, capacity_rows);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     return grow(s, capacity_rows);
@@ -585,55 +652,19 @@ MQVS_API int mqvs_reserve(mqvs_t* s, uint64_t capacity_rows) {
 
 static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uint64_t seed, uint64_t first_index,
                       uint64_t n, uint64_t* first_row_out) {
-    using namespace mqvs;
+    if (s->multi) return multi_add(s, x, x_is_device, synth, seed, first_index, n, first_row_out);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     if (first_row_out) *first_row_out = s->n;
     if (n == 0) return MQVS_OK;
-    int rc = grow(s, s->n + n);
+    AddSeg seg{(const float*)x, n, first_index};
+    AddReport rep;
+    int rc = add_stage(s, &seg, 1, x_is_device, synth, seed, &rep);
     if (rc != MQVS_OK) return rc;
-    char* dst = (char*)s->rows + s->n * s->row_bytes();
-    float* norms_dst = s->keep_norms ? s->norms + s->n : nullptr;
-    unsigned int* dev_word = (unsigned int*)(s->bad_dev + 2);
-    CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), s->st));
-    CU(cudaMemsetAsync(s->bad_dev + 2, 0, sizeof(unsigned long long), s->st));
-    uint64_t launches = 0;
-    if (synth) {
-        launch_synth_normalize(seed, first_index, n, s->dim, s->dtype, dst, s->bad_dev, s->st, norms_dst, dev_word);
-        launches = 1;
-    } else if (x_is_device) {
-        launch_normalize((const float*)x, n, s->dim, s->dtype, dst, s->bad_dev, s->st, norms_dst, dev_word);
-        launches = 1;
-    } else {
-        const uint64_t chunk = 65536;
-        if ((rc = s->stage.ensure((size_t)std::min(n, chunk) * s->dim * sizeof(float))) != MQVS_OK) return rc;
-        for (uint64_t r = 0; r < n; r += chunk) {
-            uint64_t m = std::min(chunk, n - r);
-            CU(cudaMemcpyAsync(s->stage.p, (const float*)x + r * s->dim, (size_t)m * s->dim * sizeof(float),
-                               cudaMemcpyHostToDevice, s->st));
-            launch_normalize((const float*)s->stage.p, m, s->dim, s->dtype, dst + r * s->row_bytes(), s->bad_dev, s->st,
-                             norms_dst ? norms_dst + r : nullptr, dev_word);
-            CU(cudaStreamSynchronize(s->st));  // staging buffer is reused
-            ++launches;
-        }
-    }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    s->stats.kernel_launches += launches;
-    if (*s->bad_host)
+    if (rep.bad)
         return fail(MQVS_E_INVALID, "%llu of %llu embeddings have a non-finite norm; nothing was added",
-                    *s->bad_host, (unsigned long long)n);
-    {
-        const uint32_t bits = (uint32_t)s->bad_host[2], bits_max = (uint32_t)(s->bad_host[2] >> 32);
-        float dev, mx;
-        memcpy(&dev, &bits, 4);
-        memcpy(&mx, &bits_max, 4);
-        s->norm_dev = std::max(s->norm_dev, dev);
-        s->norm_max = std::max(s->norm_max, mx);
-    }
-    s->n += n;
-    s->stats.rows = s->n;
+                    (unsigned long long)rep.bad, (unsigned long long)n);
+    add_commit(s, rep);
     return MQVS_OK;
 }
 
@@ -665,10 +696,48 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     int rc = check_search_args(s, q, B, k, out_scores, out_ids);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
+    if (s->multi)
+        return multi_search(s, q, q_is_device, B, k, mask, mask_is_device, 0, out_scores, out_ids, out_is_device, nullptr, true);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     return search_locked(s, q, q_is_device, B, k, mask, mask_is_device, out_scores, out_ids, out_is_device);
 }
+
+}  // extern "C"
+
+namespace mqvs {
+namespace api {
+
+// After the caller has synchronised the stream of a report_to_host search: repair on the device what the tensor pipeline
+// could not prove exact (band pass + exact-scan rounds sized by the flag count), then whatever even that left flagged
+// (band overflow and more flagged queries than the rounds took) on the exact scan, one query at a time.
+int finish_search(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* os, int64_t* oi,
+                  cudaStream_t st, bool* changed) {
+    *changed = false;
+    if (s->stats.last_path != 1) return MQVS_OK;
+    volatile uint32_t* fl = (volatile uint32_t*)s->flags_map.p;
+    if (fl == nullptr || fl[0] == 0) return MQVS_OK;
+    const int flagged = (int)fl[0];
+    enqueue_tensor_repair(s, B, k, mask_dev, id_base, os, oi, st, (flagged + 127) / 128,
+                          (flagged + s->max_device_fix - 1) / s->max_device_fix);
+    CU(cudaStreamSynchronize(st));
+    int rc;
+    for (int b = 0; b < B; ++b) {
+        if (!fl[2 + b]) continue;  // flags of device-repaired queries were cleared
+        uint32_t passes = 0;
+        if ((rc = enqueue_simt(s, b, 1, k, mask_dev, id_base, os, oi, st, &passes)) != MQVS_OK) return rc;
+        s->stats.kernel_launches += passes + 1;
+        s->host_fallbacks += 1;
+        fl[2 + b] = 0;
+    }
+    fl[0] = 0;
+    CU(cudaStreamSynchronize(st));
+    *changed = true;
+    return MQVS_OK;
+}
+
+}  // namespace api
+}  // namespace mqvs
 
 static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
                          float* out_scores, int64_t* out_ids, int out_is_device) {
@@ -686,95 +755,64 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
         CU(cudaMemcpyAsync(s->maskbuf.p, mask, bytes, cudaMemcpyHostToDevice, s->st));
         mask_dev = (const uint32_t*)s->maskbuf.p;
     }
+    const size_t n_out = (size_t)B * k;
     float* os = out_scores;
     int64_t* oi = out_ids;
-    // latency path (B <= 4, k <= 16, the reference's own regime) with host outputs: results and status are written by the
-    // kernel into mapped pinned memory -- the call is one H2D copy of the queries, one launch, one stream sync
-    const bool zero_copy = !out_is_device && s->host_out != nullptr && !use_tensor_path(s, B, k) && s->path != 3 &&
-                           s->metric == MQVS_METRIC_COSINE && mqvs::scan_fused_ok(B, k);
+    unsigned int* status = nullptr;
+    // Host outputs: every path writes results (and the latency kernel its status) straight into mapped pinned memory --
+    // the call is one H2D copy of the queries, the launches, one stream sync; nothing is copied back.
+    if (!out_is_device) {
+        const size_t need = n_out * 12 + 64;
+        if (need > s->host_out.bytes) {
+            if ((rc = s->host_out.ensure(need * 2)) != MQVS_OK) return rc;
+            memset(s->host_out.p, 0, s->host_out.bytes);
+        }
+        oi = (int64_t*)s->host_out.p;
+        os = (float*)((char*)s->host_out.p + n_out * sizeof(int64_t));
+        status = (unsigned int*)((char*)s->host_out.p + n_out * 12 + ((8 - (n_out * 12) % 8) % 8));
+        status[0] = 0;
+    }
+    // latency path (B <= 4, k <= 16, the reference's own regime): one launch that also reports completion + non-finite status
+    const bool zero_copy = !out_is_device && !use_tensor_path(s, B, k) && s->path != 3 && s->metric == MQVS_METRIC_COSINE &&
+                           mqvs::scan_fused_ok(B, k);
     if (zero_copy) {
-        os = (float*)s->host_out;
-        oi = (int64_t*)(s->host_out + 64 * 4);
-        unsigned int* status = (unsigned int*)(s->host_out + 64 * 4 + 64 * 8);
         if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, status)) != MQVS_OK) return rc;
         CU(cudaStreamSynchronize(s->st));
         if (status[0] != s->epoch) return fail(MQVS_E_CUDA, "latency path: the kernel did not report completion");
-        memcpy(out_scores, os, (size_t)B * k * sizeof(float));
-        memcpy(out_ids, oi, (size_t)B * k * sizeof(int64_t));
+        memcpy(out_scores, os, n_out * sizeof(float));
+        memcpy(out_ids, oi, n_out * sizeof(int64_t));
         if (status[1]) return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
         return MQVS_OK;
     }
-    const size_t n_out = (size_t)B * k;
-    float* host_s = nullptr;
-    int64_t* host_i = nullptr;
-    if (!out_is_device) {
-        if ((rc = s->out_s.ensure(n_out * sizeof(float))) != MQVS_OK) return rc;
-        if ((rc = s->out_i.ensure(n_out * sizeof(int64_t))) != MQVS_OK) return rc;
-        os = (float*)s->out_s.p;
-        oi = (int64_t*)s->out_i.p;
-        if (s->out_pinned_bytes < n_out * 12) {
-            if (s->out_pinned) cudaFreeHost(s->out_pinned);
-            s->out_pinned = nullptr;
-            s->out_pinned_bytes = 0;
-            CU(cudaMallocHost((void**)&s->out_pinned, n_out * 12));
-            s->out_pinned_bytes = n_out * 12;
-        }
-        host_i = (int64_t*)s->out_pinned;
-        host_s = (float*)(s->out_pinned + n_out * sizeof(int64_t));
-    }
-    if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, nullptr, /*defer_repair=*/true)) != MQVS_OK) return rc;
-    if (!out_is_device) {
-        CU(cudaMemcpyAsync(host_s, os, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-        CU(cudaMemcpyAsync(host_i, oi, n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
-    }
-    CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+    if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, nullptr, /*defer_repair=*/true, /*report_to_host=*/true)) != MQVS_OK)
+        return rc;
     const bool tensor = s->stats.last_path == 1;
-    if (tensor) {
-        if (s->flags_host_n < (size_t)B + 1) {
-            if (s->flags_host) cudaFreeHost(s->flags_host);
-            s->flags_host = nullptr;
-            s->flags_host_n = 0;
-            CU(cudaMallocHost(&s->flags_host, ((size_t)B + 1) * sizeof(uint32_t)));
-            s->flags_host_n = (size_t)B + 1;
-        }
-        CU(cudaMemcpyAsync(s->flags_host, s->last_flags_dev, ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
-    }
+    const bool epoch_word = tensor && s->last_fused;  // single-launch tensor pipeline: non-finite epoch in flags_map[1]
+    if (!epoch_word) CU(cudaMemcpyAsync(s->bad_host, s->bad_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    if (s->last_fused ? (unsigned int)s->bad_host[1] == s->epoch : s->bad_host[0] != 0)
-        return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
-    if (tensor && s->flags_host[0] > 0) {
-        // some shortlists were not proven exact: band pass + exact scan of up to 64 queries on the device, then look again
-        enqueue_tensor_repair(s, B, k, mask_dev, 0, os, oi, s->st, (int)((s->flags_host[0] + 127) / 128));
-        CU(cudaMemcpyAsync(s->flags_host, s->last_flags_dev, ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
-        CU(cudaStreamSynchronize(s->st));
-        // more flagged queries than the device repair takes: re-run the rest on the exact scan from here
-        for (int b = 0; b < B; ++b) {
-            if (!s->flags_host[1 + b]) continue;  // flags of device-repaired queries were cleared
-            uint32_t passes = 0;
-            if ((rc = enqueue_simt(s, b, 1, k, mask_dev, 0, os, oi, s->st, &passes)) != MQVS_OK) return rc;
-            s->stats.kernel_launches += passes + 1;
-            s->host_fallbacks += 1;
-        }
-        if (!out_is_device) {
-            CU(cudaMemcpyAsync(host_s, os, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->st));
-            CU(cudaMemcpyAsync(host_i, oi, n_out * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
-        }
-        CU(cudaStreamSynchronize(s->st));
-    }
+    const bool bad = epoch_word ? ((volatile uint32_t*)s->flags_map.p)[1] == s->epoch
+                                : (s->last_fused ? (unsigned int)s->bad_host[1] == s->epoch : s->bad_host[0] != 0);
+    if (bad) return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);
+    bool changed = false;
+    if ((rc = finish_search(s, B, k, mask_dev, 0, os, oi, s->st, &changed)) != MQVS_OK) return rc;
     if (!out_is_device) {
-        memcpy(out_scores, host_s, n_out * sizeof(float));
-        memcpy(out_ids, host_i, n_out * sizeof(int64_t));
+        memcpy(out_scores, os, n_out * sizeof(float));
+        memcpy(out_ids, oi, n_out * sizeof(int64_t));
     }
     settle_events(s);
     mqvs::tc::trace_dump();
     return MQVS_OK;
 }
 
+extern "C" {
+
 MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                       float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
     int rc = check_search_args(s, q_dev, B, k, out_scores_dev, out_ids_dev);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
+    if (s->multi)
+        return multi_search(s, q_dev, 1, B, k, mask_dev, 1, id_base, out_scores_dev, out_ids_dev, 1, (cudaStream_t)cuda_stream, false);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     return enqueue_search(s, q_dev, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, (cudaStream_t)cuda_stream);
@@ -796,7 +834,14 @@ MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float*
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (n == 0) return MQVS_OK;
     if (!row_ids || !out_host) return fail(MQVS_E_INVALID, "NULL buffer");
+    if (s->multi) return multi_get_rows(s, row_ids, n, out_host);
     std::lock_guard<std::mutex> lk(s->mu);
+    return get_rows_single(s, row_ids, n, out_host);
+}
+
+}  // extern "C"
+
+int mqvs::api::get_rows_single(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out_host) {
     for (uint64_t i = 0; i < n; ++i)
         if (row_ids[i] < 0 || (uint64_t)row_ids[i] >= s->n)
             return fail(MQVS_E_INVALID, "row id %lld out of range [0, %llu)", (long long)row_ids[i], (unsigned long long)s->n);
@@ -814,15 +859,6 @@ MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float*
 }
 
 namespace {
-struct FileHeader {
-    char magic[8];
-    uint32_t version, dim, dtype, dim_pad;
-    uint64_t rows;
-};
-struct NormsHeader {
-    char magic[8];
-    uint64_t rows;
-};
 
 // `<path>.norms`: ||x|| of every raw row, rewritten whole (4 bytes per row) through a temporary + rename
 int save_norms(mqvs_store* s, const char* path) {
@@ -836,6 +872,7 @@ int save_norms(mqvs_store* s, const char* path) {
     memcpy(h.magic, "MQVSNRM1", 8);
     h.rows = s->n;
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(host.data(), sizeof(float), (size_t)s->n, f) == (size_t)s->n;
+    ok = ok && fflush(f) == 0 && fsync(fileno(f)) == 0;
     ok = (fclose(f) == 0) && ok;
     if (!ok || rename(tmp.c_str(), dst.c_str()) != 0) {
         remove(tmp.c_str());
@@ -869,10 +906,15 @@ int load_norms(mqvs_store* s, const char* path, uint64_t rows) {
     s->bounds_rows = 0;  // other rows than the chunk bounds were computed from
     return MQVS_OK;
 }
+// flush a stdio stream all the way to the device: the orderings the row file promises must survive a power loss too
+bool flush_to_disk(FILE* f) { return fflush(f) == 0 && fsync(fileno(f)) == 0; }
 }  // namespace
+
+extern "C" {
 
 MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_save(s, path, 0);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     std::string tmp = std::string(path) + ".tmp";
@@ -898,6 +940,7 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
         }
         ok = fwrite(host.data(), s->row_bytes(), m, f) == m;
     }
+    ok = ok && flush_to_disk(f);
     ok = (fclose(f) == 0) && ok;
     if (ok) {  // norms first: a row file is never newer than its norms
         int rc = save_norms(s, path);
@@ -916,6 +959,7 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
 MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
     if (first_row == 0) return mqvs_save(s, path);
+    if (s->multi) return multi_save(s, path, first_row);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     if (first_row > s->n) return fail(MQVS_E_INVALID, "first_row %llu beyond the %llu stored rows", (unsigned long long)first_row, (unsigned long long)s->n);
@@ -950,9 +994,10 @@ MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
             return rc;
         }
     }
-    // the row count in the header moves last: a crash before this leaves the old, consistent file (plus ignored bytes)
+    // the row count in the header moves last, after the rows are ON DISK (fsync): a crash or a power loss before this
+    // leaves the old, consistent file (plus ignored bytes)
     h.rows = s->n;
-    ok = ok && fflush(f) == 0 && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof(h), 1, f) == 1;
+    ok = ok && flush_to_disk(f) && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof(h), 1, f) == 1 && flush_to_disk(f);
     ok = (fclose(f) == 0) && ok;
     if (!ok) return fail(MQVS_E_IO, "appending to %s failed", path);
     return MQVS_OK;
@@ -960,6 +1005,7 @@ MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
 
 MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_load(s, path);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     FILE* f = fopen(path, "rb");
@@ -1000,13 +1046,78 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     return MQVS_OK;
 }
 
+MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out) {
+    if (!s || !keep_words_host || !new_count_out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi)
+        return fail(MQVS_E_INVALID, "compaction of a multi-device handle is not implemented (rows would have to move between "
+                                    "devices): rebuild the collection");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    CU(cudaStreamSynchronize(s->st));
+    std::vector<uint32_t> keep;
+    keep.reserve((size_t)s->n);
+    for (uint64_t r = 0; r < s->n; ++r)
+        if ((keep_words_host[r >> 5] >> (r & 31)) & 1u) keep.push_back((uint32_t)r);
+    const uint64_t m = keep.size();
+    if (m < s->n) {
+        // survivors move down in ascending order, chunk by chunk through a bounce buffer: the destination of a chunk never
+        // reaches beyond its first source row, and every earlier source row has already been consumed
+        const uint64_t chunk = 16384;
+        DevBuf ids, tmp;
+        int rc;
+        if ((rc = ids.ensure(std::min<uint64_t>(chunk, std::max<uint64_t>(m, 1)) * sizeof(uint32_t))) != MQVS_OK) return rc;
+        if ((rc = tmp.ensure(std::min<uint64_t>(chunk, std::max<uint64_t>(m, 1)) * s->row_bytes())) != MQVS_OK) {
+            ids.release();
+            return rc;
+        }
+        cudaError_t e = cudaSuccess;
+        for (uint64_t done = 0; done < m && e == cudaSuccess; done += chunk) {
+            const uint64_t c = std::min(chunk, m - done);
+            if (keep[done + c - 1] == done + c - 1) continue;  // nothing dead up to here: rows are already in place
+            e = cudaMemcpyAsync(ids.p, keep.data() + done, c * sizeof(uint32_t), cudaMemcpyHostToDevice, s->st);
+            if (e != cudaSuccess) break;
+            mqvs::launch_gather_raw_rows(s->rows, s->row_bytes(), (const uint32_t*)ids.p, c, tmp.p, s->st);
+            e = cudaMemcpyAsync((char*)s->rows + done * s->row_bytes(), tmp.p, c * s->row_bytes(), cudaMemcpyDeviceToDevice, s->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);  // `ids` is reused
+        }
+        if (e == cudaSuccess && s->keep_norms && m) {
+            std::vector<float> nh((size_t)s->n);
+            e = cudaMemcpy(nh.data(), s->norms, s->n * sizeof(float), cudaMemcpyDeviceToHost);
+            for (uint64_t i = 0; i < m; ++i) nh[i] = nh[keep[i]];
+            if (e == cudaSuccess) e = cudaMemcpy(s->norms, nh.data(), m * sizeof(float), cudaMemcpyHostToDevice);
+        }
+        ids.release();
+        tmp.release();
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MQVS_E_CUDA, "compaction failed: %s (the store is in an undefined state)", cudaGetErrorString(e));
+        }
+        s->stats.kernel_launches += (m + chunk - 1) / chunk;
+        s->n = m;
+        s->stats.rows = m;
+        s->bounds_rows = 0;
+        for (auto& c : s->columns) c.used = false;  // row numbers changed under them
+        s->f_table_dirty = true;
+    }
+    *new_count_out = s->n;
+    return MQVS_OK;
+}
+
 MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
                              uint64_t n) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
     if (col_type != MQVS_COL_I64 && col_type != MQVS_COL_F64) return fail(MQVS_E_INVALID, "unknown column type %d", col_type);
     if (n && !values_host) return fail(MQVS_E_INVALID, "values is NULL");
+    if (s->multi) return multi_column_set(s, col_id, col_type, values_host, present_host, n);
     std::lock_guard<std::mutex> lk(s->mu);
+    return column_set_single(s, col_id, col_type, values_host, present_host, n);
+}
+
+}  // extern "C"
+
+int mqvs::api::column_set_single(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
+                                 uint64_t n) {
     CU(cudaSetDevice(s->dev));
     auto& c = s->columns[col_id];
     int rc;
@@ -1030,13 +1141,24 @@ MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* va
     return MQVS_OK;
 }
 
+extern "C" {
+
 MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                                const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out) {
     using namespace mqvs;
     if (!s || !mask_dev_out || !allowed_out) return fail(MQVS_E_INVALID, "NULL argument");
     if (n_ops < 0 || n_ops > kFilterMaxOps) return fail(MQVS_E_INVALID, "a filter program holds at most %d operations", kFilterMaxOps);
     if (n_ops && !prog) return fail(MQVS_E_INVALID, "prog is NULL");
+    if (s->multi) return multi_filter_build(s, prog, n_ops, pool, pool_len, live_words_host, mask_dev_out, allowed_out);
     std::lock_guard<std::mutex> lk(s->mu);
+    return filter_build_single(s, prog, n_ops, pool, pool_len, live_words_host, mask_dev_out, allowed_out);
+}
+
+}  // extern "C"
+
+int mqvs::api::filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
+                                   const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out) {
+    using namespace mqvs;
     CU(cudaSetDevice(s->dev));
     // validate: known columns, sets inside the pool, a well-formed postfix expression
     int depth = 0;
@@ -1103,17 +1225,24 @@ MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops,
     return MQVS_OK;
 }
 
-MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
-    if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(s->mu);
+void mqvs::api::fill_stats(mqvs_store* s) {
     cudaSetDevice(s->dev);
     settle_events(s);
     s->stats.rows = s->n;
     unsigned long long c[4] = {0, 0, 0, 0};
     if (s->fix_counters && cudaMemcpy(c, s->fix_counters, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) cudaGetLastError();
     s->stats.band_repairs = c[2];
-    s->stats.exact_fallbacks = c[0] + s->host_fallbacks;  // async callers: c[1] - host_fallbacks queries stayed unrepaired
+    s->stats.exact_fallbacks = c[0] + s->host_fallbacks;  // c[1]: queries the last device repair round of a search left flagged
     s->stats.unrepaired = c[1] > s->host_fallbacks ? c[1] - s->host_fallbacks : 0;
+}
+
+extern "C" {
+
+MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out) {
+    if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_get_stats(s, out);
+    std::lock_guard<std::mutex> lk(s->mu);
+    fill_stats(s);
     *out = s->stats;
     return MQVS_OK;
 }
@@ -1122,6 +1251,7 @@ MQVS_API int mqvs_set_metric(mqvs_t* s, int metric) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (metric != MQVS_METRIC_COSINE && metric != MQVS_METRIC_L2 && metric != MQVS_METRIC_IP)
         return fail(MQVS_E_INVALID, "unknown metric %d", metric);
+    if (s->multi) return multi_set_metric(s, metric);
     std::lock_guard<std::mutex> lk(s->mu);
     if (metric != MQVS_METRIC_COSINE && !s->keep_norms) {
         if (s->n)
@@ -1141,6 +1271,7 @@ MQVS_API int mqvs_set_metric(mqvs_t* s, int metric) {
 
 MQVS_API int mqvs_norm_deviation(mqvs_t* s, float* out) {
     if (!s || !out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_norm_deviation(s, out);
     std::lock_guard<std::mutex> lk(s->mu);
     *out = s->norm_dev;
     return MQVS_OK;
@@ -1150,6 +1281,7 @@ MQVS_API int mqvs_get_norms(mqvs_t* s, uint64_t first_row, uint64_t n, float* ou
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (n == 0) return MQVS_OK;
     if (!out_host) return fail(MQVS_E_INVALID, "NULL buffer");
+    if (s->multi) return multi_get_norms(s, first_row, n, out_host);
     std::lock_guard<std::mutex> lk(s->mu);
     if (!s->keep_norms) return fail(MQVS_E_INVALID, "norms are kept only for the l2 / ip metrics (mqvs_set_metric)");
     if (first_row > s->n || n > s->n - first_row)
@@ -1164,6 +1296,7 @@ MQVS_API int mqvs_get_norms(mqvs_t* s, uint64_t first_row, uint64_t n, float* ou
 MQVS_API int mqvs_set_path(mqvs_t* s, int path) {
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (path < 0 || path > 4) return fail(MQVS_E_INVALID, "path must be 0..4");
+    if (s->multi) return multi_set_path(s, path);
     std::lock_guard<std::mutex> lk(s->mu);
     s->path = path;
     return MQVS_OK;

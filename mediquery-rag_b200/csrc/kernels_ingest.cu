@@ -125,7 +125,23 @@ __global__ void gather_rows_kernel(const T* __restrict__ rows, const int64_t* __
     for (int j = threadIdx.x; j < dim; j += blockDim.x) out[i * (uint64_t)dim + j] = (float)r[j];
 }
 
+// one warp per row: 16-byte vectors, streaming loads
+__global__ void __launch_bounds__(256)
+gather_raw_rows_kernel(const uint4* __restrict__ rows, uint32_t vec_per_row, const uint32_t* __restrict__ ids, uint64_t n,
+                       uint4* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const uint4* src = rows + (uint64_t)ids[i] * vec_per_row;
+    uint4* dst = out + i * vec_per_row;
+    for (uint32_t v = threadIdx.x & 31; v < vec_per_row; v += 32) dst[v] = __ldcs(src + v);
+}
+
 }  // namespace
+
+void launch_gather_raw_rows(const void* rows, size_t row_bytes, const uint32_t* ids, uint64_t n, void* out, cudaStream_t st) {
+    if (n == 0) return;
+    gather_raw_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>((const uint4*)rows, (uint32_t)(row_bytes / 16), ids, n, (uint4*)out);
+}
 
 void launch_normalize(const float* x, uint64_t n, int dim, int out_dtype, void* out, unsigned long long* bad,
                       cudaStream_t st, float* norms, unsigned int* max_dev) {

@@ -246,9 +246,9 @@ scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __rest
                 const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
                 uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters,
                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride, int metric,
-                const float* __restrict__ row_norms, const float* __restrict__ q_norms_all) {
+                const float* __restrict__ row_norms, const float* __restrict__ q_norms_all, int count_leftover) {
     extern __shared__ __align__(16) uint64_t smem_keys[];
-    __shared__ uint32_t list_s[64];
+    __shared__ uint32_t list_s[256];
     __shared__ uint32_t n_s, total_s;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 32) {
@@ -272,7 +272,8 @@ scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __rest
             *fix_n = n;
             if (total_s) {
                 atomicAdd(counters + 0, (unsigned long long)n);              // repaired on the device
-                atomicAdd(counters + 1, (unsigned long long)(total_s - n));  // left flagged (the blocking call repairs them)
+                // left flagged after the LAST round of a search (earlier rounds leave them to the next one)
+                if (count_leftover) atomicAdd(counters + 1, (unsigned long long)(total_s - n));
             }
         }
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) fix_list[i] = list_s[i];
@@ -385,21 +386,23 @@ int scan_fix_grid(int sm_count) { return sm_count * 2; }
 
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
-                     int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all) {
+                     int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all,
+                     bool count_leftover) {
     const int kpl = k <= 32 ? 1 : 4;  // the tensor path serves k <= 128
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
-    if (max_fix > 64) max_fix = 64;
+    if (max_fix > 256) max_fix = 256;
+    const int leftover = count_leftover ? 1 : 0;
 #define MQVS_FIX(T_, KPL_, U_)                                                                                                     \
     do {                                                                                                                           \
         if (metric != MQVS_METRIC_COSINE)                                                                                          \
             scan_fix_kernel<T_, KPL_, U_, true><<<grid, kScanThreads, smem, st>>>(                                                 \
                 (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, metric,      \
-                row_norms, q_norms_all);                                                                                           \
+                row_norms, q_norms_all, leftover);                                                                                 \
         else                                                                                                                       \
             scan_fix_kernel<T_, KPL_, U_, false><<<grid, kScanThreads, smem, st>>>(                                                \
                 (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, 0, nullptr,  \
-                nullptr);                                                                                                          \
+                nullptr, leftover);                                                                                                \
     } while (0)
     if (dtype == MQVS_F32) {
         if (kpl == 1) MQVS_FIX(float, 1, 2); else MQVS_FIX(float, 4, 2);

@@ -80,7 +80,8 @@ __device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {  // 
 
 __global__ void __launch_bounds__(kSelThreads)
 merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int W, int B, int k,
-                        int n_pow2, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                        int n_pow2, float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int shard_shift,
+                        int64_t id_base) {
     extern __shared__ __align__(16) unsigned char raw[];
     int64_t* sid = reinterpret_cast<int64_t*>(raw);
     uint32_t* sord = reinterpret_cast<uint32_t*>(sid + n_pow2);
@@ -94,6 +95,8 @@ merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restr
             size_t src = ((size_t)w * B + b) * k + j;
             int64_t v = ids[src];
             if (v >= 0) {
+                if (shard_shift >= 0)  // local row of part w -> global row (block-cyclic, store.h:ShardMap)
+                    v = ((((v >> shard_shift) * W + w)) << shard_shift) | (v & ((1ll << shard_shift) - 1));
                 id = v;
                 ord = (uint32_t)(pack_key(scores[src], 0) >> 32);
             }
@@ -120,7 +123,7 @@ merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restr
         size_t o = (size_t)b * k + j;
         bool ok = j < n_pow2 && sord[j] != 0;
         out_scores[o] = ok ? key_score((uint64_t)sord[j] << 32) : -INFINITY;
-        out_ids[o] = ok ? sid[j] : -1;
+        out_ids[o] = ok ? sid[j] + id_base : -1;
     }
 }
 
@@ -153,13 +156,13 @@ void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_
 }
 
 void launch_merge_candidates(const float* scores, const int64_t* ids, int W, int B, int k, float* out_scores,
-                             int64_t* out_ids, cudaStream_t st) {
+                             int64_t* out_ids, cudaStream_t st, int shard_shift, int64_t id_base) {
     if (B == 0) return;
     int n_pow2 = next_pow2(W * k);
     size_t smem = (size_t)n_pow2 * (sizeof(int64_t) + sizeof(uint32_t));
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    merge_candidates_kernel<<<B, kSelThreads, smem, st>>>(scores, ids, W, B, k, n_pow2, out_scores, out_ids);
+    merge_candidates_kernel<<<B, kSelThreads, smem, st>>>(scores, ids, W, B, k, n_pow2, out_scores, out_ids, shard_shift, id_base);
 }
 
 }  // namespace mqvs

@@ -159,7 +159,10 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     CUtensorMap mq, mx;
     *coop_refused = false;
     const int rows_q = p.b_pad;  // 128 or 256 operand rows
-    if (!make_map(&mq, b.q_op, (uint64_t)rows_q, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
+    // up to 64 queries: half-height operand tiles (M = 64) -- half the query-operand traffic per corpus chunk
+    static const bool no_half = getenv("MQVS_NO_HALF_TILE") != nullptr;  // developer knob: measure what it buys
+    const bool half = B <= 64 && !no_half;
+    if (!make_map(&mq, b.q_op, (uint64_t)rows_q, dtype, half ? 64 : BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
     g_trace.mark("begin", st);
     const int vec4 = (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0;
@@ -203,7 +206,7 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     a.h_op = b.hq;  // operand row q is query q
     a.dbg = g_trace.on ? g_trace.fused_dbg(p.grid) : nullptr;
     if (a.dbg) cudaMemsetAsync(a.dbg, 0, 256 * 16 * sizeof(unsigned long long), st);
-    cudaError_t e = launch_fused_space(dtype, p.kprime, rows_q <= BM ? 1 : 2, mq, mx, a, p.grid, st);
+    cudaError_t e = launch_fused_space(dtype, p.kprime, half ? 0 : (rows_q <= BM ? 1 : 2), mq, mx, a, p.grid, st);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
         cudaGetLastError();
         *coop_refused = true;

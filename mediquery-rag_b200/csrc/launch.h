@@ -41,14 +41,15 @@ void launch_scan_simt_metric(const void* rows, int dtype, uint32_t n_rows, const
                              const float* q_norms, cudaStream_t st);
 
 // Device-driven repair of tensor-path queries flagged "not proven exact": scan_fix compacts the flags into a list itself
-// (first max_fix <= 64 flagged queries, published in fix_list / fix_n; counters[0] += listed, [1] += left over), re-scans
+// (first max_fix <= 256 flagged queries, published in fix_list / fix_n; counters[0] += listed, [1] += left over when
+// count_leftover is set -- the last round of a search), re-scans
 // the corpus exactly for the listed queries (cand [max_fix][scan_fix_grid][k]); merge_fix merges into the outputs and
 // clears their flags.
 int scan_fix_grid(int sm_count);  // CTAs (= candidate stride per listed query) of the repair scan
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
                      int sm_count, cudaStream_t st, int metric = 0, const float* row_norms = nullptr,
-                     const float* q_norms_all = nullptr);
+                     const float* q_norms_all = nullptr, bool count_leftover = true);
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
                       const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
@@ -66,9 +67,13 @@ void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float
 // Merge: keys_in [B][m] (any order, 0 = empty) -> best k per query as (score, id + id_base); (-inf, -1) fill.
 void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_base, float* out_scores,
                        int64_t* out_ids, cudaStream_t st);
-// Cross-shard merge of already-decoded candidates [W, B, k] -> [B, k].
+// Cross-shard merge of already-decoded candidates [W, B, k] -> [B, k].  shard_shift >= 0: the ids of slice w are LOCAL rows
+// of part w of a block-cyclic multi-device handle (store.h:ShardMap, blocks of 1 << shard_shift rows) and are mapped to
+// global rows before the merge; id_base is added to every id written.
 void launch_merge_candidates(const float* scores, const int64_t* ids, int W, int B, int k, float* out_scores,
-                             int64_t* out_ids, cudaStream_t st);
+                             int64_t* out_ids, cudaStream_t st, int shard_shift = -1, int64_t id_base = 0);
+// Gather stored rows bit-for-bit: out[i] = rows[ids[i]] (row_bytes each, 16-byte vectors).  Tombstone compaction.
+void launch_gather_raw_rows(const void* rows, size_t row_bytes, const uint32_t* ids, uint64_t n, void* out, cudaStream_t st);
 // Gather stored rows as fp32 [n, dim].
 void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,
                         cudaStream_t st);

@@ -109,11 +109,20 @@ __device__ __forceinline__ uint32_t kth_largest_u32(const uint32_t* __restrict__
 // query tiles through the cold phase, and alternate between the query tiles afterwards).
 // XF = the l2 / ip spaces over raw vectors (FusedArgs::norms): a separate instantiation, so the cosine kernels are the
 // same machine code with or without that feature.
-template <typename T, int CAP, int KPRIME, int MT, bool XF>
+// BMQ = rows of the query operand tile (the MMA's M): 128, or 64 for batches of up to 64 queries.  Every K-chunk stage
+// re-fetches the query operand from L2 beside the corpus chunk (16 KB beside 32 KB at M = 128); the L2 -> SM fabric, not HBM,
+// is what saturates first (~10 TB/s chip-wide, profiles/), so in the HBM-bound regime a half-height operand tile (8 KB)
+// hands the difference to the corpus stream.  With M = 64 the accumulator occupies TMEM lanes 0-15 of every 32-lane
+// quadrant (row r -> lane (r / 16) * 32 + r % 16), i.e. epilogue thread (quad, lane < 16) owns query quad * 16 + lane.
+template <typename T, int CAP, int KPRIME, int MT, bool XF, int BMQ = BM>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const FusedArgs a) {
     static_assert(MT == 1 || MT == 2, "two accumulators: at most two query tiles");
+    static_assert(BMQ == BM || (BMQ == 64 && MT == 1), "half-height query tiles serve a single query tile");
     constexpr int kQ = MT * BM;  // query slots per CTA (stride of the per-CTA list / count arrays)
+    constexpr int kABytesQ = BMQ * kRowBytes;               // query operand bytes per K-chunk
+    constexpr int kStageBytesQ = kABytesQ + kBBytes;        // one stage of the [A | B] ring
+    constexpr int kLanesPerQuad = BMQ / 4;                  // TMEM lanes of a quadrant that hold accumulator rows
     // Two query tiles over fp32 rows share every staged corpus chunk ([A0 | A1 | B] stages): the tf32 chunks are twice as
     // many bytes per flop, staging them once instead of twice is worth more than overlapping one query tile's epilogue
     // with the other's MMAs (measured at 1M x 768, B = 256: 0.95 -> 0.70 ms).  Over bf16 rows it is the other way round
@@ -124,7 +133,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     using K = Kind<T>;
     constexpr int kChunks768 = kDim / K::kElemsPerChunk;
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
-                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMQ >> 4) << 24);
 
     // Band pass (second launch, see search_band): thresholds are GIVEN (k-th exact score of the first launch minus eps),
     // every row above them is collected and rescored, nothing is learnt.  No flagged query -> nothing to do.
@@ -179,8 +188,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     for (int mt = 0; mt < MT; ++mt)
                         for (int kc = 0; kc < kChunks768; ++kc) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                            mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            const uint32_t sa = smem_base + stage * kStageBytesQ, sb = sa + kABytesQ;
+                            mbar_expect_tx(bar_full + 8 * stage, kStageBytesQ);
                             tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * K::kElemsPerChunk, mt * BM);
                             tma_load_2d(sb, &map_x, bar_full + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN));
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -213,7 +222,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     for (int kc = 0; kc < kChunks768; ++kc) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tcgen05_fence_after();
-                        const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                        const uint32_t sa = smem_base + stage * kStageBytesQ, sb = sa + kABytesQ;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
@@ -261,8 +270,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ChunkTop trk[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            q[mt] = mt * BM + quad * 32 + lane;
-            q_ok[mt] = q[mt] < n_queries;
+            q[mt] = mt * BM + quad * kLanesPerQuad + lane;
+            q_ok[mt] = lane < kLanesPerQuad && q[mt] < n_queries;
             lst[mt] = a.lists + ((size_t)blockIdx.x * kQ + q[mt]) * CAP;
             cnt[mt] = 0;
             trk[mt].out = a.cmax + (size_t)(q_ok[mt] ? q[mt] : 0) * a.ncols + blockIdx.x * 8;
@@ -538,9 +547,9 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
 }
 
 // One dispatch over (row type, k', query tiles) per value of XF.
-template <typename T, int KP, int MT, bool XF>
+template <typename T, int KP, int MT, bool XF, int BMQ = BM>
 cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const FusedArgs& a, int grid, cudaStream_t st) {
-    const void* kern = (const void*)tc_fused_kernel<T, 512, KP, MT, XF>;
+    const void* kern = (const void*)tc_fused_kernel<T, 512, KP, MT, XF, BMQ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&mq, (void*)&mx, (void*)&a};
@@ -548,11 +557,15 @@ cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const Fus
     return cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, kSmemBytes, st);
 }
 
+// query_tiles: 2, 1, or 0 = one HALF-HEIGHT tile (M = 64; the map of the query matrix then has a 64-row box)
 template <bool XF>
 cudaError_t launch_fused_any(int dtype, int kprime, int query_tiles, const CUtensorMap& mq, const CUtensorMap& mx,
                              const FusedArgs& a, int grid, cudaStream_t st) {
 #define MQVS_TCF(KP_)                                                                                     \
     if (kprime == KP_) {                                                                                  \
+        if (query_tiles == 0)                                                                             \
+            return dtype == MQVS_F32 ? launch_fused<float, KP_, 1, XF, 64>(mq, mx, a, grid, st)           \
+                                     : launch_fused<__nv_bfloat16, KP_, 1, XF, 64>(mq, mx, a, grid, st);  \
         if (query_tiles == 1)                                                                             \
             return dtype == MQVS_F32 ? launch_fused<float, KP_, 1, XF>(mq, mx, a, grid, st)               \
                                      : launch_fused<__nv_bfloat16, KP_, 1, XF>(mq, mx, a, grid, st);      \

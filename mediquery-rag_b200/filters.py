@@ -25,26 +25,33 @@ class MetadataColumns:
     """Per-field columns over row-aligned metadata dicts, built lazily and extended incrementally."""
 
     def __init__(self) -> None:
-        self._rows: List[Mapping[str, Any]] = []
+        self._n = 0                                   # rows
+        self._rows: Dict[int, Mapping[str, Any]] = {} # row -> its metadata dict; rows without per-row metadata are absent
         self._explicit: Dict[str, np.ndarray] = {}   # bulk columns supplied as arrays (no per-row dicts)
         self._cache: Dict[str, tuple] = {}           # field -> (n_rows_built, values object array, present bool array)
         self._dict_fields: set = set()               # fields that occur in per-row dicts
         self.version = 0                             # bumped by every mutation (device copies of columns key on it)
 
     def __len__(self) -> int:
-        return len(self._rows)
+        return self._n
 
     def extend(self, metadatas: Sequence[Optional[Mapping[str, Any]]]) -> None:
         for md in metadatas:
-            md = md if md else _EMPTY
-            self._dict_fields.update(md.keys())
-            self._rows.append(md)
+            if md:
+                self._dict_fields.update(md.keys())
+                self._rows[self._n] = md
+            self._n += 1
+        self.version += 1
+
+    def extend_empty(self, n: int) -> None:
+        """Append n rows without metadata (bulk loads of millions of rows cost nothing per row)."""
+        self._n += int(n)
         self.version += 1
 
     def extend_columns(self, n: int, columns: Mapping[str, np.ndarray]) -> None:
         """Append n rows whose metadata is given column-wise (bulk ingest of millions of rows)."""
-        start = len(self._rows)
-        self._rows.extend([_EMPTY] * n)
+        start = self._n
+        self._n += n
         for name, col in columns.items():
             col = np.asarray(col)
             if col.shape[0] != n:
@@ -68,21 +75,24 @@ class MetadataColumns:
         self.version += 1
 
     def row(self, r: int) -> Dict[str, Any]:
-        md = dict(self._rows[r])
+        md = dict(self._rows.get(r, _EMPTY))
         for name, (vals, present) in self._explicit.items():
             if r < present.shape[0] and present[r]:
                 md[name] = vals[r].item()
         return md
 
     def set_row(self, r: int, md: Optional[Mapping[str, Any]]) -> None:
-        self._rows[r] = md if md else _EMPTY
-        self._dict_fields.update(self._rows[r].keys())
+        if md:
+            self._rows[r] = md
+            self._dict_fields.update(md.keys())
+        else:
+            self._rows.pop(r, None)
         self._cache.clear()
         self.version += 1
 
     def column(self, field: str):
         """-> (values, present): values is a typed array when the field is homogeneous, else object."""
-        n = len(self._rows)
+        n = self._n
         if field in self._explicit:
             vals, present = self._explicit[field]
             if field not in self._dict_fields and vals.shape[0] == n:
@@ -96,7 +106,7 @@ class MetadataColumns:
             ev, ep = self._explicit[field]
             vals[: ev.shape[0]] = ev
             present[: ep.shape[0]] = ep
-        for r, md in enumerate(self._rows):
+        for r, md in self._rows.items():
             if field in md:
                 vals[r] = md[field]
                 present[r] = True

@@ -20,9 +20,12 @@ own score over the RAW vectors (mqvs_set_metric) and distances are ||q - x||^2 /
 """
 from __future__ import annotations
 
+import bisect
 import json
 import os
+import threading
 import uuid
+import warnings
 from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
 import numpy as np
@@ -64,6 +67,59 @@ def _relevance(space: str, sim: float) -> float:
     return 1.0 - d if d > 0 else -d
 
 
+class _RowColumn:
+    """Row-aligned host column (string ids, texts) that does not need a Python object per row for bulk-loaded rows:
+    a sequence of runs, each either an explicit list or an implicit run (`prefix + str(row)`, or None).  Indexing,
+    len and extend are all the store needs."""
+
+    def __init__(self) -> None:
+        self._starts: List[int] = []   # first row of every run
+        self._runs: List[Any] = []     # list | (count, prefix or None)
+        self._n = 0
+
+    def __len__(self) -> int:
+        return self._n
+
+    def extend(self, values: Sequence[Any]) -> None:
+        if not len(values):
+            return
+        if self._runs and isinstance(self._runs[-1], list):
+            self._runs[-1].extend(values)
+        else:
+            self._starts.append(self._n)
+            self._runs.append(list(values))
+        self._n += len(values)
+
+    def append(self, value: Any) -> None:
+        self.extend([value])
+
+    def extend_implicit(self, n: int, prefix: Optional[str]) -> None:
+        if n > 0:
+            self._starts.append(self._n)
+            self._runs.append((int(n), prefix))
+            self._n += int(n)
+
+    def __getitem__(self, r: int) -> Any:
+        if r < 0:
+            r += self._n
+        if not 0 <= r < self._n:
+            raise IndexError(r)
+        i = bisect.bisect_right(self._starts, r) - 1
+        run = self._runs[i]
+        if isinstance(run, list):
+            return run[r - self._starts[i]]
+        return None if run[1] is None else f"{run[1]}{r}"
+
+    def implicit_row(self, value: str) -> Optional[int]:
+        """Row behind an implicit id (`prefix + row`), or None."""
+        for start, run in zip(self._starts, self._runs):
+            if not isinstance(run, list) and run[1] is not None and value.startswith(run[1]):
+                tail = value[len(run[1]):]
+                if tail.isdigit() and start <= int(tail) < start + run[0]:
+                    return int(tail)
+        return None
+
+
 class MediQueryRetriever:
     """What `as_retriever()` returns when langchain_core is absent: `.invoke(query) -> list[Document]`."""
 
@@ -92,8 +148,12 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                  persist_directory: Optional[str] = None, collection_metadata: Optional[Dict[str, Any]] = None,
                  client_settings: Any = None, client: Any = None, relevance_score_fn: Optional[Callable] = None,
                  create_collection_if_not_exists: bool = True, *, store_dtype: str = "fp32", device: int = 0,
-                 dim: Optional[int] = None, capacity_rows: int = 0, auto_persist: bool = True,
+                 devices: Optional[Sequence[int]] = None, dim: Optional[int] = None, capacity_rows: int = 0,
+                 auto_persist: bool = True, compact_dead_fraction: float = 0.5,
                  index_factory: Optional[Callable[..., Any]] = None, **_: Any):
+        """`devices=[0, 1, ..., 7]` spreads the rows over several GPUs behind this ONE object in this one process (the
+        reference holds its store as a module global, src/medical_engine.py:52): block-cyclic row shards, every search
+        scans all of them concurrently and merges on the first device; ids, filters, persistence are unchanged."""
         self._collection_name = collection_name
         self._embedding_function = embedding_function
         self._persist_directory = persist_directory
@@ -106,30 +166,64 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if store_dtype not in _native.DTYPES:
             raise ValueError(f"store_dtype must be one of {sorted(_native.DTYPES)}")
         self._store_dtype = store_dtype
-        self._device = device
+        self._device = list(devices) if devices is not None and len(devices) > 1 else (devices[0] if devices else device)
         self._capacity = capacity_rows
+        self._compact_at = float(compact_dead_fraction)
+        # one lock over everything that touches the host tables or the handle's shared filter mask: the a* coroutines run
+        # the blocking calls in worker threads, and a device-built mask belongs to the handle until the search has used it
+        self._lock = threading.RLock()
+        self._foreign_chroma = False
         self._auto_persist = auto_persist
         self._index_factory = index_factory or _native.Index
         self._index: Any = None
         self._dim: Optional[int] = dim
-        self._ids: List[str] = []
+        self._ids = _RowColumn()
         self._id2row: Dict[str, int] = {}
-        self._texts: List[Optional[str]] = []
+        self._texts = _RowColumn()
         self._cols = MetadataColumns()
         self._live = np.zeros(0, dtype=bool)
         self._device_filter: Optional[DeviceFilter] = None
         self._raw_space = space != "cosine"  # keep ||x|| on the device so l2 / ip can rank non-unit vectors
         self._persisted_rows = 0            # rows already in rows.mqvs / docs.jsonl (appends start here)
         self._persisted_dead: Optional[List[int]] = None
+        self._dir: Optional[str] = None  # where THIS collection's files live (see _collection_dir)
         if persist_directory is not None:
             # the reference tests os.path.exists(DB_PATH) before opening (src/medical_engine.py:34-37)
             os.makedirs(persist_directory, exist_ok=True)
-            if os.path.exists(os.path.join(persist_directory, _MANIFEST)):
+            self._dir = self._collection_dir(persist_directory, collection_name)
+            if os.path.exists(os.path.join(self._dir, _MANIFEST)):
                 self._load()
+            elif os.path.exists(os.path.join(persist_directory, "chroma.sqlite3")):
+                # a directory written by the reference's real Chroma (sqlite + hnsw segments) holds nothing this backend
+                # can open: the collection starts empty, and searching it before re-ingesting is an error, not []
+                self._foreign_chroma = True
+                warnings.warn(f"{persist_directory} was written by chromadb (chroma.sqlite3); mqvs cannot read it -- re-run "
+                              "src/ingest_medical.py with the swapped import to rebuild the collection", RuntimeWarning)
         if self._index is None and self._dim is not None:
             self._ensure_index(self._dim)
 
     # ------------------------------------------------------------------------------------------- basics
+    @staticmethod
+    def _collection_dir(persist_directory: str, collection_name: str) -> str:
+        """Chroma keeps several collections in one persist_directory; here every collection owns a sub-directory
+        `mqvs.<name>/`, so opening, persisting or deleting one never touches another.  A directory written before
+        collections were namespaced (files at the top level) keeps that layout for the collection that owns it."""
+        legacy = os.path.join(persist_directory, _MANIFEST)
+        if os.path.exists(legacy):
+            try:
+                with open(legacy, "r", encoding="utf-8") as f:
+                    if json.load(f).get("collection_name", collection_name) == collection_name:
+                        return persist_directory
+            except (OSError, ValueError):
+                pass
+        safe = "".join(c if c.isalnum() or c in "-_." else "_" for c in collection_name) or "_"
+        return os.path.join(persist_directory, "mqvs." + safe)
+
+    @property
+    def collection_path(self) -> Optional[str]:
+        """Directory that holds this collection's files (rows.mqvs, docs.jsonl, dead.json, manifest.json), or None."""
+        return self._dir
+
     @property
     def embeddings(self) -> Optional[Embeddings]:
         return self._embedding_function
@@ -187,6 +281,10 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         return self._add(texts, vectors, metadatas, ids, metadata_columns)
 
     def _add(self, texts: List[Optional[str]], vectors: Any, metadatas, ids, metadata_columns=None) -> List[str]:
+        with self._lock:
+            return self._add_locked(texts, vectors, metadatas, ids, metadata_columns)
+
+    def _add_locked(self, texts: List[Optional[str]], vectors: Any, metadatas, ids, metadata_columns=None) -> List[str]:
         n = len(texts)
         if n == 0:
             return []
@@ -224,6 +322,36 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if self._persist_directory is not None and self._auto_persist:
             self.persist()
         return ids
+
+    def add_synthetic(self, seed: int, n: int, first_index: Optional[int] = None,
+                      metadata_columns: Optional[Mapping[str, Any]] = None, id_prefix: str = "row-") -> range:
+        """Bench / test utility behind BASELINE.json's configs 2-5 (synthetic 768-d unit vectors; 100M rows cannot be staged
+        through the host): appends n rows generated ON THE DEVICE by the counter-based generator of mqvs_add_synthetic
+        (row r is a function of (seed, first_index + r) only).  Ids are implicit (`id_prefix + row`), texts empty, metadata
+        optional and column-wise -- nothing is kept per row on the host.  Not persisted (in-memory collections only)."""
+        if self._persist_directory is not None:
+            raise ValueError("add_synthetic serves in-memory collections (persist_directory=None)")
+        with self._lock:
+            self._ensure_index(self._dim or _native.DIM_PAD)
+            start = len(self._ids)
+            first = self._index.add_synthetic(seed, start if first_index is None else first_index, int(n))
+            assert first == start, "host document table and device rows out of step"
+            self._live = np.concatenate([self._live, np.ones(n, dtype=bool)])
+            self._ids.extend_implicit(n, id_prefix)
+            self._texts.extend_implicit(n, None)
+            if metadata_columns is not None:
+                self._cols.extend_columns(n, metadata_columns)
+            else:
+                self._cols.extend_empty(n)
+            return range(start, start + n)
+
+    def _row_of(self, doc_id: str) -> Optional[int]:
+        r = self._id2row.get(doc_id)
+        if r is None:
+            r = self._ids.implicit_row(doc_id)
+            if r is not None and not self._live[r]:
+                r = None
+        return r
 
     @classmethod
     def from_texts(cls, texts: List[str], embedding: Optional[Embeddings] = None,
@@ -266,16 +394,20 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             q = q[None, :]
         if k < 1:
             raise ValueError("k must be >= 1")
-        if self._index is None or len(self._ids) == 0:
-            return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
-        mask, allowed = self._allow_mask(filter, where_document)
-        k_eff = min(k, allowed)  # Chroma clamps n_results to the collection size
-        if k_eff == 0:
-            return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
-        if k_eff > _native.MAX_K:
-            raise ValueError(f"k is limited to {_native.MAX_K}")
-        self.rank_space()
-        return self._index.search(q, k_eff, mask)
+        with self._lock:  # filter_build + search share the handle's mask buffer; the tables must not move underneath
+            if self._index is None or len(self._ids) == 0:
+                if self._foreign_chroma:
+                    raise RuntimeError(f"{self._persist_directory} holds a chromadb collection (chroma.sqlite3) that mqvs "
+                                       "cannot read; re-run src/ingest_medical.py with the swapped import before searching")
+                return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
+            mask, allowed = self._allow_mask(filter, where_document)
+            k_eff = min(k, allowed)  # Chroma clamps n_results to the collection size
+            if k_eff == 0:
+                return np.zeros((q.shape[0], 0), np.float32), np.zeros((q.shape[0], 0), np.int64)
+            if k_eff > _native.MAX_K:
+                raise ValueError(f"k is limited to {_native.MAX_K}")
+            self.rank_space()
+            return self._index.search(q, k_eff, mask)
 
     def _allow_mask(self, filter: Optional[Mapping[str, Any]], where_document: Optional[Mapping[str, Any]]):
         """-> (mask or None, allowed rows).  Metadata filters over typed fields are evaluated ON THE DEVICE (columns stay
@@ -393,7 +525,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self.update_documents([document_id], [document])
 
     def update_documents(self, ids: List[str], documents: List[Document]) -> None:
-        missing = [i for i in ids if str(i) not in self._id2row]
+        missing = [i for i in ids if self._row_of(str(i)) is None]
         if missing:
             raise ValueError(f"unknown document ids: {missing[:3]}")
         self.add_texts([d.page_content for d in documents], [d.metadata for d in documents], ids=[str(i) for i in ids])
@@ -440,7 +572,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if ids is not None:
             if isinstance(ids, str):
                 ids = [ids]
-            rows = [self._id2row[i] for i in ids if i in self._id2row and self._live[self._id2row[i]]]
+            rows = [r for r in (self._row_of(str(i)) for i in ids) if r is not None and self._live[r]]
             if where:
                 from .filters import evaluate
                 ok = evaluate(where, self._cols)
@@ -476,27 +608,37 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         """Rows are tombstoned (cleared from the live bitmap that is AND-ed into every search mask)."""
         if ids is None:
             return False
-        for i in ids:
-            r = self._id2row.pop(str(i), None)
-            if r is not None:
-                self._live[r] = False
-        if self._persist_directory is not None and self._auto_persist:
-            self.persist()
+        with self._lock:
+            for i in ids:
+                r = self._id2row.pop(str(i), None)
+                if r is None:
+                    r = self._ids.implicit_row(str(i))
+                if r is not None:
+                    self._live[r] = False
+            if self._persist_directory is not None and self._auto_persist:
+                self.persist()
         return True
 
     def delete_collection(self) -> None:
-        if self._index is not None:
-            self._index.close()
-        self._index, self._ids, self._id2row, self._texts = None, [], {}, []
-        self._cols, self._live = MetadataColumns(), np.zeros(0, dtype=bool)
-        self._device_filter = None
-        if self._persist_directory is not None:
-            self._persisted_rows, self._persisted_dead = 0, None
-            for f in (_ROWS_FILE, _NORMS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE):
-                try:
-                    os.remove(os.path.join(self._persist_directory, f))
-                except FileNotFoundError:
-                    pass
+        """Drops THIS collection: its rows, tables and files (other collections of the persist_directory are untouched)."""
+        with self._lock:
+            if self._index is not None:
+                self._index.close()
+            self._index, self._ids, self._id2row, self._texts = None, _RowColumn(), {}, _RowColumn()
+            self._cols, self._live = MetadataColumns(), np.zeros(0, dtype=bool)
+            self._device_filter = None
+            if self._dir is not None:
+                self._persisted_rows, self._persisted_dead = 0, None
+                for f in (_ROWS_FILE, _NORMS_FILE, _DOCS_FILE, _MANIFEST, _DEAD_FILE):
+                    try:
+                        os.remove(os.path.join(self._dir, f))
+                    except FileNotFoundError:
+                        pass
+                if self._dir != self._persist_directory:
+                    try:
+                        os.rmdir(self._dir)
+                    except OSError:
+                        pass
 
     def reset_collection(self) -> None:
         """langchain_chroma's reset_collection: drop every row and start again with an empty collection of the same name,
@@ -514,10 +656,17 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         src/ingest_medical.py:106-110), so the cost of `auto_persist` does not grow with the store.  Order of writes:
         documents, rows (their count in the file header moves last), tombstones, manifest -- a crash in between leaves a
         directory that still opens (surplus document lines are ignored)."""
-        d = self._persist_directory
+        d = self._dir
         if d is None:
             raise ValueError("no persist_directory")
+        with self._lock:
+            self._persist_locked(d)
+
+    def _persist_locked(self, d: str) -> None:
         os.makedirs(d, exist_ok=True)
+        n_dead = int((~self._live).sum())
+        if self._compact_at > 0 and len(self._ids) >= 1024 and n_dead > self._compact_at * len(self._ids):
+            self._compact_locked()  # tombstones cost scan bandwidth for ever otherwise; also resets the append position
         n, done = len(self._ids), self._persisted_rows
         rows_path, docs_path = os.path.join(d, _ROWS_FILE), os.path.join(d, _DOCS_FILE)
         append = 0 < done <= n and os.path.exists(rows_path) and os.path.exists(docs_path)
@@ -557,12 +706,43 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         os.replace(tmp, os.path.join(d, _MANIFEST))
         self._persisted_rows = n
 
+    def compact(self) -> int:
+        """Drops tombstoned rows (deleted / upserted) from HBM and from the host tables: the stored rows are gathered
+        bit-for-bit on the device (mqvs_compact), row ids are renumbered, string ids stay.  Runs by itself from persist()
+        once more than `compact_dead_fraction` of the rows are dead.  Returns the number of rows dropped."""
+        with self._lock:
+            dropped = self._compact_locked()
+            if dropped and self._dir is not None and self._auto_persist:
+                self._persist_locked(self._dir)
+            return dropped
+
+    def _compact_locked(self) -> int:
+        dead = int((~self._live).sum())
+        if dead == 0 or self._index is None or not hasattr(self._index, "compact"):
+            return 0
+        if len(getattr(self._index, "devices", [0])) > 1:
+            return 0  # rows of a multi-device handle would have to move between GPUs: rebuild such a collection instead
+        from .filters import pack_mask
+        keep = np.flatnonzero(self._live)
+        new_n = self._index.compact(pack_mask(self._live))
+        assert new_n == keep.shape[0], "device and host disagree on the live rows"
+        ids, texts = _RowColumn(), _RowColumn()
+        ids.extend([self._ids[r] for r in keep.tolist()])
+        texts.extend([self._texts[r] for r in keep.tolist()])
+        metas = [self._cols.row(r) for r in keep.tolist()]
+        self._ids, self._texts = ids, texts
+        self._cols = MetadataColumns()
+        self._cols.extend(metas)
+        self._live = np.ones(new_n, dtype=bool)
+        self._id2row = {self._ids[j]: j for j in range(new_n)}
+        self._device_filter = None
+        self._persisted_rows, self._persisted_dead = 0, None  # the files are rewritten whole on the next persist
+        return dead
+
     def _load(self) -> None:
-        d = self._persist_directory
+        d = self._dir
         with open(os.path.join(d, _MANIFEST), "r", encoding="utf-8") as f:
             manifest = json.load(f)
-        if manifest.get("collection_name", self._collection_name) != self._collection_name:
-            return  # another collection lives here; start empty like Chroma's get_or_create_collection
         self._store_dtype = manifest["store_dtype"]
         if "hnsw:space" not in self._collection_metadata:
             self._space = manifest.get("space", self._space)

@@ -27,14 +27,16 @@ def test_library_exports_every_declared_symbol_and_binding_covers_them():
     assert sorted(_native.SIGNATURES) == names
     for n in names:
         assert isinstance(getattr(lib, n), ctypes._CFuncPtr)
-    assert lib.mqvs_version() == 100
+    assert lib.mqvs_version() == 200
 
 
 def test_errors_are_codes_with_messages_not_crashes():
     lib = _native.load()
     h = ctypes.c_void_p(None)
     rc = lib.mqvs_create(2, None, 768, 0, 0, ctypes.byref(h))
-    assert rc == _native.E_INVALID and b"one device per handle" in lib.mqvs_last_error()
+    assert rc == _native.E_INVALID and b"dev_ids is NULL" in lib.mqvs_last_error()
+    rc = lib.mqvs_create(_native.MAX_DEVICES + 1, None, 768, 0, 0, ctypes.byref(h))
+    assert rc == _native.E_INVALID and b"n_dev" in lib.mqvs_last_error()
     rc = lib.mqvs_create(1, None, 4096, 0, 0, ctypes.byref(h))
     assert rc == _native.E_INVALID and b"dim" in lib.mqvs_last_error()
     assert lib.mqvs_search(None, None, 0, 1, 10, None, 0, None, None, 0) == _native.E_INVALID
@@ -74,7 +76,7 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
                     os.path.join(ROOT, "examples", "mqvs_demo.c"), "-L" + lib_dir, "-lmqvs", "-Wl,-rpath," + lib_dir, "-lm",
                     "-o", exe], check=True)
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert "libmqvs version 100" in run.stdout
+    assert "libmqvs version 200" in run.stdout
     if have_gpu():
         assert run.returncode == 0 and "row 42" in run.stdout.splitlines()[2], run.stdout
     else:
@@ -105,3 +107,23 @@ def test_the_hot_kernels_are_blackwell_native_sass():
     assert "LDG.E.NA.128.CONSTANT" in scan and "LDG.E.NA.64.CONSTANT" in scan
     xchg = _sass_mnemonics("kernels_xchg.o", r"\b(STG\.E\.STRONG\.SYS|LDG\.E\.STRONG\.SYS|MEMBAR\.\w+\.SYS)\b")
     assert {"STG.E.STRONG.SYS", "LDG.E.STRONG.SYS"} <= xchg and any(m.startswith("MEMBAR") for m in xchg)
+
+
+def test_block_cyclic_placement_of_multi_device_handles_is_a_bijection():
+    """mqvs_shard_of_row is pure host arithmetic in libmqvs.so (no GPU): every global row maps to one (shard, local row),
+    shards fill densely in global order, and the inverse documented in include/mqvs.h holds."""
+    blk = _native.SHARD_BLOCK
+    for W in (1, 2, 3, 8):
+        seen = {}
+        counts = [0] * W
+        for row in list(range(0, 3 * W * blk + 17, 97)) + [blk - 1, blk, W * blk - 1, W * blk, 2 ** 33 + 5]:
+            shard, local = _native.shard_of_row(W, row)
+            assert 0 <= shard < W
+            assert ((local // blk) * W + shard) * blk + local % blk == row
+            assert seen.setdefault((shard, local), row) == row
+        for row in range(0, 2 * W * blk + 100):  # dense prefix: every shard's local rows are 0, 1, 2, ... in global order
+            shard, local = _native.shard_of_row(W, row)
+            if row % 61 == 0 or local % blk in (0, blk - 1):
+                assert local <= counts[shard]
+            counts[shard] = max(counts[shard], local + 1)
+        assert sum(counts) == 2 * W * blk + 100 and max(counts) - min(counts) <= blk

@@ -175,9 +175,9 @@ def test_save_load_round_trip(gpu, tmp_path):
     db = str(tmp_path / "medical_db")
     vs = MediQueryVectorStore(persist_directory=db)
     vs.add_embeddings(([f"a{r}" for r in range(300)], x[:300]))
-    rows_size = os.path.getsize(os.path.join(db, "rows.mqvs"))
+    rows_size = os.path.getsize(os.path.join(vs.collection_path, "rows.mqvs"))
     vs.add_embeddings(([f"b{r}" for r in range(50)], x[300:350]))
-    assert os.path.getsize(os.path.join(db, "rows.mqvs")) == rows_size + 50 * 768 * 4
+    assert os.path.getsize(os.path.join(vs.collection_path, "rows.mqvs")) == rows_size + 50 * 768 * 4
     vs2 = MediQueryVectorStore(persist_directory=db)
     assert len(vs2) == 350 and vs2.similarity_search_by_vector(x[320], k=1)[0].page_content == "b20"
 

@@ -45,6 +45,6 @@ def test_ingest_file_builds_a_searchable_store(tmp_path, embedder):
     db = str(tmp_path / "db")
     store = ingest.ingest_file(os.path.join(GOLDEN, "splitter_cases.txt"), embedder, db, batch_size=4,
                                index_factory=OracleIndex)
-    assert len(store) == 10 and os.path.exists(os.path.join(db, "manifest.json"))
+    assert len(store) == 10 and os.path.exists(os.path.join(store.collection_path, "manifest.json"))
     hit = store.similarity_search("问题：plain record\n答案：first answer line\nsecond line", k=1)[0]
     assert hit.metadata["title"] == "plain record" and hit.metadata["tags"] == "alpha，beta"

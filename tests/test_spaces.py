@@ -100,7 +100,7 @@ def test_vectorstore_ranks_raw_vectors_in_the_collections_space(space, tmp_path)
     # the norms are persisted with the rows: a reopened store ranks the same way
     again = MediQueryVectorStore(collection_metadata={"hnsw:space": space} if space else None, index_factory=OracleIndex,
                                  persist_directory=str(tmp_path / "db"))
-    assert os.path.exists(tmp_path / "db" / "rows.mqvs.norms") and again.rank_space() == eff
+    assert os.path.exists(os.path.join(again.collection_path, "rows.mqvs.norms")) and again.rank_space() == eff
     assert [doc.page_content for doc in again.similarity_search_by_vector(q.tolist(), k=k)] == [texts[r] for r in want]
     # appending keeps working
     again.add_embeddings((["late"], x[:1] * np.float32(0.5)))
@@ -140,7 +140,7 @@ def test_directories_written_without_norms_open_with_unit_semantics(tmp_path):
     db = str(tmp_path / "db")
     vs = MediQueryVectorStore(index_factory=OracleIndex, persist_directory=db)
     vs.add_embeddings(([f"d{r}" for r in range(50)], x))
-    os.remove(os.path.join(db, "rows.mqvs.norms"))
+    os.remove(os.path.join(vs.collection_path, "rows.mqvs.norms"))
     old = MediQueryVectorStore(index_factory=OracleIndex, persist_directory=db)
     assert old.rank_space() == "cosine" and len(old) == 50
     d = f64_distances("cosine", x[7:8], x)[0]

@@ -212,15 +212,17 @@ def test_persistence_is_append_only_and_survives_reopen_delete_and_old_format(tm
     db = str(tmp_path / "db")
     docs = make_docs(medical_docs, 40)
     vs = MediQueryVectorStore.from_documents(docs[:20], embedder, persist_directory=db, index_factory=OracleIndex)
-    size0 = os.path.getsize(os.path.join(db, "docs.jsonl"))
-    first_line = open(os.path.join(db, "docs.jsonl"), encoding="utf-8").readline()
+    cdir = vs.collection_path  # every collection owns a sub-directory of the persist_directory
+    assert os.path.dirname(cdir) == db
+    size0 = os.path.getsize(os.path.join(cdir, "docs.jsonl"))
+    first_line = open(os.path.join(cdir, "docs.jsonl"), encoding="utf-8").readline()
     ids2 = vs.add_documents(docs[20:30])                      # appends 10 records, rewrites nothing
-    assert os.path.getsize(os.path.join(db, "docs.jsonl")) > size0
-    assert open(os.path.join(db, "docs.jsonl"), encoding="utf-8").readline() == first_line
-    assert sum(1 for _ in open(os.path.join(db, "docs.jsonl"), encoding="utf-8")) == 30
+    assert os.path.getsize(os.path.join(cdir, "docs.jsonl")) > size0
+    assert open(os.path.join(cdir, "docs.jsonl"), encoding="utf-8").readline() == first_line
+    assert sum(1 for _ in open(os.path.join(cdir, "docs.jsonl"), encoding="utf-8")) == 30
     vs.delete(ids2[:3])
-    assert json.load(open(os.path.join(db, "dead.json"))) == [20, 21, 22]
-    assert json.load(open(os.path.join(db, "manifest.json")))["format"] == 2
+    assert json.load(open(os.path.join(cdir, "dead.json"))) == [20, 21, 22]
+    assert json.load(open(os.path.join(cdir, "manifest.json")))["format"] == 2
     # reopen (src/medical_engine.py:52), keep appending (src/ingest_medical.py:106 re-run), reopen again
     vs2 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
     assert len(vs2) == 27 and vs2.similarity_search(docs[25].page_content, k=1)[0].page_content == docs[25].page_content
@@ -231,12 +233,12 @@ def test_persistence_is_append_only_and_survives_reopen_delete_and_old_format(tm
         [d.page_content for d in vs2.similarity_search(docs[35].page_content, k=3)]
     # surplus document lines (a crash after the documents of an append were written but before its rows): ignored, and
     # the next persist rewrites the directory cleanly
-    with open(os.path.join(db, "docs.jsonl"), "a", encoding="utf-8") as f:
+    with open(os.path.join(cdir, "docs.jsonl"), "a", encoding="utf-8") as f:
         f.write(json.dumps({"id": "ghost", "text": "never stored", "metadata": {}}) + "\n")
     vs4 = MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
     assert len(vs4) == 37 and "ghost" not in vs4.get()["ids"]
     vs4.add_documents(docs[:1])
-    assert sum(1 for _ in open(os.path.join(db, "docs.jsonl"), encoding="utf-8")) == 41
+    assert sum(1 for _ in open(os.path.join(cdir, "docs.jsonl"), encoding="utf-8")) == 41
     assert len(MediQueryVectorStore(persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)) == 38
     # a format-1 directory (tombstones inside the records) still opens
     old = str(tmp_path / "old")
