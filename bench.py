@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- queries/sec at exact top-10 on synthetic 768-d unit vectors (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload c2|c3|c4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload c2|c3|c4|c5] [--impl reference]
 
-A "step" is one search of a batch of B queries over the whole corpus.
-  N = 1 (default)  workload c2 = BASELINE config 2: 1M x 768 fp32 corpus, k=10, one B200 (HBM-bound scan).
-  N > 1 (torchrun) workload c4 = BASELINE config 4: 100M x 768 bf16 corpus row-sharded over the N ranks, k=10,
-                   the [B, k] candidates exchanged + merged by ONE kernel over NVLink peer memory per batch (NCCL
-                   all-gathers + merge kernel when MQVS_XCHG=nccl or peer mapping fails) ("strong": the corpus is
-                   fixed, each rank scans 1/N of it).  `--workload c4 --gpus 1` runs the same corpus on one GPU.
-`value` times K steps with the queries already in HBM (CUDA events, max over ranks); `e2e` times the public API
-with HOST query buffers (pinned) and host results, copies inside the timed region.  `roofline` is the scan
-kernel's algorithmic bytes per launch over its average launch duration, measured by CUDA events the library
-records on its launch stream.  `cpu_baseline` (rank 0, N=1) and `--impl reference` time the same search as numpy
-sgemm + partition on the host cores (chromadb is not installable offline; this is the arithmetic of its
-brute-force path), on a bounded sample.
+ONE workload at every N, so the driver's 1 -> 8 curve compares like with like: BASELINE config 4, a 100M x 768 bf16 corpus
+(153.6 GB: it fits the 180 GB of one B200), k = 10, headline batch 64.  N = 1 scans it on one GPU; N > 1 (torchrun, one rank
+per GPU) row-shards it, every rank scans 1/N and the [B, k] candidates are exchanged + merged by ONE kernel over NVLink peer
+memory per batch ("strong" scaling: the corpus is fixed).  A "step" is one search of a batch of B queries over the corpus.
+
+  value     K steps with the queries already in HBM (CUDA events on the launch stream, max over ranks).
+  e2e       the same batch through the object the reference holds -- ONE MediQueryVectorStore in ONE process over all N
+            devices (`devices=[0..N)`, src/medical_engine.py:52) -- with HOST query buffers and host results, copies inside
+            the timed region.  Under torchrun the ranks release their shards first and rank 0 alone drives the N GPUs.
+  roofline  the scan kernel's algorithmic bytes (or flops past the ridge) per launch over its average launch duration,
+            from CUDA events the library records on its launch stream; peak = MEASURED_PEAKS.json.
+  points    the same corpus at B = 1, 1024 and 4096 (north_star: batch-1 HBM fraction, batch-4096 tensor fraction), each
+            with its own roofline, clocks and a >= 1 s sustained loop.
+  secondary N = 1: config 2 (1M x 768 fp32; B = 1, 64) and config 3 (10M x 768 bf16, B = 4096, k = 100);
+            N = 8: config 5 (10M x 768 bf16 + where-filter bitmask, B = 16384).
+  check     after the timed region (rank 0): every returned id is re-scored by the CPU oracle from the regenerated row
+            (score bits must match), and a 2M-row slice of the corpus is brute-forced on the CPU -- no row of it may beat
+            the k-th returned score without being returned.
+  cpu_baseline / --impl reference: the reference's CPU retrieval on the host cores over a bounded slice of the same corpus:
+            real chromadb when it is importable on the box (baseline/_ref or site-packages), else numpy sgemm + partition
+            (= the arithmetic of Chroma's brute-force path); QPS scaled by slice / corpus.
 """
 from __future__ import annotations
 
@@ -45,10 +54,12 @@ WORKLOADS = {
 }
 MASK_SEED = 0xF117E4
 ELEM = {"fp32": 4, "bf16": 2}
+METRIC = "queries_per_sec_exact_top%d"
 
 
+# ------------------------------------------------------------------------------------------------ synthetic inputs
 def splitmix64_np(seed: int, idx: np.ndarray) -> np.ndarray:
-    """Counter-based hash used for the synthetic metadata column of config 5 (host-side input generation)."""
+    """Counter-based hash (host copy of the generator libmqvs runs on the device)."""
     with np.errstate(over="ignore"):
         z = np.uint64(seed) + (idx.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
@@ -57,8 +68,7 @@ def splitmix64_np(seed: int, idx: np.ndarray) -> np.ndarray:
 
 
 def synth_rows_np(seed: int, first_row: int, n: int, dim: int = 768) -> np.ndarray:
-    """Host copy of the counter-based generator libmqvs uses on the device (mqvs_add_synthetic):
-    v[r, c] = uniform[-1, 1) from splitmix64(seed, r * dim + c).  Keeps the measured arm free of oracle/ imports."""
+    """v[r, c] = uniform[-1, 1) from splitmix64(seed, r * dim + c): what mqvs_add_synthetic stores (before K1)."""
     idx = (np.arange(first_row, first_row + n, dtype=np.uint64)[:, None] * np.uint64(dim)
            + np.arange(dim, dtype=np.uint64)[None, :])
     z = splitmix64_np(seed, idx)
@@ -91,7 +101,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING a timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -112,106 +122,306 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """windows: [(t0, t1)] host-clock intervals the GPU was under load; only samples that arrived inside one of them
+        count (a sample describes the ~20 ms before it arrives).  None = every sample."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.03)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 8 and (windows is None or any(a + 0.01 <= t <= b + 0.02 for a, b in windows))]
+        if not rows and self.rows:  # a region shorter than one sampling period: the sample right after it
+            rows = [r for _, r in self.rows[-1:] if len(r) >= 8]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
-def host_corpus(workload: str, rows: int):
-    import oracle as O
-    x = O.synth_rows(CORPUS_SEED[workload], 0, rows, 768)
-    st, _ = O.normalize_rows(x, "fp32", 768)
-    del x
-    return st
-
-
-def cpu_port_qps(workload: str, rows: int, batch: int, k: int, steps: int, warmup: int):
-    """numpy sgemm + partition over the same rows, all host threads; returns (qps, cores, sample description)."""
-    import oracle as O
-    cores = len(os.sched_getaffinity(0))
-    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=cores)
-    except Exception:
-        pass
-    wl = WORKLOADS[workload]
-    st = host_corpus(workload, rows)
-    if wl["dtype"] == "bf16":  # same stored values the GPU scans: bf16-rounded rows, upcast
-        st = O.stored_as_f32(O.normalize_rows(st, "bf16", 768)[0])
-    q, _ = O.planted_queries(QUERY_SEED, batch, CORPUS_SEED[workload], rows, 768)
-    qn, _ = O.normalize_rows(q, "fp32", 768)
-    for _ in range(warmup):
-        O.sgemm_topk(qn, st, k)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.sgemm_topk(qn, st, k)
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, cores, dt / steps
-
-
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_sample_rows(rows: int, batch: int) -> int:
     """Rows the CPU legs scan per step: the whole corpus when that is <= ~1.5 TFLOP and <= 2M rows, else a slice."""
     cap = int(1.5e12 / (2 * 768 * max(batch, 1)))
     return min(rows, max(50_000, min(2_000_000, cap)))
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU retrieval arithmetic (oracle port; chromadb cannot be installed
-    offline here) on the host cores, same config / metric / unit."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def host_slice(workload: str, rows: int):
+    """Rows [0, rows) of the workload's corpus as the GPU stores them (oracle K1: normalised, bf16-rounded where the
+    workload says so) -> (stored bits, fp32 view)."""
+    import oracle as O
+    wl = WORKLOADS[workload]
+    x = O.synth_rows(CORPUS_SEED[workload], 0, rows, 768)
+    st, _ = O.normalize_rows(x, wl["dtype"], 768)
+    del x
+    return st, (O.stored_as_f32(st) if wl["dtype"] == "bf16" else st)
+
+
+def use_all_cores() -> int:
+    cores = len(os.sched_getaffinity(0))
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    return cores
+
+
+def probe_chromadb():
+    """The reference's real backend (langchain_chroma -> chromadb -> chroma-hnswlib, src/medical_engine.py:26,52) when the
+    box has it: an offline install under baseline/_ref, or site-packages.  -> module or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import chromadb  # type: ignore
+        return chromadb
+    except Exception:
+        return None
+
+
+def chroma_qps(chromadb, rows_f32: np.ndarray, qn: np.ndarray, k: int, steps: int, warmup: int):
+    """Chroma's own query path (HNSW, cosine space) over the slice: collection.query(query_embeddings, n_results=k)."""
+    client = chromadb.EphemeralClient()
+    coll = client.create_collection("bench", metadata={"hnsw:space": "cosine"})
+    n = rows_f32.shape[0]
+    for a in range(0, n, 40000):
+        b = min(n, a + 40000)
+        coll.add(ids=[str(i) for i in range(a, b)], embeddings=rows_f32[a:b].tolist())
+    for _ in range(warmup):
+        coll.query(query_embeddings=qn.tolist(), n_results=k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        coll.query(query_embeddings=qn.tolist(), n_results=k)
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_arm(workload: str, batch: int, k: int, steps: int, warmup: int, rows_cap=None, want_candidates: bool = False):
+    """Times the reference's CPU retrieval on a bounded slice.  -> dict(qps scaled to the full corpus, cores, kind, sample,
+    s_per_step) and, optionally, (slice bits, normalised queries, the slice's top-k by the CPU) for the completeness check."""
+    import oracle as O
+    cores = use_all_cores()
+    rows = WORKLOADS[workload]["rows"]
+    rows_s = cpu_sample_rows(rows, batch) if rows_cap is None else min(rows, rows_cap)
+    st, f32 = host_slice(workload, rows_s)
+    q, _ = O.planted_queries(QUERY_SEED, batch, CORPUS_SEED[workload], rows, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    chroma = probe_chromadb()
+    kind, how = "port", "numpy sgemm + partition (chromadb not importable on this box: no wheel offline)"
+    if chroma is not None and rows_s <= 2_000_000:
+        try:
+            rows_c = min(rows_s, 200_000)  # HNSW build time bounds the slice
+            s_per = chroma_qps(chroma, f32[:rows_c], qn, k, steps, warmup)
+            kind, how, rows_s_eff = "reference", f"chromadb {getattr(chroma, '__version__', '?')} HNSW collection.query", rows_c
+            out = {"qps": batch / s_per * rows_c / rows, "cores": cores, "kind": kind, "s_per_step": s_per,
+                   "sample": f"{how}, {rows_c} of {rows} rows x {batch} queries x {steps} steps, QPS scaled by {rows_c}/{rows}"}
+            return (out, (st, qn, None)) if want_candidates else out
+        except Exception as exc:  # a broken install: fall back to the port and say so
+            how = f"numpy sgemm + partition (chromadb import worked but failed: {str(exc)[:80]})"
+    for _ in range(warmup):
+        O.sgemm_topk(qn, f32, k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cand = O.sgemm_topk(qn, f32, k)
+    s_per = (time.perf_counter() - t0) / steps
+    out = {"qps": batch / s_per * rows_s / rows, "cores": cores, "kind": kind, "s_per_step": s_per,
+           "sample": f"{how}, {rows_s} of {rows} rows x {batch} queries x {steps} steps ({s_per:.2f} s/step)"
+                     + ("" if rows_s == rows else f", QPS scaled by {rows_s}/{rows}")}
+    return (out, (st, qn, cand)) if want_candidates else out
+
+
+def shared_config(args, wl):
+    """The part of `config` both arms print identically (the driver compares them)."""
+    return {"workload": wl["desc"], "batch": args.batch, "k": wl["k"], "rows": wl["rows"], "store_dtype": wl["dtype"],
+            "space": args.space}
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU retrieval on the host cores, same config / metric / unit / steps; each step
+    is a bounded sample (a slice of the corpus), QPS scaled by slice / corpus."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    wl = WORKLOADS[args.workload]
-    rows = wl["rows"]
-    sample = f"full {rows} rows x {args.batch} queries per step"
-    rows_s = cpu_sample_rows(rows, args.batch)
-    if rows_s < rows:  # bound host memory/time: scan a slice, scale QPS by the row ratio
-        sample = f"{rows_s} of {rows} rows x {args.batch} queries per step, QPS scaled by {rows_s}/{rows}"
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    qps, cores, s_per_step = cpu_port_qps(args.workload, rows_s, args.batch, wl["k"], steps, warmup)
-    qps *= rows_s / rows
-    line = {"impl": "reference", "metric": "queries_per_sec_exact_top%d" % wl["k"], "value": qps, "unit": "queries/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * s_per_step * rows / rows_s,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "batch": args.batch, "k": wl["k"], "rows": wl["rows"],
-                       "note": "chromadb/hnswlib not installable offline; numpy sgemm + partition = its brute-force arithmetic"},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    res = cpu_arm(args.workload, args.batch, wl["k"], max(1, args.steps), max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC % wl["k"], "value": res["qps"], "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / res["qps"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": shared_config(args, wl),
+            "cpu_baseline": {"value": res["qps"], "unit": "queries/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": res["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Harness:
+    """Timing plumbing shared by the headline, the extra points and the secondary workloads."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank, self.local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.host_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.host_group = dist.new_group(backend="gloo")  # host-side barriers: no kernel spins on a GPU while others work
+        self.pk = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K calls bracketed by barrier + synchronize on both sides; CUDA events; max over ranks.  -> (ms total, last result)."""
+        torch, dist = self.torch, self.dist
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        self.last_window = (t0, time.perf_counter())
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    def roofline(self, sh, dtype, B, scan_ms, scan_launches, ms_total, pipeline, space="cosine", traffic=None):
+        pk = self.pk
+        algo_bytes = sh.local_rows * 768 * ELEM[dtype]
+        avg = scan_ms / max(1, scan_launches)
+        kernel = {0: "scan_simt_kernel (+ candidate memset, bracketed together)",
+                  1: "scan_fused_kernel (single-launch SIMT search)",
+                  2: "tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, bracketed together)",
+                  3: "prep_fused_kernel + tc_fused_kernel (one cooperative launch: tcgen05 scoring of the whole corpus, in-kernel "
+                     "threshold learning, selection, fp32 rescoring; bracketed together)"}[pipeline]
+        # intensity = B flop per corpus byte (bf16) or B/2 (fp32): above the ridge the tensor pipe bounds the search
+        ridge = pk["tf_burst"] * 1e3 / pk["hbm"] * (1 if dtype == "bf16" else 2)
+        share = scan_ms / ms_total if ms_total else None
+        if B >= ridge:
+            flops = 2.0 * sh.local_rows * 768 * B
+            ach = flops / 1e12 / (avg / 1e3) if avg else 0.0
+            return {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                    "traffic": traffic, "peak_source": pk["src"] + " bf16_tflops (burst)", "frac_of_sustained": ach / pk["tf_sustained"],
+                    "kernel": kernel, "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg, "scan_share_of_step": share}
+        ach = algo_bytes / 1e9 / (avg / 1e3) if avg else 0.0
+        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
+                "peak_source": pk["src"] + " hbm_gbs", "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes,
+                "avg_launch_ms": avg, "scan_share_of_step": share, "frac_of_nominal_8TBps": ach / 8000.0}
+
+    def point(self, sh, workload, B, k, steps, warmup, mask=None, sustained_s=1.0, space="cosine"):
+        """One (workload, batch) measurement with device-resident queries: W warm-up steps, K timed steps with the clocks
+        sampled meanwhile, then a sustained loop of at least `sustained_s` seconds (its own clocks).  -> (dict, last result)."""
+        torch = self.torch
+        wl = WORKLOADS[workload]
+        q_np, planted = planted_queries_np(QUERY_SEED, B, CORPUS_SEED[workload], wl["rows"])
+        q_dev = torch.from_numpy(q_np).to(self.dev)
+        fn = lambda: sh.search(q_dev, k, mask)  # noqa: E731
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        st0 = sh.index.stats()
+        sampler = ClockSampler(self.local_rank).start() if self.rank == 0 else None
+        ms_total, out = self.timed(fn, steps)
+        windows = [self.last_window]
+        st1 = sh.index.stats()
+        res = {"batch": B, "k": k, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+               "qps": B * steps / (ms_total / 1e3), "clocks": None,
+               "launches": int(st1["kernel_launches"] - st0["kernel_launches"]) + (steps if self.world > 1 else 0),
+               "scan_passes_per_step": (st1["scan_launches"] - st0["scan_launches"]) / steps,
+               "unrepaired": int(st1["unrepaired"] - st0["unrepaired"]),
+               "roofline": self.roofline(sh, wl["dtype"], B, st1["scan_ms"] - st0["scan_ms"],
+                                         st1["scan_launches"] - st0["scan_launches"], ms_total, st1["last_pipeline"], space)}
+        if sustained_s > 0:
+            n_sus = max(steps, int(np.ceil(sustained_s * 1e3 / max(res["ms_per_step"], 1e-3))))
+            ms_sus, _ = self.timed(fn, n_sus)
+            windows.append(self.last_window)
+            res["sustained"] = {"steps": n_sus, "seconds": ms_sus / 1e3, "qps": B * n_sus / (ms_sus / 1e3),
+                                "ms_per_step": ms_sus / n_sus}
+        if sampler:
+            # one nvidia-smi stream over the K timed steps and the sustained loop right after them; only samples that
+            # arrived while the GPU was inside one of the two regions count
+            res["clocks"] = sampler.stop(windows)
+            res["clocks"]["covers"] = "the K timed steps + the sustained loop that follows them (samples taken under load only)"
+        assert res["unrepaired"] == 0, "the asynchronous search left flagged queries unrepaired"
+        return res, out, (q_np, planted)
+
+
+def check_results(workload, q_np, planted, scores, ids, k, cpu_slice=None, mask_fn=None):
+    """Rank 0, after the timed region: (a) planted neighbours come first; (b) every returned id re-scored by the CPU oracle
+    from the regenerated row -- the score bits must match and the rows must be in order; (c) completeness against a CPU
+    brute force over a slice of the corpus: no row of the slice may beat the k-th returned (score, id) unless returned."""
+    import oracle as O
+    wl = WORKLOADS[workload]
+    B = q_np.shape[0]
+    out = {"planted_first": True, "rescored_ids": 0, "slice_rows": 0, "slice_candidates": 0}
+    if mask_fn is None:
+        assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
+    else:
+        got = ids[ids >= 0]
+        assert mask_fn(got).all(), "a returned row is not allowed by the filter"
+    qn, _ = O.normalize_rows(q_np, "fp32", 768)
+    nb = min(B, 64)  # (regenerating rows one by one is host work: a 64-query sample of large batches)
+    pick = np.linspace(0, B - 1, nb).astype(int)
+    for b in pick:
+        row_ids = ids[b][ids[b] >= 0]
+        x = np.concatenate([O.synth_rows(CORPUS_SEED[workload], int(r), 1, 768) for r in row_ids])
+        st, _ = O.normalize_rows(x, wl["dtype"], 768)
+        es, ei = O.brute_force_topk(qn[b:b + 1], st, len(row_ids))  # (ties -> lower position = lower id: the order returned)
+        assert np.array_equal(ei[0], np.arange(len(row_ids))), f"query {b}: returned rows are not in exact-score order"
+        assert np.array_equal(es[0].view(np.uint32), scores[b][:len(row_ids)].view(np.uint32)), f"query {b}: score bits differ from the oracle"
+        out["rescored_ids"] += len(row_ids)
+    if cpu_slice is not None and cpu_slice[2] is not None:
+        st_slice, qn_s, (cs, ci) = cpu_slice
+        out["slice_rows"] = int(st_slice.shape[0])
+        for b in pick:
+            cand = ci[b][ci[b] >= 0]
+            if mask_fn is not None:
+                cand = cand[mask_fn(cand)]
+            if cand.size == 0:
+                continue
+            es, ei = O.brute_force_topk(qn[b:b + 1], st_slice[cand], cand.size)  # canonical fp32 scores of the slice's best rows
+            kth_s, kth_i = scores[b, k - 1], ids[b, k - 1]
+            returned = set(ids[b].tolist())
+            for s, j in zip(es[0], ei[0]):
+                r = int(cand[j])
+                beats = kth_i < 0 or s > kth_s or (s == kth_s and r < kth_i)
+                assert not beats or r in returned, f"query {b}: corpus row {r} (score {s}) beats the k-th result but was not returned"
+            out["slice_candidates"] += int(cand.size)
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=None)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
     ap.add_argument("--rows", type=int, default=None, help="override the corpus size (debug)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", type=str, default=None, help="comma-separated extra batch sizes to report")
+    ap.add_argument("--points", type=str, default=None, help="comma-separated extra batch sizes on the headline corpus (default 1,1024,4096)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (config 2 / 3 at N=1, config 5 at N=8)")
+    ap.add_argument("--no-store-e2e", action="store_true", help="N>1: measure e2e through the per-rank path instead of one "
+                                                                "MediQueryVectorStore over all devices")
     ap.add_argument("--selectivity", type=float, default=0.1, help="c5: fraction of rows the where-filter allows")
     ap.add_argument("--space", choices=["cosine", "l2", "ip"], default="cosine",
-                    help="hnsw:space the rows are ranked in; l2 / ip rank the RAW synthetic vectors (norms 15.5-16.5) with the "
-                         "stored row norms on the exact SIMT scan (SURVEY.md section 8 f3); the default is the headline config")
-    ap.add_argument("--no-scaling-base", action="store_true",
-                    help="N=1 default run: skip the extra config-4 (100M x 768 bf16) measurement on this one GPU")
+                    help="hnsw:space the rows are ranked in; l2 / ip rank the RAW synthetic vectors (norms 15.5-16.5); "
+                         "the default is the headline config")
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload is None:
-        args.workload = "c2" if max(args.gpus, world) == 1 else "c4"
     wl = dict(WORKLOADS[args.workload])
     if args.rows:
         wl["rows"] = args.rows
@@ -220,261 +430,254 @@ def main():
         args.batch = wl["batch"]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, wl)
 
-    import torch
-    import torch.distributed as dist
-
-    from mediquery_rag_b200 import _native
+    H = Harness(args)
+    torch, dist, world, rank, dev = H.torch, H.dist, H.world, H.rank, H.dev
+    from mediquery_rag_b200 import MediQueryVectorStore
+    from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns
     from mediquery_rag_b200.sharded import ShardedIndex
 
-    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     k, B, rows = wl["k"], args.batch, wl["rows"]
+    headline = args.workload
+    secondary = {}
 
-    sh = ShardedIndex(768, wl["dtype"], rows, metric=args.space)
+    def source_ids(lo, hi):
+        return (splitmix64_np(MASK_SEED, np.arange(lo, hi, dtype=np.uint64)) % np.uint64(100)).astype(np.int64)
+
+    def allowed_fn(sel):
+        return lambda got: (splitmix64_np(MASK_SEED, got.astype(np.uint64)) % np.uint64(100)) < max(1, round(sel * 100))
+
+    def build_filter(sh, sel, state):
+        """where -> packed bitmask, evaluated ON THE DEVICE (K5 filter_eval_kernel) over the resident source_id column."""
+        if "f" not in state:
+            cols = MetadataColumns()
+            cols.extend_columns(sh.hi - sh.lo, {"source_id": source_ids(sh.lo, sh.hi)})
+            state["f"] = DeviceFilter(sh.index, cols)
+        where = {"source_id": {"$in": list(range(max(1, round(sel * 100))))}}
+        t0 = time.perf_counter()
+        mask, allowed = state["f"].build(where, None)
+        state["ms"] = 1e3 * (time.perf_counter() - t0)
+        return mask, allowed, where
+
+    def run_secondary(name, batches, steps):
+        """A secondary workload on its own corpus (freed afterwards): every batch size with roofline, clocks, sustained loop."""
+        w = WORKLOADS[name]
+        sh = ShardedIndex(768, w["dtype"], w["rows"])
+        sh.add_synthetic(CORPUS_SEED[name])
+        torch.cuda.synchronize()
+        block = {"workload": w["desc"], "rows": w["rows"], "rows_per_gpu": sh.local_rows, "k": w["k"], "store_dtype": w["dtype"],
+                 "points": []}
+        mask, mask_fn, fstate = None, None, {}
+        if name == "c5":
+            mask, allowed, where = build_filter(sh, args.selectivity, fstate)
+            build_filter(sh, args.selectivity, fstate)  # second build: the column is resident now = the per-filter cost
+            mask_fn = allowed_fn(args.selectivity)
+            block["filter"] = {"where": str(where)[:60] + "...", "selectivity": args.selectivity, "allowed_rows_rank0": allowed,
+                               "evaluated": "on device (filter_eval_kernel), column resident in HBM",
+                               "filter_build_ms": round(fstate["ms"], 3)}
+        for b in batches:
+            res, out, (q_np, planted) = H.point(sh, name, b, w["k"], steps, 3, mask)
+            if rank == 0:
+                res["check"] = check_results(name, q_np, planted, out[0].cpu().numpy(), out[1].cpu().numpy(), w["k"], None, mask_fn)
+            block["points"].append(res)
+        sh.index.close()
+        del sh
+        torch.cuda.empty_cache()
+        return block
+
+    do_secondary = not args.no_secondary and headline == "c4" and not args.rows and args.space == "cosine"
+    if do_secondary and world == 1:
+        try:
+            secondary["config2"] = run_secondary("c2", (1, 64), max(10, args.steps))
+            secondary["config3"] = run_secondary("c3", (4096,), 5)
+        except Exception as exc:  # e.g. not enough free HBM on a shared box: the headline still runs
+            secondary["error"] = str(exc)[:300]
+
+    # ---- headline corpus.  N = 1: behind the MediQueryVectorStore the e2e leg searches through (same handle, no second copy);
+    # N > 1: one shard per rank for `value`, the single-process store is built afterwards for `e2e`
     t0 = time.perf_counter()
-    sh.add_synthetic(CORPUS_SEED[args.workload])
+    store = None
+    if world == 1:
+        store = MediQueryVectorStore(devices=[H.local_rank], store_dtype=wl["dtype"], capacity_rows=rows,
+                                     collection_metadata={"hnsw:space": args.space})
+        store.add_synthetic(CORPUS_SEED[headline], rows)
+        sh = ShardedIndex(768, wl["dtype"], rows, index_factory=lambda *a: store._index, metric=args.space)
+    else:
+        sh = ShardedIndex(768, wl["dtype"], rows, metric=args.space)
+        sh.add_synthetic(CORPUS_SEED[headline])
     torch.cuda.synchronize()
     ingest_s = time.perf_counter() - t0
 
-    q_host_np, planted = planted_queries_np(QUERY_SEED, B, CORPUS_SEED[args.workload], rows)
-    q_pinned = torch.from_numpy(q_host_np).pin_memory()
-    q_dev = q_pinned.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # config 5: a synthetic categorical metadata column source_id in {0..99} (hash of the row id), filtered with the
-    # Chroma grammar {"source_id": {"$in": [...]}} through the product's where -> bitmask compiler
-    dev_filter = {}
-
-    def build_mask(selectivity):
-        """where -> packed bitmask, evaluated ON THE DEVICE (K5 filter_eval_kernel) over the resident source_id column."""
-        from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns
-        if "f" not in dev_filter:
-            lo, hi = sh.lo, sh.hi
-            ids = (splitmix64_np(MASK_SEED, np.arange(lo, hi, dtype=np.uint64)) % np.uint64(100)).astype(np.int64)
-            cols = MetadataColumns()
-            cols.extend_columns(hi - lo, {"source_id": ids})
-            dev_filter["f"] = DeviceFilter(sh.index, cols)
-        where = {"source_id": {"$in": list(range(max(1, round(selectivity * 100))))}}
-        t0 = time.perf_counter()
-        mask, allowed = dev_filter["f"].build(where, None)
-        dev_filter["ms"] = 1e3 * (time.perf_counter() - t0)
-        return mask, allowed, where
-
-    mask_dev, mask_info = None, None
-    if args.workload == "c5":
-        mask_dev, allowed, where = build_mask(args.selectivity)
-        build_mask(args.selectivity)  # second build: the column is resident now, this is the per-query-filter cost
+    mask, mask_info, mask_fn, fstate = None, None, None, {}
+    if headline == "c5":
+        mask, allowed, where = build_filter(sh, args.selectivity, fstate)
+        build_filter(sh, args.selectivity, fstate)
+        mask_fn = allowed_fn(args.selectivity)
         mask_info = {"where": str(where)[:60] + "...", "selectivity": args.selectivity, "allowed_rows_rank0": allowed,
-                     "evaluated": "on device (filter_eval_kernel), column resident in HBM",
-                     "filter_build_ms": round(dev_filter["ms"], 3)}
+                     "evaluated": "on device (filter_eval_kernel), column resident in HBM", "filter_build_ms": round(fstate["ms"], 3)}
 
-    def step_device(q):
-        return sh.search(q, k, mask_dev)
+    head, out, (q_np, planted) = H.point(sh, headline, B, k, args.steps, args.warmup, mask, space=args.space)
+    head_scores, head_ids = out[0].cpu().numpy(), out[1].cpu().numpy()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
+    points = []
+    extra = [int(v) for v in args.points.split(",")] if args.points else ([1, 1024, 4096] if headline == "c4" else [])
+    for b in extra:
+        if b == B:
+            continue
+        per_step_s = 2.0 * sh.local_rows * 768 * b / 1.1e15 + sh.local_rows * 768 * ELEM[wl["dtype"]] / 6.5e12
+        steps_b = max(3, min(args.steps, int(2.0 / per_step_s)))
+        res, o, (qb, pl) = H.point(sh, headline, b, k, steps_b, 3, mask, space=args.space)
+        if rank == 0 and args.space == "cosine":
+            res["check"] = check_results(headline, qb, pl, o[0].cpu().numpy(), o[1].cpu().numpy(), k, None, mask_fn)
+        points.append(res)
 
-    # ---- value: inputs resident in HBM
-    for _ in range(args.warmup):
-        out = step_device(q_dev)
-    barrier()
-    st0 = sh.index.stats()
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    ms_total, out = timed(lambda: step_device(q_dev), args.steps)
-    clocks = sampler.stop() if sampler else None
-    st1 = sh.index.stats()
-    launches = (st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if world > 1 else 0)  # + exchange/merge kernel
-    scan_launches = st1["scan_launches"] - st0["scan_launches"]
-    scan_ms = st1["scan_ms"] - st0["scan_ms"]
-    ms_per_step = ms_total / args.steps
-    value = B * args.steps / (ms_total / 1e3)
+    # ---- e2e: the public object, host buffers; H2D of the queries and D2H of the results inside the timed region
+    q_pinned = torch.from_numpy(q_np).pin_memory()
+    q_host = q_pinned.numpy()
+    e2e_how, e2e_extra = None, {}
 
-    # correctness guard on the timed configuration: planted neighbours must come first
-    ids = out[1].cpu().numpy()
-    if args.space != "cosine":  # unit queries against rows of norm ~16: the planted row is not the l2 / ip neighbour
-        sc = out[0].cpu().numpy()
-        assert (ids >= 0).all() and (np.diff(sc, axis=1) <= 0).all(), "results are not sorted best-first"
-    elif mask_dev is None:
-        assert all(ids[b, 0] == planted[b] for b in range(0, B, 2)), "planted neighbours not found: result is wrong"
-    else:  # every returned row must carry an allowed source_id
-        got = ids[ids >= 0].astype(np.uint64)
-        assert ((splitmix64_np(MASK_SEED, got) % np.uint64(100)) < max(1, round(args.selectivity * 100))).all()
+    def e2e_loop(fn):
+        for _ in range(args.warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            got = fn()
+        return time.perf_counter() - t0, got
 
-    # ---- e2e: public API, host buffers; H2D of the queries and D2H of the results inside the timed region
-    q_np_pinned = q_pinned.numpy()
-    res_s = torch.empty((B, k), dtype=torch.float32).pin_memory()
-    res_i = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    if world == 1:
+        H.barrier()
+        if mask is None:
+            dt, got = e2e_loop(lambda: store.search_batch(q_host, k))
+        else:
+            dt, got = e2e_loop(lambda: sh.index.search(q_host, k, mask))
+        e2e_qps = B * args.steps / dt
+        e2e_how = "MediQueryVectorStore.search_batch (one handle, this GPU): pinned host queries -> mqvs_search -> host results"
+        assert np.array_equal(got[1], head_ids) and np.array_equal(got[0].view(np.uint32), head_scores.view(np.uint32)), \
+            "e2e results differ from the device-resident path"
+    elif args.no_store_e2e or mask is not None:
+        res_s = torch.empty((B, k), dtype=torch.float32).pin_memory()
+        res_i = torch.empty((B, k), dtype=torch.int64).pin_memory()
+        q_dev = torch.empty((B, 768), dtype=torch.float32, device=dev)
 
-    def step_e2e():
-        if world == 1:
-            return sh.index.search(q_np_pinned, k, mask_dev)  # mqvs_search: host in, host out, blocking
-        qd = q_pinned.to(dev, non_blocking=True) if rank == 0 else torch.empty_like(q_dev)
-        dist.broadcast(qd, 0)
-        s, i = sh.search(qd, k, mask_dev)
+        def step():
+            qd = q_pinned.to(dev, non_blocking=True) if rank == 0 else q_dev
+            dist.broadcast(qd, 0)
+            s, i = sh.search(qd, k, mask)
+            if rank == 0:
+                res_s.copy_(s, non_blocking=True)
+                res_i.copy_(i, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            step()
+        H.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        H.barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_qps = B * args.steps / float(t.item())
+        e2e_how = "one process per GPU: rank 0 copies pinned queries in, NCCL broadcast, sharded search + peer exchange, results to pinned host"
+    else:
+        # every rank releases its shard; rank 0 alone then drives all N GPUs through ONE MediQueryVectorStore, the way the
+        # reference holds its vector store (one object, one process); the other ranks wait on a host-side barrier
+        xchg_kind = sh.exchange
+        sh.index.close()
+        if sh._xchg is not None:
+            sh._xchg.close()
+        torch.cuda.empty_cache()
+        H.barrier()
+        e2e_qps = 0.0
         if rank == 0:
-            res_s.copy_(s, non_blocking=True)
-            res_i.copy_(i, non_blocking=True)
-        torch.cuda.synchronize()
-        return res_s, res_i
+            t0 = time.perf_counter()
+            store = MediQueryVectorStore(devices=list(range(world)), store_dtype=wl["dtype"], capacity_rows=rows,
+                                         collection_metadata={"hnsw:space": args.space})
+            store.add_synthetic(CORPUS_SEED[headline], rows)
+            e2e_extra["store_ingest_s"] = round(time.perf_counter() - t0, 3)
+            dt, got = e2e_loop(lambda: store.search_batch(q_host, k))
+            e2e_qps = B * args.steps / dt
+            assert np.array_equal(got[1], head_ids) and np.array_equal(got[0].view(np.uint32), head_scores.view(np.uint32)), \
+                "the single-process store over all devices disagrees with the per-rank shards"
+            # the same object with device-resident queries (mqvs_search_async on the multi-device handle)
+            qd = torch.from_numpy(q_np).to(dev)
+            o_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+            o_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+            stream = torch.cuda.current_stream().cuda_stream
+            for _ in range(args.warmup):
+                store._index.search_device(qd, k, o_s, o_i, stream=stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                store._index.search_device(qd, k, o_s, o_i, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            e2e_extra["single_process_device_resident_qps"] = B * args.steps / (e0.elapsed_time(e1) / 1e3)
+            assert np.array_equal(o_i.cpu().numpy(), head_ids)
+            e2e_extra["single_process_stats"] = {kk: vv for kk, vv in store._index.stats().items()
+                                                 if kk in ("kernel_launches", "scan_launches", "last_pipeline", "unrepaired")}
+            store._index.close()
+        dist.barrier(group=H.host_group)
+        e2e_how = (f"ONE MediQueryVectorStore(devices=[0..{world})) in ONE process (rank 0; the other ranks released their shards): "
+                   "pinned host queries -> mqvs_search on the multi-device handle (per-device scans, results stored into the home "
+                   "device over NVLink peer access, one merge kernel) -> host results")
+        e2e_extra["per_rank_exchange"] = xchg_kind
+        sh = None
 
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_qps = B * args.steps / float(e2e_s.item())
-
-    # ---- optional sweep over other batch sizes (device-resident), reported beside the headline
-    sweep = []
-    for b in [int(v) for v in args.sweep.split(",")] if args.sweep else []:
-        qb, _ = planted_queries_np(QUERY_SEED, b, CORPUS_SEED[args.workload], rows)
-        qb_dev = torch.from_numpy(qb).to(dev)
-        for _ in range(3):
-            sh.search(qb_dev, k)
-        s0 = sh.index.stats()
-        ms_b, _ = timed(lambda: sh.search(qb_dev, k), max(5, args.steps // 2))
-        s1 = sh.index.stats()
-        n_steps = max(5, args.steps // 2)
-        scan_b = (s1["scan_ms"] - s0["scan_ms"]) / max(1, s1["scan_launches"] - s0["scan_launches"])
-        sweep.append({"batch": b, "qps": b * n_steps / (ms_b / 1e3), "ms_per_step": ms_b / n_steps,
-                      "scan_gbps_per_gpu": sh.local_rows * 768 * ELEM[wl["dtype"]] / 1e9 / (scan_b / 1e3) if scan_b else None})
-
-    sel_sweep = []
-    if args.workload == "c5":
-        for sel in (0.5, 0.1, 0.01):
-            m_dev, allowed, _ = build_mask(sel)
-            for _ in range(2):
-                sh.search(q_dev, k, m_dev)
-            n_steps = max(3, args.steps // 2)
-            ms_s, _ = timed(lambda: sh.search(q_dev, k, m_dev), n_steps)
-            sel_sweep.append({"selectivity": sel, "qps": B * n_steps / (ms_s / 1e3), "ms_per_step": ms_s / n_steps})
+    # ---- N = 8: config 5 as a secondary block (after the headline corpus is gone)
+    if do_secondary and world == 8:
+        try:
+            secondary["config5"] = run_secondary("c5", (16384,), 5)
+        except Exception as exc:
+            secondary["error"] = str(exc)[:300]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
-    algo_bytes = sh.local_rows * 768 * ELEM[wl["dtype"]]  # corpus bytes one scan streams on this rank
-    avg_launch_ms = scan_ms / max(1, scan_launches)
-    kernel = {0: ("scan_simt_kernel" if args.space == "cosine" else f"scan_simt_metric_kernel ({args.space} space, row norms)")
-                 + " (+ candidate memset, bracketed together)",
-              1: "scan_fused_kernel (single-launch SIMT search)",
-              2: "tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, bracketed together)",
-              3: "prep_fused_kernel + tc_fused_kernel (one cooperative launch: tcgen05 scoring of the whole corpus, in-kernel "
-                 "threshold learning, selection, fp32 rescoring; bracketed together)"}[st1["last_pipeline"]]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.workload}_b{B}" + ("" if args.space == "cosine" else f"_{args.space}"))
-    # intensity = B flop per corpus byte (bf16) or B/2 (fp32): above the ridge the tensor pipe bounds the search
-    ridge = pk["tf_burst"] * 1e3 / pk["hbm"] * (1 if wl["dtype"] == "bf16" else 2)
-    if B >= ridge:
-        flops = 2.0 * sh.local_rows * 768 * B
-        achieved = flops / 1e12 / (avg_launch_ms / 1e3) if avg_launch_ms else 0.0
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tf_burst"], "traffic": traffic, "peak_source": pk["src"] + " bf16_tflops (burst)",
-                    "frac_of_sustained": achieved / pk["tf_sustained"], "kernel": kernel,
-                    "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg_launch_ms,
-                    "scan_share_of_step": scan_ms / ms_total if ms_total else None}
-    else:
-        achieved = algo_bytes / 1e9 / (avg_launch_ms / 1e3) if avg_launch_ms else 0.0
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " hbm_gbs",
-                    "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,
-                    "scan_share_of_step": scan_ms / ms_total if ms_total else None,
-                    "frac_of_nominal_8TBps": achieved / 8000.0}
-
+            traffic = json.load(f).get(f"{headline}_b{B}" + ("" if args.space == "cosine" else f"_{args.space}"))
+    roofline = dict(head["roofline"])
+    roofline["traffic"] = traffic
+    local_rows = (rows + world - 1) // world
+    algo_bytes = local_rows * 768 * ELEM[wl["dtype"]]
+    config = shared_config(args, wl)
     line = {
-        "metric": "queries_per_sec_exact_top%d" % k, "value": value, "unit": "queries/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch": B, "k": k, "rows": rows, "rows_per_gpu": sh.local_rows,
-                   "store_dtype": wl["dtype"], "space": args.space,
-                   "parallelism": (f"row-shard x{world}, candidate exchange: {sh.exchange}" if world > 1 else "single GPU"),
-                   "l2": ("inputs larger than L2 (corpus per GPU %.2f GB vs 126 MB L2); no flush needed" % (algo_bytes / 1e9)
-                          if algo_bytes > 126e6 else "corpus fits in L2 (%.1f KB): launch-latency-bound case, no flush" % (algo_bytes / 1e3)),
-                   "ingest_s": round(ingest_s, 3), "scan_passes_per_step": scan_launches / args.steps},
+        "metric": METRIC % k, "value": head["qps"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config,
+        "details": {"rows_per_gpu": local_rows,
+                    "parallelism": (f"row-shard x{world}, one process per GPU, candidate exchange: {e2e_extra.get('per_rank_exchange', getattr(sh, 'exchange', 'none'))}"
+                                    if world > 1 else "single GPU"),
+                    "l2": "inputs larger than L2 (corpus per GPU %.2f GB vs 126 MB L2); no flush needed" % (algo_bytes / 1e9),
+                    "ingest_s": round(ingest_s, 3), "scan_passes_per_step": head["scan_passes_per_step"],
+                    "scaling_note": "strong scaling over the FIXED corpus of the workload: the same corpus at every N (each rank scans 1/N)"},
         "roofline": roofline,
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 768 * 4, "d2h_bytes_per_step": B * k * 12},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 768 * 4 * (world if world > 1 and not args.no_store_e2e else 1),
+                "d2h_bytes_per_step": B * k * 12, "through": e2e_how, **e2e_extra},
+        "gpu_launches": head["launches"], "clocks": head["clocks"], "sustained": head.get("sustained"),
+        "points": points,
     }
-    # what the N = 1, 2, 4, 8 lines of one scaling run have in common (the driver compares their `value`s)
-    line["scaling_note"] = (
-        "value is config 2 (the metric's single-GPU configuration); the 1-GPU point of the config-4 strong-scaling curve "
-        "that --gpus 2/4/8 measure is scaling_base_config4_n1.points[batch=64].qps in this line"
-        if world == 1 and args.workload == "c2" else
-        "strong scaling over the FIXED 100M x 768 bf16 corpus of config 4 (each rank scans 1/N of it); its 1-GPU point is "
-        "scaling_base_config4_n1 in the --gpus 1 line (that line's `value` is config 2, a different workload)"
-        if args.workload == "c4" else "single workload, no scaling curve")
-    if sweep:
-        line["sweep"] = sweep
+    if secondary:
+        line["secondary"] = secondary
     if mask_info:
-        line["config"]["filter"] = mask_info
-        line["selectivity_sweep"] = sel_sweep
-    # N=1 default run only: the multi-GPU runs use config 4 (strong scaling over a fixed 100M-row corpus), so the
-    # same corpus is also measured here on ONE GPU (153.6 GB of the 180 GB) -- the base point of that scaling curve.
-    if world == 1 and args.workload == "c2" and not args.rows and not args.no_scaling_base and args.space == "cosine":
-        try:
-            del sh
-            torch.cuda.empty_cache()
-            c4 = WORKLOADS["c4"]
-            sh4 = ShardedIndex(768, c4["dtype"], c4["rows"])
-            sh4.add_synthetic(CORPUS_SEED["c4"])
-            base = {"workload": c4["desc"] + " on 1 GPU", "rows": c4["rows"], "k": c4["k"], "points": []}
-            for b in (1, c4["batch"]):
-                qb, pl = planted_queries_np(QUERY_SEED, b, CORPUS_SEED["c4"], c4["rows"])
-                qb_dev = torch.from_numpy(qb).to(dev)
-                for _ in range(2):
-                    o4 = sh4.search(qb_dev, c4["k"])
-                torch.cuda.synchronize()
-                assert all(int(o4[1][j, 0]) == pl[j] for j in range(0, b, 2))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    sh4.search(qb_dev, c4["k"])
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 5
-                base["points"].append({"batch": b, "qps": b / (ms / 1e3), "ms_per_step": ms,
-                                       "scan_gbps": c4["rows"] * 768 * 2 / 1e9 / (ms / 1e3)})
-            line["scaling_base_config4_n1"] = base
-            del sh4
-        except Exception as exc:  # e.g. not enough free HBM on a shared box
-            line["scaling_base_config4_n1"] = {"unavailable": str(exc)[:200]}
-    if world == 1 and not args.no_cpu_baseline:
-        rows_s = cpu_sample_rows(rows, B)
-        qps, cores, s_per = cpu_port_qps(args.workload, rows_s, B, k, steps=3, warmup=1)
-        line["cpu_baseline"] = {"value": qps * rows_s / rows, "unit": "queries/s", "cores": cores, "kind": "port",
-                                "sample": f"numpy sgemm+partition, {rows_s} rows x {B} queries x 3 steps ({s_per:.2f} s/step)"
-                                          + ("" if rows_s == rows else f", scaled by {rows_s}/{rows}")}
-    else:
-        line["cpu_baseline"] = None
+        line["details"]["filter"] = mask_info
+    # ---- CPU leg (rank 0): baseline at N = 1, and at every N the slice brute force the completeness check needs
+    cpu_slice = None
+    if not args.no_cpu_baseline and args.space == "cosine":
+        res, cpu_slice = cpu_arm(headline, B, k, steps=3, warmup=1, want_candidates=True)
+        if world == 1:
+            line["cpu_baseline"] = {"value": res["qps"], "unit": "queries/s", "cores": res["cores"], "kind": res["kind"],
+                                    "sample": res["sample"]}
+    line.setdefault("cpu_baseline", None)
+    if args.space == "cosine":
+        line["check"] = check_results(headline, q_np, planted, head_scores, head_ids, k, cpu_slice, mask_fn)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

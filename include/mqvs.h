@@ -146,6 +146,12 @@ MQVS_API int mqvs_xchg_connect_ptrs(mqvs_xchg_t* x, void* const* bases);
 MQVS_API int mqvs_xchg_max_entries(mqvs_xchg_t* x, uint64_t* out);
 MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k,
                              float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
+/* The same call for ALL ranks of an exchange that live on ONE device (logical shards sharing a GPU): one cooperative launch
+ * does every rank's work.  Separate launches must not be used there -- a kernel that spins on a flag another launch has
+ * yet to write may never see that launch scheduled.  ranks / buffers: arrays of W entries in rank order.  Synchronous. */
+MQVS_API int mqvs_xchg_merge_colocated(mqvs_xchg_t* const* ranks, int W, const float* const* scores_dev,
+                                       const int64_t* const* ids_dev, int B, int k, float* const* out_scores_dev,
+                                       int64_t* const* out_ids_dev, void* cuda_stream);
 MQVS_API void mqvs_xchg_destroy(mqvs_xchg_t* x);
 
 /* Chroma `where` filters evaluated ON THE DEVICE (collection.query(where=...)): metadata

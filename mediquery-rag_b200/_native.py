@@ -96,6 +96,8 @@ SIGNATURES = {
     "mqvs_xchg_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
     "mqvs_xchg_max_entries": (_i, [_vp, ctypes.POINTER(_u64)]),
     "mqvs_xchg_merge": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "mqvs_xchg_merge_colocated": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i,
+                                       ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
     "mqvs_xchg_destroy": (None, [_vp]),
 }
 
@@ -364,6 +366,16 @@ class PeerExchange:
         """scores/ids [B, k] device tensors of this rank -> out [B, k]: best k of all ranks' candidates."""
         B, k = scores.shape
         check(load().mqvs_xchg_merge(self._h, _ptr(scores), _ptr(ids), B, k, _ptr(out_scores), _ptr(out_ids), _vp(stream)))
+
+    @staticmethod
+    def merge_colocated(ranks, scores, ids, out_scores, out_ids, stream: int = 0) -> None:
+        """All ranks of one exchange that share ONE device, in a single cooperative launch (include/mqvs.h): lists of W
+        exchanges / [B, k] tensors in rank order."""
+        W = len(ranks)
+        B, k = scores[0].shape
+        arr = lambda xs: (_vp * W)(*[_ptr(t) for t in xs])  # noqa: E731
+        hs = (_vp * W)(*[r._h for r in ranks])
+        check(load().mqvs_xchg_merge_colocated(hs, W, arr(scores), arr(ids), B, k, arr(out_scores), arr(out_ids), _vp(stream)))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

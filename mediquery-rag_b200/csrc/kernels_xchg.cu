@@ -52,7 +52,8 @@ __device__ __forceinline__ bool before(uint32_t ao, int64_t ai, uint32_t bo, int
     return ao > bo || (ao == bo && ai < bi);
 }
 
-__global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a) {
+// The work of CTA `cta` of `n_cta` of the rank described by `a`.
+__device__ __forceinline__ void xchg_body(const XchgArgs& a, const int cta, const int n_cta) {
     extern __shared__ __align__(16) unsigned char raw[];
     int64_t* sid = reinterpret_cast<int64_t*>(raw);
     uint32_t* sord = reinterpret_cast<uint32_t*>(sid + a.n_pow2);
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a)
     const int per = a.W * a.k;
 
     // 1. this CTA's queries -> every inbox (own included), slot [rank]
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x)
+    for (int b = cta; b < a.B; b += n_cta)
         for (int idx = tid; idx < per; idx += kXThreads) {
             const int r = idx / a.k, j = idx - r * a.k;
             const size_t src = (size_t)b * a.k + j, dst = (size_t)a.rank * a.cap + src;
@@ -71,8 +72,8 @@ __global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a)
     // 2. signal every peer, 3. wait for every peer
     if (tid < a.W) {
         __threadfence_system();
-        st_release_sys(a.peer_flag[tid] + (size_t)a.rank * kMaxGrid + blockIdx.x, a.epoch);
-        const uint32_t* mine = a.peer_flag[a.rank] + (size_t)tid * kMaxGrid + blockIdx.x;
+        st_release_sys(a.peer_flag[tid] + (size_t)a.rank * kMaxGrid + cta, a.epoch);
+        const uint32_t* mine = a.peer_flag[a.rank] + (size_t)tid * kMaxGrid + cta;
         const long long t0 = clock64();
         while (ld_acquire_sys(mine) != a.epoch) {
             __nanosleep(100);
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a)
     // 4. merge W*k -> k per query
     const float* in_s = a.peer_s[a.rank];
     const int64_t* in_i = a.peer_i[a.rank];
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int b = cta; b < a.B; b += n_cta) {
         for (int i = tid; i < a.n_pow2; i += kXThreads) {
             uint32_t ord = 0;
             int64_t id = INT64_MAX;
@@ -124,6 +125,17 @@ __global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a)
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(kXThreads) xchg_merge_kernel(const XchgArgs a) { xchg_body(a, (int)blockIdx.x, (int)gridDim.x); }
+
+// All W ranks of an exchange in ONE cooperative launch (every CTA co-resident): CTAs [r * per_rank, (r + 1) * per_rank) do
+// rank r's work.  Ranks that share a GPU must not run as separate launches -- a kernel spinning on a flag that another
+// launch has yet to write is not guaranteed to ever see that launch scheduled -- so this is how W logical ranks on one
+// device are exercised (tests) or served (several shards of one exchange placed on one GPU).
+__global__ void __launch_bounds__(kXThreads) xchg_merge_all_kernel(const XchgArgs* __restrict__ all, int per_rank) {
+    const int rank = (int)blockIdx.x / per_rank;
+    xchg_body(all[rank], (int)blockIdx.x % per_rank, per_rank);
 }
 
 }  // namespace
@@ -254,16 +266,22 @@ MQVS_API int mqvs_xchg_max_entries(mqvs_xchg_t* x, uint64_t* out) {
     return MQVS_OK;
 }
 
-MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k,
-                             float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+}  // extern "C"
+
+static int xchg_check(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k, float* out_scores_dev,
+                      int64_t* out_ids_dev) {
     using namespace mqvs;
     if (!x || !x->connected) return mqvs_fail(MQVS_E_INVALID, "exchange is not connected");
     if (B < 0 || k < 1 || (uint64_t)B * k > x->cap || (long long)x->world * k > 16384)
         return mqvs_fail(MQVS_E_INVALID, "exchange shape B=%d k=%d exceeds the inbox (%llu entries)", B, k, (unsigned long long)x->cap);
-    if (B == 0) return MQVS_OK;
-    if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev) return mqvs_fail(MQVS_E_INVALID, "NULL buffer");
-    cudaError_t e = cudaSetDevice(x->device);
-    if (e != cudaSuccess) return mqvs_fail(MQVS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (B && (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev)) return mqvs_fail(MQVS_E_INVALID, "NULL buffer");
+    return MQVS_OK;
+}
+
+// argument block of this rank's next call (advances its epoch)
+static mqvs::XchgArgs xchg_args(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k, float* out_scores_dev,
+                                int64_t* out_ids_dev) {
+    using namespace mqvs;
     const uint32_t epoch = ++x->epoch;
     const int parity = (int)(epoch & 1u);
     XchgArgs a{};
@@ -283,6 +301,20 @@ MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int6
     a.epoch = epoch;
     a.out_s = out_scores_dev;
     a.out_i = out_ids_dev;
+    return a;
+}
+
+extern "C" {
+
+MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int64_t* ids_dev, int B, int k,
+                             float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    using namespace mqvs;
+    int rc = xchg_check(x, scores_dev, ids_dev, B, k, out_scores_dev, out_ids_dev);
+    if (rc != MQVS_OK) return rc;
+    if (B == 0) return MQVS_OK;
+    cudaError_t e = cudaSetDevice(x->device);
+    if (e != cudaSuccess) return mqvs_fail(MQVS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    const XchgArgs a = xchg_args(x, scores_dev, ids_dev, B, k, out_scores_dev, out_ids_dev);
     // every CTA must be able to run without waiting for another CTA of this grid to retire (CTA i waits for the peers'
     // CTA i): keep the grid within what is resident at once
     int grid = B < x->sm_count * 8 ? B : x->sm_count * 8;
@@ -292,6 +324,53 @@ MQVS_API int mqvs_xchg_merge(mqvs_xchg_t* x, const float* scores_dev, const int6
     xchg_merge_kernel<<<grid, kXThreads, smem, (cudaStream_t)cuda_stream>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return mqvs_fail(MQVS_E_CUDA, "xchg_merge_kernel launch: %s", cudaGetErrorString(e));
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_xchg_merge_colocated(mqvs_xchg_t* const* ranks, int W, const float* const* scores_dev,
+                                       const int64_t* const* ids_dev, int B, int k, float* const* out_scores_dev,
+                                       int64_t* const* out_ids_dev, void* cuda_stream) {
+    using namespace mqvs;
+    if (!ranks || W < 2 || W > kMaxWorld || !scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev)
+        return mqvs_fail(MQVS_E_INVALID, "need the 2..%d ranks of one exchange and their buffers", kMaxWorld);
+    for (int r = 0; r < W; ++r) {
+        if (!ranks[r] || ranks[r]->world != W || ranks[r]->rank != r || ranks[r]->device != ranks[0]->device)
+            return mqvs_fail(MQVS_E_INVALID, "rank %d: the exchanges must be ranks 0..W-1 of one world on one device", r);
+        int rc = xchg_check(ranks[r], scores_dev[r], ids_dev[r], B, k, out_scores_dev[r], out_ids_dev[r]);
+        if (rc != MQVS_OK) return rc;
+    }
+    if (B == 0) return MQVS_OK;
+    cudaError_t e = cudaSetDevice(ranks[0]->device);
+    if (e != cudaSuccess) return mqvs_fail(MQVS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    XchgArgs host[kMaxWorld];
+    for (int r = 0; r < W; ++r) host[r] = xchg_args(ranks[r], scores_dev[r], ids_dev[r], B, k, out_scores_dev[r], out_ids_dev[r]);
+    XchgArgs* dev = nullptr;
+    e = cudaMalloc(&dev, sizeof(XchgArgs) * W);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev, host, sizeof(XchgArgs) * W, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (dev) cudaFree(dev);
+        return mqvs_fail(MQVS_E_CUDA, "argument upload failed: %s", cudaGetErrorString(e));
+    }
+    const size_t smem = (size_t)host[0].n_pow2 * (sizeof(int64_t) + sizeof(uint32_t));
+    if (smem > 48 * 1024) cudaFuncSetAttribute(xchg_merge_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xchg_merge_all_kernel, kXThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    int per_rank = ranks[0]->sm_count * occ / W;  // the whole grid must be resident at once (cooperative launch)
+    if (per_rank > B) per_rank = B;
+    if (per_rank > kMaxGrid) per_rank = kMaxGrid;
+    if (per_rank < 1) {
+        cudaFree(dev);
+        return mqvs_fail(MQVS_E_INVALID, "%d ranks do not fit on the device at once", W);
+    }
+    void* args[] = {(void*)&dev, (void*)&per_rank};
+    e = cudaLaunchCooperativeKernel((const void*)xchg_merge_all_kernel, dim3(per_rank * W), dim3(kXThreads), args, smem, (cudaStream_t)cuda_stream);
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)cuda_stream);  // `dev` is freed below; this entry point is not a hot path
+    cudaFree(dev);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        cudaGetLastError();
+        return mqvs_fail(MQVS_E_CUDA, "xchg_merge_all_kernel: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
     return MQVS_OK;
 }
 

@@ -118,6 +118,14 @@ class OracleIndex:
                 self.norms = np.load(f)[: len(self)]
             self._dev = float(np.abs(self.norms - np.float32(1.0)).max()) if len(self.norms) else 0.0
 
+    def compact(self, keep_words):
+        n = len(self)
+        keep = ((np.asarray(keep_words, np.uint32)[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+        self.rows = self.rows[keep]
+        if self.norms is not None:
+            self.norms = self.norms[keep]
+        return len(self)
+
     def close(self):
         pass
 

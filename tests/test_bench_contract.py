@@ -38,11 +38,22 @@ def test_cpu_sample_rows_is_bounded_and_never_exceeds_the_corpus():
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "20000",
-                          "--batch", "4", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+                          "--batch", "4", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "config2" in line["config"]["workload"]
+    # the default workload is config 4 at every N (one workload across the scaling curve), steps / warm-up as asked for
+    assert "config4" in line["config"]["workload"] and line["steps"] == 2
+    assert set(line["config"]) == {"workload", "batch", "k", "rows", "store_dtype", "space"}
+
+
+def test_both_arms_print_the_same_config_block():
+    """The driver compares the `config` of the two arms: both come from one function."""
+    b = load_bench()
+    import argparse
+    args = argparse.Namespace(batch=64, space="cosine")
+    cfg = b.shared_config(args, b.WORKLOADS["c4"])
+    assert cfg["rows"] == 100_000_000 and cfg["batch"] == 64 and cfg["store_dtype"] == "bf16"

@@ -413,6 +413,15 @@ def test_device_side_repair_on_the_async_path_and_host_repair_beyond_its_capacit
     torch.cuda.synchronize()
     assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es[:40], ei[:40])
     assert idx.stats()["unrepaired"] == 0
+    # async, MORE flagged queries than one device repair round takes: the rounds are sized to the batch, so the asynchronous
+    # search is exact on its own (nothing is left for a host that is not looking)
+    qd = torch.from_numpy(q).cuda()
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    idx.search_device(qd, k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    assert idx.stats()["unrepaired"] == 0
 
 
 def test_hypothesis_random_shapes_tensor_path(gpu):
@@ -541,17 +550,17 @@ def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segment
 
 @pytest.mark.parametrize("W,B,k", [(2, 1, 10), (4, 37, 10), (8, 100, 10), (3, 5, 100)])
 def test_peer_exchange_kernel_equals_merge_of_gathered_candidates(gpu, W, B, k):
-    """mqvs_xchg_merge (candidate exchange through peer inboxes + merge, one kernel per rank) against
-    mqvs_merge_candidates on the gathered candidates and the oracle merge.  W logical ranks share this one GPU (one
-    stream each, inboxes connected by pointer), so the kernels really wait for each other's flags; ties across ranks
-    (equal scores) must resolve to the lower global id; repeated calls exercise the parity double-buffering."""
+    """The peer exchange kernel (candidate exchange through peer inboxes + flags + merge) against mqvs_merge_candidates on the
+    gathered candidates and the oracle merge.  W logical ranks share this one GPU, inboxes connected by pointer; all
+    ranks run in ONE cooperative launch (mqvs_xchg_merge_colocated: kernels that spin on each other's flags must not be
+    separate launches on one device), so the CTAs really wait for each other's flags; ties across ranks (equal scores)
+    must resolve to the lower global id; repeated calls exercise the parity double-buffering."""
     import torch
     M = native()
     ex = [M._native.PeerExchange(0, r, W, max_entries=4096) for r in range(W)]
     try:
         for e in ex:
             e.connect_ptrs([x.base for x in ex])
-        streams = [torch.cuda.Stream() for _ in range(W)]
         rng = np.random.default_rng(W * 1000 + B)
         for call in range(3):
             sc = np.sort(rng.integers(0, 50, size=(W, B, k)).astype(np.float32) / 7.0, axis=2)[:, :, ::-1].copy()  # many ties
@@ -563,8 +572,7 @@ def test_peer_exchange_kernel_equals_merge_of_gathered_candidates(gpu, W, B, k):
             o_s = [torch.empty((B, k), dtype=torch.float32, device="cuda") for _ in range(W)]
             o_i = [torch.empty((B, k), dtype=torch.int64, device="cuda") for _ in range(W)]
             torch.cuda.synchronize()
-            for r in range(W):
-                ex[r].merge(d_s[r], d_i[r], o_s[r], o_i[r], stream=streams[r].cuda_stream)
+            M._native.PeerExchange.merge_colocated(ex, d_s, d_i, o_s, o_i, stream=torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             es, ei = O.merge_topk(sc.transpose(1, 0, 2).reshape(B, W * k), ids.transpose(1, 0, 2).reshape(B, W * k), k)
             g_s, g_i = torch.empty_like(o_s[0]), torch.empty_like(o_i[0])
@@ -1020,3 +1028,228 @@ def test_full_size_config2_in_the_l2_and_ip_spaces_properties(gpu, space):
     for b in range(B):  # the sample's best row is either in the result or no better than its k-th entry
         assert si[b, 0] in i[b] or ss[b, 0] <= s[b, k - 1]
     assert np.array_equal(idx.get_norms(lo, 1000).view(np.uint32), O.row_norms(sample[:1000], 768).view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- one handle, several shards
+MULTI_CASES = [
+    # W, n, dtype, B, k, mask fraction
+    (2, 20000, "fp32", 9, 10, None),       # SIMT scans in every shard
+    (3, 9000, "bf16", 3, 5, 0.3),          # latency kernel per shard, a shard with a partial block, mask
+    (8, 5000, "fp32", 4, 10, None),        # more shards than blocks: empty shards
+    (2, 140001, "bf16", 64, 10, None),     # single-launch tensor pipeline per shard (half-height query tiles)
+    (3, 250000, "fp32", 130, 32, 0.2),     # two query tiles, mask split on block boundaries
+    (4, 300000, "bf16", 300, 10, None),    # segmented pipeline per shard
+    (2, 70000, "bf16", 5, 200, None),      # k > 128
+]
+
+
+@pytest.mark.parametrize("W,n,dtype,B,k,frac", MULTI_CASES)
+def test_multi_device_handle_equals_single_shard_handle_and_oracle(gpu, W, n, dtype, B, k, frac):
+    """mqvs_create(n_dev = W): one handle over W block-cyclic row shards (all on this one GPU here; one per GPU on a
+    box).  Global ids, scores and tie order must be bit-identical to a single-shard handle over the same rows and to
+    the oracle -- through host calls, device calls (mqvs_search_async), get_rows and a device-built filter."""
+    import torch
+    M = native()
+    x = O.synth_rows(0x5EED0007, 0, n, 768)
+    x[n - 7] = x[11]  # a tie that straddles shards: the lower GLOBAL id must win
+    multi = M.Index(768, dtype, device=[0] * W)
+    for a in range(0, n, 33333):  # appended in pieces that end inside blocks
+        assert multi.add(x[a:a + 33333]) == a
+    assert len(multi) == n
+    st, _ = O.normalize_rows(x, dtype, 768)
+    q, planted = O.planted_queries(QSEED, B, 0x5EED0007, n, 768)
+    q[0] = x[11]
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(5).random(n) < frac)
+    es, ei = O.brute_force_topk(qn, st, k, mask)
+    s, i = multi.search(q, k, mask)
+    assert_bit_equal(s, i, es, ei)
+    if frac is None:
+        assert i[0, 0] == 11 and i[0, 1] == n - 7
+    # device buffers on the home device, asynchronous
+    qd = torch.from_numpy(q).cuda()
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    if mask is None:
+        multi.search_device(qd, k, out_s, out_i, id_base=1000, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got_i = out_i.cpu().numpy()
+        assert_bit_equal(out_s.cpu().numpy(), np.where(got_i >= 0, got_i - 1000, got_i), es, ei)
+    rows = np.array([0, 4095, 4096, n - 1, n // 2, 4096 * W + 17 if 4096 * W + 17 < n else 1])
+    assert np.array_equal(multi.get_rows(rows).view(np.uint32), O.stored_as_f32(st)[rows].view(np.uint32))
+    st8 = multi.stats()
+    assert st8["rows"] == n and st8["unrepaired"] == 0
+    # Chroma `where` evaluated on every shard's device; the token goes back into search
+    from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns, evaluate
+    cols = MetadataColumns()
+    cols.extend_columns(n, {"source_id": (np.arange(n) * 7919) % 23, "score": np.linspace(0.0, 1.0, n)})
+    live = np.ones(n, bool)
+    live[[3, 4096, n - 1]] = False
+    where = {"$and": [{"source_id": {"$in": [1, 5, 9, 22]}}, {"score": {"$gte": 0.25}}]}
+    dmask, allowed = DeviceFilter(multi, cols).build(where, live)
+    ok = evaluate(where, cols) & live
+    assert allowed == int(ok.sum())
+    s, i = multi.search(q, min(k, 128), dmask)
+    assert_bit_equal(s, i, *O.brute_force_topk(qn, st, min(k, 128), O.mask_from_bool(ok)))
+    multi.close()
+
+
+def test_multi_device_handle_persistence_is_device_count_independent(gpu, tmp_path):
+    """A row file written by a 3-shard handle opens in a 1-shard and a 2-shard handle (and the other way round), appends
+    included; l2-space norms travel with it."""
+    M = native()
+    n = 30000
+    x = O.synth_rows(0x5EED0008, 0, n, 768) * np.linspace(0.5, 2.0, n, dtype=np.float32)[:, None]
+    q = x[[5, 9000, 29999]] * np.float32(0.9)
+    path = str(tmp_path / "rows.mqvs")
+    a = M.Index(768, "bf16", device=[0, 0, 0])
+    a.set_metric("l2")
+    a.add(x[:20000])
+    a.save(path)
+    a.add(x[20000:])
+    a.save_append(path, 20000)
+    want = a.search(q, 7)
+    es, ei = O.brute_force_topk(O.normalize_rows(q, "fp32", 768)[0], O.normalize_rows(x, "bf16", 768)[0], 7, metric="l2",
+                                norms=O.row_norms(x, 768), q_norms=O.row_norms(q, 768))
+    assert_bit_equal(want[0], want[1], es, ei)
+    for devs in (0, [0, 0]):
+        b = M.Index(768, "bf16", device=devs)
+        b.set_metric("l2")
+        b.load_file(path)
+        assert len(b) == n and abs(b.norm_deviation() - a.norm_deviation()) < 1e-6
+        got = b.search(q, 7)
+        assert_bit_equal(got[0], got[1], es, ei)
+        assert np.array_equal(b.get_norms(4090, 20), a.get_norms(4090, 20))
+        b.close()
+    single = M.Index(768, "bf16")
+    single.set_metric("l2")
+    single.add(x)
+    p2 = str(tmp_path / "single.mqvs")
+    single.save(p2)
+    c = M.Index(768, "bf16", device=[0, 0, 0, 0])
+    c.set_metric("l2")
+    c.load_file(p2)
+    got = c.search(q, 7)
+    assert_bit_equal(got[0], got[1], es, ei)
+    bad = x[:3].copy()
+    bad[1, 0] = np.inf
+    with pytest.raises(M.MqvsError):
+        c.add(bad)          # rejected by one shard: nothing is appended anywhere
+    assert len(c) == n
+    for h in (a, single, c):
+        h.close()
+
+
+def test_vectorstore_over_several_shards_equals_the_unsharded_store(gpu, tmp_path, embedder):
+    """MediQueryVectorStore(devices=[...]): the object the reference constructs (src/medical_engine.py:52) over a
+    sharded corpus -- documents, ids, filters from metadata, tombstones and persistence as on one shard."""
+    from mediquery_rag_b200 import MediQueryVectorStore
+    n = 12000
+    x = O.synth_rows(0x5EED0009, 0, n, 768)
+    texts = [f"chunk {r}" for r in range(n)]
+    metas = [{"title": f"t{r}", "group": r % 7, "tags": "a，b" if r % 2 else "c"} for r in range(n)]
+    stores = {}
+    for name, kw in (("one", dict(device=0)), ("many", dict(devices=[0, 0, 0]))):
+        vs = MediQueryVectorStore(persist_directory=str(tmp_path / name), embedding_function=embedder, **kw)
+        ids = vs.add_embeddings((texts, x), metadatas=metas, ids=[f"id{r}" for r in range(n)])
+        vs.delete(ids[100:140])
+        vs.add_embeddings(([f"again {r}" for r in range(50)], x[200:250]), ids=ids[200:250])  # upsert: old rows die
+        stores[name] = vs
+    q = x[220] + 0.01 * x[5]
+    for filt in (None, {"group": {"$in": [2, 3]}}, {"$and": [{"group": {"$ne": 1}}, {"title": {"$gte": "t5"}}]}):
+        a = stores["one"].similarity_search_with_score("", k=6, filter=filt) if False else stores["one"]._similar(q, 6, filt)
+        b = stores["many"]._similar(q, 6, filt)
+        assert [(d.page_content, d.metadata, d.id) for d, _ in a] == [(d.page_content, d.metadata, d.id) for d, _ in b]
+        assert [s for _, s in a] == [s for _, s in b]
+    assert stores["many"]._similar(q, 1, None)[0][0].page_content == "again 20"
+    again = MediQueryVectorStore(persist_directory=str(tmp_path / "many"), embedding_function=embedder, devices=[0, 0])
+    assert len(again) == len(stores["one"]) == n - 40
+    assert [d.id for d, _ in again._similar(q, 6, {"group": 3})] == [d.id for d, _ in stores["one"]._similar(q, 6, {"group": 3})]
+    # bulk synthetic rows without a Python object per row, through the same object
+    big = MediQueryVectorStore(devices=[0, 0], store_dtype="bf16", collection_metadata={"hnsw:space": "cosine"})
+    big.add_synthetic(0x5EED0004, 100000, metadata_columns={"source_id": np.arange(100000) % 10})
+    qs, planted = O.planted_queries(QSEED, 8, 0x5EED0004, 100000, 768)
+    sc, rows = big.search_batch(qs, 10, filter={"source_id": {"$lt": 5}})
+    st, _ = O.normalize_rows(O.synth_rows(0x5EED0004, 0, 100000, 768), "bf16", 768)
+    es, ei = O.brute_force_topk(O.normalize_rows(qs, "fp32", 768)[0], st, 10, O.mask_from_bool(np.arange(100000) % 10 < 5))
+    assert_bit_equal(sc, rows, es, ei)
+    doc = big.similarity_search_by_vector(qs[0], k=1)[0]
+    assert doc.id == f"row-{planted[0]}" and doc.metadata == {"source_id": int(planted[0] % 10)}
+
+
+def test_filtered_searches_from_several_threads_do_not_share_a_mask(gpu, embedder):
+    """The handle's device-built filter mask is one buffer: the store holds its lock across build + search, so concurrent
+    filtered searches (the a* coroutines run in worker threads) each see their own filter."""
+    import threading
+    from mediquery_rag_b200 import MediQueryVectorStore
+    n = 30000
+    x = O.synth_rows(0x5EED000A, 0, n, 768)
+    vs = MediQueryVectorStore()
+    vs.add_embeddings(([None] * n, x), metadata_columns={"g": np.arange(n) % 5})
+    q = O.synth_rows(99, 0, 4, 768)
+    want = {g: vs.search_batch(q, 10, filter={"g": g})[1] for g in range(5)}
+    errors = []
+
+    def worker(g):
+        for _ in range(20):
+            rows = vs.search_batch(q, 10, filter={"g": g})[1]
+            if not np.array_equal(rows, want[g]) or not ((rows % 5) == g).all():
+                errors.append(g)
+
+    th = [threading.Thread(target=worker, args=(g,)) for g in range(5)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors
+
+
+def test_tombstone_compaction_keeps_rows_bit_for_bit(gpu, tmp_path):
+    from mediquery_rag_b200 import MediQueryVectorStore
+    M = native()
+    n = 40000
+    x = O.synth_rows(0x5EED000B, 0, n, 768) * np.float32(1.7)
+    for dtype in ("fp32", "bf16"):
+        idx = M.Index(768, dtype)
+        idx.set_metric("l2")
+        idx.add(x)
+        keep = np.random.default_rng(3).random(n) < 0.4
+        keep[:5000] = True          # a long prefix that stays where it is
+        before = idx.get_rows(np.flatnonzero(keep))
+        norms = idx.get_norms()[keep]
+        assert idx.compact(O.mask_from_bool(keep)) == int(keep.sum()) == len(idx)
+        assert np.array_equal(idx.get_rows(np.arange(len(idx))).view(np.uint32), before.view(np.uint32))
+        assert np.array_equal(idx.get_norms(), norms)
+        q = x[np.flatnonzero(keep)[[7, 9000]]]
+        s, i = idx.search(q, 5)
+        xs = x[keep]
+        es, ei = O.brute_force_topk(O.normalize_rows(q, "fp32", 768)[0], O.normalize_rows(xs, dtype, 768)[0], 5, metric="l2",
+                                    norms=O.row_norms(xs, 768), q_norms=O.row_norms(q, 768))
+        assert_bit_equal(s, i, es, ei)
+        idx.close()
+    # the store compacts by itself once most rows are dead, and the directory reopens
+    vs = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"})
+    ids = vs.add_embeddings(([f"c{r}" for r in range(3000)], x[:3000]))
+    vs.delete(ids[:2000])
+    assert len(vs._ids) == 1000 and len(vs) == 1000 and len(vs._index) == 1000
+    assert vs.similarity_search_by_vector(x[2500], k=1)[0].page_content == "c2500"
+    re = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"})
+    assert len(re) == 1000 and re.similarity_search_by_vector(x[2999], k=1)[0].id == ids[2999]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_host_ingest_pipeline_is_bit_exact_over_many_chunks(gpu, dtype):
+    """mqvs_add from host memory streams 8192-row chunks through two staging slots (pageable rows bounced through pinned
+    buffers by host threads, pinned rows copied from where they lie): same stored bits as the oracle's K1 either way."""
+    import torch
+    n = 30000
+    x = O.synth_rows(0x5EED000C, 0, n, 768) * np.float32(2.5)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    want = O.stored_as_f32(st)
+    for src in (x, torch.from_numpy(x).pin_memory().numpy()):
+        idx = native().Index(768, dtype)
+        idx.add(src[:100])
+        idx.add(src[100:])
+        probe = np.r_[0:50, 8150:8250, 16380:16400, n - 30:n]
+        assert np.array_equal(idx.get_rows(probe).view(np.uint32), want[probe].view(np.uint32))
+        idx.close()

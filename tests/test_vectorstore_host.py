@@ -271,3 +271,73 @@ def test_similarity_search_with_vectors_and_reset_collection(embedder, tmp_path)
     vs.add_texts(["again"], ids=["0"])
     assert [d.page_content for d in vs.similarity_search("again", k=2)] == ["again"]
     assert len(MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex, persist_directory=db)) == 1
+
+
+def test_collections_sharing_a_persist_directory_do_not_touch_each_other(tmp_path, medical_docs, embedder):
+    """Chroma keeps several collections in one persist_directory; opening, persisting or deleting one must leave the
+    others alone (every collection owns `mqvs.<name>/`)."""
+    import os
+    db = str(tmp_path / "db")
+    docs = make_docs(medical_docs, 12)
+    a = MediQueryVectorStore.from_documents(docs[:8], embedder, collection_name="alpha", persist_directory=db, index_factory=OracleIndex)
+    b = MediQueryVectorStore(collection_name="beta", persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(b) == 0 and a.collection_path != b.collection_path
+    b.add_documents(docs[8:12])
+    assert len(MediQueryVectorStore(collection_name="alpha", persist_directory=db, embedding_function=embedder,
+                                    index_factory=OracleIndex)) == 8
+    b.delete_collection()
+    assert not os.path.exists(os.path.join(b.collection_path, "manifest.json"))
+    again = MediQueryVectorStore(collection_name="alpha", persist_directory=db, embedding_function=embedder, index_factory=OracleIndex)
+    assert len(again) == 8 and again.similarity_search(docs[3].page_content, k=1)[0].page_content == docs[3].page_content
+    # a directory of the older layout (files at the top level) belongs to the collection named in its manifest only
+    old = str(tmp_path / "old")
+    legacy = MediQueryVectorStore.from_documents(docs[:5], embedder, persist_directory=old, index_factory=OracleIndex)
+    for f in os.listdir(legacy.collection_path):
+        os.replace(os.path.join(legacy.collection_path, f), os.path.join(old, f))
+    os.rmdir(legacy.collection_path)
+    assert len(MediQueryVectorStore(persist_directory=old, embedding_function=embedder, index_factory=OracleIndex)) == 5
+    other = MediQueryVectorStore(collection_name="other", persist_directory=old, embedding_function=embedder, index_factory=OracleIndex)
+    other.add_documents(docs[5:7])
+    assert len(other) == 2
+    assert len(MediQueryVectorStore(persist_directory=old, embedding_function=embedder, index_factory=OracleIndex)) == 5
+
+
+def test_a_directory_written_by_real_chroma_is_reported_not_silently_empty(tmp_path, medical_docs, embedder):
+    import warnings
+    db = tmp_path / "medical_db"
+    db.mkdir()
+    (db / "chroma.sqlite3").write_bytes(b"SQLite format 3\0")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        vs = MediQueryVectorStore(persist_directory=str(db), embedding_function=embedder, index_factory=OracleIndex)
+    assert any("re-run src/ingest_medical.py" in str(x.message) for x in w)
+    with pytest.raises(RuntimeError, match="chromadb"):
+        vs.similarity_search("高血压", k=5)
+    docs = make_docs(medical_docs, 6)
+    vs.add_documents(docs)  # re-running the ingest (src/ingest_medical.py:106) fills the collection: searches work again
+    assert vs.similarity_search(docs[2].page_content, k=1)[0].page_content == docs[2].page_content
+
+
+def test_bulk_rows_with_implicit_ids_and_tombstone_compaction(tmp_path, embedder):
+    vs = MediQueryVectorStore(index_factory=OracleIndex, dim=768, collection_metadata={"hnsw:space": "cosine"})
+    rows = vs.add_synthetic(0x5EED0002, 5000, metadata_columns={"g": np.arange(5000) % 3})
+    assert rows == range(0, 5000) and len(vs) == 5000 and len(vs._ids._runs) == 1
+    q, planted = O.planted_queries(0x0BADC0DE, 2, 0x5EED0002, 5000, 768)
+    doc = vs.similarity_search_by_vector(q[0], k=1)[0]
+    assert doc.id == f"row-{planted[0]}" and doc.metadata == {"g": int(planted[0] % 3)} and doc.page_content == ""
+    assert vs.get(ids=[f"row-{planted[0]}", "row-99999", "nope"])["ids"] == [f"row-{planted[0]}"]
+    vs.delete([f"row-{planted[0]}"])
+    assert vs.similarity_search_by_vector(q[0], k=1)[0].id != f"row-{planted[0]}" and len(vs) == 4999
+    more = vs.add_embeddings(([f"t{i}" for i in range(3)], O.synth_rows(5, 0, 3, 768)), ids=["x", "y", "z"])
+    assert more == ["x", "y", "z"] and vs.get(ids=["y"])["documents"] == ["t1"] and len(vs) == 5002
+    # compaction: rows renumbered, string ids stay, results unchanged
+    before = [d.id for d in vs.similarity_search_by_vector(q[1], k=5)]
+    vs.delete([f"row-{r}" for r in range(0, 5000, 2)])
+    kept = [d.id for d in vs.similarity_search_by_vector(q[1], k=5)]
+    dead = 2500 + int(planted[0] % 2 == 1)
+    assert vs.compact() == dead and len(vs._index) == len(vs) == 5003 - dead
+    assert [d.id for d in vs.similarity_search_by_vector(q[1], k=5)] == kept
+    assert [i for i in before if int(i.split("-")[1]) % 2 == 1] == kept[:sum(int(i.split("-")[1]) % 2 == 1 for i in before)]
+    assert vs.get(ids=["z"])["documents"] == ["t2"] and vs.get(ids=["row-0"])["ids"] == []
+    sc, rid = vs.search_batch(q, 3, filter={"g": 1})
+    assert all(vs._cols.row(int(r))["g"] == 1 for r in rid.ravel())

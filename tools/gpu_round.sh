@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call's worth of checks; every step logs to gpurun_out/ and the script goes on whatever fails.
+#   tools/gpu_round.sh [tag] [steps...]   steps: tests bench c2cmp ingest  (default: all)
+cd "$(dirname "$0")/.." || exit 1
+TAG=${1:-r02}; shift
+STEPS=${*:-tests bench c2cmp ingest}
+OUT=gpurun_out; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > $OUT/${TAG}_smi.txt 2>&1
+for s in $STEPS; do
+  case $s in
+    tests)  timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 --timeout 600 -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "tests rc=$?" ;;
+    bench)  timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?" ;;
+    c2cmp)  for v in half full; do
+              if [ $v = full ]; then export MQVS_NO_HALF_TILE=1; else unset MQVS_NO_HALF_TILE; fi
+              timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,128 --steps 30 --warmup 5 \
+                  > $OUT/${TAG}_bench_c2_${v}.json 2> $OUT/${TAG}_bench_c2_${v}.err; echo "c2 $v rc=$?"
+              timeout 300 python bench.py --workload c4 --rows 12500000 --no-secondary --no-cpu-baseline --points 1,128,256,1024 --steps 20 --warmup 5 \
+                  > $OUT/${TAG}_bench_c4shard_${v}.json 2> $OUT/${TAG}_bench_c4shard_${v}.err; echo "c4 shard $v rc=$?"
+            done; unset MQVS_NO_HALF_TILE ;;
+    ingest) timeout 300 python tools/ingest_check.py 1000000 > $OUT/${TAG}_ingest.log 2>&1; echo "ingest rc=$?"; cp $OUT/ingest_check.json $OUT/${TAG}_ingest_check.json 2>/dev/null ;;
+    smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
+  esac
+done
+tail -5 $OUT/${TAG}_pytest_gpu.log 2>/dev/null

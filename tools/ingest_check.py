@@ -21,12 +21,21 @@ for dtype in ("fp32", "bf16"):
                     rows_per_s=round(n / dt)))
     print(out[-1], flush=True)
     idx.close()
-x_host = x_dev[: n // 4].cpu().numpy()
-idx = M.Index(768, "bf16", capacity_rows=n)
-t0 = time.perf_counter(); idx.add(x_host); dt = time.perf_counter() - t0
-out.append(dict(path="host (pageable) input", store="bf16", rows=n // 4, ms=round(dt * 1e3, 1), rows_per_s=round(n / 4 / dt),
-                h2d_gbps=round(n / 4 * 3072 / dt / 1e9, 2)))
-print(out[-1])
+m = n // 2
+x_host = x_dev[:m].cpu().numpy()
+x_pin = torch.empty((m, 768), dtype=torch.float32).pin_memory()
+x_pin.copy_(torch.from_numpy(x_host))
+for name, src in (("host (pageable) input", x_host), ("host (pinned) input", x_pin.numpy())):
+    for devices in ([0], [0, 0]):  # one shard; two logical shards (one host thread per shard)
+        idx = M.Index(768, "bf16", device=devices, capacity_rows=n)
+        idx.add(src[:1000])
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter(); idx.add(src); best = min(best, time.perf_counter() - t0)
+        out.append(dict(path=name, shards=len(devices), store="bf16", rows=m, ms=round(best * 1e3, 1), rows_per_s=round(m / best),
+                        h2d_gbps=round(m * 3072 / best / 1e9, 2)))
+        print(out[-1], flush=True)
+        idx.close()
 idx2 = M.Index(768, "bf16", capacity_rows=100_000_000 // 8)
 t0 = time.perf_counter(); idx2.add_synthetic(1, 0, 100_000_000 // 8); dt = time.perf_counter() - t0
 out.append(dict(path="device generator + K1 (bench configs)", store="bf16", rows=100_000_000 // 8, ms=round(dt * 1e3, 1), rows_per_s=round(12.5e6 / dt)))

@@ -38,13 +38,13 @@ W, B, k = 3, 20, 10
 ex = [M._native.PeerExchange(0, r, W, max_entries=1024) for r in range(W)]
 for e in ex:
     e.connect_ptrs([y.base for y in ex])
-st = [torch.cuda.Stream() for _ in range(W)]
 sc = [torch.rand((B, k), device="cuda").sort(dim=1, descending=True).values for _ in range(W)]
 ids = [(torch.arange(B * k, device="cuda").view(B, k) * W + r) for r in range(W)]
 outs = [(torch.empty((B, k), device="cuda"), torch.empty((B, k), dtype=torch.int64, device="cuda")) for _ in range(W)]
 torch.cuda.synchronize()
-for r in range(W):
-    ex[r].merge(sc[r], ids[r], outs[r][0], outs[r][1], stream=st[r].cuda_stream)
+# all ranks in ONE cooperative launch: kernels that spin on each other's flags must not be separate launches on one GPU
+M._native.PeerExchange.merge_colocated(ex, sc, ids, [o[0] for o in outs], [o[1] for o in outs],
+                                       stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 print("xchg", bool(torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][1], outs[2][1])))
 for e in ex:
