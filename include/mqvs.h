@@ -160,8 +160,8 @@ MQVS_API void mqvs_xchg_destroy(mqvs_xchg_t* x);
  * takes (mask_is_device = 1) without the mask ever visiting the host.  Semantics as Chroma's: a row whose field is
  * missing matches only $ne / $nin.  live_words (host, ceil(rows/32) words, nullable) is AND-ed in (tombstones). */
 enum { MQVS_OP_EQ = 0, MQVS_OP_NE = 1, MQVS_OP_GT = 2, MQVS_OP_GTE = 3, MQVS_OP_LT = 4, MQVS_OP_LTE = 5, MQVS_OP_IN = 6,
-       MQVS_OP_NIN = 7, MQVS_OP_AND = 16, MQVS_OP_OR = 17 };
-enum { MQVS_COL_I64 = 0, MQVS_COL_F64 = 1 };
+       MQVS_OP_NIN = 7, MQVS_OP_CONTAINS = 8, MQVS_OP_NOT_CONTAINS = 9, MQVS_OP_AND = 16, MQVS_OP_OR = 17 };
+enum { MQVS_COL_I64 = 0, MQVS_COL_F64 = 1, MQVS_COL_TOKENS = 2 };
 typedef struct mqvs_filter_op {
     int32_t op;        /* MQVS_OP_* */
     int32_t col;       /* leaves: column id given to mqvs_column_set */
@@ -174,6 +174,12 @@ typedef struct mqvs_filter_op {
  * Replaces column col_id (0..63).  n may be smaller than the row count: later rows count as "field missing". */
 MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
                              uint64_t n);
+/* Token-set columns: the reference stores `tags` as ONE comma-joined string per chunk (src/ingest_medical.py:66-67,75-79:
+ * "慢性病，代谢性疾病，发病率"), so a per-tag filter is set membership, not string equality.  The host tokenises (on "," and
+ * "，"), assigns token ids from a dictionary and uploads the rows' token lists in CSR form: tokens of row r are
+ * tokens_host[offsets_host[r] .. offsets_host[r + 1]).  Leaves MQVS_OP_CONTAINS / MQVS_OP_NOT_CONTAINS test ival (a token id;
+ * -1 = a token no row carries) against a row's list; a row without tokens matches only NOT_CONTAINS. */
+MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
 /* prog: n_ops <= 64 operations in postfix order; pool: pool_len 8-byte constants (int64 or float64 bit patterns) the
  * $in / $nin leaves point into.  *mask_dev_out is owned by the handle and valid until the next mqvs_filter_build.
  * Multi-device handles evaluate every shard's slice on its own device; *mask_dev_out is then an opaque token for

@@ -27,8 +27,9 @@ class FilterOp(ctypes.Structure):
                 ("set_off", ctypes.c_uint32), ("set_len", ctypes.c_uint32)]
 
 
-OP = {"$eq": 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5, "$in": 6, "$nin": 7, "$and": 16, "$or": 17}
-COL_I64, COL_F64 = 0, 1
+OP = {"$eq": 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5, "$in": 6, "$nin": 7, "$contains": 8, "$not_contains": 9,
+      "$and": 16, "$or": 17}
+COL_I64, COL_F64, COL_TOKENS = 0, 1, 2
 
 
 class DeviceMask:
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mqvs_norm_deviation": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "mqvs_get_norms": (_i, [_vp, _u64, _u64, _vp]),
     "mqvs_column_set": (_i, [_vp, _i, _i, _vp, _vp, _u64]),
+    "mqvs_column_set_tokens": (_i, [_vp, _i, _vp, _vp, _u64]),
     "mqvs_filter_build": (_i, [_vp, _vp, _i, _vp, _u64, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "mqvs_shard_of_row": (_i, [_i, _u64, ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
     "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
@@ -275,6 +277,14 @@ class Index:
             raise ValueError("device columns are int64 or float64")
         pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
         check(load().mqvs_column_set(self._h, int(col_id), ctype, _ptr(values), _ptr(pres), values.shape[0]))
+
+    def column_set_tokens(self, col_id: int, offsets: np.ndarray, tokens: np.ndarray) -> None:
+        """Upload a token-set column (comma-joined `tags`): CSR offsets [n + 1] (uint64) and token ids (int64)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        tokens = np.ascontiguousarray(tokens, dtype=np.int64)
+        if offsets.ndim != 1 or offsets.shape[0] < 1 or int(offsets[-1]) != tokens.shape[0]:
+            raise ValueError("offsets must be [n + 1] and end at len(tokens)")
+        check(load().mqvs_column_set_tokens(self._h, int(col_id), _ptr(offsets), _ptr(tokens), offsets.shape[0] - 1))
 
     def filter_build(self, ops, pool: Optional[np.ndarray] = None, live_words: Optional[np.ndarray] = None):
         """ops: list of FilterOp in postfix order -> (DeviceMask, number of allowed rows)."""

@@ -33,7 +33,8 @@ using mqvs::elem_size;
 namespace mqvs {
 namespace api {
 
-constexpr int kMaxFixRound = 256;  // capacity of the device-side repair list (flagged queries per exact-scan round)
+constexpr int kMaxFixRound = 256;
+constexpr int kWideChunk = 256;    // queries per pass of a k > 128 search (the single-launch tensor pipeline's two query tiles)  // capacity of the device-side repair list (flagged queries per exact-scan round)
 
 int grow(mqvs_store* s, uint64_t need_rows) {
     if (need_rows <= s->cap) return MQVS_OK;
@@ -101,7 +102,9 @@ void settle_events(mqvs_store* s) {
 // Tensor-core path is worth it once the batch amortises its fixed launches and the corpus fills the machine.
 static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     if (s->path == 1 || s->path == 3) return false;
-    if (k > 128 || s->n < 4096) return false;
+    if (s->n < 4096) return false;
+    // k > 128: wide shortlists exist in the single-launch pipeline only (larger batches run it 256 queries at a time)
+    if (k > 128 && (s->path == 4 || !s->coop_ok || !mqvs::tc::fused_ok(1, k, s->sm_count))) return false;
     if (s->path == 2 || s->path == 4) return true;
     // measured on B200 (profiles/r01_*): the register-resident SIMT scan holds the HBM roofline for 1 query (bf16 rows)
     // or 1-2 queries (fp32 rows); beyond that its multi-query variants fall to 2-3.4 TB/s while the tensor path streams
@@ -465,6 +468,7 @@ void destroy_single(mqvs_store* s) {
     for (auto& c : s->columns) {
         c.values.release();
         c.present.release();
+        c.offsets.release();
     }
     for (DevBuf* b : {&s->f_table, &s->f_prog, &s->f_pool, &s->f_live, &s->f_mask}) b->release();
     if (s->f_count_dev) cudaFree(s->f_count_dev);
@@ -696,6 +700,16 @@ MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int 
     int rc = check_search_args(s, q, B, k, out_scores, out_ids);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
+    if (k > 128 && B > kWideChunk) {
+        // wide shortlists (k > 128) live in the single-launch pipeline, which takes up to 256 queries: larger batches go
+        // through it 256 at a time (one corpus pass per 256 queries; the SIMT scan this replaces took 1-4 per pass)
+        for (int b0 = 0; b0 < B; b0 += kWideChunk) {
+            rc = mqvs_search(s, q + (size_t)b0 * s->dim, q_is_device, std::min(kWideChunk, B - b0), k, mask, mask_is_device,
+                             out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, out_is_device);
+            if (rc != MQVS_OK) return rc;
+        }
+        return MQVS_OK;
+    }
     if (s->multi)
         return multi_search(s, q, q_is_device, B, k, mask, mask_is_device, 0, out_scores, out_ids, out_is_device, nullptr, true);
     std::lock_guard<std::mutex> lk(s->mu);
@@ -811,6 +825,14 @@ MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, cons
     int rc = check_search_args(s, q_dev, B, k, out_scores_dev, out_ids_dev);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
+    if (k > 128 && B > kWideChunk) {
+        for (int b0 = 0; b0 < B; b0 += kWideChunk) {
+            rc = mqvs_search_async(s, q_dev + (size_t)b0 * s->dim, std::min(kWideChunk, B - b0), k, mask_dev, id_base,
+                                   out_scores_dev + (size_t)b0 * k, out_ids_dev + (size_t)b0 * k, cuda_stream);
+            if (rc != MQVS_OK) return rc;
+        }
+        return MQVS_OK;
+    }
     if (s->multi)
         return multi_search(s, q_dev, 1, B, k, mask_dev, 1, id_base, out_scores_dev, out_ids_dev, 1, (cudaStream_t)cuda_stream, false);
     std::lock_guard<std::mutex> lk(s->mu);
@@ -1046,6 +1068,19 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     return MQVS_OK;
 }
 
+MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
+    if (!offsets_host) return fail(MQVS_E_INVALID, "offsets is NULL");
+    if (offsets_host[0] != 0) return fail(MQVS_E_INVALID, "offsets must start at 0");
+    for (uint64_t r = 0; r < n; ++r)
+        if (offsets_host[r + 1] < offsets_host[r]) return fail(MQVS_E_INVALID, "offsets must not decrease (row %llu)", (unsigned long long)r);
+    if (offsets_host[n] && !tokens_host) return fail(MQVS_E_INVALID, "tokens is NULL");
+    if (s->multi) return multi_column_set_tokens(s, col_id, offsets_host, tokens_host, n);
+    std::lock_guard<std::mutex> lk(s->mu);
+    return column_set_tokens_single(s, col_id, offsets_host, tokens_host, n);
+}
+
 MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out) {
     if (!s || !keep_words_host || !new_count_out) return fail(MQVS_E_INVALID, "NULL argument");
     if (s->multi)
@@ -1116,6 +1151,24 @@ MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* va
 
 }  // extern "C"
 
+int mqvs::api::column_set_tokens_single(mqvs_store* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n) {
+    CU(cudaSetDevice(s->dev));
+    auto& c = s->columns[col_id];
+    int rc;
+    const uint64_t nnz = offsets_host[n];
+    if ((rc = c.offsets.ensure((n + 1) * 8)) != MQVS_OK) return rc;
+    if ((rc = c.values.ensure(std::max<uint64_t>(nnz, 1) * 8)) != MQVS_OK) return rc;
+    CU(cudaMemcpyAsync(c.offsets.p, offsets_host, (n + 1) * 8, cudaMemcpyHostToDevice, s->st));
+    if (nnz) CU(cudaMemcpyAsync(c.values.p, tokens_host, nnz * 8, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    c.n = n;
+    c.type = MQVS_COL_TOKENS;
+    c.used = true;
+    c.has_present = false;
+    s->f_table_dirty = true;
+    return MQVS_OK;
+}
+
 int mqvs::api::column_set_single(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
                                  uint64_t n) {
     CU(cudaSetDevice(s->dev));
@@ -1167,9 +1220,12 @@ int mqvs::api::filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, in
         if (o.op == MQVS_OP_AND || o.op == MQVS_OP_OR) {
             if (depth < 2) return fail(MQVS_E_INVALID, "filter program: operator %d at %d lacks operands", o.op, i);
             --depth;
-        } else if (o.op >= MQVS_OP_EQ && o.op <= MQVS_OP_NIN) {
+        } else if (o.op >= MQVS_OP_EQ && o.op <= MQVS_OP_NOT_CONTAINS) {
             if (o.col < 0 || o.col >= kFilterMaxCols || !s->columns[o.col].used)
                 return fail(MQVS_E_INVALID, "filter program: column %d was never set", o.col);
+            const bool token_op = o.op == MQVS_OP_CONTAINS || o.op == MQVS_OP_NOT_CONTAINS;
+            if (token_op != (s->columns[o.col].type == MQVS_COL_TOKENS))
+                return fail(MQVS_E_INVALID, "filter program: operation %d does not fit the type of column %d", o.op, o.col);
             if ((o.op == MQVS_OP_IN || o.op == MQVS_OP_NIN) && (uint64_t)o.set_off + o.set_len > pool_len)
                 return fail(MQVS_E_INVALID, "filter program: set of operation %d leaves the constant pool", i);
             if (++depth > 32) return fail(MQVS_E_INVALID, "filter program nests deeper than 32");
@@ -1188,7 +1244,8 @@ int mqvs::api::filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, in
         FilterColumn table[kFilterMaxCols];
         for (int i = 0; i < kFilterMaxCols; ++i) {
             const auto& c = s->columns[i];
-            table[i] = FilterColumn{c.values.p, c.has_present ? (const uint32_t*)c.present.p : nullptr, c.used ? c.n : 0, c.type};
+            table[i] = FilterColumn{c.values.p, c.has_present ? (const uint32_t*)c.present.p : nullptr, c.used ? c.n : 0, c.type,
+                                    (const uint64_t*)c.offsets.p};
         }
         if ((rc = s->f_table.ensure(sizeof(table))) != MQVS_OK) return rc;
         CU(cudaMemcpyAsync(s->f_table.p, table, sizeof(table), cudaMemcpyHostToDevice, s->st));

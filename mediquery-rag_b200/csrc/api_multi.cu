@@ -622,6 +622,26 @@ int multi_column_set(mqvs_store* P, int col_id, int col_type, const void* values
     return MQVS_OK;
 }
 
+int multi_column_set_tokens(mqvs_store* P, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard guard;
+    Multi* M = P->multi;
+    std::vector<std::vector<uint64_t>> off(M->W);
+    std::vector<std::vector<int64_t>> tok(M->W);
+    for (int p = 0; p < M->W; ++p) off[p].push_back(0);
+    for_block_runs(M->map, 0, n, [&](int p, uint64_t, uint64_t cnt, uint64_t first) {
+        for (uint64_t r = first; r < first + cnt; ++r) {
+            tok[p].insert(tok[p].end(), tokens_host + offsets_host[r], tokens_host + offsets_host[r + 1]);
+            off[p].push_back(tok[p].size());
+        }
+    });
+    for (int p = 0; p < M->W; ++p) {
+        int rc = column_set_tokens_single(M->parts[p], col_id, off[p].data(), tok[p].data(), off[p].size() - 1);
+        if (rc != MQVS_OK) return rc;
+    }
+    return MQVS_OK;
+}
+
 int multi_filter_build(mqvs_store* P, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                        const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out) {
     std::lock_guard<std::mutex> lk(P->mu);

@@ -55,8 +55,16 @@ filter_eval_kernel(const FilterArgs a) {
             const FilterColumn col = a.cols[op.col];
             // rows beyond the column's length (added since it was uploaded) count as "field missing"
             const bool present = r < col.n && (col.present == nullptr || ((col.present[r >> 5] >> (r & 31)) & 1u));
-            const bool negated = op.op == MQVS_OP_NE || op.op == MQVS_OP_NIN;
-            if (!present) {
+            const bool negated = op.op == MQVS_OP_NE || op.op == MQVS_OP_NIN || op.op == MQVS_OP_NOT_CONTAINS;
+            if (col.type == MQVS_COL_TOKENS) {
+                // token-set membership (comma-joined `tags`): a handful of token ids per row, CSR
+                bool found = false;
+                if (r < col.n) {
+                    const long long* tok = reinterpret_cast<const long long*>(col.values);
+                    for (uint64_t j = col.offsets[r], e = col.offsets[r + 1]; j < e; ++j) found |= tok[j] == (long long)op.ival;
+                }
+                hit = found != negated;
+            } else if (!present) {
                 hit = negated;  // a missing field matches only $ne / $nin
             } else if (op.op == MQVS_OP_IN || op.op == MQVS_OP_NIN) {
                 bool found = false;

@@ -388,13 +388,17 @@ void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* 
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
                      int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all,
                      bool count_leftover) {
-    const int kpl = k <= 32 ? 1 : 4;  // the tensor path serves k <= 128
+    const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
     if (max_fix > 256) max_fix = 256;
     const int leftover = count_leftover ? 1 : 0;
 #define MQVS_FIX(T_, KPL_, U_)                                                                                                     \
     do {                                                                                                                           \
+        if (smem > 48 * 1024) {                                                                                                    \
+            cudaFuncSetAttribute(scan_fix_kernel<T_, KPL_, U_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+            cudaFuncSetAttribute(scan_fix_kernel<T_, KPL_, U_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        }                                                                                                                          \
         if (metric != MQVS_METRIC_COSINE)                                                                                          \
             scan_fix_kernel<T_, KPL_, U_, true><<<grid, kScanThreads, smem, st>>>(                                                 \
                 (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, metric,      \
@@ -405,9 +409,9 @@ void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* 
                 nullptr, leftover);                                                                                                \
     } while (0)
     if (dtype == MQVS_F32) {
-        if (kpl == 1) MQVS_FIX(float, 1, 2); else MQVS_FIX(float, 4, 2);
+        if (kpl == 1) MQVS_FIX(float, 1, 2); else if (kpl == 4) MQVS_FIX(float, 4, 2); else MQVS_FIX(float, 32, 2);
     } else {
-        if (kpl == 1) MQVS_FIX(__nv_bfloat16, 1, 4); else MQVS_FIX(__nv_bfloat16, 4, 4);
+        if (kpl == 1) MQVS_FIX(__nv_bfloat16, 1, 4); else if (kpl == 4) MQVS_FIX(__nv_bfloat16, 4, 4); else MQVS_FIX(__nv_bfloat16, 32, 4);
     }
 #undef MQVS_FIX
 }

@@ -191,6 +191,173 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// The same scoring + shortlist kernel on CTA PAIRS (cta_group::2), for batches of more than one query tile.
+//
+// Why: with single-CTA 128 x 256 tiles every K-chunk stage moves 16 KB of query operand + 32 KB of corpus through the SM's
+// L2 port for 2 * 128 * 256 * 64 flop.  That is 590 KB per tile step against ~4.6 us of MMA time: 128 GB/s per SM, more than
+// one SM's L2 port delivers (64 B/clk: 75-95 GB/s at the 1.2-1.5 GHz these parts sustain under the power cap), so large
+// batches ran port-bound at ~1.22 PFLOP/s whatever the tensor pipe could do.  A pair issues ONE 256 (queries) x 256 (rows)
+// MMA per K-slice: each CTA stages only ITS 128 queries and ITS 128 of the tile's 256 corpus rows (16 + 16 KB per stage),
+// the tensor cores of both SMs read both halves.  Per SM and unit of MMA work the staged bytes drop from 48 to 32 KB and,
+// more to the point, each SM's port carries half a corpus tile instead of a whole one per query tile.
+//
+// Layout of the work: pair p (cluster p, CTAs 2p and 2p + 1) takes corpus tiles tile_begin + p, + n_pairs, ...; for every
+// corpus tile it walks the query-tile PAIRS (2 mp, 2 mp + 1): CTA rank r owns query tile 2 mp + r -- its TMEM lanes are
+// those 128 queries, so the epilogue, the per-(CTA, query) lists and everything downstream are exactly the single-CTA
+// kernel's.  An odd last query tile leaves rank 1 idle for that step (its operand box is out of range: zero-filled).
+// Synchronisation: TMA of both CTAs counts on the LEADER's full barrier (expect_tx of both halves there); the leader's MMA
+// warp issues, commits with multicast to both CTAs' empty and accumulator-full barriers; both CTAs' epilogue warps
+// arrive on the leader's accumulator-empty barrier (count 8).
+constexpr int kPairStages = 6;
+constexpr int kPairBBytes = (BN / 2) * kRowBytes;           // this CTA's half of the corpus tile: 16 KB
+constexpr int kPairStageBytes = kABytes + kPairBBytes;      // 32 KB
+static_assert((size_t)kPairStages * kPairStageBytes <= (size_t)kStages * kStageBytes, "the pair ring must fit the shared memory of the single-CTA ring");
+
+template <typename T, int CAP, int KPRIME, bool XF>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_score_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_xh, ScoreArgs a) {
+    using K = Kind<T>;
+    constexpr int kChunks768 = kDim / K::kElemsPerChunk;
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)K::kFmt << 7) | ((uint32_t)K::kFmt << 10) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256 across the pair
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + (size_t)kStages * kStageBytes);
+    // bars[0..S): full, [S..2S): empty, [2S..2S+2): tmem_full, [2S+2..2S+4): tmem_empty   (S = kPairStages)
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kPairStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kPairStages, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+    uint32_t* hit_stage = reinterpret_cast<uint32_t*>(smem_al + (size_t)kStages * kStageBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(bar_full + 8 * s, 2);   // the two producers (the leader's arrive carries the expect_tx of both halves)
+            mbar_init(bar_empty + 8 * s, 1);  // one multicast commit from the leader's MMA warp
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 8);  // four epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const uint32_t first_tile = a.tile_begin + pair;
+    const uint32_t mp_count = (a.m_tiles + 1) >> 1;
+    const uint32_t n_my = a.tile_end > first_tile ? (a.tile_end - first_tile + n_pairs - 1) / n_pairs : 0;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs: own halves, counted on the leader's barrier) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t full0 = mapa_u32(bar_full, 0);  // the leader's full barriers, cluster address space
+            for (uint32_t nt = first_tile; nt < a.tile_end; nt += n_pairs)
+                for (uint32_t mp = 0; mp < mp_count; ++mp)
+                    for (int kc = 0; kc < kChunks768; ++kc) {
+                        mbar_wait_bounded(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * kPairStageBytes, sb = sa + kABytes;
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * kPairStageBytes);
+                        tma_load_2d_pair(sa, &map_q, full0 + 8 * stage, kc * K::kElemsPerChunk, (int)((2 * mp + rank) * BM));
+                        tma_load_2d_pair(sb, &map_xh, full0 + 8 * stage, kc * K::kElemsPerChunk, (int)(nt * BN + rank * (BN / 2)));
+                        if (rank != 0) mbar_arrive_cluster(full0 + 8 * stage);
+                        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader only) =====================
+        if (lane == 0 && rank == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t total_work = n_my * mp_count;
+            for (uint32_t w = 0; w < total_work; ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                mbar_wait_bounded(bar_tempty + 8 * acc, acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kc = 0; kc < kChunks768; ++kc) {
+                    mbar_wait_bounded(bar_full + 8 * stage, phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * kPairStageBytes, sb = sa + kABytes;
+                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_pair<K::kTf32>(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, kIdesc, (kc | kk) != 0);
+                    tcgen05_commit_pair(bar_empty + 8 * stage);  // frees the slot in BOTH CTAs when these MMAs retire
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit_pair(bar_tfull + 8 * acc);  // accumulator complete -> both epilogues
+            }
+        }
+    } else {
+        // ===================== epilogue: this CTA's 128 queries =====================
+        const int quad = warp & 3;
+        const uint32_t tempty0 = mapa_u32(bar_tempty, 0);
+        uint32_t w = 0;
+        for (uint32_t nt = first_tile; nt < a.tile_end; nt += n_pairs)
+            for (uint32_t mp = 0; mp < mp_count; ++mp, ++w) {
+                const uint32_t acc = w & 1, acc_phase = (w >> 1) & 1;
+                const uint32_t mt = 2 * mp + rank;
+                const uint32_t q = mt * BM + quad * 32 + lane;
+                const bool q_ok = mt < a.m_tiles && q < a.n_queries;
+                const size_t slot = (size_t)blockIdx.x * a.b_pad + (q_ok ? q : 0);
+                uint64_t* lst = a.lists + slot * CAP;
+                uint32_t cnt = q_ok ? a.cnt[slot] : 0;
+                float tau = q_ok ? ord_to_float(__ldcg(a.tau + q)) : INFINITY;
+                TileSpace sp;
+                if constexpr (XF) {
+                    sp.norms = a.norms;
+                    sp.bounds = a.nbounds;
+                    sp.h = q_ok ? __ldg(a.hq + q) : 0.0f;
+                }
+                mbar_wait_bounded(bar_tfull + 8 * acc, acc_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+                if (mt < a.m_tiles) {  // (uniform over the CTA; an idle half only keeps the barrier protocol going)
+                    if (a.cmax != nullptr) {  // cold pass: only the chunk maxima that seed the thresholds
+                        uint32_t cm[BN / 32];
+                        tile_chunk_maxima(taddr, nt * BN, a.n_rows, a.mask, cm, sp, lane);
+                        if (q_ok) {
+                            uint4* dst = reinterpret_cast<uint4*>(a.cmax + (size_t)q * a.ncols + (size_t)(nt - a.tile_begin) * 8);
+                            dst[0] = make_uint4(cm[0], cm[1], cm[2], cm[3]);
+                            dst[1] = make_uint4(cm[4], cm[5], cm[6], cm[7]);
+                        }
+                    } else {
+                        epilogue_tile<CAP, KPRIME>(taddr, nt * BN, a.n_rows, a.mask, hit_stage + (warp - 2) * 1024, a.tau + (q_ok ? q : 0), lane,
+                                                   tau, cnt, lst, nullptr, sp);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);  // hand the accumulator back to the leader's MMA warp
+                if (q_ok) a.cnt[slot] = cnt;
+            }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves (or frees tensor memory) while the partner may still use this CTA's half
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ prep
 // Normalised fp32 queries -> operand matrix [b_pad, 768] (bf16-rounded or fp32 copy), zero rows for padding,
 // and eps[q], the rigorous bound on |tensor-core score - exact fp32 score| for unit-norm rows.
@@ -533,6 +700,27 @@ Trace& trace() {
 namespace {
 Trace& g_trace = trace();
 
+// CTA pairs: clusters of two CTAs, an even grid; `mxh` is the corpus map with 128-row boxes (each CTA stages half a tile)
+template <typename T, int CAP, int KPRIME>
+cudaError_t launch_score_pair(const CUtensorMap& mq, const CUtensorMap& mxh, const ScoreArgs& a, int grid, cudaStream_t st) {
+    auto kern = a.norms != nullptr ? tc_score_pair_kernel<T, CAP, KPRIME, true> : tc_score_pair_kernel<T, CAP, KPRIME, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mq, mxh, a);
+}
+
 template <typename T, int CAP, int KPRIME>
 cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a, int grid, cudaStream_t st) {
     auto kern = a.norms != nullptr ? tc_score_kernel<T, CAP, KPRIME, true> : tc_score_kernel<T, CAP, KPRIME, false>;
@@ -546,10 +734,12 @@ cudaError_t launch_score(const CUtensorMap& mq, const CUtensorMap& mx, const Sco
 
 Plan plan(int k, int B, int sm_count) {
     Plan p{};
-    p.kprime = k <= 10 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : 256));
+    // k' = 512 / 1152 (k <= 256 / 1024) exist in the single-launch pipeline only (wide shortlists: lists of 2048, no
+    // in-kernel compaction; 1152 <= the 8 chunk maxima x 148 CTAs the thresholds are learnt from)
+    p.kprime = k <= 10 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 128 ? 256 : (k <= 256 ? 512 : 1152))));
     static const int kp_min = getenv("MQVS_KP_MIN") ? atoi(getenv("MQVS_KP_MIN")) : 0;  // developer knob: wider shortlists
-    if (kp_min == 64 || kp_min == 128 || kp_min == 256) p.kprime = std::max(p.kprime, kp_min);
-    p.cap = 512;  // per-(CTA, query) list capacity; a list is compacted to its k' best once it passes cap - 32 entries
+    if ((kp_min == 64 || kp_min == 128 || kp_min == 256) && p.kprime <= 256) p.kprime = std::max(p.kprime, kp_min);
+    p.cap = p.kprime > 256 ? 2048 : 512;  // per-(CTA, query) list capacity; narrow lists are compacted to their k' best near cap
     const int chunk = B < kMaxQueriesPerLaunch ? B : kMaxQueriesPerLaunch;
     p.b_pad = (chunk + BM - 1) / BM * BM;
     p.grid = sm_count;
@@ -571,10 +761,14 @@ int launches_per_search(const Plan& p, uint32_t n_rows, int B) {
 const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype, uint32_t n_rows, const float* qn_all, int B_all,
                    int k, const uint32_t* mask, int64_t id_base, float* out_scores_all, int64_t* out_ids_all, cudaStream_t st,
                    const Space& space) {
-    CUtensorMap mq, mx;
+    CUtensorMap mq, mx, mxh;
     const bool xf = space.metric != MQVS_METRIC_COSINE;
     if (!make_map(&mq, b.q_op, (uint64_t)p.b_pad, dtype, BM)) return "cuTensorMapEncodeTiled failed for the query matrix";
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
+    if (!make_map(&mxh, rows, (uint64_t)n_rows, dtype, BN / 2)) return "cuTensorMapEncodeTiled failed for the corpus (half tiles)";
+    // CTA pairs (cta_group::2) once there is more than one query tile and the grid can be split into pairs
+    static const bool no_pair = getenv("MQVS_NO_PAIR") != nullptr;  // developer knob: the single-CTA kernel, for comparison
+    const bool pairs = !no_pair && B_all > BM && p.grid >= 2;
     const uint32_t n_tiles = (n_rows + BN - 1) / BN;
     if (cudaMemsetAsync(b.flag_count, 0, sizeof(uint32_t), st) != cudaSuccess) return "cudaMemsetAsync failed";
 
@@ -608,10 +802,15 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         a.nbounds = xf ? reinterpret_cast<const float2*>(space.norm_bounds) : nullptr;
         a.hq = xf ? b.hq + q0 : nullptr;
         cudaError_t e = cudaSuccess;
-#define MQVS_TC(KP_)                                                                          \
-    if (p.kprime == KP_)                                                                      \
-        e = dtype == MQVS_F32 ? launch_score<float, 512, KP_>(mq, mx, a, grid, st)            \
-                              : launch_score<__nv_bfloat16, 512, KP_>(mq, mx, a, grid, st);
+#define MQVS_TC(KP_)                                                                                     \
+    if (p.kprime == KP_) {                                                                               \
+        if (pairs && grid >= 2)                                                                          \
+            e = dtype == MQVS_F32 ? launch_score_pair<float, 512, KP_>(mq, mxh, a, grid & ~1, st)        \
+                                  : launch_score_pair<__nv_bfloat16, 512, KP_>(mq, mxh, a, grid & ~1, st); \
+        else                                                                                             \
+            e = dtype == MQVS_F32 ? launch_score<float, 512, KP_>(mq, mx, a, grid, st)                   \
+                                  : launch_score<__nv_bfloat16, 512, KP_>(mq, mx, a, grid, st);          \
+    }
         // Cold pass: one tile per CTA, no list appends -- the epilogue only records the maximum of every 32-row chunk,
         // and the k'-th largest of a query's G*8 chunk maxima becomes its first threshold (>= k' distinct rows score that
         // much).  Costs one tile per CTA per query tile at tensor speed; the appending cold segment it replaces (4096 rows

@@ -140,7 +140,8 @@ prep_band_kernel(const float* __restrict__ qn, const uint32_t* __restrict__ flag
 bool fused_ok(int B, int k, int sm_count) {
     // one or two query tiles (the two TMEM accumulators); one list / 8 chunk maxima per CTA must fit
     // select_lists_body<192> and kth_largest_u32 (1280 values); CTA c finishes queries c and c + G, so 2 G >= B
-    return B >= 1 && B <= 2 * BM && k <= 128 && sm_count >= BM && sm_count <= 160;
+    // (k' = 1152 must not exceed the sm_count * 8 chunk maxima a threshold is the k'-th largest of)
+    return B >= 1 && B <= 2 * BM && k <= MQVS_MAX_K && sm_count >= BM && sm_count <= 160 && (k <= 256 || sm_count * 8 >= 1152);
 }
 size_t cmax_bytes(const Plan& p) { return (size_t)p.b_pad * p.grid * 8 * sizeof(uint32_t); }
 

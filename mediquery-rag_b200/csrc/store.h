@@ -164,7 +164,7 @@ struct mqvs_store {
     uint64_t host_fallbacks = 0;
     // device-side `where` evaluation
     struct Column {
-        mqvs::DevBuf values, present;
+        mqvs::DevBuf values, present, offsets;  // offsets: MQVS_COL_TOKENS only
         uint64_t n = 0;
         int type = 0;
         bool used = false, has_present = false;
@@ -209,6 +209,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
 int finish_search(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
                   int64_t* out_ids_dev, cudaStream_t st, bool* changed);
 int column_set_single(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host, uint64_t n);
+int column_set_tokens_single(mqvs_store* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
 int filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                         const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 int get_rows_single(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out_host);
@@ -240,6 +241,7 @@ int multi_get_rows(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out
 int multi_save(mqvs_store* s, const char* path, uint64_t first_row);
 int multi_load(mqvs_store* s, const char* path);
 int multi_column_set(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host, uint64_t n);
+int multi_column_set_tokens(mqvs_store* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
 int multi_filter_build(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                        const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 int multi_get_stats(mqvs_store* s, mqvs_stats* out);

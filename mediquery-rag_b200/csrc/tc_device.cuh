@@ -82,6 +82,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// The same wait with a ceiling: a CTA pair whose partner never arrives must fail loudly (a trap the host sees as an error)
+// instead of hanging the device -- seconds, where a healthy wait takes microseconds.
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && (spins & 0xfffu) == 0xfffu) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -107,6 +126,56 @@ __device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t adesc, uin
             : "memory");
     }
 }
+// ---- CTA pairs (cta_group::2): two CTAs of one cluster, on the two SMs of a TPC, issue ONE 256-row MMA together.  Each CTA
+// stages its own half of both operands (its 128 queries, its 128 of the tile's 256 corpus rows), the leader (cluster rank 0)
+// issues the MMAs, each CTA's TMEM receives its own 128 accumulator rows (all 256 columns).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of this CTA's half of a pair operand; the bytes are counted on the LEADER's barrier (`bar_cluster`: its
+// shared::cluster address), where the MMA issuer waits
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the pair's MMAs issued so far have retired
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if constexpr (kTf32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -315,22 +384,34 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
             }
             __syncwarp();
         }
+        if constexpr (CAP > 512) {
+            // Wide shortlists (k > 128: k' = 512 / 1152, lists of 2048): no in-kernel compaction -- a warp cannot sort 2048 keys in
+            // registers.  Thresholds learnt from the chunk maxima keep a list at a few dozen entries; one that fills up anyway
+            // (adversarial order, thousands of ties) stops collecting and raises the query's threshold to +inf: the tail
+            // then finds no candidates, flags the query, and the repair chain (band pass, exact scan) answers it.
+            if (cnt > CAP - 32 && tau != INFINITY) {
+                atomicMax(tau_glob_q, 0xFF800000u);  // ord(+inf)
+                tau = INFINITY;
+            }
+            continue;
+        }
         // lists that could overflow on the next chunk are compacted now (warp-cooperative)
-        unsigned todo = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+        unsigned todo = __ballot_sync(0xffffffffu, CAP <= 512 && cnt > CAP - 32);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             __syncwarp();
             const uint64_t* L = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)lst, src));
             const uint32_t c = min(__shfl_sync(0xffffffffu, cnt, src), (uint32_t)CAP);
-            uint64_t key[KPL];
+            constexpr int KS = CAP <= 512 ? KPL : 1;  // (the wide-list instantiations never get here)
+            uint64_t key[KS];
 #pragma unroll
-            for (int r = 0; r < KPL; ++r) key[r] = (uint32_t)(r * 32 + lane) < c ? __ldcg(L + r * 32 + lane) : 0ull;
-            warp_sort_desc<KPL>(key, lane);
+            for (int r = 0; r < KS; ++r) key[r] = (uint32_t)(r * 32 + lane) < c ? __ldcg(L + r * 32 + lane) : 0ull;
+            warp_sort_desc<KS>(key, lane);
 #pragma unroll
-            for (int r = 0; r < KPL; ++r)
+            for (int r = 0; r < KS; ++r)
                 if (r * 32 + lane < KPRIME) const_cast<uint64_t*>(L)[r * 32 + lane] = key[r];
-            const uint64_t kth = __shfl_sync(0xffffffffu, key[(KPRIME - 1) >> 5], (KPRIME - 1) & 31);
+            const uint64_t kth = __shfl_sync(0xffffffffu, key[((KPRIME - 1) >> 5) % KS], (KPRIME - 1) & 31);
             if (lane == src) {
                 cnt = KPRIME;  // c > CAP - 32 >= KPRIME, so the list is full down to its k'-th entry
                 const uint32_t t = (uint32_t)(kth >> 32);

@@ -398,10 +398,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 template <typename T, int CAP, int KPRIME, bool XF>
 __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* smem_al, const int slot, const int b_pad) {
     constexpr int NW = kThreads / 32;
-    constexpr int kCcap = 1024;  // shortlist capacity of the direct path (>= 2 k' with room for ties)
+    constexpr int kCcap = KPRIME > 256 ? 4096 : 1024;  // shortlist capacity of the direct path (>= 2 k' with room for ties)
+    constexpr int kCbuf = kCcap > 2048 ? kCcap : 2048;
     // the operand ring is idle now (every TMA load was consumed by an MMA that has retired): reuse it
-    uint64_t* C = reinterpret_cast<uint64_t*>(smem_al);   // 2048 keys (direct path uses kCcap; the fallback all of it)
-    uint64_t* ex = C + 2048;                              // kCcap exact keys
+    uint64_t* C = reinterpret_cast<uint64_t*>(smem_al);   // kCbuf keys (direct path uses kCcap; the fallback 2048)
+    uint64_t* ex = C + kCbuf;                             // kCcap exact keys
     int* pre_s = reinterpret_cast<int*>(ex + kCcap);      // kThreads + 1
     int* warp_tot = pre_s + kThreads + 1;                 // NW
     int* fill_s = warp_tot + NW;
@@ -451,12 +452,22 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
     int nC = *fill_s;
     if (band && nC > kCcap) return;  // too many rows inside the band to rescore here: stays flagged
     if (nC > kCcap) {
-        // far more survivors than k' (hundreds of exact ties, adversarial orderings): the general streaming selection
-        // picks the k' best approximate keys; its k'-th key then bounds everything it left out
-        __syncthreads();
-        select_lists_body<kThreads>(a.lists, a.cnt, G, b_pad, CAP, KPRIME, nullptr, slot, C, pre_s, warp_tot, fill_s);
-        if (C[KPRIME - 1]) tq = max(tq, (uint32_t)(C[KPRIME - 1] >> 32));
-        nC = KPRIME;
+        if constexpr (KPRIME > 256) {
+            // wide shortlists: the streaming selection's buffer cannot hold 2 k' keys -- flag the query for the repair chain
+            if (tid == 0) {
+                a.flags[qf] = 1u;
+                atomicAdd(a.flag_count, 1u);
+                a.band[qf] = tq;  // (everything at or above the learnt threshold: the band pass retries with its own capacity)
+            }
+            return;
+        } else {
+            // far more survivors than k' (hundreds of exact ties, adversarial orderings): the general streaming selection
+            // picks the k' best approximate keys; its k'-th key then bounds everything it left out
+            __syncthreads();
+            select_lists_body<kThreads>(a.lists, a.cnt, G, b_pad, CAP, KPRIME, nullptr, slot, C, pre_s, warp_tot, fill_s);
+            if (C[KPRIME - 1]) tq = max(tq, (uint32_t)(C[KPRIME - 1] >> 32));
+            nC = KPRIME;
+        }
     }
     const float tt = ord_to_float(tq);
     if (tid == 0) MQVS_STAMP(8);
@@ -549,7 +560,7 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
 // One dispatch over (row type, k', query tiles) per value of XF.
 template <typename T, int KP, int MT, bool XF, int BMQ = BM>
 cudaError_t launch_fused(const CUtensorMap& mq, const CUtensorMap& mx, const FusedArgs& a, int grid, cudaStream_t st) {
-    const void* kern = (const void*)tc_fused_kernel<T, 512, KP, MT, XF, BMQ>;
+    const void* kern = (const void*)tc_fused_kernel<T, (KP > 256 ? 2048 : 512), KP, MT, XF, BMQ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&mq, (void*)&mx, (void*)&a};
@@ -576,6 +587,8 @@ cudaError_t launch_fused_any(int dtype, int kprime, int query_tiles, const CUten
     MQVS_TCF(64)
     MQVS_TCF(128)
     MQVS_TCF(256)
+    MQVS_TCF(512)
+    MQVS_TCF(1152)
 #undef MQVS_TCF
     return cudaErrorInvalidValue;
 }

@@ -3,18 +3,32 @@
 The reference passes no filter today (/root/reference/src/agents/nodes.py:93 calls similarity_search(q, k=5)),
 but the Chroma surface it programs against takes `filter=` and BASELINE.json config 5 exercises it.  Grammar:
 {"field": v} (== $eq) | {"field": {"$eq|$ne|$gt|$gte|$lt|$lte": v}} | {"field": {"$in|$nin": [..]}} |
-{"$and": [..]} | {"$or": [..]}.  Evaluation is columnar (one numpy pass per leaf); a field missing from a row
+{"field": {"$contains|$not_contains": token}} | {"$and": [..]} | {"$or": [..]}.
+$contains / $not_contains on a METADATA field is token-set membership: the reference stores `tags` as one comma-joined
+string per chunk (/root/reference/src/ingest_medical.py:66-67,75-79, e.g. "慢性病，代谢性疾病，发病率"), so "chunks tagged X" is
+`{"tags": {"$contains": "X"}}`: the value is split on "," and "，", tokens are stripped, X must equal one of them
+(a row without the field, or whose value is not a string, matches only $not_contains).  Evaluation is columnar (one numpy pass per leaf); a field missing from a row
 matches only $ne / $nin.  The result is AND-ed with the live-row bitmap and packed little-endian into uint32
 words: bit (r & 31) of word (r >> 5) is row r.
 """
 from __future__ import annotations
 
+import re
 from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence
 
 import numpy as np
 
 _COMPARE = ("$gt", "$gte", "$lt", "$lte")
-_LEAF_OPS = ("$eq", "$ne", "$in", "$nin") + _COMPARE
+_TOKEN_OPS = ("$contains", "$not_contains")
+_LEAF_OPS = ("$eq", "$ne", "$in", "$nin") + _COMPARE + _TOKEN_OPS
+_TOKEN_SPLIT = re.compile("[,\uff0c]")
+
+
+def tokens_of(value: Any) -> List[str]:
+    """Tokens of a comma-joined metadata value ("," or "，" separated, stripped, empties dropped); [] for non-strings."""
+    if not isinstance(value, str):
+        return []
+    return [t for t in (p.strip() for p in _TOKEN_SPLIT.split(value)) if t]
 
 
 class FilterError(ValueError):
@@ -120,6 +134,12 @@ _EMPTY: Mapping[str, Any] = {}
 def _leaf(cols: MetadataColumns, field: str, op: str, want: Any) -> np.ndarray:
     vals, present = cols.column(field)
     n = len(cols)
+    if op in _TOKEN_OPS:
+        if not isinstance(want, str):
+            raise FilterError(f"{op} expects a string token")
+        want = want.strip()
+        hit = np.fromiter((bool(p) and want in tokens_of(v) for v, p in zip(vals, present)), dtype=bool, count=n)
+        return hit if op == "$contains" else ~hit
     if op in ("$in", "$nin"):
         if not isinstance(want, (list, tuple, set, frozenset, np.ndarray)):
             raise FilterError(f"{op} expects a list, got {type(want).__name__}")
@@ -304,6 +324,27 @@ class DeviceFilter:
         self._resident[field] = (self.cols.version, col_id, kind, uniq)
         return col_id, kind, uniq
 
+    def _token_column(self, field: str):
+        """Token-set view of a field (comma-joined strings): dictionary + CSR token lists, resident on the device under its
+        own column id.  -> (column id, sorted token dictionary)."""
+        key = field + "\0tokens"
+        hit = self._resident.get(key)
+        if hit is not None and hit[0] == self.cols.version:
+            return hit[1], hit[3]
+        vals, present = self.cols.column(field)
+        lists = [tokens_of(v) if p else [] for v, p in zip(vals, present)]
+        uniq = np.unique(np.asarray([t for ts in lists for t in ts], dtype=str)) if any(lists) else np.zeros(0, dtype=str)
+        offsets = np.zeros(len(lists) + 1, np.uint64)
+        np.cumsum([len(ts) for ts in lists], out=offsets[1:])
+        flat = [t for ts in lists for t in ts]
+        tokens = np.searchsorted(uniq, np.asarray(flat, dtype=str)).astype(np.int64) if flat else np.zeros(0, np.int64)
+        col_id = hit[1] if hit is not None else len(self._resident)
+        if col_id >= 64:
+            raise NotOnDevice("more than 64 filterable fields")
+        self.index.column_set_tokens(col_id, offsets, tokens)
+        self._resident[key] = (self.cols.version, col_id, "t", uniq)
+        return col_id, uniq
+
     def _const(self, kind: str, uniq, op: str, want: Any):
         """-> (op, ival, fval) for a scalar leaf; raises NotOnDevice where host and device semantics could differ."""
         if kind == "n":
@@ -359,6 +400,17 @@ class DeviceFilter:
                     raise FilterError(f"unknown operator {op}")
             else:
                 op, want = "$eq", val
+            if op in _TOKEN_OPS:
+                if not isinstance(want, str):
+                    raise FilterError(f"{op} expects a string token")
+                if not hasattr(self.index, "column_set_tokens"):
+                    raise NotOnDevice("this index has no token columns")
+                col_id, uniq = self._token_column(key)
+                want = want.strip()
+                at = int(np.searchsorted(uniq, want)) if uniq.shape[0] else 0
+                tok = at if at < uniq.shape[0] and uniq[at] == want else -1
+                ops.append(FilterOp(OP[op], col_id, tok, 0.0, 0, 0))
+                return
             col_id, kind, uniq = self._column(key)
             if op in ("$in", "$nin"):
                 if not isinstance(want, (list, tuple, set, frozenset, np.ndarray)):

@@ -23,12 +23,23 @@ class ProgramInterpreter:
         assert values.dtype in (np.int64, np.float64)
         self.cols[col_id] = (values.copy(), None if present is None else np.asarray(present, bool).copy())
 
+    def column_set_tokens(self, col_id, offsets, tokens):
+        assert offsets.dtype == np.uint64 and tokens.dtype == np.int64 and offsets[0] == 0 and offsets[-1] == tokens.shape[0]
+        self.cols[col_id] = ("tokens", offsets.copy(), tokens.copy())
+
     def filter_build(self, ops, pool=None, live_words=None):
         n, stack = self.n, []
         for o in ops:
             if o.op in (_native.OP["$and"], _native.OP["$or"]):
                 b2, b1 = stack.pop(), stack.pop()
                 stack.append(b1 & b2 if o.op == _native.OP["$and"] else b1 | b2)
+                continue
+            if o.op in (_native.OP["$contains"], _native.OP["$not_contains"]):  # token-set membership, CSR rows
+                _, off, tok = self.cols[o.col]
+                found = np.zeros(n, bool)
+                for r in range(min(n, off.shape[0] - 1)):
+                    found[r] = (tok[int(off[r]):int(off[r + 1])] == o.ival).any()
+                stack.append(found != (o.op == _native.OP["$not_contains"]))
                 continue
             vals, present = self.cols[o.col]
             m = vals.shape[0]
@@ -155,3 +166,33 @@ def test_random_where_trees_compile_to_programs_that_equal_the_host_evaluator():
         assert np.array_equal(words, pack_mask(want)) and allowed == int(want.sum())
 
     run()
+
+
+def test_tag_token_filters_on_the_reference_knowledge_base(medical_docs):
+    """`tags` is ONE comma-joined string per chunk (src/ingest_medical.py:66-67,75-79): $contains / $not_contains on a
+    metadata field is token membership.  Host evaluator and the compiled program (token dictionary + CSR lists) agree with
+    a plain Python restatement on the 154 real chunks, for every tag that occurs and for combinations."""
+    import re
+    metas = [d["metadata"] for d in medical_docs["docs"]]
+    cols = MetadataColumns()
+    cols.extend(metas)
+    n = len(metas)
+    split = [[t.strip() for t in re.split("[,\uff0c]", m["tags"]) if t.strip()] for m in metas]
+    every = sorted({t for ts in split for t in ts})
+    assert len(every) > 100
+    dev = DeviceFilter(ProgramInterpreter(n), cols)
+    for tag in every[::7] + ["癌症", "运动", "no such tag", " 癌症 "]:
+        want = np.array([tag.strip() in ts for ts in split])
+        for where, expect in (({"tags": {"$contains": tag}}, want), ({"tags": {"$not_contains": tag}}, ~want)):
+            assert np.array_equal(evaluate(where, cols), expect)
+            words, allowed = dev.build(where, None)
+            assert np.array_equal(words, pack_mask(expect)) and allowed == int(expect.sum())
+    both = {"$and": [{"tags": {"$contains": "癌症"}}, {"$or": [{"tags": {"$contains": "癌症检测"}}, {"title": {"$gte": "癌"}}]}]}
+    words, allowed = dev.build(both, None)
+    assert np.array_equal(words, pack_mask(evaluate(both, cols))) and 0 < allowed < n
+    assert len(dev.index.cols) == 2  # one token column for `tags`, one dictionary-coded column for `title`
+    # a substring of a tag is not a tag; a whole-string equality still goes through $eq
+    assert not evaluate({"tags": {"$contains": "癌"}}, cols).any()
+    assert evaluate({"tags": metas[0]["tags"]}, cols)[0]
+    with pytest.raises(Exception):
+        evaluate({"tags": {"$contains": 5}}, cols)

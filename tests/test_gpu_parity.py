@@ -1253,3 +1253,112 @@ def test_host_ingest_pipeline_is_bit_exact_over_many_chunks(gpu, dtype):
         probe = np.r_[0:50, 8150:8250, 16380:16400, n - 30:n]
         assert np.array_equal(idx.get_rows(probe).view(np.uint32), want[probe].view(np.uint32))
         idx.close()
+
+
+WIDE_K_CASES = [
+    # n, dtype, B, k, mask fraction: k > 128 on the single-launch tensor pipeline (wide shortlists, k' = 512 / 1152)
+    (100003, "bf16", 64, 200, None),
+    (100003, "fp32", 20, 1000, None),
+    (300000, "bf16", 130, 256, 0.3),
+    (70000, "fp32", 1, 129, None),
+    (70000, "bf16", 300, 150, None),     # more than 256 queries: 256 at a time
+    (40000, "bf16", 8, 1024, 0.02),      # about 800 allowed rows: fewer than k, padded
+]
+
+
+@pytest.mark.parametrize("n,dtype,B,k,frac", WIDE_K_CASES)
+def test_wide_k_on_the_tensor_pipeline_matches_oracle_bitwise(gpu, n, dtype, B, k, frac):
+    idx, x, st = build(n, 768, dtype, seed=0x5EED000D)
+    idx.set_path(2)
+    q, planted = O.planted_queries(QSEED, B, 0x5EED000D, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(13).random(n) < frac)
+    s, i = idx.search(q, k, mask)
+    stt = idx.stats()
+    assert stt["last_path"] == 1 and stt["last_pipeline"] == 3
+    assert_bit_equal(s, i, *O.brute_force_topk(qn, st, k, mask))
+    idx.close()
+
+
+def test_wide_k_with_thousands_of_ties_falls_back_and_stays_exact(gpu):
+    """6000 exact copies of the best row against k = 300: the wide per-CTA lists (2048 entries, no in-kernel compaction) fill up,
+    the query is flagged and the repair chain answers it -- same ids (lowest row ids of the tie) and bits as the oracle; the
+    asynchronous call does the same on its own."""
+    import torch
+    n, k = 60000, 300
+    x = O.synth_rows(SEED, 0, n, 768)
+    x[20000:26000] = x[77]
+    idx = native().Index(768, "bf16")
+    idx.add(x)
+    idx.set_path(2)
+    q = np.stack([x[77] + 0.01 * O.synth_rows(5, 0, 1, 768)[0], x[40000]])
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    s, i = idx.search(q, k)
+    assert_bit_equal(s, i, es, ei)
+    out_s = torch.empty((2, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((2, k), dtype=torch.int64, device="cuda")
+    idx.search_device(torch.from_numpy(q).cuda(), k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    assert idx.stats()["unrepaired"] == 0
+    idx.close()
+
+
+@pytest.mark.parametrize("devices", [0, [0, 0, 0]])
+def test_tag_token_filter_on_the_device_equals_the_host_evaluator(gpu, medical_docs, devices):
+    """f4: the comma-joined `tags` of the reference's 154 chunks as a token-set column on the device
+    (mqvs_column_set_tokens + MQVS_OP_CONTAINS / NOT_CONTAINS in filter_eval_kernel), one shard and three; the searches
+    through the resulting masks equal the oracle under the host evaluator's mask."""
+    from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns, evaluate
+    metas = [d["metadata"] for d in medical_docs["docs"]] * 60   # 9240 rows: three blocks of a sharded handle
+    n = len(metas)
+    cols = MetadataColumns()
+    cols.extend(metas)
+    x = O.synth_rows(0x5EED000E, 0, n, 768)
+    idx = native().Index(768, "fp32", device=devices)
+    idx.add(x)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    q = O.synth_rows(QSEED, 0, 3, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    dev = DeviceFilter(idx, cols)
+    live = np.ones(n, bool)
+    live[::11] = False
+    for where in ({"tags": {"$contains": "癌症"}}, {"tags": {"$not_contains": "运动"}}, {"tags": {"$contains": "no such tag"}},
+                  {"$and": [{"tags": {"$contains": "代谢性疾病"}}, {"tags": {"$not_contains": "糖尿病"}}]},
+                  {"$or": [{"tags": {"$contains": "睡眠"}}, {"title": {"$lt": "什"}}]}):
+        ok = evaluate(where, cols) & live
+        mask, allowed = dev.build(where, live)
+        assert allowed == int(ok.sum())
+        s, i = idx.search(q, 5, mask)
+        assert_bit_equal(s, i, *O.brute_force_topk(qn, st, 5, O.mask_from_bool(ok)))
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_kernels_against_the_independent_float64_referee_at_one_million_rows(gpu, dtype):
+    """The parity claim without the kernel-ordered oracle in between: the CUDA results themselves (single-launch tensor
+    pipeline at B = 16, SIMT scan at B = 1, all three spaces over raw non-unit vectors) against float64 numpy over the
+    stored values, under north_star's stated tolerance -- ids identical apart from near ties, scores within 1e-5 relative."""
+    from referee import assert_within_north_star, f64_topk
+    n, B, k = 1_000_000, 16, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x *= np.linspace(0.03, 0.09, n, dtype=np.float32)[:, None]
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    q = (q * np.float32(1.3)).astype(np.float32)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    norms = O.row_norms(x, 768)
+    idx = native().Index(768, dtype, capacity_rows=n)
+    idx.set_metric("l2")
+    idx.add(x)
+    del x
+    for space in ("cosine", "l2", "ip"):
+        idx.set_metric(space)
+        ref_d, ref_i = f64_topk(q, st, norms, k, space)
+        s, i = idx.search(q, k)
+        assert idx.stats()["last_path"] == 1
+        assert_within_north_star(space, s, i, q, ref_d, ref_i)
+        s1, i1 = idx.search(q[:1], k)
+        assert_within_north_star(space, s1, i1, q[:1], ref_d[:1], ref_i[:1])
+    idx.close()

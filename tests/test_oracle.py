@@ -125,3 +125,25 @@ def test_where_evaluator_grammar():
     assert ev({"$and": [{"title": "a"}, {"n": {"$lt": 3}}]}) == [1, 0, 0, 0]
     assert ev({"$or": [{"title": "b"}, {"n": {"$in": [3]}}]}) == [0, 1, 0, 1]
     assert ev(None) == [1, 1, 1, 1]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_oracle_against_an_independent_float64_referee_at_one_million_rows(dtype):
+    """The canonical-order oracle is what the kernels are compared with bit for bit; this ties IT to arithmetic that shares
+    nothing with the kernels (float64 numpy over the stored values, chromadb's distance definitions) at config 2's full
+    size, for both storage types and all three spaces, within north_star's tolerance."""
+    from referee import assert_within_north_star, f64_topk
+    n, B, k = 1_000_000, 6, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x *= np.linspace(0.03, 0.09, n, dtype=np.float32)[:, None]       # raw norms 0.5 .. 1.5: the spaces really differ
+    q, _ = O.planted_queries(0x0BADC0DE, B, SEED, n, 768)
+    q = (q * np.float32(1.3)).astype(np.float32)
+    st, _ = O.normalize_rows(x, dtype, 768)
+    norms = O.row_norms(x, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    del x
+    for space in ("cosine", "l2", "ip"):
+        kw = {} if space == "cosine" else dict(metric=space, norms=norms, q_norms=O.row_norms(q, 768))
+        s, i = O.brute_force_topk(qn, st, k, **kw)
+        ref_d, ref_i = f64_topk(q, st, norms, k, space)
+        assert_within_north_star(space, s, i, q, ref_d, ref_i)

@@ -18,6 +18,16 @@ for s in $STEPS; do
                   > $OUT/${TAG}_bench_c4shard_${v}.json 2> $OUT/${TAG}_bench_c4shard_${v}.err; echo "c4 shard $v rc=$?"
             done; unset MQVS_NO_HALF_TILE ;;
     ingest) timeout 300 python tools/ingest_check.py 1000000 > $OUT/${TAG}_ingest.log 2>&1; echo "ingest rc=$?"; cp $OUT/ingest_check.json $OUT/${TAG}_ingest_check.json 2>/dev/null ;;
+    e2e)    timeout 300 python tools/e2e_breakdown.py 1000000 64 fp32 > $OUT/${TAG}_e2e_c2.log 2>&1; echo "e2e rc=$?"
+            timeout 300 python tools/e2e_breakdown.py 1000000 1 fp32 > $OUT/${TAG}_e2e_c2_b1.log 2>&1 ;;
+    paircmp) for v in pair nopair; do
+              if [ $v = nopair ]; then export MQVS_NO_PAIR=1; else unset MQVS_NO_PAIR; fi
+              timeout 400 python bench.py --workload c4 --rows 12500000 --batch 1024 --no-secondary --no-cpu-baseline --points 512,4096 --steps 10 --warmup 3 \
+                  > $OUT/${TAG}_bench_c4shard_${v}.json 2> $OUT/${TAG}_bench_c4shard_${v}.err; echo "c4 shard $v rc=$?"
+              timeout 400 python bench.py --workload c3 --no-secondary --no-cpu-baseline --steps 5 --warmup 3 \
+                  > $OUT/${TAG}_bench_c3_${v}.json 2> $OUT/${TAG}_bench_c3_${v}.err; echo "c3 $v rc=$?"
+              MQVS_TRACE=1 timeout 300 python tools/tc_one.py 12500000 bf16 256 10 4 > $OUT/${TAG}_trace_b256_seg_${v}.log 2>&1
+            done; unset MQVS_NO_PAIR ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
 done
