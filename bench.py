@@ -304,7 +304,8 @@ class Harness:
         avg = scan_ms / max(1, scan_launches)
         kernel = {0: "scan_simt_kernel (+ candidate memset, bracketed together)",
                   1: "scan_fused_kernel (single-launch SIMT search)",
-                  2: "tc_score_kernel (tcgen05 scoring of all corpus segments + shortlist selection + fp32 rescoring, bracketed together)",
+                  2: ("tc_score_pair_kernel (cta_group::2 CTA pairs: tcgen05 scoring of all corpus segments" if B > 128 else
+                      "tc_score_kernel (tcgen05 scoring of all corpus segments") + " + shortlist selection + fp32 rescoring, bracketed together)",
                   3: "prep_fused_kernel + tc_fused_kernel (one cooperative launch: tcgen05 scoring of the whole corpus, in-kernel "
                      "threshold learning, selection, fp32 rescoring; bracketed together)"}[pipeline]
         # intensity = B flop per corpus byte (bf16) or B/2 (fp32): above the ridge the tensor pipe bounds the search
@@ -584,6 +585,7 @@ def main():
         # every rank releases its shard; rank 0 alone then drives all N GPUs through ONE MediQueryVectorStore, the way the
         # reference holds its vector store (one object, one process); the other ranks wait on a host-side barrier
         xchg_kind = sh.exchange
+        H.barrier()  # nobody unmaps or frees an inbox a peer's exchange kernel may still be writing
         sh.index.close()
         if sh._xchg is not None:
             sh._xchg.close()

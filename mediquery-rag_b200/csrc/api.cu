@@ -225,6 +225,10 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     }
     // single-launch tensor pipeline for one or two query tiles (B <= 256); path 4 = keep the segmented pipeline (tests compare)
     bool tc_one = tensor && s->path != 4 && s->coop_ok && tc::fused_ok(B, k, s->sm_count);
+    // Two query tiles over a long corpus: the segmented pipeline's CTA-pair kernel (cta_group::2: each SM stages half a corpus
+    // tile) scans at the tensor roof where the single-launch kernel's two-tile ring is bound by the SM's L2 port -- 3.95 vs
+    // 4.3-4.5 ms at 12.5M bf16 rows, B = 256 (profiles/r02_*); its extra launches (~0.15 ms) win from ~3M rows on.
+    if (tc_one && s->path == 0 && B > 128 && k <= 128 && s->n >= 3000000ull) tc_one = false;
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
         const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 4 + 128 + 256 + 32 + 144) * sizeof(uint32_t);

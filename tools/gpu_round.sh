@@ -8,6 +8,9 @@ OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > $OUT/${TAG}_smi.txt 2>&1
 for s in $STEPS; do
   case $s in
+    pairsanity) timeout 200 python tools/tc_one.py 300000 bf16 512 10 2 > $OUT/${TAG}_pairsanity.log 2>&1; rc=$?; echo "pairsanity rc=$rc"
+            tail -2 $OUT/${TAG}_pairsanity.log
+            if [ $rc -ne 0 ] || ! grep -q "planted ok True" $OUT/${TAG}_pairsanity.log; then export MQVS_NO_PAIR=1; echo "PAIR KERNEL DISABLED for the rest of this call"; fi ;;
     tests)  timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 --timeout 600 -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "tests rc=$?" ;;
     bench)  timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?" ;;
     c2cmp)  for v in half full; do
