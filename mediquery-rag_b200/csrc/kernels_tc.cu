@@ -837,11 +837,8 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         // Corpus segments of geometrically growing size.  After each one the per-query threshold becomes the k'-th
         // best score over EVERYTHING scored so far (select_lists_kernel), so a segment g times larger than all before
         // it appends only ~g k' candidates per query instead of re-learning its threshold in every CTA.
-        static bool sel_attr = false;
-        if (!sel_attr) {
-            cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxKeys * (int)sizeof(uint64_t));
-            sel_attr = true;
-        }
+        // (function attributes are per DEVICE: a handle on another GPU of this process needs its own -- set it every time)
+        cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxKeys * (int)sizeof(uint64_t));
         uint32_t begin = 0;
         for (uint64_t end = first_segment_end(a.m_tiles, p.grid); begin < n_tiles; end = next_segment_end(end, a.m_tiles)) {
             a.tile_begin = begin;

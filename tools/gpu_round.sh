@@ -31,6 +31,20 @@ for s in $STEPS; do
                   > $OUT/${TAG}_bench_c3_${v}.json 2> $OUT/${TAG}_bench_c3_${v}.err; echo "c3 $v rc=$?"
               MQVS_TRACE=1 timeout 300 python tools/tc_one.py 12500000 bf16 256 10 4 > $OUT/${TAG}_trace_b256_seg_${v}.log 2>&1
             done; unset MQVS_NO_PAIR ;;
+    ncu)    # launch list of the default bench (headline only) + full captures of the dominant kernels; plain run first
+            CMD="python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --no-store-e2e --points 1"
+            timeout 300 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
+            timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_ncu_launches_bench_default.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
+            echo "ncu launches rc=$?"
+            timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_fused_kernel -s 3 -c 1 -o $OUT/${TAG}_prof_c4_b64_fused $CMD > $OUT/${TAG}_ncu_fused.log 2>&1
+            echo "ncu fused rc=$?"
+            for B in 256 1024; do
+              CMD2="python tools/tc_one.py 12500000 bf16 $B 10 0 2"
+              timeout 300 $CMD2 > $OUT/${TAG}_ncu_plain_b$B.log 2>&1 &&
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_score_pair -s 3 -c 1 -o $OUT/${TAG}_prof_pair_b$B $CMD2 > $OUT/${TAG}_ncu_pair_b$B.log 2>&1
+              echo "ncu pair B=$B rc=$?"
+            done ;;
+    widek)  for kk in 100 200 1000; do timeout 200 python tools/tc_one.py 1000000 fp32 64 $kk 0 5 > $OUT/${TAG}_widek_$kk.log 2>&1; tail -1 $OUT/${TAG}_widek_$kk.log; done ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
 done

@@ -7,7 +7,10 @@ KEEP = ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
-        "sm__cycles_elapsed.avg", "smsp__cycles_active.avg")
+        "sm__cycles_elapsed.avg", "smsp__cycles_active.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex.sum", "lts__t_bytes_srcunit_tex.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__cycles_active.avg", "gpc__cycles_elapsed.max", "smsp__cycles_elapsed.avg.per_second")
 out = {}
 for rep in sys.argv[1:]:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
