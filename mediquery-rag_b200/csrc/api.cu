@@ -121,6 +121,11 @@ static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     return B > simt_max && s->n >= 65536;
 }
 
+// Will this search run the single-launch latency kernel (every CTA reads the raw queries itself)?
+bool takes_latency_kernel(const mqvs_store* s, int B, int k) {
+    return !use_tensor_path(s, B, k) && s->path != 3 && s->metric == MQVS_METRIC_COSINE && mqvs::scan_fused_ok(B, k);
+}
+
 // Exact SIMT scan of queries [b0, b0 + nb) of s->qn into out rows [b0, ...).  Returns passes launched.
 static int enqueue_simt(mqvs_store* s, int b0, int nb, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,
                  int64_t* out_ids_dev, cudaStream_t st, uint32_t* passes_out) {
@@ -196,6 +201,9 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
     settle_slot(s, slot);  // oldest entry of the ring: long finished unless 32 searches are in flight
     cudaEvent_t* ev = s->evr[slot].e;
+// (the shards of a multi-device handle skip the four timing events per search: at eight devices driven by one host thread
+// every API call is on the critical path of the last device's start)
+#define MQVS_EV(i_) do { if (s->timing) CU(cudaEventRecord(ev[i_], st)); } while (0)
     const bool tensor = use_tensor_path(s, B, k);
     const bool fused = !tensor && s->path != 3 && s->metric == MQVS_METRIC_COSINE && scan_fused_ok(B, k);
     s->last_fused = fused;
@@ -204,15 +212,15 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     if (fused) {
         // latency path: normalisation, scan, top-k and the final merge in one launch
         if ((rc = s->cand.ensure((size_t)B * scan_fused_max_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
-        CU(cudaEventRecord(ev[0], st));
-        CU(cudaEventRecord(ev[1], st));
+        MQVS_EV(0);
+        MQVS_EV(1);
         launch_scan_fused(s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, B, mask_dev, k, (uint64_t*)s->cand.p,
                           out_scores_dev, out_ids_dev, id_base, s->ticket_dev, (unsigned int*)(s->bad_dev + 1), ++s->epoch,
                           s->sm_count, st, host_status);
-        CU(cudaEventRecord(ev[2], st));
-        CU(cudaEventRecord(ev[3], st));
+        MQVS_EV(2);
+        MQVS_EV(3);
         CU(cudaGetLastError());
-        s->evr[slot].pending = true;
+        s->evr[slot].pending = s->timing;
         s->stats.kernel_launches += 1;
         s->stats.scan_launches += 1;
         s->stats.scan_bytes += s->n * s->row_bytes();
@@ -312,8 +320,8 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     if (report_to_host && tc_one) bad_epoch = (unsigned int*)s->flags_map.p + 1;
     if (tc_one) {
         s->last_fused = true;  // non-finite queries are reported through the epoch word, as on the latency path
-        CU(cudaEventRecord(ev[0], st));
-        CU(cudaEventRecord(ev[1], st));
+        MQVS_EV(0);
+        MQVS_EV(1);
         bool coop_refused = false;
         const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
                                            mask_dev, id_base, out_scores_dev, out_ids_dev, bad_epoch,
@@ -329,11 +337,11 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         }
     }
     if (tc_one) {
-        CU(cudaEventRecord(ev[2], st));  // brackets prep + the single scan/select/rescore launch
+        MQVS_EV(2);  // brackets prep + the single scan/select/rescore launch
         enqueue_repair();
-        CU(cudaEventRecord(ev[3], st));
+        MQVS_EV(3);
         CU(cudaGetLastError());
-        s->evr[slot].pending = true;
+        s->evr[slot].pending = s->timing;
         s->stats.kernel_launches += 2;
         s->stats.scan_launches += 1;
         s->stats.scan_bytes += s->n * s->row_bytes();
@@ -345,36 +353,36 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         return MQVS_OK;
     }
 
-    CU(cudaEventRecord(ev[0], st));
+    MQVS_EV(0);
     CU(cudaMemsetAsync(s->bad_dev, 0, sizeof(unsigned long long), st));
     launch_normalize(q_raw_dev, (uint64_t)B, s->dim, MQVS_F32, s->qn.p, s->bad_dev, st,
                      s->metric != MQVS_METRIC_COSINE ? (float*)s->qnorm.p : nullptr);
     s->stats.kernel_launches += 1;
     uint32_t passes = 0;
     if (tensor) {
-        CU(cudaEventRecord(ev[1], st));
+        MQVS_EV(1);
         const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
                                      id_base, out_scores_dev, out_ids_dev, st, space);
         if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
-        CU(cudaEventRecord(ev[2], st));  // brackets prep + score + select + rescore + finalize
+        MQVS_EV(2);  // brackets prep + score + select + rescore + finalize
         enqueue_repair();
         passes = 1;
         s->stats.kernel_launches += tc::launches_per_search(plan, (uint32_t)s->n, B);
         s->stats.last_path = 1;
         s->stats.last_pipeline = 2;
     } else {
-        CU(cudaEventRecord(ev[1], st));
+        MQVS_EV(1);
         // scan launches are bracketed together with the (tiny) candidate memset
         if ((rc = enqueue_simt(s, 0, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, &passes)) != MQVS_OK) return rc;
-        CU(cudaEventRecord(ev[2], st));
+        MQVS_EV(2);
         s->stats.kernel_launches += passes + 1;
         s->stats.last_path = 0;
         s->stats.last_pipeline = 0;
     }
-    CU(cudaEventRecord(ev[3], st));
+    MQVS_EV(3);
     CU(cudaGetLastError());
 
-    s->evr[slot].pending = true;
+    s->evr[slot].pending = s->timing;
     s->stats.scan_launches += passes;
     s->stats.scan_bytes += (uint64_t)passes * s->n * s->row_bytes();
     s->stats.last_scan_passes = passes;

@@ -102,6 +102,7 @@ int multi_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64
         int rc = create_single(dev_ids[p], dim, store_dtype, M->map.count(p, capacity_rows), &c);
         if (rc != MQVS_OK) return bail(rc);
         M->parts.push_back(c);
+        c->timing = false;
         P->sm_count = c->sm_count;
         if (cudaEventCreateWithFlags(&M->done[p], cudaEventDisableTiming) != cudaSuccess) return bail(mqvs_fail(MQVS_E_CUDA, "event creation failed"));
         if (dev_ids[p] == M->home) {
@@ -276,7 +277,11 @@ int multi_search(mqvs_store* P, const float* q, int q_is_device, int B, int k, c
         if (c->n == 0 && p != 0) continue;  // (part 0 always runs: it validates the queries even when the store is empty)
         MQVS_CU(cudaSetDevice(M->devs[p]));
         const float* q_dev = nullptr;
-        if (!q_is_device) {
+        if (!q_is_device && !takes_latency_kernel(c, B, k)) {
+            // zero-copy: the first kernel of the search (query normalisation / operand build) reads the raw queries once,
+            // straight from the mapped pinned copy over this device's own PCIe link -- no copy to enqueue per device
+            q_dev = (const float*)M->q_pin.p;
+        } else if (!q_is_device) {
             if ((rc = c->qraw.ensure(q_bytes)) != MQVS_OK) return rc;
             MQVS_CU(cudaMemcpyAsync(c->qraw.p, M->q_pin.p, q_bytes, cudaMemcpyHostToDevice, c->st));
             q_dev = (const float*)c->qraw.p;

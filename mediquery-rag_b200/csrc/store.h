@@ -133,6 +133,7 @@ struct mqvs_store {
         bool pending = false;
     } evr[kEvRing];
     int ev_cursor = 0;
+    bool timing = true;  // record the CUDA events behind stats.scan_ms / last_search_ms (off for the shards of a multi-device handle)
     mqvs::DevBuf qraw, qn, qnorm, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
     mqvs::DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
     // host ingest pipeline (mqvs_add from host memory): two device staging buffers fed by a copy stream, two pinned
@@ -213,6 +214,7 @@ int column_set_tokens_single(mqvs_store* s, int col_id, const uint64_t* offsets_
 int filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                         const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 int get_rows_single(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out_host);
+bool takes_latency_kernel(const mqvs_store* s, int B, int k);
 void settle_events(mqvs_store* s);
 void fill_stats(mqvs_store* s);  // settles events + repair counters into s->stats
 

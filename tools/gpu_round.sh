@@ -44,6 +44,10 @@ for s in $STEPS; do
               timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_score_pair -s 3 -c 1 -o $OUT/${TAG}_prof_pair_b$B $CMD2 > $OUT/${TAG}_ncu_pair_b$B.log 2>&1
               echo "ncu pair B=$B rc=$?"
             done ;;
+    ncufused) CMD="python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --no-store-e2e --points 1"
+            timeout 300 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
+            timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_fused_kernel.*, 64>" -s 2 -c 1 -o $OUT/${TAG}_prof_c4_b64_fused $CMD > $OUT/${TAG}_ncu_fused.log 2>&1
+            echo "ncu fused rc=$?" ;;
     widek)  for kk in 100 200 1000; do timeout 200 python tools/tc_one.py 1000000 fp32 64 $kk 0 5 > $OUT/${TAG}_widek_$kk.log 2>&1; tail -1 $OUT/${TAG}_widek_$kk.log; done ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
