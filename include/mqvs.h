@@ -160,16 +160,18 @@ MQVS_API void mqvs_xchg_destroy(mqvs_xchg_t* x);
  * takes (mask_is_device = 1) without the mask ever visiting the host.  Semantics as Chroma's: a row whose field is
  * missing matches only $ne / $nin.  live_words (host, ceil(rows/32) words, nullable) is AND-ed in (tombstones). */
 enum { MQVS_OP_EQ = 0, MQVS_OP_NE = 1, MQVS_OP_GT = 2, MQVS_OP_GTE = 3, MQVS_OP_LT = 4, MQVS_OP_LTE = 5, MQVS_OP_IN = 6,
-       MQVS_OP_NIN = 7, MQVS_OP_CONTAINS = 8, MQVS_OP_NOT_CONTAINS = 9, MQVS_OP_AND = 16, MQVS_OP_OR = 17 };
-enum { MQVS_COL_I64 = 0, MQVS_COL_F64 = 1, MQVS_COL_TOKENS = 2 };
+       MQVS_OP_NIN = 7, MQVS_OP_CONTAINS = 8, MQVS_OP_NOT_CONTAINS = 9, MQVS_OP_TEXT_CONTAINS = 10,
+       MQVS_OP_TEXT_NOT_CONTAINS = 11, MQVS_OP_AND = 16, MQVS_OP_OR = 17 };
+enum { MQVS_COL_I64 = 0, MQVS_COL_F64 = 1, MQVS_COL_TOKENS = 2, MQVS_COL_TEXT = 3 };
 typedef struct mqvs_filter_op {
     int32_t op;        /* MQVS_OP_* */
     int32_t col;       /* leaves: column id given to mqvs_column_set */
     int64_t ival;      /* comparison constant for MQVS_COL_I64 columns */
     double fval;       /* comparison constant for MQVS_COL_F64 columns */
-    uint32_t set_off;  /* $in / $nin: first element of the set in the constant pool */
-    uint32_t set_len;
+    uint32_t set_off;  /* $in / $nin: first element of the set in the constant pool; text leaves: first 8-byte word of the needle */
+    uint32_t set_len;  /* $in / $nin: elements of the set; text leaves: BYTES of the needle (1 .. MQVS_MAX_NEEDLE) */
 } mqvs_filter_op;
+#define MQVS_MAX_NEEDLE 1024
 /* values_host: n 8-byte values (int64 or float64); present_host: n bytes (0 = field missing) or NULL = all present.
  * Replaces column col_id (0..63).  n may be smaller than the row count: later rows count as "field missing". */
 MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
@@ -180,6 +182,14 @@ MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* va
  * tokens_host[offsets_host[r] .. offsets_host[r + 1]).  Leaves MQVS_OP_CONTAINS / MQVS_OP_NOT_CONTAINS test ival (a token id;
  * -1 = a token no row carries) against a row's list; a row without tokens matches only NOT_CONTAINS. */
 MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
+/* Text columns -- Chroma's `where_document` ({"$contains": s} / {"$not_contains": s} over the stored documents; the
+ * reference's page_content is "问题：{title}\n答案：{content}", src/ingest_medical.py:71): the documents' UTF-8 bytes, all rows
+ * concatenated, in CSR form (row r = bytes_host[offsets_host[r] .. offsets_host[r + 1])); present_host: n bytes (0 = the
+ * row has no document) or NULL.  Leaves MQVS_OP_TEXT_CONTAINS / MQVS_OP_TEXT_NOT_CONTAINS search every row for the
+ * needle stored in the constant pool (set_len bytes from 8-byte word set_off; byte-wise equality on UTF-8 = substring
+ * equality on code points); a row without a document matches only NOT_CONTAINS. */
+MQVS_API int mqvs_column_set_text(mqvs_t* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                                  const uint8_t* present_host, uint64_t n);
 /* prog: n_ops <= 64 operations in postfix order; pool: pool_len 8-byte constants (int64 or float64 bit patterns) the
  * $in / $nin leaves point into.  *mask_dev_out is owned by the handle and valid until the next mqvs_filter_build.
  * Multi-device handles evaluate every shard's slice on its own device; *mask_dev_out is then an opaque token for
@@ -225,6 +235,17 @@ MQVS_API int mqvs_get_stats(mqvs_t* s, mqvs_stats* out);
  * 3 = SIMT scan without the single-launch latency kernel, 4 = tensor-core path without the single-launch pipeline
  * for B <= 256 and without the band pass (tests compare the variants) */
 MQVS_API int mqvs_set_path(mqvs_t* s, int path);
+
+/* bf16 scoring shadow of an fp32 store (MQVS_F32 handles; on by default, MQVS_NO_SHADOW=1 in the environment or enable = 0
+ * turns it off; no effect on MQVS_BF16 handles).  The tensor-core pipelines are bound by the bytes they stream, so an fp32
+ * store keeps a second, bf16-rounded copy of its rows (+50 % HBM; built on the device before the first tensor search after
+ * an add, and dropped for good if HBM cannot hold it) and streams THAT: half the bytes per row and kind::f16 MMAs at twice
+ * the kind::tf32 rate.  Tensor-core scores only ever shortlist; every score that is returned or compared -- K4 rescoring
+ * of the shortlist, the band pass, the exact-scan repair, the SIMT paths -- is computed from the stored fp32 rows, and the
+ * exactness margin accounts for the rounding of both operands (||q - bf16(q)|| ||x~|| + ||q|| max ||x - bf16(x)||), so
+ * results are bit-identical with the shadow on or off.  *bytes_out (nullable) receives the shadow's current size. */
+MQVS_API int mqvs_set_shadow(mqvs_t* s, int enable);
+MQVS_API int mqvs_shadow_bytes(mqvs_t* s, uint64_t* bytes_out);
 
 #ifdef __cplusplus
 }

@@ -28,8 +28,10 @@ class FilterOp(ctypes.Structure):
 
 
 OP = {"$eq": 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5, "$in": 6, "$nin": 7, "$contains": 8, "$not_contains": 9,
+      "$text_contains": 10, "$text_not_contains": 11,  # where_document leaves over a text column
       "$and": 16, "$or": 17}
-COL_I64, COL_F64, COL_TOKENS = 0, 1, 2
+COL_I64, COL_F64, COL_TOKENS, COL_TEXT = 0, 1, 2, 3
+MAX_NEEDLE = 1024  # MQVS_MAX_NEEDLE
 
 
 class DeviceMask:
@@ -84,11 +86,14 @@ SIGNATURES = {
     "mqvs_compact": (_i, [_vp, _vp, ctypes.POINTER(_u64)]),
     "mqvs_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "mqvs_set_path": (_i, [_vp, _i]),
+    "mqvs_set_shadow": (_i, [_vp, _i]),
+    "mqvs_shadow_bytes": (_i, [_vp, ctypes.POINTER(_u64)]),
     "mqvs_set_metric": (_i, [_vp, _i]),
     "mqvs_norm_deviation": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "mqvs_get_norms": (_i, [_vp, _u64, _u64, _vp]),
     "mqvs_column_set": (_i, [_vp, _i, _i, _vp, _vp, _u64]),
     "mqvs_column_set_tokens": (_i, [_vp, _i, _vp, _vp, _u64]),
+    "mqvs_column_set_text": (_i, [_vp, _i, _vp, _vp, _vp, _u64]),
     "mqvs_filter_build": (_i, [_vp, _vp, _i, _vp, _u64, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "mqvs_shard_of_row": (_i, [_i, _u64, ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
     "mqvs_xchg_create": (_i, [_i, _i, _i, _u64, ctypes.POINTER(_vp)]),
@@ -154,7 +159,9 @@ class Index:
     in this process (`device` = a sequence of device ids, e.g. range(8); a device may repeat -- several shards on one GPU).
     Row ids are global in both cases; device tensors handed to a multi-device index live on its first device."""
 
-    def __init__(self, dim: int, store_dtype: str = "fp32", device=0, capacity_rows: int = 0):
+    def __init__(self, dim: int, store_dtype: str = "fp32", device=0, capacity_rows: int = 0, shadow: Optional[bool] = None):
+        """shadow: fp32 stores keep a bf16 scoring copy of their rows for the tensor pipelines (include/mqvs.h,
+        mqvs_set_shadow; +50 % HBM, same results); None = the library default (on), False = score the fp32 rows."""
         self._h = _vp(None)
         self.dim = int(dim)
         self.store_dtype = store_dtype
@@ -166,6 +173,8 @@ class Index:
         dev = (_i * len(self.devices))(*self.devices)
         check(load().mqvs_create(len(self.devices), dev, self.dim, DTYPES[store_dtype], int(capacity_rows),
                                  ctypes.byref(self._h)))
+        if shadow is not None:
+            self.set_shadow(shadow)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -286,6 +295,18 @@ class Index:
             raise ValueError("offsets must be [n + 1] and end at len(tokens)")
         check(load().mqvs_column_set_tokens(self._h, int(col_id), _ptr(offsets), _ptr(tokens), offsets.shape[0] - 1))
 
+    def column_set_text(self, col_id: int, offsets: np.ndarray, data: np.ndarray, present: Optional[np.ndarray] = None) -> None:
+        """Upload a text column (the stored documents, for `where_document`): CSR offsets [n + 1] (uint64) into the rows'
+        concatenated UTF-8 bytes (uint8); present: optional flags (0 = the row has no document)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        if offsets.ndim != 1 or offsets.shape[0] < 1 or int(offsets[-1]) != data.shape[0]:
+            raise ValueError("offsets must be [n + 1] and end at len(data)")
+        pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+        if pres is not None and pres.shape[0] != offsets.shape[0] - 1:
+            raise ValueError("one presence flag per row")
+        check(load().mqvs_column_set_text(self._h, int(col_id), _ptr(offsets), _ptr(data), _ptr(pres), offsets.shape[0] - 1))
+
     def filter_build(self, ops, pool: Optional[np.ndarray] = None, live_words: Optional[np.ndarray] = None):
         """ops: list of FilterOp in postfix order -> (DeviceMask, number of allowed rows)."""
         arr = (FilterOp * max(len(ops), 1))(*ops)
@@ -305,6 +326,15 @@ class Index:
 
     def set_path(self, path: int) -> None:
         check(load().mqvs_set_path(self._h, int(path)))
+
+    def set_shadow(self, enable: bool) -> None:
+        """fp32 stores: stream a bf16 scoring shadow on the tensor pipelines (default) or the fp32 rows themselves."""
+        check(load().mqvs_set_shadow(self._h, 1 if enable else 0))
+
+    def shadow_bytes(self) -> int:
+        n = _u64(0)
+        check(load().mqvs_shadow_bytes(self._h, ctypes.byref(n)))
+        return n.value
 
     def set_metric(self, space: str) -> None:
         """Space the rows are ranked in ("cosine" | "l2" | "ip"); a non-cosine space must first be chosen while the

@@ -121,6 +121,41 @@ static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     return B > simt_max && s->n >= 65536;
 }
 
+// Brings the bf16 scoring shadow of an fp32 store up to date (store.h).  -> true when the tensor pipelines may stream it.
+// Allocation follows the store's capacity; when HBM cannot hold the extra 50 % the store goes on scoring its fp32 rows.
+static bool shadow_sync(mqvs_store* s) {
+    if (!s->shadow_on || s->dtype != MQVS_F32 || s->n == 0) return false;
+    if (s->shadow_cap < s->n) {
+        if (s->shadow) cudaFree(s->shadow);  // (cudaFree waits for work that may still read it)
+        s->shadow = nullptr;
+        s->shadow_cap = s->shadow_rows = 0;
+        if (cudaMalloc(&s->shadow, s->cap * (size_t)MQVS_DIM_PAD * 2) != cudaSuccess) {
+            cudaGetLastError();
+            s->shadow = nullptr;
+            s->shadow_on = false;
+            return false;
+        }
+        s->shadow_cap = s->cap;
+    }
+    if (!s->shadow_err && cudaMalloc(&s->shadow_err, sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        s->shadow_err = nullptr;
+        return false;
+    }
+    if (s->shadow_rows < s->n) {
+        if (s->shadow_rows == 0 && cudaMemsetAsync(s->shadow_err, 0, sizeof(unsigned int), s->st) != cudaSuccess) return false;
+        mqvs::launch_shadow_build((const float*)s->rows, s->shadow_rows, s->n - s->shadow_rows, s->shadow, s->shadow_err, s->st);
+        // searches may run on a caller's stream: the conversion (rare: once per add) is finished before any of them starts
+        if (cudaStreamSynchronize(s->st) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        s->stats.kernel_launches += 1;
+        s->shadow_rows = s->n;
+    }
+    return true;
+}
+
 // Will this search run the single-launch latency kernel (every CTA reads the raw queries itself)?
 bool takes_latency_kernel(const mqvs_store* s, int B, int k) {
     return !use_tensor_path(s, B, k) && s->path != 3 && s->metric == MQVS_METRIC_COSINE && mqvs::scan_fused_ok(B, k);
@@ -168,7 +203,7 @@ static void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* m
     static const bool no_band = getenv("MQVS_NO_BAND") != nullptr;  // developer knob: measure what the band pass costs
     if (!no_band && s->coop_ok && s->path != 4 && tc::fused_ok(1, k, s->sm_count)) {
         for (int r = 0; r < band_rounds; ++r) {  // 128 flagged queries per round
-            const char* err = tc::search_band(b, s->last_plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k,
+            const char* err = tc::search_band(b, s->last_plan, s->last_score_rows, s->last_score_dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k,
                                               mask_dev, id_base, out_scores_dev, out_ids_dev, s->fix_counters, st, s->last_space);
             if (err) {
                 cudaGetLastError();  // a refused cooperative launch: the exact scan below still repairs everything
@@ -237,6 +272,14 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     // tile) scans at the tensor roof where the single-launch kernel's two-tile ring is bound by the SM's L2 port -- 3.95 vs
     // 4.3-4.5 ms at 12.5M bf16 rows, B = 256 (profiles/r02_*); its extra launches (~0.15 ms) win from ~3M rows on.
     if (tc_one && s->path == 0 && B > 128 && k <= 128 && s->n >= 3000000ull) tc_one = false;
+    // fp32 stores: the tensor pipelines stream the bf16 shadow (exact scores still come from the fp32 rows)
+    const void* score_rows = s->rows;
+    int score_dtype = s->dtype;
+    const bool shadowed = tensor && shadow_sync(s);
+    if (shadowed) {
+        score_rows = s->shadow;
+        score_dtype = MQVS_BF16;
+    }
     if (tensor) {
         plan = tc::plan(k, B, s->sm_count);
         const size_t small = ((size_t)plan.b_pad * 2 + (size_t)B * 4 + 128 + 256 + 32 + 144) * sizeof(uint32_t);
@@ -304,6 +347,12 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
             }
             space.norm_bounds = (const float*)s->norm_bounds.p;
         }
+        if (shadowed) {
+            space.exact_rows = s->rows;
+            space.shadow_err = s->shadow_err;
+        }
+        s->last_score_rows = score_rows;
+        s->last_score_dtype = score_dtype;
         s->last_b = b;
         s->last_plan = plan;
         s->last_space = space;
@@ -323,7 +372,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         MQVS_EV(0);
         MQVS_EV(1);
         bool coop_refused = false;
-        const char* err = tc::search_fused(b, plan, s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
+        const char* err = tc::search_fused(b, plan, score_rows, score_dtype, (uint32_t)s->n, q_raw_dev, s->dim, (float*)s->qn.p, B, k,
                                            mask_dev, id_base, out_scores_dev, out_ids_dev, bad_epoch,
                                            ++s->epoch, st, &coop_refused, space);
         if (err && coop_refused) {
@@ -344,7 +393,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         s->evr[slot].pending = s->timing;
         s->stats.kernel_launches += 2;
         s->stats.scan_launches += 1;
-        s->stats.scan_bytes += s->n * s->row_bytes();
+        s->stats.scan_bytes += s->n * (uint64_t)MQVS_DIM_PAD * elem_size(score_dtype);  // what the scan streamed (the shadow when there is one)
         s->stats.last_scan_passes = 1;
         s->stats.last_path = 1;
         s->stats.last_pipeline = 3;
@@ -361,7 +410,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     uint32_t passes = 0;
     if (tensor) {
         MQVS_EV(1);
-        const char* err = tc::search(b, plan, s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
+        const char* err = tc::search(b, plan, score_rows, score_dtype, (uint32_t)s->n, (const float*)s->qn.p, B, k, mask_dev,
                                      id_base, out_scores_dev, out_ids_dev, st, space);
         if (err) return fail(MQVS_E_CUDA, "tensor-core search: %s", err);
         MQVS_EV(2);  // brackets prep + score + select + rescore + finalize
@@ -384,7 +433,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
 
     s->evr[slot].pending = s->timing;
     s->stats.scan_launches += passes;
-    s->stats.scan_bytes += (uint64_t)passes * s->n * s->row_bytes();
+    s->stats.scan_bytes += (uint64_t)passes * s->n * (uint64_t)MQVS_DIM_PAD * elem_size(score_dtype);
     s->stats.last_scan_passes = passes;
     s->stats.searches += 1;
     s->stats.queries += (uint64_t)B;
@@ -442,6 +491,7 @@ int create_single(int dev, int dim, int store_dtype, uint64_t capacity_rows, mqv
     s->dev = dev;
     s->dim = dim;
     s->dtype = store_dtype;
+    s->shadow_on = store_dtype == MQVS_F32 && getenv("MQVS_NO_SHADOW") == nullptr;
     s->sm_count = prop.multiProcessorCount;
     s->coop_ok = prop.cooperativeLaunch != 0;
     auto bail = [&](int rc) {
@@ -493,6 +543,8 @@ void destroy_single(mqvs_store* s) {
     if (s->fix_dev) cudaFree(s->fix_dev);
     if (s->fix_counters) cudaFree(s->fix_counters);
     if (s->rows) cudaFree(s->rows);
+    if (s->shadow) cudaFree(s->shadow);
+    if (s->shadow_err) cudaFree(s->shadow_err);
     if (s->norms) cudaFree(s->norms);
     if (s->bad_dev) cudaFree(s->bad_dev);
     if (s->ticket_dev) cudaFree(s->ticket_dev);
@@ -1076,6 +1128,7 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
     fclose(f);
     if ((rc = load_norms(s, path, h.rows)) != MQVS_OK) return rc;
     s->n = h.rows;
+    s->shadow_rows = 0;  // rows were rewritten in place
     s->stats.rows = s->n;
     return MQVS_OK;
 }
@@ -1091,6 +1144,20 @@ MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offse
     if (s->multi) return multi_column_set_tokens(s, col_id, offsets_host, tokens_host, n);
     std::lock_guard<std::mutex> lk(s->mu);
     return column_set_tokens_single(s, col_id, offsets_host, tokens_host, n);
+}
+
+MQVS_API int mqvs_column_set_text(mqvs_t* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                                  const uint8_t* present_host, uint64_t n) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
+    if (!offsets_host) return fail(MQVS_E_INVALID, "offsets is NULL");
+    if (offsets_host[0] != 0) return fail(MQVS_E_INVALID, "offsets must start at 0");
+    for (uint64_t r = 0; r < n; ++r)
+        if (offsets_host[r + 1] < offsets_host[r]) return fail(MQVS_E_INVALID, "offsets must not decrease (row %llu)", (unsigned long long)r);
+    if (offsets_host[n] && !bytes_host) return fail(MQVS_E_INVALID, "bytes is NULL");
+    if (s->multi) return multi_column_set_text(s, col_id, offsets_host, bytes_host, present_host, n);
+    std::lock_guard<std::mutex> lk(s->mu);
+    return column_set_text_single(s, col_id, offsets_host, bytes_host, present_host, n);
 }
 
 MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out) {
@@ -1143,6 +1210,7 @@ MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* 
         s->n = m;
         s->stats.rows = m;
         s->bounds_rows = 0;
+        s->shadow_rows = 0;  // rows moved: the scoring shadow is rebuilt before the next tensor search
         for (auto& c : s->columns) c.used = false;  // row numbers changed under them
         s->f_table_dirty = true;
     }
@@ -1177,6 +1245,33 @@ int mqvs::api::column_set_tokens_single(mqvs_store* s, int col_id, const uint64_
     c.type = MQVS_COL_TOKENS;
     c.used = true;
     c.has_present = false;
+    s->f_table_dirty = true;
+    return MQVS_OK;
+}
+
+int mqvs::api::column_set_text_single(mqvs_store* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                                      const uint8_t* present_host, uint64_t n) {
+    CU(cudaSetDevice(s->dev));
+    auto& c = s->columns[col_id];
+    int rc;
+    const uint64_t nbytes = offsets_host[n];
+    if ((rc = c.offsets.ensure((n + 1) * 8)) != MQVS_OK) return rc;
+    if ((rc = c.values.ensure(std::max<uint64_t>(nbytes, 8))) != MQVS_OK) return rc;
+    CU(cudaMemcpyAsync(c.offsets.p, offsets_host, (n + 1) * 8, cudaMemcpyHostToDevice, s->st));
+    if (nbytes) CU(cudaMemcpyAsync(c.values.p, bytes_host, nbytes, cudaMemcpyHostToDevice, s->st));
+    c.has_present = present_host != nullptr;
+    std::vector<uint32_t> bits;
+    if (present_host) {
+        bits.assign(std::max<uint64_t>((n + 31) / 32, 1), 0u);
+        for (uint64_t r = 0; r < n; ++r)
+            if (present_host[r]) bits[r >> 5] |= 1u << (r & 31);
+        if ((rc = c.present.ensure(bits.size() * 4)) != MQVS_OK) return rc;
+        CU(cudaMemcpyAsync(c.present.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    c.n = n;
+    c.type = MQVS_COL_TEXT;
+    c.used = true;
     s->f_table_dirty = true;
     return MQVS_OK;
 }
@@ -1232,12 +1327,16 @@ int mqvs::api::filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, in
         if (o.op == MQVS_OP_AND || o.op == MQVS_OP_OR) {
             if (depth < 2) return fail(MQVS_E_INVALID, "filter program: operator %d at %d lacks operands", o.op, i);
             --depth;
-        } else if (o.op >= MQVS_OP_EQ && o.op <= MQVS_OP_NOT_CONTAINS) {
+        } else if (o.op >= MQVS_OP_EQ && o.op <= MQVS_OP_TEXT_NOT_CONTAINS) {
             if (o.col < 0 || o.col >= kFilterMaxCols || !s->columns[o.col].used)
                 return fail(MQVS_E_INVALID, "filter program: column %d was never set", o.col);
             const bool token_op = o.op == MQVS_OP_CONTAINS || o.op == MQVS_OP_NOT_CONTAINS;
-            if (token_op != (s->columns[o.col].type == MQVS_COL_TOKENS))
+            const bool text_op = o.op == MQVS_OP_TEXT_CONTAINS || o.op == MQVS_OP_TEXT_NOT_CONTAINS;
+            if (token_op != (s->columns[o.col].type == MQVS_COL_TOKENS) || text_op != (s->columns[o.col].type == MQVS_COL_TEXT))
                 return fail(MQVS_E_INVALID, "filter program: operation %d does not fit the type of column %d", o.op, o.col);
+            if (text_op && (o.set_len < 1 || o.set_len > MQVS_MAX_NEEDLE || (uint64_t)o.set_off * 8 + o.set_len > pool_len * 8))
+                return fail(MQVS_E_INVALID, "filter program: needle of operation %d is empty, longer than %d bytes or leaves the "
+                                            "constant pool", i, MQVS_MAX_NEEDLE);
             if ((o.op == MQVS_OP_IN || o.op == MQVS_OP_NIN) && (uint64_t)o.set_off + o.set_len > pool_len)
                 return fail(MQVS_E_INVALID, "filter program: set of operation %d leaves the constant pool", i);
             if (++depth > 32) return fail(MQVS_E_INVALID, "filter program nests deeper than 32");
@@ -1359,6 +1458,29 @@ MQVS_API int mqvs_get_norms(mqvs_t* s, uint64_t first_row, uint64_t n, float* ou
     CU(cudaSetDevice(s->dev));
     CU(cudaStreamSynchronize(s->st));
     CU(cudaMemcpy(out_host, s->norms + first_row, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_set_shadow(mqvs_t* s, int enable) {
+    if (!s) return fail(MQVS_E_INVALID, "NULL handle");
+    if (s->multi) return multi_set_shadow(s, enable);
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->dev));
+    s->shadow_on = enable != 0 && s->dtype == MQVS_F32;
+    if (!s->shadow_on && s->shadow) {
+        CU(cudaStreamSynchronize(s->st));
+        cudaFree(s->shadow);
+        s->shadow = nullptr;
+        s->shadow_cap = s->shadow_rows = 0;
+    }
+    return MQVS_OK;
+}
+
+MQVS_API int mqvs_shadow_bytes(mqvs_t* s, uint64_t* bytes_out) {
+    if (!s || !bytes_out) return fail(MQVS_E_INVALID, "NULL argument");
+    if (s->multi) return multi_shadow_bytes(s, bytes_out);
+    std::lock_guard<std::mutex> lk(s->mu);
+    *bytes_out = s->shadow ? s->shadow_cap * (uint64_t)MQVS_DIM_PAD * 2 : 0;
     return MQVS_OK;
 }
 

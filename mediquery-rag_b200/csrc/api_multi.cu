@@ -543,6 +543,7 @@ int multi_load(mqvs_store* P, const char* path) {
     for (int p = 0; p < M->W && rc == MQVS_OK; ++p) {
         cudaSetDevice(M->devs[p]);
         M->parts[p]->n = 0;
+        M->parts[p]->shadow_rows = 0;  // rows are rewritten in place below
         rc = grow(M->parts[p], M->map.count(p, h.rows));
     }
     M->n = 0;
@@ -642,6 +643,29 @@ int multi_column_set_tokens(mqvs_store* P, int col_id, const uint64_t* offsets_h
     });
     for (int p = 0; p < M->W; ++p) {
         int rc = column_set_tokens_single(M->parts[p], col_id, off[p].data(), tok[p].data(), off[p].size() - 1);
+        if (rc != MQVS_OK) return rc;
+    }
+    return MQVS_OK;
+}
+
+int multi_column_set_text(mqvs_store* P, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                          const uint8_t* present_host, uint64_t n) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard guard;
+    Multi* M = P->multi;
+    std::vector<std::vector<uint64_t>> off(M->W);
+    std::vector<std::vector<uint8_t>> txt(M->W), pres(M->W);
+    for (int p = 0; p < M->W; ++p) off[p].push_back(0);
+    for_block_runs(M->map, 0, n, [&](int p, uint64_t, uint64_t cnt, uint64_t first) {
+        // a run of rows is a contiguous byte range of the CSR text
+        txt[p].insert(txt[p].end(), bytes_host + offsets_host[first], bytes_host + offsets_host[first + cnt]);
+        const uint64_t shift = off[p].back() - offsets_host[first];
+        for (uint64_t r = first; r < first + cnt; ++r) off[p].push_back(offsets_host[r + 1] + shift);
+        if (present_host) pres[p].insert(pres[p].end(), present_host + first, present_host + first + cnt);
+    });
+    for (int p = 0; p < M->W; ++p) {
+        int rc = column_set_text_single(M->parts[p], col_id, off[p].data(), txt[p].data(), present_host ? pres[p].data() : nullptr,
+                                        off[p].size() - 1);
         if (rc != MQVS_OK) return rc;
     }
     return MQVS_OK;
@@ -753,6 +777,31 @@ int multi_set_path(mqvs_store* P, int path) {
         c->path = path;
     }
     P->path = path;
+    return MQVS_OK;
+}
+
+int multi_set_shadow(mqvs_store* P, int enable) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard guard;
+    for (mqvs_store* c : P->multi->parts) {
+        std::lock_guard<std::mutex> lc(c->mu);
+        cudaSetDevice(c->dev);
+        c->shadow_on = enable != 0 && c->dtype == MQVS_F32;
+        if (!c->shadow_on && c->shadow) {
+            cudaStreamSynchronize(c->st);
+            cudaFree(c->shadow);
+            c->shadow = nullptr;
+            c->shadow_cap = c->shadow_rows = 0;
+        }
+    }
+    return MQVS_OK;
+}
+
+int multi_shadow_bytes(mqvs_store* P, uint64_t* bytes_out) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    uint64_t total = 0;
+    for (mqvs_store* c : P->multi->parts) total += c->shadow ? c->shadow_cap * (uint64_t)MQVS_DIM_PAD * 2 : 0;
+    *bytes_out = total;
     return MQVS_OK;
 }
 

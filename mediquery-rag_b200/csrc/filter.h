@@ -12,11 +12,12 @@ constexpr int kFilterMaxOps = 64;
 constexpr int kFilterMaxCols = 64;
 
 struct FilterColumn {
-    const void* values;       // int64 or float64 [n]; MQVS_COL_TOKENS: int64 token ids, all rows concatenated
+    const void* values;       // int64 or float64 [n]; MQVS_COL_TOKENS: int64 token ids, all rows concatenated;
+                              // MQVS_COL_TEXT: the documents' UTF-8 bytes, all rows concatenated
     const uint32_t* present;  // presence bits, or nullptr = every row has the field
     uint64_t n;
-    int type;                 // MQVS_COL_I64 / MQVS_COL_F64 / MQVS_COL_TOKENS
-    const uint64_t* offsets;  // MQVS_COL_TOKENS: [n + 1] CSR offsets into values
+    int type;                 // MQVS_COL_I64 / MQVS_COL_F64 / MQVS_COL_TOKENS / MQVS_COL_TEXT
+    const uint64_t* offsets;  // MQVS_COL_TOKENS / MQVS_COL_TEXT: [n + 1] CSR offsets into values
 };
 
 struct FilterArgs {

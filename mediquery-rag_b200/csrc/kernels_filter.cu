@@ -3,6 +3,8 @@
 // dictionary codes assigned by the host, ordered like the strings) with one presence bit per row; the filter arrives as
 // a postfix program of leaf comparisons and AND / OR.  One thread per row, one ballot per warp = one mask word.
 // HBM-bound: 8 bytes per row per referenced column (+ 1 bit presence, + 1 bit live) -> 4 bytes per 32 rows out.
+// `where_document` ($contains over the stored documents) is a leaf of the same program: the documents' UTF-8 bytes are a
+// CSR text column and a warp searches its 32 rows one after another with coalesced byte loads (warp_text_contains).
 #include "common.cuh"
 #include "filter.h"
 #include "launch.h"
@@ -33,6 +35,33 @@ __device__ __forceinline__ bool leaf_f64(int op, double v, double c) {
     }
 }
 
+// where_document leaf: does row `row`'s document contain the needle?  The WARP searches one row at a time (lane l tests the
+// start positions b + l, b + l + 32, ...: byte loads of neighbouring lanes coalesce) and takes its 32 rows in turn; the
+// answer for lane l's own row comes back as bit l.  Every argument but the lane id is warp-uniform.
+__device__ __forceinline__ uint32_t warp_text_contains(const FilterColumn& col, uint64_t warp_row0, uint64_t n_rows,
+                                                       const uint8_t* __restrict__ needle, uint32_t m, int lane) {
+    const uint8_t* __restrict__ text = reinterpret_cast<const uint8_t*>(col.values);
+    const uint8_t n0 = __ldg(needle);
+    uint32_t hits = 0;
+    for (int rr = 0; rr < 32; ++rr) {
+        const uint64_t row = warp_row0 + rr;
+        if (row >= n_rows || row >= col.n) break;
+        const uint64_t b = col.offsets[row], e = col.offsets[row + 1];
+        if (e - b < m) continue;
+        const uint64_t last = e - m;  // last start position
+        for (uint64_t base = b; base <= last; base += 32) {
+            const uint64_t pos = base + lane;
+            bool found = pos <= last && text[pos] == n0;
+            for (uint32_t j = 1; found && j < m; ++j) found = text[pos + j] == __ldg(needle + j);
+            if (__any_sync(0xffffffffu, found)) {
+                hits |= 1u << rr;
+                break;
+            }
+        }
+    }
+    return hits;
+}
+
 __global__ void __launch_bounds__(kFilterThreads)
 filter_eval_kernel(const FilterArgs a) {
     __shared__ mqvs_filter_op prog[kFilterMaxOps];
@@ -51,7 +80,14 @@ filter_eval_kernel(const FilterArgs a) {
             continue;
         }
         bool hit = false;
-        if (in_range) {
+        if (op.op == MQVS_OP_TEXT_CONTAINS || op.op == MQVS_OP_TEXT_NOT_CONTAINS) {  // warp-uniform branch (one program)
+            const FilterColumn col = a.cols[op.col];
+            const int lane = threadIdx.x & 31;
+            const uint32_t hits = warp_text_contains(col, r - lane, a.n_rows, reinterpret_cast<const uint8_t*>(a.pool) + 8ull * op.set_off,
+                                                     op.set_len, lane);
+            const bool present = r < col.n && (col.present == nullptr || ((col.present[r >> 5] >> (r & 31)) & 1u));
+            hit = in_range && ((present && ((hits >> lane) & 1u)) != (op.op == MQVS_OP_TEXT_NOT_CONTAINS));
+        } else if (in_range) {
             const FilterColumn col = a.cols[op.col];
             // rows beyond the column's length (added since it was uploaded) count as "field missing"
             const bool present = r < col.n && (col.present == nullptr || ((col.present[r >> 5] >> (r & 31)) & 1u));

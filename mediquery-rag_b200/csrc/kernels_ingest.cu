@@ -116,6 +116,39 @@ __global__ void norm_bounds_kernel(const float* __restrict__ norms, uint64_t n_r
     if (lane == 0) bounds[chunk] = make_float2(hi, lo);
 }
 
+// bf16 scoring shadow of an fp32 store (store.h: mqvs_store::shadow): one warp per row, 16-byte loads / 8-byte stores; the
+// largest ||x - bf16(x)|| over the rows converted (what the tensor path's error bound adds for the rounded corpus operand)
+// is raised into *err_bits -- non-negative floats order like their bit patterns.
+__global__ void __launch_bounds__(kIngestWarps * 32)
+shadow_build_kernel(const float* __restrict__ rows, uint64_t first, uint64_t n, __nv_bfloat16* __restrict__ shadow,
+                    unsigned int* __restrict__ err_bits) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * kIngestWarps;
+    float err_max = 0.0f;
+    for (uint64_t i = (uint64_t)blockIdx.x * kIngestWarps + (threadIdx.x >> 5); i < n; i += warps_total) {
+        const float* src = rows + (first + i) * (uint64_t)kDim;
+        __nv_bfloat16* dst = shadow + (first + i) * (uint64_t)kDim;
+        float err2 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const float4 y = ld_stream_f4(src + c * 128 + lane * 4);
+            const __nv_bfloat162 a = __floats2bfloat162_rn(y.x, y.y), b = __floats2bfloat162_rn(y.z, y.w);
+            const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+            const float d0 = y.x - fa.x, d1 = y.y - fa.y, d2 = y.z - fb.x, d3 = y.w - fb.y;
+            err2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            uint2 w;
+            w.x = *reinterpret_cast<const uint32_t*>(&a);
+            w.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(dst + c * 128 + lane * 4) = w;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, m);
+        err_max = fmaxf(err_max, err2);
+    }
+    // sqrt rounded up a little: the bound must not be smaller than the true norm of the rounding error
+    if (lane == 0 && err_max > 0.0f) atomicMax(err_bits, __float_as_uint(sqrtf(err_max) * 1.0001f));
+}
+
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ rows, const int64_t* __restrict__ ids, uint64_t n, int dim,
                                    float* __restrict__ out) {
@@ -160,6 +193,13 @@ void launch_norm_bounds(const float* norms, uint64_t n_rows, uint64_t first_chun
     if (first_chunk >= n_chunks) return;
     const uint64_t blocks = (n_chunks - first_chunk + 7) / 8;
     norm_bounds_kernel<<<(unsigned)blocks, 256, 0, st>>>(norms, n_rows, first_chunk, n_chunks, reinterpret_cast<float2*>(bounds));
+}
+
+void launch_shadow_build(const float* rows, uint64_t first, uint64_t n, void* shadow, unsigned int* err_bits, cudaStream_t st) {
+    if (n == 0) return;
+    const uint64_t blocks = (n + kIngestWarps - 1) / kIngestWarps;
+    const int grid = (int)(blocks < 148ull * 16 ? blocks : 148ull * 16);
+    shadow_build_kernel<<<grid, kIngestWarps * 32, 0, st>>>(rows, first, n, (__nv_bfloat16*)shadow, err_bits);
 }
 
 void launch_gather_rows(const void* rows, int dtype, const int64_t* ids, uint64_t n, int dim, float* out,

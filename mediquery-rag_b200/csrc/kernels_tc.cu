@@ -364,7 +364,8 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 template <typename T>
 __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_pad, T* __restrict__ q_op,
                                     float* __restrict__ eps, uint32_t* __restrict__ tau, int metric, float amax,
-                                    const float* __restrict__ qnorm, float* __restrict__ hq) {
+                                    const float* __restrict__ qnorm, float* __restrict__ hq,
+                                    const unsigned int* __restrict__ shadow_err) {
     const int q = blockIdx.x, lane = threadIdx.x;  // one warp per query row
     float err2 = 0.f;
     for (int j = lane; j < kDim; j += 32) {
@@ -386,6 +387,8 @@ __global__ void prep_queries_kernel(const float* __restrict__ qn, int B, int b_p
         // error < 2^-10 each): |err| <= 2^-9 * sum|q_i x_i| <= 2^-9 * 1.001.  Both get 1e-4 for the tensor core's fp32
         // accumulation (768 additions, each off by at most 2^-23 of a partial sum bounded by ||q|| ||x||).
         float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 1e-4f : 2.0f * 0.0009765625f * 1.001f + 1e-4f;
+        // bf16 SHADOW of an fp32 store: the corpus operand is rounded too: + ||q|| ||x - bf16(x)||, the largest over the rows
+        if (sizeof(T) == 2 && shadow_err != nullptr) e += __uint_as_float(__ldg(shadow_err)) * 1.0002f;
         if (metric != MQVS_METRIC_COSINE) {  // l2 / ip ranking scores t = a s - a^2 h: same bound as prep_fused_kernel
             const float h = metric == MQVS_METRIC_L2 && q < B ? __fdiv_rn(0.5f, fmaxf(qnorm[q], kEps)) : 0.0f;
             if (q < B) hq[q] = h;  // (padding rows never read theirs)
@@ -780,11 +783,12 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
         const float* qn = qn_all + (size_t)q0 * kDim;
         if (dtype == MQVS_F32)
             prep_queries_kernel<float><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (float*)b.q_op, b.eps + q0, b.tau, space.metric,
-                                                               space.amax, xf ? space.qnorm + q0 : nullptr, xf ? b.hq + q0 : nullptr);
+                                                               space.amax, xf ? space.qnorm + q0 : nullptr, xf ? b.hq + q0 : nullptr,
+                                                               nullptr);
         else
             prep_queries_kernel<__nv_bfloat16><<<p.b_pad, 32, 0, st>>>(qn, B, p.b_pad, (__nv_bfloat16*)b.q_op, b.eps + q0, b.tau,
                                                                        space.metric, space.amax, xf ? space.qnorm + q0 : nullptr,
-                                                                       xf ? b.hq + q0 : nullptr);
+                                                                       xf ? b.hq + q0 : nullptr, space.exact_rows ? space.shadow_err : nullptr);
 
         g_trace.mark("prep", st);
         ScoreArgs a{};
@@ -860,9 +864,9 @@ const char* search(const Buffers& b, const Plan& p, const void* rows, int dtype,
 
         const size_t items = (size_t)B * p.kprime;
         const unsigned rs_grid = (unsigned)((items + 7) / 8);
-        if (dtype == MQVS_F32)
-            rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)rows, qn, b.short_keys, B, p.kprime, b.exact_keys, space.metric,
-                                                           space.norms, b.hq + q0);
+        if (dtype == MQVS_F32 || space.exact_rows != nullptr)  // (scored over the bf16 shadow: the exact scores come from the fp32 rows)
+            rescore_kernel<float><<<rs_grid, 256, 0, st>>>((const float*)(space.exact_rows ? space.exact_rows : rows), qn, b.short_keys, B,
+                                                           p.kprime, b.exact_keys, space.metric, space.norms, b.hq + q0);
         else
             rescore_kernel<__nv_bfloat16><<<rs_grid, 256, 0, st>>>((const __nv_bfloat16*)rows, qn, b.short_keys, B, p.kprime,
                                                                    b.exact_keys, space.metric, space.norms, b.hq + q0);

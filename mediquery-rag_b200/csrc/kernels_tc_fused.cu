@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(128)
 prep_fused_kernel(const float* __restrict__ q_raw, int dim, int vec4, int B, float* __restrict__ qn, T* __restrict__ q_op,
                   float* __restrict__ eps, uint32_t* __restrict__ tau, unsigned int* __restrict__ gbar,
                   uint32_t* __restrict__ flag_count, unsigned int* __restrict__ bad_epoch, unsigned int epoch,
-                  int metric, float amax, float* __restrict__ hq, float* __restrict__ qnorm) {
+                  int metric, float amax, float* __restrict__ hq, float* __restrict__ qnorm,
+                  const unsigned int* __restrict__ shadow_err) {
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         gbar[0] = gbar[1] = gbar[2] = 0u;
@@ -67,6 +68,7 @@ prep_fused_kernel(const float* __restrict__ q_raw, int dim, int vec4, int B, flo
     if (lane == 0) {
         // same bounds as prep_queries_kernel
         float e = sizeof(T) == 2 ? sqrtf(err2) * 1.004f * 1.0001f + 1e-4f : 2.0f * 0.0009765625f * 1.001f + 1e-4f;
+        if (sizeof(T) == 2 && shadow_err != nullptr) e += __uint_as_float(__ldg(shadow_err)) * 1.0002f;  // rounded corpus operand
         if (metric != MQVS_METRIC_COSINE) {
             // ranking score t = a s - a^2 h: an error of e in the cosine is at most amax e in t, plus the fp32 rounding of
             // the transform itself (three roundings of terms no larger than amax + amax^2 h)
@@ -170,11 +172,11 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     if (dtype == MQVS_F32)
         prep_fused_kernel<float><<<rows_q / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (float*)b.q_op, b.eps, b.tau, b.gbar,
                                                          b.flag_count, bad_epoch, epoch, space.metric, space.amax, b.hq,
-                                                         space.qnorm);
+                                                         space.qnorm, nullptr);
     else
         prep_fused_kernel<__nv_bfloat16><<<rows_q / 4, 128, 0, st>>>(q_raw, dim, vec4, B, qn, (__nv_bfloat16*)b.q_op, b.eps, b.tau,
                                                                  b.gbar, b.flag_count, bad_epoch, epoch, space.metric,
-                                                                 space.amax, b.hq, space.qnorm);
+                                                                 space.amax, b.hq, space.qnorm, space.exact_rows ? space.shadow_err : nullptr);
     g_trace.mark("prep", st);
     FusedArgs a{};
     a.n_rows = n_rows;
@@ -188,6 +190,7 @@ const char* search_fused(const Buffers& b, const Plan& p, const void* rows, int 
     a.lists = b.lists;
     a.gbar = b.gbar;
     a.rows = rows;
+    a.rows_f32 = dtype == MQVS_BF16 ? space.exact_rows : nullptr;
     a.qn = qn;
     a.eps = b.eps;
     a.k = k;
@@ -251,6 +254,7 @@ const char* search_band(const Buffers& b, const Plan& p, const void* rows, int d
     a.lists = b.lists;
     a.gbar = b.gbar;
     a.rows = rows;
+    a.rows_f32 = dtype == MQVS_BF16 ? space.exact_rows : nullptr;
     a.qn = qn;
     a.eps = b.eps;
     a.k = k;

@@ -25,6 +25,11 @@ void launch_synth_normalize(uint64_t seed, uint64_t first_index, uint64_t n, int
 // l2 / ip spaces reject a chunk without transforming its scores (tc_device.cuh:chunk_score_bound).
 void launch_norm_bounds(const float* norms, uint64_t n_rows, uint64_t first_chunk, float* bounds, cudaStream_t st);
 
+// bf16 scoring shadow of an fp32 store: rows [first, first + n) of `rows` ([*, 768] fp32, normalised) -> the same rows of
+// `shadow` ([*, 768] bf16, round to nearest); *err_bits is raised (atomicMax on the bit pattern) to the largest
+// ||x - bf16(x)|| among them, rounded up.
+void launch_shadow_build(const float* rows, uint64_t first, uint64_t n, void* shadow, unsigned int* err_bits, cudaStream_t st);
+
 // K2 (SIMT) + K3: exact fp32 scan of `n_rows` stored rows against nq (<= scan_max_queries_per_pass) normalised
 // queries, fused per-warp top-k with optional allow-mask; writes per-CTA sorted candidate keys
 // cand[q][cta][k].  Returns the grid size used (number of CTAs) so the merge knows the layout.

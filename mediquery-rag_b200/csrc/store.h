@@ -125,6 +125,17 @@ struct mqvs_store {
     float norm_max = 0.0f;    // largest ||x|| over the rows accepted so far
     mqvs::DevBuf norm_bounds; // [ceil(n / 32)][2] (max, min) norm per 32-row chunk, brought up to date before a tensor search
     uint64_t bounds_rows = 0; // rows the bounds cover
+    // bf16 scoring SHADOW of an fp32 store (mqvs_set_shadow; on by default): the tensor pipelines stream this copy -- half
+    // the bytes per row, kind::f16 instead of kind::tf32 -- and take every exact score (shortlist rescoring, band pass,
+    // exact-scan repair) from the fp32 rows, so results are the same bits with or without it.  Built lazily: rows
+    // [shadow_rows, n) are converted before the next tensor search; anything that rewrites rows in place resets shadow_rows.
+    bool shadow_on = true;
+    void* shadow = nullptr;              // [shadow_cap, 768] bf16
+    uint64_t shadow_cap = 0;             // rows allocated
+    uint64_t shadow_rows = 0;            // rows converted so far
+    unsigned int* shadow_err = nullptr;  // device word: bits of the largest ||x - bf16(x)|| over the converted rows
+    const void* last_score_rows = nullptr;  // what the last tensor search streamed (the band pass streams the same)
+    int last_score_dtype = MQVS_F32;
     cudaStream_t st = nullptr;
     // ring of event quads so that back-to-back async searches never wait on each other's timing
     static constexpr int kEvRing = 32;
@@ -211,6 +222,8 @@ int finish_search(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t
                   int64_t* out_ids_dev, cudaStream_t st, bool* changed);
 int column_set_single(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host, uint64_t n);
 int column_set_tokens_single(mqvs_store* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
+int column_set_text_single(mqvs_store* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                           const uint8_t* present_host, uint64_t n);
 int filter_build_single(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                         const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 int get_rows_single(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out_host);
@@ -244,6 +257,8 @@ int multi_save(mqvs_store* s, const char* path, uint64_t first_row);
 int multi_load(mqvs_store* s, const char* path);
 int multi_column_set(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host, uint64_t n);
 int multi_column_set_tokens(mqvs_store* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n);
+int multi_column_set_text(mqvs_store* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
+                          const uint8_t* present_host, uint64_t n);
 int multi_filter_build(mqvs_store* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                        const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out);
 int multi_get_stats(mqvs_store* s, mqvs_stats* out);
@@ -251,6 +266,8 @@ int multi_set_metric(mqvs_store* s, int metric);
 int multi_norm_deviation(mqvs_store* s, float* out);
 int multi_get_norms(mqvs_store* s, uint64_t first_row, uint64_t n, float* out_host);
 int multi_set_path(mqvs_store* s, int path);
+int multi_set_shadow(mqvs_store* s, int enable);
+int multi_shadow_bytes(mqvs_store* s, uint64_t* bytes_out);
 
 }  // namespace api
 }  // namespace mqvs

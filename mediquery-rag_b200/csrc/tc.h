@@ -41,6 +41,10 @@ struct Space {
     const float* norm_bounds = nullptr;  // [ceil(n_rows / 32)][2] largest and smallest norm of every 32-row chunk
     float amax = 1.0f;             // largest ||x||: the tensor-core error bound of a ranking score is amax * eps
     float* qnorm = nullptr;        // [B] out: ||q|| of the raw queries (the exact-scan repair ranks with them)
+    // bf16 scoring shadow of an fp32 store: the `rows` / `dtype` arguments of the searches below are then the SHADOW (what
+    // the tensor cores stream), and everything exact -- K4 rescoring, the tail of the single-launch kernel -- reads these:
+    const void* exact_rows = nullptr;         // fp32 rows [n_rows, 768], or nullptr = `rows` are the stored rows themselves
+    const unsigned int* shadow_err = nullptr; // device: bits of the largest ||x - bf16(x)|| over the rows (added to eps)
 };
 
 Plan plan(int k, int B, int sm_count);

@@ -3,6 +3,8 @@
 // false) and kernels_tc_fused_space.cu (the l2 / ip spaces over raw vectors, XF = true).
 #pragma once
 
+#include <type_traits>
+
 #include "launch.h"
 #include "tc_device.cuh"
 
@@ -35,7 +37,9 @@ struct FusedArgs {
     uint32_t* cnt;         // [grid][128]
     uint64_t* lists;       // [grid][128][CAP]
     unsigned int* gbar;    // [3] grid barrier counters, zero on entry (prep)
-    const void* rows;      // corpus, for the exact rescoring
+    const void* rows;      // corpus as the tensor cores stream it (and, unless rows_f32 is set, as the exact rescoring reads it)
+    const void* rows_f32;  // bf16 instantiations over the scoring SHADOW of an fp32 store: the stored fp32 rows the exact
+                           // rescoring reads instead; nullptr otherwise
     const float* qn;       // [B][768] normalised fp32 queries
     const float* eps;      // [B]
     int k;
@@ -473,36 +477,45 @@ __device__ __forceinline__ void fused_tail(const FusedArgs& a, int G, uint8_t* s
     if (tid == 0) MQVS_STAMP(8);
 
     // K4: canonical fp32 rescoring, one warp per row, four rows in flight per warp
-    const T* rows = reinterpret_cast<const T*>(a.rows);
     float4 qv[kChunks];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) qv[c] = *reinterpret_cast<const float4*>(a.qn + (size_t)qf * kDim + c * 128 + lane * 4);
     float hq = 0.0f;
     if constexpr (XF) hq = __ldg(a.hq + qf);
-    constexpr int kInFlight = 4;
     int n_valid = 0;
-    for (int i0 = warp * kInFlight; i0 < nC; i0 += NW * kInFlight) {
-        uint64_t key[kInFlight];
-        RowFrag<T> x[kInFlight];
+    auto rescore = [&](auto* rows) {  // rows: the stored rows, in their own type
+        using TR = std::remove_cv_t<std::remove_pointer_t<decltype(rows)>>;
+        constexpr int kInFlight = 4;
+        for (int i0 = warp * kInFlight; i0 < nC; i0 += NW * kInFlight) {
+            uint64_t key[kInFlight];
+            RowFrag<TR> x[kInFlight];
 #pragma unroll
-        for (int u = 0; u < kInFlight; ++u) {
-            key[u] = i0 + u < nC ? C[i0 + u] : 0ull;
-            if (key[u] != 0ull) x[u].load(rows + (size_t)key_id(key[u]) * kDim, lane);  // warp-uniform
-        }
-#pragma unroll
-        for (int u = 0; u < kInFlight; ++u) {
-            uint64_t out = 0ull;
-            if (key[u] != 0ull) {
-                float4 xv[kChunks];
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) xv[c] = x[u].get(c);
-                float sc = warp_butterfly_sum(lane_dot(qv, xv));
-                if constexpr (XF) sc = rank_score(a.metric, sc, __ldg(a.norms + key_id(key[u])), hq);  // exact, as the SIMT scan
-                out = pack_key(sc, key_id(key[u]));
-                ++n_valid;
+            for (int u = 0; u < kInFlight; ++u) {
+                key[u] = i0 + u < nC ? C[i0 + u] : 0ull;
+                if (key[u] != 0ull) x[u].load(rows + (size_t)key_id(key[u]) * kDim, lane);  // warp-uniform
             }
-            if (lane == 0 && i0 + u < nC) ex[i0 + u] = out;
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) {
+                uint64_t out = 0ull;
+                if (key[u] != 0ull) {
+                    float4 xv[kChunks];
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c) xv[c] = x[u].get(c);
+                    float sc = warp_butterfly_sum(lane_dot(qv, xv));
+                    if constexpr (XF) sc = rank_score(a.metric, sc, __ldg(a.norms + key_id(key[u])), hq);  // exact, as the SIMT scan
+                    out = pack_key(sc, key_id(key[u]));
+                    ++n_valid;
+                }
+                if (lane == 0 && i0 + u < nC) ex[i0 + u] = out;
+            }
         }
+    };
+    if constexpr (sizeof(T) == 2) {
+        // scored over the bf16 shadow of an fp32 store: the exact scores come from the stored fp32 rows (block-uniform branch)
+        if (a.rows_f32 != nullptr) rescore(reinterpret_cast<const float*>(a.rows_f32));
+        else rescore(reinterpret_cast<const T*>(a.rows));
+    } else {
+        rescore(reinterpret_cast<const T*>(a.rows));
     }
     if (lane == 0 && n_valid) atomicAdd(valid_s, n_valid);
     __syncthreads();

@@ -3,7 +3,8 @@
 The reference passes no filter today (/root/reference/src/agents/nodes.py:93 calls similarity_search(q, k=5)),
 but the Chroma surface it programs against takes `filter=` and BASELINE.json config 5 exercises it.  Grammar:
 {"field": v} (== $eq) | {"field": {"$eq|$ne|$gt|$gte|$lt|$lte": v}} | {"field": {"$in|$nin": [..]}} |
-{"field": {"$contains|$not_contains": token}} | {"$and": [..]} | {"$or": [..]}.
+{"field": {"$contains|$not_contains": token}} | {"$and": [..]} | {"$or": [..]}; `where_document` ($contains /
+$not_contains over the stored documents, $and / $or) is the same kind of program over a text column (DeviceFilter).
 $contains / $not_contains on a METADATA field is token-set membership: the reference stores `tags` as one comma-joined
 string per chunk (/root/reference/src/ingest_medical.py:66-67,75-79, e.g. "慢性病，代谢性疾病，发病率"), so "chunks tagged X" is
 `{"tags": {"$contains": "X"}}`: the value is split on "," and "，", tokens are stripped, X must equal one of them
@@ -231,6 +232,24 @@ def evaluate_document(where_document: Optional[Mapping[str, Any]], texts: Sequen
     raise FilterError(f"unknown where_document operator {op}")
 
 
+def texts_csr(texts: Sequence[Optional[str]]):
+    """Stored documents -> (offsets uint64 [n + 1], UTF-8 bytes uint8, present bool [n]): the text column of the device-side
+    `where_document` (mqvs_column_set_text).  Byte-wise search over UTF-8 finds exactly the substrings `str.__contains__`
+    finds (UTF-8 is self-synchronising).  Sequences that know their own layout (vectorstore._RowColumn: millions of
+    bulk-loaded rows without a document) provide `utf8_csr` themselves."""
+    own = getattr(texts, "utf8_csr", None)
+    if own is not None:
+        return own()
+    n = len(texts)
+    present = np.fromiter((t is not None for t in texts), dtype=bool, count=n)
+    enc = [t.encode("utf-8", "surrogatepass") if t is not None else b"" for t in texts]
+    offsets = np.zeros(n + 1, np.uint64)
+    if n:
+        np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.uint64, count=n), out=offsets[1:])
+    data = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    return offsets, data, present
+
+
 def pack_mask(allowed: np.ndarray) -> np.ndarray:
     """bool[n] -> uint32[ceil(n/32)], bit r&31 of word r>>5 == allowed[r] (padding bits are 0)."""
     allowed = np.asarray(allowed, dtype=bool)
@@ -304,12 +323,34 @@ def _typed_column(vals: np.ndarray, present: np.ndarray):
 
 
 class DeviceFilter:
-    """Compiles Chroma `where` dicts to mqvs_filter_op programs and keeps the referenced metadata columns resident on
-    the device (re-uploaded when MetadataColumns.version moves).  `index` is a _native.Index."""
+    """Compiles Chroma `where` / `where_document` dicts to mqvs_filter_op programs and keeps the referenced metadata
+    columns (and, for where_document, the documents' UTF-8 text) resident on the device, re-uploaded when
+    MetadataColumns.version moves.  `index` is a _native.Index; `texts` the row-aligned documents (a sequence of
+    Optional[str], or a callable returning the current one)."""
 
-    def __init__(self, index: Any, cols: MetadataColumns):
+    def __init__(self, index: Any, cols: MetadataColumns, texts: Any = None):
         self.index, self.cols = index, cols
+        self._texts = texts
         self._resident: Dict[str, tuple] = {}  # field -> (version, column id, kind, dictionary)
+
+    def _text_column(self) -> int:
+        """The documents as a CSR text column under its own column id -> column id."""
+        key = "\0document"
+        texts = self._texts() if callable(self._texts) else self._texts
+        if texts is None or not hasattr(self.index, "column_set_text"):
+            raise NotOnDevice("no documents / no text columns on this index")
+        hit = self._resident.get(key)
+        if hit is not None and hit[0] == self.cols.version and hit[2] == len(texts):
+            return hit[1]
+        if len(texts) != len(self.cols):
+            raise NotOnDevice("documents and metadata out of step")
+        offsets, data, present = texts_csr(texts)
+        col_id = hit[1] if hit is not None else len(self._resident)
+        if col_id >= 64:
+            raise NotOnDevice("more than 64 filterable fields")
+        self.index.column_set_text(col_id, offsets, data, None if present.all() else present)
+        self._resident[key] = (self.cols.version, col_id, len(texts), None)
+        return col_id
 
     def _column(self, field: str):
         hit = self._resident.get(field)
@@ -371,9 +412,9 @@ class DeviceFilter:
             return op, int(want), 0.0
         return op, 0, float(want)
 
-    def program(self, where: Mapping[str, Any]):
-        """-> (list of FilterOp, constant pool as uint64 bit patterns)."""
-        from ._native import OP, FilterOp
+    def program(self, where: Optional[Mapping[str, Any]], where_document: Optional[Mapping[str, Any]] = None):
+        """-> (list of FilterOp, constant pool as uint64 bit patterns): `where`, then `where_document`, AND-ed."""
+        from ._native import MAX_NEEDLE, OP, FilterOp
 
         ops: List[Any] = []
         pool: List[int] = []
@@ -426,13 +467,44 @@ class DeviceFilter:
             op2, iv, fv = self._const(kind, uniq, op, want)
             ops.append(FilterOp(OP[op2], col_id, iv, fv, 0, 0))
 
-        emit(where)
+        def emit_document(w: Mapping[str, Any]) -> None:
+            if not isinstance(w, Mapping) or len(w) != 1:
+                raise FilterError("where_document expects a dict with exactly one key per level")
+            (op, val), = w.items()
+            if op in ("$and", "$or"):
+                if not isinstance(val, (list, tuple)) or not val:
+                    raise FilterError(f"{op} expects a non-empty list of filters")
+                for i, part in enumerate(val):
+                    emit_document(part)
+                    if i:
+                        ops.append(FilterOp(OP[op], 0, 0, 0.0, 0, 0))
+                return
+            if op not in _TOKEN_OPS:
+                raise FilterError(f"unknown where_document operator {op}")
+            if not isinstance(val, str):
+                raise FilterError(f"{op} expects a string")
+            needle = val.encode("utf-8", "surrogatepass")
+            if not 1 <= len(needle) <= MAX_NEEDLE:
+                raise NotOnDevice("empty needle (matches every document) or one beyond the device limit")
+            col_id = self._text_column()
+            off = len(pool)
+            padded = needle + b"\0" * (-len(needle) % 8)
+            pool.extend(int(v) for v in np.frombuffer(padded, dtype="<u8"))
+            ops.append(FilterOp(OP["$text_contains" if op == "$contains" else "$text_not_contains"], col_id, 0, 0.0, off, len(needle)))
+
+        if where:
+            emit(where)
+        if where_document:
+            emit_document(where_document)
+            if where:
+                ops.append(FilterOp(OP["$and"], 0, 0, 0.0, 0, 0))
         if len(ops) > 64:
             raise NotOnDevice("filter program longer than 64 operations")
         return ops, np.asarray(pool, dtype=np.uint64)
 
-    def build(self, where: Mapping[str, Any], live: Optional[np.ndarray]):
+    def build(self, where: Optional[Mapping[str, Any]], live: Optional[np.ndarray],
+              where_document: Optional[Mapping[str, Any]] = None):
         """-> (DeviceMask, allowed rows).  Raises NotOnDevice when the host evaluator must be used."""
-        ops, pool = self.program(where)
+        ops, pool = self.program(where, where_document)
         live_words = None if live is None or live.all() else pack_mask(live)
         return self.index.filter_build(ops, pool, live_words)

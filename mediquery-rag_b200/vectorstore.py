@@ -110,6 +110,27 @@ class _RowColumn:
             return run[r - self._starts[i]]
         return None if run[1] is None else f"{run[1]}{r}"
 
+    def utf8_csr(self):
+        """-> (offsets uint64 [n + 1], UTF-8 bytes, present bool [n]) of a text column (filters.texts_csr): explicit runs are
+        encoded row by row, implicit runs without a value cost one slice assignment whatever their length."""
+        lengths = np.zeros(self._n, np.uint64)
+        present = np.zeros(self._n, bool)
+        parts: List[bytes] = []
+        for start, run in zip(self._starts, self._runs):
+            if isinstance(run, list):
+                enc = [v.encode("utf-8", "surrogatepass") if v is not None else b"" for v in run]
+                present[start:start + len(run)] = [v is not None for v in run]
+            elif run[1] is None:
+                continue
+            else:
+                enc = [f"{run[1]}{r}".encode("utf-8") for r in range(start, start + run[0])]
+                present[start:start + run[0]] = True
+            lengths[start:start + len(enc)] = [len(b) for b in enc]
+            parts.extend(enc)
+        offsets = np.zeros(self._n + 1, np.uint64)
+        np.cumsum(lengths, out=offsets[1:])
+        return offsets, np.frombuffer(b"".join(parts), dtype=np.uint8), present
+
     def implicit_row(self, value: str) -> Optional[int]:
         """Row behind an implicit id (`prefix + row`), or None."""
         for start, run in zip(self._starts, self._runs):
@@ -149,11 +170,14 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                  client_settings: Any = None, client: Any = None, relevance_score_fn: Optional[Callable] = None,
                  create_collection_if_not_exists: bool = True, *, store_dtype: str = "fp32", device: int = 0,
                  devices: Optional[Sequence[int]] = None, dim: Optional[int] = None, capacity_rows: int = 0,
-                 auto_persist: bool = True, compact_dead_fraction: float = 0.5,
+                 auto_persist: bool = True, compact_dead_fraction: float = 0.5, scoring_shadow: Optional[bool] = None,
                  index_factory: Optional[Callable[..., Any]] = None, **_: Any):
         """`devices=[0, 1, ..., 7]` spreads the rows over several GPUs behind this ONE object in this one process (the
         reference holds its store as a module global, src/medical_engine.py:52): block-cyclic row shards, every search
-        scans all of them concurrently and merges on the first device; ids, filters, persistence are unchanged."""
+        scans all of them concurrently and merges on the first device; ids, filters, persistence are unchanged.
+        `scoring_shadow`: fp32 collections keep a bf16 copy of their rows for the tensor-core scan (half the bytes streamed
+        per search, +50 % HBM; results are identical because every returned score is recomputed from the fp32 rows --
+        include/mqvs.h, mqvs_set_shadow).  None = the library default (on), False = scan the fp32 rows themselves."""
         self._collection_name = collection_name
         self._embedding_function = embedding_function
         self._persist_directory = persist_directory
@@ -168,6 +192,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._store_dtype = store_dtype
         self._device = list(devices) if devices is not None and len(devices) > 1 else (devices[0] if devices else device)
         self._capacity = capacity_rows
+        self._scoring_shadow = scoring_shadow
         self._compact_at = float(compact_dead_fraction)
         # one lock over everything that touches the host tables or the handle's shared filter mask: the a* coroutines run
         # the blocking calls in worker threads, and a device-built mask belongs to the handle until the search has used it
@@ -236,6 +261,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         if self._index is None:
             self._dim = int(dim)
             self._index = self._index_factory(self._dim, self._store_dtype, self._device, self._capacity)
+            if self._scoring_shadow is not None and hasattr(self._index, "set_shadow"):
+                self._index.set_shadow(self._scoring_shadow)
             if self._raw_space and self._space != "cosine" and hasattr(self._index, "set_metric"):
                 self._index.set_metric(self._space)  # while empty: row norms are kept from here on
             else:
@@ -413,15 +440,17 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
 
     def _allow_mask(self, filter: Optional[Mapping[str, Any]], where_document: Optional[Mapping[str, Any]]):
         """-> (mask or None, allowed rows).  Metadata filters over typed fields are evaluated ON THE DEVICE (columns stay
-        resident in HBM, the bitmask never visits the host); where_document, mixed-type fields and bool / None constants
-        use the host evaluator.  Both produce the same bitmask (tests/test_gpu_parity.py)."""
+        resident in HBM, the bitmask never visits the host) and so is where_document ($contains over the documents' UTF-8
+        text, resident as a CSR text column); mixed-type fields, bool / None constants and empty needles use the host
+        evaluator.  Both produce the same bitmask (tests/test_gpu_parity.py)."""
         if not filter and not where_document and self._all_live():
             return None, len(self._ids)  # nothing to mask: no pass over the live bitmap either (100M rows = 30 ms of numpy)
-        if filter and not where_document and hasattr(self._index, "filter_build"):
-            if self._device_filter is None or self._device_filter.index is not self._index:
-                self._device_filter = DeviceFilter(self._index, self._cols)
+        if (filter or where_document) and hasattr(self._index, "filter_build"):
+            if (self._device_filter is None or self._device_filter.index is not self._index
+                    or self._device_filter.cols is not self._cols):
+                self._device_filter = DeviceFilter(self._index, self._cols, lambda: self._texts)
             try:
-                return self._device_filter.build(filter, self._live)
+                return self._device_filter.build(filter, self._live, where_document)
             except NotOnDevice:
                 pass
         return compile_mask(filter, self._cols, self._live, where_document, self._texts)

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from mediquery_rag_b200 import _native
-from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns, NotOnDevice, evaluate, pack_mask
+from mediquery_rag_b200.filters import (DeviceFilter, MetadataColumns, NotOnDevice, evaluate, evaluate_document, pack_mask,
+                                        texts_csr)
 
 
 class ProgramInterpreter:
@@ -27,9 +28,22 @@ class ProgramInterpreter:
         assert offsets.dtype == np.uint64 and tokens.dtype == np.int64 and offsets[0] == 0 and offsets[-1] == tokens.shape[0]
         self.cols[col_id] = ("tokens", offsets.copy(), tokens.copy())
 
+    def column_set_text(self, col_id, offsets, data, present=None):
+        assert offsets.dtype == np.uint64 and data.dtype == np.uint8 and offsets[0] == 0 and offsets[-1] == data.shape[0]
+        self.cols[col_id] = ("text", offsets.copy(), data.tobytes(), None if present is None else np.asarray(present, bool).copy())
+
     def filter_build(self, ops, pool=None, live_words=None):
         n, stack = self.n, []
         for o in ops:
+            if o.op in (_native.OP["$text_contains"], _native.OP["$text_not_contains"]):  # byte-wise search, CSR rows
+                _, off, data, present = self.cols[o.col]
+                assert 1 <= o.set_len <= _native.MAX_NEEDLE and o.set_off * 8 + o.set_len <= pool.shape[0] * 8
+                needle = pool.tobytes()[o.set_off * 8:o.set_off * 8 + o.set_len]
+                found = np.zeros(n, bool)
+                for r in range(min(n, off.shape[0] - 1)):
+                    found[r] = (present is None or present[r]) and needle in data[int(off[r]):int(off[r + 1])]
+                stack.append(found != (o.op == _native.OP["$text_not_contains"]))
+                continue
             if o.op in (_native.OP["$and"], _native.OP["$or"]):
                 b2, b1 = stack.pop(), stack.pop()
                 stack.append(b1 & b2 if o.op == _native.OP["$and"] else b1 | b2)
@@ -196,3 +210,71 @@ def test_tag_token_filters_on_the_reference_knowledge_base(medical_docs):
     assert evaluate({"tags": metas[0]["tags"]}, cols)[0]
     with pytest.raises(Exception):
         evaluate({"tags": {"$contains": 5}}, cols)
+
+
+DOCUMENT_FILTERS = [
+    {"$contains": "血压"}, {"$not_contains": "血压"}, {"$contains": "问题："}, {"$contains": "no such text"}, {"$contains": "\n答案："},
+    {"$and": [{"$contains": "运动"}, {"$not_contains": "癌"}]}, {"$or": [{"$contains": "睡眠"}, {"$contains": "饮食"}, {"$contains": "VO2"}]},
+    {"$and": [{"$or": [{"$contains": "糖"}, {"$contains": "脂"}]}, {"$not_contains": "胰岛素"}]},
+]
+
+
+def test_where_document_programs_on_the_reference_knowledge_base(medical_docs):
+    """where_document over the reference's real page_content ("问题：{title}\\n答案：{content}", src/ingest_medical.py:71): the
+    compiled program (text column = the documents' UTF-8 bytes in CSR form, needle in the constant pool, byte-wise search as
+    in kernels_filter.cu) agrees with the host evaluator (`needle in text` on str), alone and AND-ed with a metadata filter."""
+    texts = [d["page_content"] for d in medical_docs["docs"]] + [None, "", "血"]
+    metas = [d["metadata"] for d in medical_docs["docs"]] + [None, {"tags": "x"}, None]
+    cols = MetadataColumns()
+    cols.extend(metas)
+    n = len(texts)
+    dev = DeviceFilter(ProgramInterpreter(n), cols, texts)
+    live = np.ones(n, bool)
+    live[::9] = False
+    for wd in DOCUMENT_FILTERS:
+        want = evaluate_document(wd, texts)
+        words, allowed = dev.build(None, None, wd)
+        assert np.array_equal(words, pack_mask(want)) and allowed == int(want.sum()), wd
+        where = {"tags": {"$not_contains": "运动"}}
+        both = want & evaluate(where, cols) & live
+        words, allowed = dev.build(where, live, wd)
+        assert np.array_equal(words, pack_mask(both)) and allowed == int(both.sum()), wd
+    assert 0 < int(evaluate_document({"$contains": "血压"}, texts).sum()) < n
+    # one text column and one token column, uploaded once
+    assert sorted(type(c[0]) is str and c[0] for c in dev.index.cols.values()) == ["text", "tokens"]
+    # what only the host evaluator reproduces: the empty needle (matches every row that has a document), oversized needles
+    for wd in ({"$contains": ""}, {"$contains": "x" * 2000}):
+        with pytest.raises(NotOnDevice):
+            dev.build(None, None, wd)
+    with pytest.raises(Exception):
+        dev.build(None, None, {"$regex": "a"})
+
+
+def test_text_columns_follow_the_documents():
+    """The text column is rebuilt when rows are added; bulk rows without documents cost no bytes; a needle that straddles two
+    documents is not found (rows are searched one by one)."""
+    from mediquery_rag_b200.vectorstore import _RowColumn
+    texts = _RowColumn()
+    texts.extend(["alpha beta", "gamma"])
+    texts.extend_implicit(1000, None)
+    texts.extend(["beta\u00e9", None, "\U0001f600 beta"])
+    cols = MetadataColumns()
+    cols.extend_empty(len(texts))
+    off, data, present = texts_csr(texts)
+    assert off.shape[0] == len(texts) + 1 and int(off[-1]) == data.shape[0] == len("alpha betagammabeta\u00e9\U0001f600 beta".encode())
+    assert present.sum() == 4 and not present[2:1002].any()
+    plain = [texts[r] for r in range(len(texts))]
+    off2, data2, present2 = texts_csr(plain)
+    assert np.array_equal(off, off2) and np.array_equal(data, data2) and np.array_equal(present, present2)
+    idx = ProgramInterpreter(len(texts))
+    dev = DeviceFilter(idx, cols, lambda: texts)
+    for needle in ("beta", "a", "betagamma", "\u00e9", "\U0001f600", "gamma"):
+        wd = {"$contains": needle}
+        words, allowed = dev.build(None, None, wd)
+        assert np.array_equal(words, pack_mask(evaluate_document(wd, plain))), needle
+    texts.extend(["new beta"])
+    plain.append("new beta")
+    cols.extend_empty(1)
+    idx.n = len(texts)
+    words, allowed = dev.build(None, None, {"$contains": "beta"})
+    assert allowed == 4 and np.array_equal(words, pack_mask(evaluate_document({"$contains": "beta"}, plain)))

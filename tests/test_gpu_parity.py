@@ -523,8 +523,10 @@ def test_single_launch_tensor_pipeline_one_launch_and_agreement_with_the_segment
     l0 = idx.stats()["kernel_launches"]
     one = idx.search(q, k)
     st = idx.stats()
-    assert st["last_path"] == 1 and st["kernel_launches"] - l0 == 2 and st["exact_fallbacks"] == 0
+    # (an fp32 store's first tensor search after an add also converts the new rows into the bf16 scoring shadow: one launch)
+    assert st["last_path"] == 1 and st["kernel_launches"] - l0 == 3 and st["exact_fallbacks"] == 0
     again = idx.search(q, k)
+    assert idx.stats()["kernel_launches"] - st["kernel_launches"] == 2
     assert all(one[1][b, 0] == planted[b] for b in range(0, B, 2))
     idx.set_path(4)
     seg = idx.search(q, k)
@@ -1334,6 +1336,159 @@ def test_tag_token_filter_on_the_device_equals_the_host_evaluator(gpu, medical_d
         s, i = idx.search(q, 5, mask)
         assert_bit_equal(s, i, *O.brute_force_topk(qn, st, 5, O.mask_from_bool(ok)))
     idx.close()
+
+
+@pytest.mark.parametrize("devices", [0, [0, 0, 0]])
+def test_where_document_on_the_device_equals_the_host_evaluator(gpu, medical_docs, devices):
+    """f4: Chroma's where_document ($contains / $not_contains over the stored documents, $and / $or) evaluated by
+    filter_eval_kernel over a CSR text column (mqvs_column_set_text: the reference's real page_content strings, UTF-8), one
+    shard and three (the text is split on block boundaries with the rows); masks and searches equal the host evaluator's,
+    alone and AND-ed with a metadata filter and tombstones.  Then the same through the object the reference holds."""
+    from mediquery_rag_b200 import MediQueryVectorStore
+    from mediquery_rag_b200.filters import DeviceFilter, MetadataColumns, compile_mask, evaluate, evaluate_document
+    base_t = [d["page_content"] for d in medical_docs["docs"]]
+    base_m = [d["metadata"] for d in medical_docs["docs"]]
+    texts = (base_t + [None, "", "血"]) * 58            # 9106 rows: three blocks of a sharded handle, rows without documents
+    metas = (base_m + [None, {"tags": "x"}, None]) * 58
+    n = len(texts)
+    cols = MetadataColumns()
+    cols.extend(metas)
+    x = O.synth_rows(0x5EED000F, 0, n, 768)
+    idx = native().Index(768, "fp32", device=devices)
+    idx.add(x)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    q = O.synth_rows(QSEED, 0, 3, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    dev = DeviceFilter(idx, cols, texts)
+    live = np.ones(n, bool)
+    live[::11] = False
+    long_needle = base_t[7][3:120]  # a needle longer than a warp's stride of start positions
+    for wd in ({"$contains": "血压"}, {"$not_contains": "血压"}, {"$contains": "问题："}, {"$contains": "no such text"},
+               {"$contains": long_needle}, {"$contains": base_t[3][-9:]}, {"$contains": base_t[5][:4]},
+               {"$and": [{"$contains": "运动"}, {"$not_contains": "癌"}]},
+               {"$or": [{"$contains": "睡眠"}, {"$contains": "饮食"}, {"$and": [{"$contains": "糖"}, {"$not_contains": "胰岛素"}]}]}):
+        for where in (None, {"tags": {"$not_contains": "运动"}}):
+            ok = evaluate_document(wd, texts) & live
+            if where:
+                ok &= evaluate(where, cols)
+            mask, allowed = dev.build(where, live, wd)
+            assert allowed == int(ok.sum()), (wd, where)
+            s, i = idx.search(q, 5, mask)
+            assert_bit_equal(s, i, *O.brute_force_topk(qn, st, 5, O.mask_from_bool(ok)))
+    assert 0 < int(evaluate_document({"$contains": long_needle}, texts).sum()) <= 58
+    idx.close()
+
+    kw = dict(device=0) if devices == 0 else dict(devices=devices)
+    vs = MediQueryVectorStore(collection_metadata={"hnsw:space": "cosine"}, **kw)
+    ids = vs.add_embeddings((texts, x), metadatas=metas)
+    vs.delete(ids[::11])
+    built = []
+    orig = DeviceFilter.build
+    try:
+        DeviceFilter.build = lambda self, *a, **k: (built.append(a), orig(self, *a, **k))[1]
+        for wd, filt in (({"$contains": "血压"}, None), ({"$not_contains": "运动"}, {"tags": {"$contains": "癌症"}})):
+            got = vs._similar(q[0], 6, filt, wd)
+            host_mask, host_allowed = compile_mask(filt, cols, live, wd, texts)
+            es, ei = O.brute_force_topk(qn[:1], st, 6, host_mask)
+            assert [d.id for d, _ in got] == [ids[r] for r in ei[0]]
+            assert all(("血压" in d.page_content) if "$contains" in wd else ("运动" not in d.page_content) for d, _ in got)
+    finally:
+        DeviceFilter.build = orig
+    assert len(built) == 2  # both filters went through the device program (no host fallback)
+
+
+FP32_CASES = [c for c in TC_CASES if c[1] == "fp32"] + [(300000, "fp32", 300, 10, None), (120000, "fp32", 1, 10, None)]
+
+
+@pytest.mark.parametrize("n,dtype,B,k,frac", FP32_CASES)
+def test_fp32_store_returns_the_same_bits_with_and_without_its_scoring_shadow(gpu, n, dtype, B, k, frac):
+    """fp32 stores: the tensor pipelines stream a bf16 SHADOW of the rows by default (half the bytes, kind::f16) and take
+    every exact score from the fp32 rows; with the shadow off they stream the fp32 rows themselves (kind::tf32) as in
+    round 1.  Both legs, on both tensor pipelines, must be the oracle's bits -- and stats.scan_bytes says which
+    representation was streamed."""
+    idx, x, st = build(n, 768, "fp32", seed=0x5EED0003)
+    q, _ = O.planted_queries(QSEED, B, 0x5EED0003, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(11).random(n) < frac)
+    want = O.brute_force_topk(qn, st, k, mask)
+    for path in (2, 4):
+        idx.set_path(path)
+        for shadow in (True, False, True):
+            idx.set_shadow(shadow)
+            before = idx.stats()["scan_bytes"]
+            s, i = idx.search(q, k, mask)
+            assert idx.stats()["last_path"] == 1
+            assert_bit_equal(s, i, *want)
+            assert idx.stats()["scan_bytes"] - before == n * 768 * (2 if shadow else 4), (path, shadow)
+            assert (idx.shadow_bytes() > 0) == shadow
+    idx.close()
+
+
+def test_scoring_shadow_on_hard_corpora_and_across_growth_compaction_and_reload(gpu, tmp_path):
+    """The shadow's error bound (both operands rounded) through the repair chain -- a corpus made of ties, a clustered
+    corpus of non-unit rows in the l2 space -- and its upkeep: rows added later are converted before the next tensor
+    search, compaction and mqvs_load rebuild it, a sharded handle keeps one per shard."""
+    M = native()
+    # (1) 40 distinct vectors: thresholds tie with thousands of rows, lists overflow, margins cannot be proven
+    n, B, k = 100_000, 24, 10
+    rng = np.random.default_rng(7)
+    base = O.synth_rows(SEED, 0, 40, 768)
+    x = base[rng.integers(0, 40, n)]
+    q = base[rng.integers(0, 40, B)] + 0.05 * O.synth_rows(QSEED, 0, B, 768)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    want = O.brute_force_topk(qn, st, k)
+    idx = M.Index(768, "fp32")
+    idx.add(x)
+    for path in (2, 4):
+        idx.set_path(path)
+        assert_bit_equal(*idx.search(q, k), *want)
+    assert idx.shadow_bytes() >= n * 1536 and idx.stats()["unrepaired"] == 0
+    idx.close()
+    # (2) clustered non-unit rows, l2 space: flagged queries go through the band pass over the shadow
+    n, members, B = 120_000, 1500, 40
+    rng = np.random.default_rng(1)
+    sigma = np.sqrt((1.0 / 0.98 ** 2 - 1.0) / 256.0)
+    centres = rng.standard_normal((n // members, 768)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    length = np.repeat(rng.uniform(0.5, 3.0, n // members), members) * rng.uniform(0.98, 1.02, n)
+    x = ((np.repeat(centres, members, axis=0) + sigma * rng.uniform(-1, 1, (n, 768))) * length[:, None]).astype(np.float32)
+    q = (x[rng.integers(0, n, B)] + 0.5 * sigma * rng.uniform(-1, 1, (B, 768))).astype(np.float32)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    want = O.brute_force_topk(qn, st, k, metric="l2", norms=O.row_norms(x, 768), q_norms=O.row_norms(q, 768))
+    for devices in (0, [0, 0, 0]):
+        idx = M.Index(768, "fp32", device=devices)
+        idx.set_metric("l2")
+        idx.add(x)
+        idx.set_path(2)
+        assert_bit_equal(*idx.search(q, k), *want)
+        assert idx.stats()["band_repairs"] > 0 and idx.shadow_bytes() >= n * 1536
+        idx.close()
+    # (3) upkeep: incremental adds with regrowth, compaction, save + load
+    n = 90_000
+    x = O.synth_rows(0x5EED0010, 0, n, 768)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    q, _ = O.planted_queries(QSEED, 8, 0x5EED0010, n, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    idx = M.Index(768, "fp32")
+    idx.set_path(2)
+    for lo, hi in ((0, 30_000), (30_000, 31_000), (31_000, n)):
+        idx.add(x[lo:hi])
+        assert_bit_equal(*idx.search(q, 10), *O.brute_force_topk(qn, st[:hi], 10))
+    keep = np.random.default_rng(5).random(n) < 0.5
+    assert idx.compact(O.mask_from_bool(keep)) == int(keep.sum())
+    assert_bit_equal(*idx.search(q, 10), *O.brute_force_topk(qn, st[keep], 10))
+    path = str(tmp_path / "rows.mqvs")
+    idx.save(path)
+    idx.close()
+    again = M.Index(768, "fp32")
+    again.load_file(path)
+    again.set_path(2)
+    before = again.stats()["scan_bytes"]
+    assert_bit_equal(*again.search(q, 10), *O.brute_force_topk(qn, st[keep], 10))
+    assert again.stats()["scan_bytes"] - before == int(keep.sum()) * 1536
+    again.close()
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])

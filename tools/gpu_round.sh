@@ -12,6 +12,7 @@ for s in $STEPS; do
             tail -2 $OUT/${TAG}_pairsanity.log
             if [ $rc -ne 0 ] || ! grep -q "planted ok True" $OUT/${TAG}_pairsanity.log; then export MQVS_NO_PAIR=1; echo "PAIR KERNEL DISABLED for the rest of this call"; fi ;;
     tests)  timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 --timeout 600 -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "tests rc=$?" ;;
+    ktests) timeout 900 python -m pytest tests -m gpu -q --maxfail=25 --timeout 600 -p no:cacheprovider -k "$KEXPR" > $OUT/${TAG}_pytest_gpu_k.log 2>&1; echo "ktests rc=$?"; tail -15 $OUT/${TAG}_pytest_gpu_k.log ;;
     bench)  timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?" ;;
     c2cmp)  for v in half full; do
               if [ $v = full ]; then export MQVS_NO_HALF_TILE=1; else unset MQVS_NO_HALF_TILE; fi
@@ -46,8 +47,17 @@ for s in $STEPS; do
             done ;;
     ncufused) CMD="python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --no-store-e2e --points 1"
             timeout 300 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
-            timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_fused_kernel.*, 64>" -s 2 -c 1 -o $OUT/${TAG}_prof_c4_b64_fused $CMD > $OUT/${TAG}_ncu_fused.log 2>&1
+            timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_fused_kernel -s 2 -c 2 -o $OUT/${TAG}_prof_c4_b64_fused $CMD > $OUT/${TAG}_ncu_fused.log 2>&1
             echo "ncu fused rc=$?" ;;
+    shadowx) timeout 600 python tools/shadow_crossover.py > $OUT/${TAG}_shadow_crossover.json 2> $OUT/${TAG}_shadow_crossover.err; echo "shadowx rc=$?" ;;
+    ncuc2)  CMD="python bench.py --workload c2 --steps 2 --warmup 3 --no-secondary --no-cpu-baseline --points 1"
+            timeout 300 $CMD > $OUT/${TAG}_ncu_c2_plain.log 2>&1 &&
+            timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_ncu_launches_c2.csv $CMD > $OUT/${TAG}_ncu_launches_c2.log 2>&1
+            echo "ncu c2 launches rc=$?"
+            timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_fused_kernel -s 2 -c 2 -o $OUT/${TAG}_prof_c2_b64_fused $CMD > $OUT/${TAG}_ncu_c2_fused.log 2>&1
+            echo "ncu c2 fused rc=$?" ;;
+    c2)     timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,256,1024 --steps 30 --warmup 5 > $OUT/${TAG}_bench_c2.json 2> $OUT/${TAG}_bench_c2.err; echo "c2 rc=$?"
+            MQVS_NO_SHADOW=1 timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,256,1024 --steps 30 --warmup 5 > $OUT/${TAG}_bench_c2_noshadow.json 2> $OUT/${TAG}_bench_c2_noshadow.err; echo "c2 noshadow rc=$?" ;;
     widek)  for kk in 100 200 1000; do timeout 200 python tools/tc_one.py 1000000 fp32 64 $kk 0 5 > $OUT/${TAG}_widek_$kk.log 2>&1; tail -1 $OUT/${TAG}_widek_$kk.log; done ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
