@@ -36,9 +36,14 @@ enum { MQVS_F32 = 0, MQVS_BF16 = 1 };
 /* Chroma's `hnsw:space` (collection_metadata; the reference passes none, so upstream it is "l2" -- src/medical_engine.py:52) */
 enum { MQVS_METRIC_COSINE = 0, MQVS_METRIC_L2 = 1, MQVS_METRIC_IP = 2 };
 
-/* widest embedding the kernels are built for; rows are zero-padded to MQVS_DIM_PAD elements in HBM
- * (768 = width of shaw/dmeta-embedding-zh, src/medical_engine.py:43) */
+/* widest embedding the kernels of THIS BUILD take; rows are zero-padded to MQVS_DIM_PAD elements in HBM
+ * (768 = width of shaw/dmeta-embedding-zh, src/medical_engine.py:43).  A build-time constant of the kernels (any multiple
+ * of 128): `make -C mediquery-rag_b200/csrc WIDTH=1024` builds libmqvs_w1024.so from the same sources with the same ABI, and
+ * mqvs_dim_pad() tells a caller what a loaded library was built for (the Python binding picks the narrowest build that
+ * holds the collection's dimension). */
+#ifndef MQVS_DIM_PAD
 #define MQVS_DIM_PAD 768
+#endif
 #define MQVS_MAX_K 1024
 #define MQVS_MAX_DEVICES 16      /* row shards one handle can drive (one B200 box has 8) */
 #define MQVS_SHARD_BLOCK 4096    /* rows per block of the block-cyclic placement of a multi-device handle */
@@ -69,6 +74,7 @@ typedef struct mqvs_stats {
 } mqvs_stats;
 
 MQVS_API int mqvs_version(void);
+MQVS_API int mqvs_dim_pad(void);   /* MQVS_DIM_PAD of this build */
 MQVS_API const char* mqvs_last_error(void);
 MQVS_API int mqvs_device_count(int* out);
 

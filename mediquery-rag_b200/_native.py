@@ -62,12 +62,13 @@ class Stats(ctypes.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
-_lib: Optional[ctypes.CDLL] = None
+_libs: dict = {}  # row width -> loaded library
 
 # name -> (restype, argtypes); the loader test checks every symbol include/mqvs.h declares is here and exported
 _vp, _i, _u64, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64
 SIGNATURES = {
     "mqvs_version": (_i, []),
+    "mqvs_dim_pad": (_i, []),
     "mqvs_last_error": (ctypes.c_char_p, []),
     "mqvs_device_count": (_i, [ctypes.POINTER(_i)]),
     "mqvs_create": (_i, [_i, ctypes.POINTER(_i), _i, _i, _u64, ctypes.POINTER(_vp)]),
@@ -109,23 +110,51 @@ SIGNATURES = {
 }
 
 
-def load() -> ctypes.CDLL:
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+def lib_path(width: int = DIM_PAD) -> str:
+    """Row width is a build-time constant of the kernels (include/mqvs.h, MQVS_DIM_PAD): libmqvs.so is the 768 build, the
+    others are libmqvs_w<width>.so (csrc/Makefile, `make WIDTH=...`)."""
+    return LIB_PATH if width == DIM_PAD else os.path.join(_HERE, f"libmqvs_w{int(width)}.so")
+
+
+def built_widths() -> list:
+    """Row widths a library has been built for, ascending."""
+    out = [DIM_PAD] if os.path.exists(LIB_PATH) else []
+    for name in os.listdir(_HERE):
+        if name.startswith("libmqvs_w") and name.endswith(".so") and name[9:-3].isdigit():
+            out.append(int(name[9:-3]))
+    return sorted(set(out))
+
+
+def width_for(dim: int) -> int:
+    """The narrowest built row width that holds `dim` elements (rows are zero-padded to it in HBM)."""
+    have = built_widths()
+    for w in have:
+        if w >= dim:
+            return w
+    raise ValueError(f"no libmqvs build holds {dim}-dimensional rows (built: {have or 'none'}); build one with "
+                     f"`make -C mediquery-rag_b200/csrc WIDTH={(int(dim) + 127) // 128 * 128}`")
+
+
+def load(width: int = DIM_PAD) -> ctypes.CDLL:
+    lib = _libs.get(width)
+    if lib is None:
+        path = lib_path(width)
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `python __graft_entry__.py` "
                               "(nvcc, sm_100a); there is no CPU fallback")
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        _lib = lib
-    return _lib
+        if lib.mqvs_dim_pad() != width:
+            raise ImportError(f"{path} was built for rows of {lib.mqvs_dim_pad()} elements, not {width}")
+        _libs[width] = lib
+    return lib
 
 
-def check(rc: int) -> None:
+def check(rc: int, lib: Optional[ctypes.CDLL] = None) -> None:
     if rc != OK:
-        raise MqvsError(rc, load().mqvs_last_error().decode("utf-8", "replace"))
+        raise MqvsError(rc, (lib or load()).mqvs_last_error().decode("utf-8", "replace"))
 
 
 def device_count() -> int:
@@ -170,15 +199,20 @@ class Index:
             raise ValueError(f"an index drives 1..{MAX_DEVICES} devices, got {len(self.devices)}")
         self.device = self.devices[0]
         self.metric = "cosine"
+        self.width = width_for(self.dim)  # rows are zero-padded to this many elements (the build that serves them)
+        self._lib = load(self.width)
         dev = (_i * len(self.devices))(*self.devices)
-        check(load().mqvs_create(len(self.devices), dev, self.dim, DTYPES[store_dtype], int(capacity_rows),
+        self._check(self._lib.mqvs_create(len(self.devices), dev, self.dim, DTYPES[store_dtype], int(capacity_rows),
                                  ctypes.byref(self._h)))
         if shadow is not None:
             self.set_shadow(shadow)
 
+    def _check(self, rc: int) -> None:
+        check(rc, self._lib)
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
-            load().mqvs_destroy(self._h)
+            self._lib.mqvs_destroy(self._h)
             self._h = _vp(None)
 
     def __del__(self):
@@ -189,11 +223,11 @@ class Index:
 
     def __len__(self) -> int:
         n = _u64(0)
-        check(load().mqvs_count(self._h, ctypes.byref(n)))
+        self._check(self._lib.mqvs_count(self._h, ctypes.byref(n)))
         return n.value
 
     def reserve(self, rows: int) -> None:
-        check(load().mqvs_reserve(self._h, int(rows)))
+        self._check(self._lib.mqvs_reserve(self._h, int(rows)))
 
     def add(self, x) -> int:
         """x: [n, dim] fp32 numpy array (host) or CUDA torch tensor on this index's device.  -> first row id."""
@@ -209,12 +243,12 @@ class Index:
             if x.ndim != 2 or x.shape[1] != self.dim:
                 raise ValueError(f"embeddings must be [n, {self.dim}], got {x.shape}")
             n, dev = x.shape[0], 0
-        check(load().mqvs_add(self._h, _ptr(x), F32, dev, n, ctypes.byref(first)))
+        self._check(self._lib.mqvs_add(self._h, _ptr(x), F32, dev, n, ctypes.byref(first)))
         return first.value
 
     def add_synthetic(self, seed: int, first_index: int, n: int) -> int:
         first = _u64(0)
-        check(load().mqvs_add_synthetic(self._h, seed & 0xFFFFFFFFFFFFFFFF, int(first_index), int(n), ctypes.byref(first)))
+        self._check(self._lib.mqvs_add_synthetic(self._h, seed & 0xFFFFFFFFFFFFFFFF, int(first_index), int(n), ctypes.byref(first)))
         return first.value
 
     def search(self, q, k: int, mask=None):
@@ -235,7 +269,7 @@ class Index:
                 mask = np.ascontiguousarray(mask, dtype=np.uint32)
                 if mask.shape[0] < (len(self) + 31) // 32:
                     raise ValueError("mask has fewer than ceil(rows/32) words")
-        check(load().mqvs_search(self._h, _ptr(q), 0, B, int(k), _ptr(mask), mask_dev, _ptr(scores), _ptr(ids), 0))
+        self._check(self._lib.mqvs_search(self._h, _ptr(q), 0, B, int(k), _ptr(mask), mask_dev, _ptr(scores), _ptr(ids), 0))
         return scores, ids
 
     def search_device(self, q, k: int, out_scores, out_ids, mask=None, id_base: int = 0, stream: int = 0) -> None:
@@ -246,24 +280,24 @@ class Index:
                                      ("out_ids", out_ids, "int64", (B, int(k)))):
             if not str(t.dtype).endswith(want) or tuple(t.shape) != shape or not t.is_contiguous():
                 raise TypeError(f"{name} must be a contiguous {want} tensor of shape {shape}, got {t.dtype} {tuple(t.shape)}")
-        check(load().mqvs_search_async(self._h, _ptr(q), B, int(k), _ptr(mask), int(id_base), _ptr(out_scores),
+        self._check(self._lib.mqvs_search_async(self._h, _ptr(q), B, int(k), _ptr(mask), int(id_base), _ptr(out_scores),
                                        _ptr(out_ids), _vp(stream)))
 
     def get_rows(self, row_ids) -> np.ndarray:
         row_ids = np.ascontiguousarray(row_ids, dtype=np.int64)
         out = np.empty((row_ids.shape[0], self.dim), np.float32)
-        check(load().mqvs_get_rows(self._h, _ptr(row_ids), row_ids.shape[0], _ptr(out)))
+        self._check(self._lib.mqvs_get_rows(self._h, _ptr(row_ids), row_ids.shape[0], _ptr(out)))
         return out
 
     def save(self, path: str) -> None:
-        check(load().mqvs_save(self._h, os.fsencode(path)))
+        self._check(self._lib.mqvs_save(self._h, os.fsencode(path)))
 
     def save_append(self, path: str, first_row: int) -> None:
         """Append rows [first_row, len) to a row file that holds exactly first_row rows (0 = rewrite everything)."""
-        check(load().mqvs_save_append(self._h, os.fsencode(path), int(first_row)))
+        self._check(self._lib.mqvs_save_append(self._h, os.fsencode(path), int(first_row)))
 
     def load_file(self, path: str) -> None:
-        check(load().mqvs_load(self._h, os.fsencode(path)))
+        self._check(self._lib.mqvs_load(self._h, os.fsencode(path)))
 
     def compact(self, keep_words: np.ndarray) -> int:
         """Keep only the rows whose bit is set in the packed bitmap (bit r & 31 of word r >> 5), bit-for-bit, renumbered
@@ -272,7 +306,7 @@ class Index:
         if words.shape[0] < (len(self) + 31) // 32:
             raise ValueError("bitmap has fewer than ceil(rows/32) words")
         n = _u64(0)
-        check(load().mqvs_compact(self._h, _ptr(words), ctypes.byref(n)))
+        self._check(self._lib.mqvs_compact(self._h, _ptr(words), ctypes.byref(n)))
         return n.value
 
     def column_set(self, col_id: int, values: np.ndarray, present: Optional[np.ndarray] = None) -> None:
@@ -285,7 +319,7 @@ class Index:
         else:
             raise ValueError("device columns are int64 or float64")
         pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
-        check(load().mqvs_column_set(self._h, int(col_id), ctype, _ptr(values), _ptr(pres), values.shape[0]))
+        self._check(self._lib.mqvs_column_set(self._h, int(col_id), ctype, _ptr(values), _ptr(pres), values.shape[0]))
 
     def column_set_tokens(self, col_id: int, offsets: np.ndarray, tokens: np.ndarray) -> None:
         """Upload a token-set column (comma-joined `tags`): CSR offsets [n + 1] (uint64) and token ids (int64)."""
@@ -293,7 +327,7 @@ class Index:
         tokens = np.ascontiguousarray(tokens, dtype=np.int64)
         if offsets.ndim != 1 or offsets.shape[0] < 1 or int(offsets[-1]) != tokens.shape[0]:
             raise ValueError("offsets must be [n + 1] and end at len(tokens)")
-        check(load().mqvs_column_set_tokens(self._h, int(col_id), _ptr(offsets), _ptr(tokens), offsets.shape[0] - 1))
+        self._check(self._lib.mqvs_column_set_tokens(self._h, int(col_id), _ptr(offsets), _ptr(tokens), offsets.shape[0] - 1))
 
     def column_set_text(self, col_id: int, offsets: np.ndarray, data: np.ndarray, present: Optional[np.ndarray] = None) -> None:
         """Upload a text column (the stored documents, for `where_document`): CSR offsets [n + 1] (uint64) into the rows'
@@ -305,7 +339,7 @@ class Index:
         pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
         if pres is not None and pres.shape[0] != offsets.shape[0] - 1:
             raise ValueError("one presence flag per row")
-        check(load().mqvs_column_set_text(self._h, int(col_id), _ptr(offsets), _ptr(data), _ptr(pres), offsets.shape[0] - 1))
+        self._check(self._lib.mqvs_column_set_text(self._h, int(col_id), _ptr(offsets), _ptr(data), _ptr(pres), offsets.shape[0] - 1))
 
     def filter_build(self, ops, pool: Optional[np.ndarray] = None, live_words: Optional[np.ndarray] = None):
         """ops: list of FilterOp in postfix order -> (DeviceMask, number of allowed rows)."""
@@ -315,43 +349,43 @@ class Index:
             raise ValueError("the constant pool holds 8-byte values")
         live = None if live_words is None else np.ascontiguousarray(live_words, dtype=np.uint32)
         ptr, allowed = _vp(), _u64(0)
-        check(load().mqvs_filter_build(self._h, arr, len(ops), _ptr(pool), pool.shape[0], _ptr(live), ctypes.byref(ptr),
+        self._check(self._lib.mqvs_filter_build(self._h, arr, len(ops), _ptr(pool), pool.shape[0], _ptr(live), ctypes.byref(ptr),
                                        ctypes.byref(allowed)))
         return DeviceMask(ptr.value or 0, (len(self) + 31) // 32), int(allowed.value)
 
     def stats(self) -> dict:
         st = Stats()
-        check(load().mqvs_get_stats(self._h, ctypes.byref(st)))
+        self._check(self._lib.mqvs_get_stats(self._h, ctypes.byref(st)))
         return st.as_dict()
 
     def set_path(self, path: int) -> None:
-        check(load().mqvs_set_path(self._h, int(path)))
+        self._check(self._lib.mqvs_set_path(self._h, int(path)))
 
     def set_shadow(self, enable: bool) -> None:
         """fp32 stores: stream a bf16 scoring shadow on the tensor pipelines (default) or the fp32 rows themselves."""
-        check(load().mqvs_set_shadow(self._h, 1 if enable else 0))
+        self._check(self._lib.mqvs_set_shadow(self._h, 1 if enable else 0))
 
     def shadow_bytes(self) -> int:
         n = _u64(0)
-        check(load().mqvs_shadow_bytes(self._h, ctypes.byref(n)))
+        self._check(self._lib.mqvs_shadow_bytes(self._h, ctypes.byref(n)))
         return n.value
 
     def set_metric(self, space: str) -> None:
         """Space the rows are ranked in ("cosine" | "l2" | "ip"); a non-cosine space must first be chosen while the
         index is empty (row norms are kept from then on).  Scores of later searches are that space's ranking score."""
-        check(load().mqvs_set_metric(self._h, METRICS[space]))
+        self._check(self._lib.mqvs_set_metric(self._h, METRICS[space]))
         self.metric = space
 
     def norm_deviation(self) -> float:
         """Largest | ||x|| - 1 | over the raw rows added so far (0: every row was a unit vector)."""
         d = ctypes.c_float(0.0)
-        check(load().mqvs_norm_deviation(self._h, ctypes.byref(d)))
+        self._check(self._lib.mqvs_norm_deviation(self._h, ctypes.byref(d)))
         return float(d.value)
 
     def get_norms(self, first_row: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = len(self) - int(first_row) if n is None else int(n)
         out = np.empty(max(n, 0), np.float32)
-        check(load().mqvs_get_norms(self._h, int(first_row), n, _ptr(out)))
+        self._check(self._lib.mqvs_get_norms(self._h, int(first_row), n, _ptr(out)))
         return out
 
 

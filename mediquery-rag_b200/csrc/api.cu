@@ -114,7 +114,13 @@ static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     // the clock drops under a power cap -- on 8 power-capped GPUs the SIMT scan alternated between 2.72 and 3.17 ms per
     // 12.5M-row shard while the TMA-fed pipeline stayed at 2.71-2.75 (profiles/r01_b1_paths_w8.json).  Below 1M rows the
     // SIMT path's single launch wins on latency.
-    const int simt_max = s->dtype == MQVS_F32 ? 2 : 1;
+    int simt_max = s->dtype == MQVS_F32 ? 2 : 1;
+    // fp32 store with its bf16 scoring shadow (half the bytes per scan): the tensor pipelines overtake the fp32 SIMT scan for
+    // single queries at ~100k rows and for 2 queries at every size measured (profiles/r02_shadow_crossover.json: B=1 at 131k /
+    // 262k / 524k rows: 101 / 127 / 183 us vs 109 / 168 / 299 us; B=2 at 65k rows: 85 vs 103 us)
+    const bool shadow = s->dtype == MQVS_F32 && s->shadow_on && s->metric == MQVS_METRIC_COSINE;
+    if (shadow) simt_max = 1;
+    if (shadow && s->n >= 131072ull) return true;
     // (l2 / ip spaces: the transform makes the tensor epilogue ~4 % slower than the SIMT scan for the 1-2 queries that scan
     // holds the roofline for -- 0.508 vs 0.489 ms at 1M x 768 fp32, B=1 -- so those stay on the SIMT scan at every size)
     if (s->n >= 1000000ull && (s->metric == MQVS_METRIC_COSINE || B > simt_max)) return true;
@@ -448,6 +454,7 @@ using namespace mqvs::api;
 extern "C" {
 
 MQVS_API int mqvs_version(void) { return MQVS_VERSION; }
+MQVS_API int mqvs_dim_pad(void) { return MQVS_DIM_PAD; }
 
 MQVS_API const char* mqvs_last_error(void) { return g_err.c_str(); }
 
@@ -465,7 +472,9 @@ MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype
     if (n_dev < 1 || n_dev > MQVS_MAX_DEVICES)
         return fail(MQVS_E_INVALID, "n_dev must be in [1, %d], got %d", MQVS_MAX_DEVICES, n_dev);
     if (n_dev > 1 && !dev_ids) return fail(MQVS_E_INVALID, "dev_ids is NULL with n_dev=%d", n_dev);
-    if (dim < 1 || dim > MQVS_DIM_PAD) return fail(MQVS_E_INVALID, "dim must be in [1, %d], got %d", MQVS_DIM_PAD, dim);
+    if (dim < 1 || dim > MQVS_DIM_PAD)
+        return fail(MQVS_E_INVALID, "dim must be in [1, %d] for this build of libmqvs (MQVS_DIM_PAD; wider rows: make WIDTH=<multiple "
+                                    "of 128 >= dim>), got %d", MQVS_DIM_PAD, dim);
     if (store_dtype != MQVS_F32 && store_dtype != MQVS_BF16) return fail(MQVS_E_INVALID, "unknown store_dtype %d", store_dtype);
     if (n_dev > 1) return multi_create(n_dev, dev_ids, dim, store_dtype, capacity_rows, out);
     return create_single(dev_ids ? dev_ids[0] : 0, dim, store_dtype, capacity_rows, out);

@@ -27,7 +27,24 @@ def test_library_exports_every_declared_symbol_and_binding_covers_them():
     assert sorted(_native.SIGNATURES) == names
     for n in names:
         assert isinstance(getattr(lib, n), ctypes._CFuncPtr)
-    assert lib.mqvs_version() == 200
+    assert lib.mqvs_version() == 200 and lib.mqvs_dim_pad() == 768
+
+
+def test_the_wider_build_is_the_same_abi_and_the_binding_picks_the_narrowest_build_that_fits():
+    """Row width is a build-time constant of the kernels: build() also makes libmqvs_w1024.so from the same sources.  Same
+    symbols, its own MQVS_DIM_PAD; Index chooses by dimension and a dimension no build holds fails loudly."""
+    assert _native.built_widths()[:2] == [768, 1024]
+    wide = _native.load(1024)
+    for n in declared_symbols():
+        assert isinstance(getattr(wide, n), ctypes._CFuncPtr)
+    assert wide.mqvs_dim_pad() == 1024 and wide.mqvs_version() == 200
+    assert [_native.width_for(d) for d in (1, 384, 768, 769, 1000, 1024)] == [768, 768, 768, 1024, 1024, 1024]
+    with pytest.raises(ValueError, match="WIDTH=1536"):
+        _native.width_for(1500)
+    h = ctypes.c_void_p()
+    dev = (ctypes.c_int * 1)(0)
+    assert _native.load().mqvs_create(1, dev, 1024, 0, 0, ctypes.byref(h)) == _native.E_INVALID   # the 768 build refuses
+    assert b"WIDTH" in _native.load().mqvs_last_error()
 
 
 def test_errors_are_codes_with_messages_not_crashes():

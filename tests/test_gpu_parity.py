@@ -1491,6 +1491,47 @@ def test_scoring_shadow_on_hard_corpora_and_across_growth_compaction_and_reload(
     again.close()
 
 
+@pytest.mark.parametrize("dim,dtype,n,B,k,frac", [(1024, "fp32", 30000, 1, 5, None), (1024, "bf16", 70000, 64, 10, None),
+                                                  (900, "fp32", 100003, 130, 10, 0.3), (1024, "bf16", 150000, 300, 100, None),
+                                                  (1000, "fp32", 5000, 3, 10, None), (1024, "fp32", 131072, 2, 10, None)])
+def test_rows_wider_than_768_run_on_the_1024_build(gpu, dim, dtype, n, B, k, frac):
+    """Embedding models wider than dmeta-embedding-zh (bge-large / mxbai: 1024): MQVS_DIM_PAD is a build-time constant, the
+    package builds libmqvs_w1024.so from the same sources and the binding picks it by dimension.  Every pipeline (SIMT,
+    latency kernel, single-launch tensor, segmented tensor on CTA pairs, the fp32 store's bf16 shadow) against the oracle
+    restated at that width: same bits."""
+    idx = native().Index(dim, dtype)
+    assert idx.width == 1024
+    x = O.synth_rows(0x5EED0011, 0, n, dim)
+    idx.add(x)
+    st, _ = O.normalize_rows(x, dtype, 1024)
+    q, planted = O.planted_queries(QSEED, B, 0x5EED0011, n, dim)
+    qn, _ = O.normalize_rows(q, "fp32", 1024)
+    mask = None if frac is None else O.mask_from_bool(np.random.default_rng(11).random(n) < frac)
+    want = O.brute_force_topk(qn, st, k, mask)
+    for path in (0, 1, 3, 2, 4):
+        idx.set_path(path)
+        assert_bit_equal(*idx.search(q, k, mask), *want)
+        if path in (2, 4):
+            assert idx.stats()["last_path"] == 1
+    assert np.array_equal(idx.get_rows(np.arange(5)).view(np.uint32), O.stored_as_f32(st[:5])[:, :dim].view(np.uint32))
+    idx.close()
+
+
+def test_vectorstore_with_a_1024_dimensional_embedder(gpu, tmp_path):
+    from mediquery_rag_b200 import MediQueryVectorStore
+    n, dim = 3000, 1024
+    x = O.synth_rows(0x5EED0012, 0, n, dim)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    vs = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"})
+    ids = vs.add_embeddings(([f"doc {r}" for r in range(n)], x), metadatas=[{"g": r % 3} for r in range(n)])
+    got = vs.similarity_search_by_vector(x[1234], k=3, filter={"g": 1234 % 3})
+    assert got[0].page_content == "doc 1234" and vs._index.width == 1024
+    again = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"})
+    assert len(again) == n and again._index.width == 1024
+    assert [d.id for d in again.similarity_search_by_vector(x[77], k=4)] == [d.id for d in vs.similarity_search_by_vector(x[77], k=4)]
+    assert again.similarity_search_by_vector(x[77], k=1)[0].id == ids[77]
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_kernels_against_the_independent_float64_referee_at_one_million_rows(gpu, dtype):
     """The parity claim without the kernel-ordered oracle in between: the CUDA results themselves (single-launch tensor

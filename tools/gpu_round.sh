@@ -58,8 +58,11 @@ for s in $STEPS; do
             echo "ncu c2 fused rc=$?" ;;
     c2)     timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,256,1024 --steps 30 --warmup 5 > $OUT/${TAG}_bench_c2.json 2> $OUT/${TAG}_bench_c2.err; echo "c2 rc=$?"
             MQVS_NO_SHADOW=1 timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,256,1024 --steps 30 --warmup 5 > $OUT/${TAG}_bench_c2_noshadow.json 2> $OUT/${TAG}_bench_c2_noshadow.err; echo "c2 noshadow rc=$?" ;;
+    tracec2) MQVS_TRACE=1 timeout 200 python tools/tc_one.py 1000000 fp32 64 10 0 4 > $OUT/${TAG}_trace_c2_b64.log 2>&1; echo "trace rc=$?"
+            MQVS_TRACE=1 timeout 200 python tools/tc_one.py 1000000 fp32 1 10 0 4 > $OUT/${TAG}_trace_c2_b1.log 2>&1 ;;
     widek)  for kk in 100 200 1000; do timeout 200 python tools/tc_one.py 1000000 fp32 64 $kk 0 5 > $OUT/${TAG}_widek_$kk.log 2>&1; tail -1 $OUT/${TAG}_widek_$kk.log; done ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
 done
 tail -5 $OUT/${TAG}_pytest_gpu.log 2>/dev/null
+exit 0
