@@ -236,7 +236,7 @@ static void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* m
 // (flags_map word [1 + B]), so the blocking call needs no device-to-host copy at all.
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                    float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status,
-                   bool defer_repair, bool report_to_host) {
+                   bool defer_repair, bool report_to_host, const float* q_raw_host) {
     using namespace mqvs;
     const int slot = s->ev_cursor;
     s->ev_cursor = (s->ev_cursor + 1) % mqvs_store::kEvRing;
@@ -255,9 +255,10 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if ((rc = s->cand.ensure((size_t)B * scan_fused_max_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
         MQVS_EV(0);
         MQVS_EV(1);
+        // (q_raw_host: a host caller's queries ride in the kernel's parameter block -- no copy of their own)
         launch_scan_fused(s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, B, mask_dev, k, (uint64_t*)s->cand.p,
                           out_scores_dev, out_ids_dev, id_base, s->ticket_dev, (unsigned int*)(s->bad_dev + 1), ++s->epoch,
-                          s->sm_count, st, host_status);
+                          s->sm_count, st, host_status, q_raw_host);
         MQVS_EV(2);
         MQVS_EV(3);
         CU(cudaGetLastError());
@@ -830,7 +831,15 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
                          float* out_scores, int64_t* out_ids, int out_is_device) {
     int rc;
     const float* q_dev = q;
-    if (!q_is_device) {
+    // latency path (B <= 4, k <= 16, the reference's own regime): one launch that also reports completion + non-finite status;
+    // a host caller's queries travel inside that launch's parameter block, so the call is ONE launch and one stream sync
+    const bool zero_copy = !out_is_device && !use_tensor_path(s, B, k) && s->path != 3 && s->metric == MQVS_METRIC_COSINE &&
+                           mqvs::scan_fused_ok(B, k);
+    static const bool no_inline = getenv("MQVS_NO_INLINE_QUERIES") != nullptr;  // developer knob: measure what it buys
+    const bool inline_q = zero_copy && !q_is_device && !no_inline;
+    if (inline_q) {
+        q_dev = nullptr;
+    } else if (!q_is_device) {
         if ((rc = s->qraw.ensure((size_t)B * s->dim * sizeof(float))) != MQVS_OK) return rc;
         CU(cudaMemcpyAsync(s->qraw.p, q, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->st));
         q_dev = (const float*)s->qraw.p;
@@ -859,11 +868,9 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
         status = (unsigned int*)((char*)s->host_out.p + n_out * 12 + ((8 - (n_out * 12) % 8) % 8));
         status[0] = 0;
     }
-    // latency path (B <= 4, k <= 16, the reference's own regime): one launch that also reports completion + non-finite status
-    const bool zero_copy = !out_is_device && !use_tensor_path(s, B, k) && s->path != 3 && s->metric == MQVS_METRIC_COSINE &&
-                           mqvs::scan_fused_ok(B, k);
     if (zero_copy) {
-        if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, status)) != MQVS_OK) return rc;
+        if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, status, false, false, inline_q ? q : nullptr)) != MQVS_OK)
+            return rc;
         CU(cudaStreamSynchronize(s->st));
         if (status[0] != s->epoch) return fail(MQVS_E_CUDA, "latency path: the kernel did not report completion");
         memcpy(out_scores, os, n_out * sizeof(float));

@@ -170,9 +170,8 @@ struct FusedArgs {
 };
 
 template <typename T, int QB, int U>
-__global__ void __launch_bounds__(kScanThreads)
-scan_fused_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uint32_t* __restrict__ mask, int k,
-                  uint64_t* __restrict__ cand, FusedArgs a) {
+__device__ __forceinline__ void scan_fused_body(const T* __restrict__ rows, uint32_t n_rows, int nq, const uint32_t* __restrict__ mask,
+                                                int k, uint64_t* __restrict__ cand, const FusedArgs& a) {
     __shared__ __align__(16) uint64_t smem_keys[QB * 128];  // next_pow2(8 warps * k), k <= 16
     __shared__ uint64_t win[8 * 32];
     __shared__ unsigned int s_ticket;
@@ -211,6 +210,30 @@ scan_fused_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uin
             a.host_status[0] = a.epoch;
         }
     }
+}
+
+template <typename T, int QB, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_fused_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uint32_t* __restrict__ mask, int k,
+                  uint64_t* __restrict__ cand, FusedArgs a) {
+    scan_fused_body<T, QB, U>(rows, n_rows, nq, mask, k, cand, a);
+}
+
+// The same search with the raw queries INSIDE the kernel's parameter block (up to 4 x MQVS_DIM_PAD floats: 12 KB at 768 --
+// kernel parameters may be ~32 KB from CUDA 12.1 on): a host caller's queries then need no host-to-device copy of their own,
+// the launch itself carries them (the reference's regime -- one query, 154 chunks -- is launch-latency-bound, and the
+// separate copy was a quarter of the call).  __grid_constant__: the address of the parameter may be taken, every warp
+// reads its lane shares from it as from any other read-only memory.
+template <int QB>
+struct InlineQueries {
+    float v[QB * kDim];
+};
+template <typename T, int QB, int U>
+__global__ void __launch_bounds__(kScanThreads)
+scan_fused_inline_kernel(const T* __restrict__ rows, uint32_t n_rows, int nq, const uint32_t* __restrict__ mask, int k,
+                         uint64_t* __restrict__ cand, FusedArgs a, const __grid_constant__ InlineQueries<QB> q) {
+    a.q_raw = q.v;
+    scan_fused_body<T, QB, U>(rows, n_rows, nq, mask, k, cand, a);
 }
 
 template <typename T, int QB, int KPL, int U>
@@ -346,10 +369,11 @@ bool scan_fused_ok(int B, int k) { return B >= 1 && B <= 4 && k <= 16; }
 
 template <typename T, int QB, int U>
 int launch_fused_t(const void* rows, uint32_t n_rows, int nq, const uint32_t* mask, int k, uint64_t* cand, int sm_count,
-                   const FusedArgs& a, cudaStream_t st) {
+                   const FusedArgs& a, cudaStream_t st, const float* q_host) {
     auto kern = scan_fused_kernel<T, QB, U>;
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, 0) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)(q_host ? (const void*)scan_fused_inline_kernel<T, QB, U> : (const void*)kern),
+                                                      kScanThreads, 0) != cudaSuccess || occ < 1) {
         cudaGetLastError();
         occ = 1;
     }
@@ -358,6 +382,13 @@ int launch_fused_t(const void* rows, uint32_t n_rows, int nq, const uint32_t* ma
     // a handful of candidate lists instead of 296 mostly empty ones
     const uint32_t groups = (n_rows + kScanWarps * U - 1) / (kScanWarps * U);
     if ((uint32_t)grid > groups) grid = groups > 0 ? (int)groups : 1;
+    if (q_host != nullptr) {
+        // the queries ride in the parameter block: rows of a.dim floats each, packed (the kernel reads them with stride a.dim)
+        InlineQueries<QB> q;
+        memcpy(q.v, q_host, (size_t)nq * a.dim * sizeof(float));
+        scan_fused_inline_kernel<T, QB, U><<<grid, kScanThreads, 0, st>>>((const T*)rows, n_rows, nq, mask, k, cand, a, q);
+        return grid;
+    }
     kern<<<grid, kScanThreads, 0, st>>>((const T*)rows, n_rows, nq, mask, k, cand, a);
     return grid;
 }
@@ -367,14 +398,16 @@ int scan_fused_max_grid(int sm_count) { return sm_count * 2; }
 void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float* q_raw, int dim, int nq,
                        const uint32_t* mask, int k, uint64_t* cand, float* out_scores, int64_t* out_ids, int64_t id_base,
                        unsigned int* ticket, unsigned int* bad_epoch, unsigned int epoch, int sm_count, cudaStream_t st,
-                       unsigned int* host_status) {
-    FusedArgs a{q_raw, dim, (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0,
+                       unsigned int* host_status, const float* q_host) {
+    // q_host: the raw queries in HOST memory -- they travel inside the kernel's parameter block (q_raw is then unused)
+    // (parameter space is not global memory: the streaming 128-bit ld.global path is for q_raw only)
+    FusedArgs a{q_raw, dim, q_host ? 0 : ((dim % 4 == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) ? 1 : 0),
                 out_scores, out_ids, id_base, ticket, bad_epoch, epoch, host_status};
     const int qb = nq >= 3 ? 4 : nq;  // 1, 2 or 4 register-resident queries
 #define MQVS_FUSED(T_, U_)                                                                                     \
-    (qb == 1   ? launch_fused_t<T_, 1, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st)                     \
-     : qb == 2 ? launch_fused_t<T_, 2, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st)                     \
-               : launch_fused_t<T_, 4, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st))
+    (qb == 1   ? launch_fused_t<T_, 1, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st, q_host)             \
+     : qb == 2 ? launch_fused_t<T_, 2, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st, q_host)             \
+               : launch_fused_t<T_, 4, U_>(rows, n_rows, nq, mask, k, cand, sm_count, a, st, q_host))
     if (dtype == MQVS_F32)
         MQVS_FUSED(float, 2);
     else

@@ -62,12 +62,14 @@ void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_
 // cand: scratch of B * scan_fused_max_grid * k keys (no memset needed); ticket: device uint32, zero between calls;
 // bad_epoch: device uint32 raised to `epoch` when a query is non-finite.  out_scores / out_ids may be MAPPED HOST memory
 // (the last CTA writes them with plain stores); host_status (mapped host, optional) then receives {epoch, non-finite flag}.
+// q_host (optional): the raw queries in HOST memory; they are then carried inside the kernel's parameter block instead of
+// being read from q_raw (no host-to-device copy of the queries at all).
 bool scan_fused_ok(int B, int k);
 int scan_fused_max_grid(int sm_count);
 void launch_scan_fused(const void* rows, int dtype, uint32_t n_rows, const float* q_raw, int dim, int nq,
                        const uint32_t* mask, int k, uint64_t* cand, float* out_scores, int64_t* out_ids, int64_t id_base,
                        unsigned int* ticket, unsigned int* bad_epoch, unsigned int epoch, int sm_count, cudaStream_t st,
-                       unsigned int* host_status = nullptr);
+                       unsigned int* host_status = nullptr, const float* q_host = nullptr);
 
 // Merge: keys_in [B][m] (any order, 0 = empty) -> best k per query as (score, id + id_base); (-inf, -1) fill.
 void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_base, float* out_scores,

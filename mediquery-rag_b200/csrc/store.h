@@ -215,7 +215,7 @@ void add_commit(mqvs_store* s, const AddReport& rep);
 
 int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                    float* out_scores_dev, int64_t* out_ids_dev, cudaStream_t st, unsigned int* host_status = nullptr,
-                   bool defer_repair = false, bool report_to_host = false);
+                   bool defer_repair = false, bool report_to_host = false, const float* q_raw_host = nullptr);
 // after the stream has been synchronised: host-driven repair of whatever the device-side repair left flagged (reads the
 // flags the last tensor search reported; *changed says whether outputs were rewritten and the stream synchronised again)
 int finish_search(mqvs_store* s, int B, int k, const uint32_t* mask_dev, int64_t id_base, float* out_scores_dev,

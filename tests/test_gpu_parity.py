@@ -471,6 +471,17 @@ def test_single_launch_latency_path_equals_multi_launch_path_and_oracle(gpu, n, 
     with pytest.raises(native().MqvsError):
         idx.search(bad, k)
     assert_bit_equal(*idx.search(q, k, mask), *want)              # and the handle keeps working afterwards
+    # a host caller's queries ride in the kernel's parameter block (scan_fused_inline_kernel); device-resident queries take
+    # the same kernel reading them from global memory
+    import torch
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    mask_dev = None if mask is None else torch.from_numpy(mask.view(np.int32)).cuda()
+    l0 = idx.stats()["kernel_launches"]
+    idx.search_device(torch.from_numpy(q).cuda(), k, out_s, out_i, mask=mask_dev)
+    torch.cuda.synchronize()
+    assert idx.stats()["kernel_launches"] - l0 == 1 and idx.stats()["last_pipeline"] == 1
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), *want)
 
 
 def test_tensor_path_batches_larger_than_one_launch_chunk(gpu):
@@ -1535,8 +1546,8 @@ def test_vectorstore_with_a_1024_dimensional_embedder(gpu, tmp_path):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_kernels_against_the_independent_float64_referee_at_one_million_rows(gpu, dtype):
     """The parity claim without the kernel-ordered oracle in between: the CUDA results themselves (single-launch tensor
-    pipeline at B = 16, SIMT scan at B = 1, all three spaces over raw non-unit vectors) against float64 numpy over the
-    stored values, under north_star's stated tolerance -- ids identical apart from near ties, scores within 1e-5 relative."""
+    pipeline and segmented pipeline at B = 16, SIMT scan at B = 1, all three spaces over raw non-unit vectors; the CTA-pair
+    kernel at B = 160; fp32 stores through their bf16 scoring shadow) against float64 numpy over the stored values, under north_star's stated tolerance -- ids identical apart from near ties, scores within 1e-5 relative."""
     from referee import assert_within_north_star, f64_topk
     n, B, k = 1_000_000, 16, 10
     x = O.synth_rows(SEED, 0, n, 768)
@@ -1557,4 +1568,17 @@ def test_kernels_against_the_independent_float64_referee_at_one_million_rows(gpu
         assert_within_north_star(space, s, i, q, ref_d, ref_i)
         s1, i1 = idx.search(q[:1], k)
         assert_within_north_star(space, s1, i1, q[:1], ref_d[:1], ref_i[:1])
+        idx.set_path(4)                      # the segmented tensor pipeline (cold pass, radix selection, rescore kernel)
+        s4, i4 = idx.search(q, k)
+        assert idx.stats()["last_pipeline"] == 2
+        assert_within_north_star(space, s4, i4, q, ref_d, ref_i)
+        idx.set_path(0)
+    # a batch of more than one query tile: the CTA-pair (cta_group::2) scoring kernel of the segmented pipeline, cosine space
+    idx.set_metric("cosine")
+    qb, _ = O.planted_queries(QSEED + 1, 160, SEED, n, 768)
+    ref_d, ref_i = f64_topk(qb, st, norms, k, "cosine")
+    idx.set_path(4)
+    sb, ib = idx.search(qb, k)
+    assert idx.stats()["last_pipeline"] == 2
+    assert_within_north_star("cosine", sb, ib, qb, ref_d, ref_i)
     idx.close()

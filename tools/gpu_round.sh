@@ -60,6 +60,11 @@ for s in $STEPS; do
             MQVS_NO_SHADOW=1 timeout 300 python bench.py --workload c2 --no-secondary --no-cpu-baseline --points 1,16,256,1024 --steps 30 --warmup 5 > $OUT/${TAG}_bench_c2_noshadow.json 2> $OUT/${TAG}_bench_c2_noshadow.err; echo "c2 noshadow rc=$?" ;;
     tracec2) MQVS_TRACE=1 timeout 200 python tools/tc_one.py 1000000 fp32 64 10 0 4 > $OUT/${TAG}_trace_c2_b64.log 2>&1; echo "trace rc=$?"
             MQVS_TRACE=1 timeout 200 python tools/tc_one.py 1000000 fp32 1 10 0 4 > $OUT/${TAG}_trace_c2_b1.log 2>&1 ;;
+    latency) for r in 154 10000 100000; do
+              timeout 120 python tools/latency_one.py $r fp32 3000 > $OUT/${TAG}_latency_${r}.log 2>&1; tail -1 $OUT/${TAG}_latency_${r}.log
+              MQVS_NO_INLINE_QUERIES=1 timeout 120 python tools/latency_one.py $r fp32 3000 > $OUT/${TAG}_latency_${r}_copied.log 2>&1; tail -1 $OUT/${TAG}_latency_${r}_copied.log
+            done ;;
+    c3ip)   timeout 400 python bench.py --workload c3 --space ip --no-secondary --no-cpu-baseline --steps 5 --warmup 3 > $OUT/${TAG}_bench_c3_ip.json 2> $OUT/${TAG}_bench_c3_ip.err; echo "c3 ip rc=$?" ;;
     widek)  for kk in 100 200 1000; do timeout 200 python tools/tc_one.py 1000000 fp32 64 $kk 0 5 > $OUT/${TAG}_widek_$kk.log 2>&1; tail -1 $OUT/${TAG}_widek_$kk.log; done ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
   esac
