@@ -468,6 +468,7 @@ MQVS_API int mqvs_device_count(int* out) {
 }
 
 MQVS_API int mqvs_create(int n_dev, const int* dev_ids, int dim, int store_dtype, uint64_t capacity_rows, mqvs_t** out) {
+    MQVS_RANGE("mqvs_create");
     if (!out) return fail(MQVS_E_INVALID, "out is NULL");
     *out = nullptr;
     if (n_dev < 1 || n_dev > MQVS_MAX_DEVICES)
@@ -747,6 +748,7 @@ static int add_common(mqvs_t* s, const void* x, int x_is_device, bool synth, uin
 }
 
 MQVS_API int mqvs_add(mqvs_t* s, const void* x, int x_dtype, int x_is_device, uint64_t n, uint64_t* first_row_out) {
+    MQVS_RANGE("mqvs_add");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (n && !x) return fail(MQVS_E_INVALID, "x is NULL");
     if (x_dtype != MQVS_F32) return fail(MQVS_E_INVALID, "embeddings must be fp32 (x_dtype=%d)", x_dtype);
@@ -754,6 +756,7 @@ MQVS_API int mqvs_add(mqvs_t* s, const void* x, int x_dtype, int x_is_device, ui
 }
 
 MQVS_API int mqvs_add_synthetic(mqvs_t* s, uint64_t seed, uint64_t first_index, uint64_t n, uint64_t* first_row_out) {
+    MQVS_RANGE("mqvs_add_synthetic");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     return add_common(s, nullptr, 1, true, seed, first_index, n, first_row_out);
 }
@@ -771,6 +774,7 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
 
 MQVS_API int mqvs_search(mqvs_t* s, const float* q, int q_is_device, int B, int k, const uint32_t* mask, int mask_is_device,
                 float* out_scores, int64_t* out_ids, int out_is_device) {
+    MQVS_RANGE("mqvs_search");
     int rc = check_search_args(s, q, B, k, out_scores, out_ids);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
@@ -840,9 +844,19 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
     if (inline_q) {
         q_dev = nullptr;
     } else if (!q_is_device) {
-        if ((rc = s->qraw.ensure((size_t)B * s->dim * sizeof(float))) != MQVS_OK) return rc;
-        CU(cudaMemcpyAsync(s->qraw.p, q, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->st));
-        q_dev = (const float*)s->qraw.p;
+        // Pinned caller memory, up to 256 queries (768 KB): the first kernel of the search (query normalisation) reads the raw
+        // queries straight from the host over PCIe -- no copy-engine launch in front of it.  Larger batches and pageable
+        // memory go through the copy engine.
+        static const bool no_zero_copy = getenv("MQVS_NO_ZERO_COPY_QUERIES") != nullptr;  // developer knob: measure what it buys
+        void* mapped = nullptr;
+        if (!no_zero_copy && B <= 256 && is_pinned_host(q) && cudaHostGetDevicePointer(&mapped, (void*)q, 0) == cudaSuccess && mapped) {
+            q_dev = (const float*)mapped;
+        } else {
+            cudaGetLastError();
+            if ((rc = s->qraw.ensure((size_t)B * s->dim * sizeof(float))) != MQVS_OK) return rc;
+            CU(cudaMemcpyAsync(s->qraw.p, q, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->st));
+            q_dev = (const float*)s->qraw.p;
+        }
     }
     const uint32_t* mask_dev = mask;
     if (mask && !mask_is_device) {
@@ -902,6 +916,7 @@ extern "C" {
 
 MQVS_API int mqvs_search_async(mqvs_t* s, const float* q_dev, int B, int k, const uint32_t* mask_dev, int64_t id_base,
                       float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    MQVS_RANGE("mqvs_search_async");
     int rc = check_search_args(s, q_dev, B, k, out_scores_dev, out_ids_dev);
     if (rc != MQVS_OK) return rc;
     if (B == 0) return MQVS_OK;
@@ -933,6 +948,7 @@ MQVS_API int mqvs_merge_candidates(int device, const float* scores_dev, const in
 }
 
 MQVS_API int mqvs_get_rows(mqvs_t* s, const int64_t* row_ids, uint64_t n, float* out_host) {
+    MQVS_RANGE("mqvs_get_rows");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (n == 0) return MQVS_OK;
     if (!row_ids || !out_host) return fail(MQVS_E_INVALID, "NULL buffer");
@@ -1015,6 +1031,7 @@ bool flush_to_disk(FILE* f) { return fflush(f) == 0 && fsync(fileno(f)) == 0; }
 extern "C" {
 
 MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
+    MQVS_RANGE("mqvs_save");
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
     if (s->multi) return multi_save(s, path, 0);
     std::lock_guard<std::mutex> lk(s->mu);
@@ -1059,6 +1076,7 @@ MQVS_API int mqvs_save(mqvs_t* s, const char* path) {
 }
 
 MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
+    MQVS_RANGE("mqvs_save_append");
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
     if (first_row == 0) return mqvs_save(s, path);
     if (s->multi) return multi_save(s, path, first_row);
@@ -1106,6 +1124,7 @@ MQVS_API int mqvs_save_append(mqvs_t* s, const char* path, uint64_t first_row) {
 }
 
 MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
+    MQVS_RANGE("mqvs_load");
     if (!s || !path) return fail(MQVS_E_INVALID, "NULL argument");
     if (s->multi) return multi_load(s, path);
     std::lock_guard<std::mutex> lk(s->mu);
@@ -1150,6 +1169,7 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path) {
 }
 
 MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offsets_host, const int64_t* tokens_host, uint64_t n) {
+    MQVS_RANGE("mqvs_column_set_tokens");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
     if (!offsets_host) return fail(MQVS_E_INVALID, "offsets is NULL");
@@ -1164,6 +1184,7 @@ MQVS_API int mqvs_column_set_tokens(mqvs_t* s, int col_id, const uint64_t* offse
 
 MQVS_API int mqvs_column_set_text(mqvs_t* s, int col_id, const uint64_t* offsets_host, const uint8_t* bytes_host,
                                   const uint8_t* present_host, uint64_t n) {
+    MQVS_RANGE("mqvs_column_set_text");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
     if (!offsets_host) return fail(MQVS_E_INVALID, "offsets is NULL");
@@ -1177,6 +1198,7 @@ MQVS_API int mqvs_column_set_text(mqvs_t* s, int col_id, const uint64_t* offsets
 }
 
 MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out) {
+    MQVS_RANGE("mqvs_compact");
     if (!s || !keep_words_host || !new_count_out) return fail(MQVS_E_INVALID, "NULL argument");
     if (s->multi)
         return fail(MQVS_E_INVALID, "compaction of a multi-device handle is not implemented (rows would have to move between "
@@ -1236,6 +1258,7 @@ MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* 
 
 MQVS_API int mqvs_column_set(mqvs_t* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host,
                              uint64_t n) {
+    MQVS_RANGE("mqvs_column_set");
     if (!s) return fail(MQVS_E_INVALID, "NULL handle");
     if (col_id < 0 || col_id >= mqvs::kFilterMaxCols) return fail(MQVS_E_INVALID, "column id must be in [0, %d)", mqvs::kFilterMaxCols);
     if (col_type != MQVS_COL_I64 && col_type != MQVS_COL_F64) return fail(MQVS_E_INVALID, "unknown column type %d", col_type);
@@ -1321,6 +1344,7 @@ extern "C" {
 
 MQVS_API int mqvs_filter_build(mqvs_t* s, const mqvs_filter_op* prog, int n_ops, const void* pool, uint64_t pool_len,
                                const uint32_t* live_words_host, const uint32_t** mask_dev_out, uint64_t* allowed_out) {
+    MQVS_RANGE("mqvs_filter_build");
     using namespace mqvs;
     if (!s || !mask_dev_out || !allowed_out) return fail(MQVS_E_INVALID, "NULL argument");
     if (n_ops < 0 || n_ops > kFilterMaxOps) return fail(MQVS_E_INVALID, "a filter program holds at most %d operations", kFilterMaxOps);

@@ -4,6 +4,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <unistd.h>
 
@@ -24,6 +25,16 @@
 #include "tc.h"
 
 namespace mqvs {
+
+// One NVTX range per API call (visible in nsys timelines and to `ncu --nvtx --nvtx-include`): header-only NVTX3, a no-op
+// (one load + branch) while no tool is attached to the process.
+struct ApiRange {
+    explicit ApiRange(const char* name) { nvtxRangePushA(name); }
+    ~ApiRange() { nvtxRangePop(); }
+    ApiRange(const ApiRange&) = delete;
+    ApiRange& operator=(const ApiRange&) = delete;
+};
+#define MQVS_RANGE(name_) ::mqvs::ApiRange mqvs_api_range_(name_)
 
 // thread-local error message + code (api.cu); every failure path goes through this
 int mqvs_fail(int code, const char* fmt, ...);

@@ -312,6 +312,16 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         with self._lock:
             return self._add_locked(texts, vectors, metadatas, ids, metadata_columns)
 
+    @staticmethod
+    def _check_columns(n: int, metadatas, metadata_columns) -> None:
+        if metadata_columns is None:
+            return
+        if metadatas is not None:
+            raise ValueError("give metadatas or metadata_columns, not both")
+        for name, col in metadata_columns.items():
+            if np.asarray(col).shape[:1] != (n,):
+                raise ValueError(f"column {name!r} has shape {np.asarray(col).shape} for {n} rows")
+
     def _add_locked(self, texts: List[Optional[str]], vectors: Any, metadatas, ids, metadata_columns=None) -> List[str]:
         n = len(texts)
         if n == 0:
@@ -329,6 +339,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             raise ValueError(f"{len(ids)} ids for {n} texts")
         if len(set(ids)) != n:
             raise ValueError("duplicate ids within one call")
+        self._check_columns(n, metadatas, metadata_columns)  # before anything reaches the device: rows and tables move together
         self._ensure_index(vectors.shape[1])
         first = self._index.add(vectors)  # raises (and appends nothing) on non-finite rows
         assert first == len(self._ids), "host document table and device rows out of step"
@@ -343,8 +354,6 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self._ids.extend(ids)
         self._texts.extend(texts)
         if metadata_columns is not None:
-            if metadatas is not None:
-                raise ValueError("give metadatas or metadata_columns, not both")
             self._cols.extend_columns(n, metadata_columns)
         else:
             self._cols.extend(metadatas if metadatas is not None else [None] * n)
@@ -360,6 +369,7 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         optional and column-wise -- nothing is kept per row on the host.  Not persisted (in-memory collections only)."""
         if self._persist_directory is not None:
             raise ValueError("add_synthetic serves in-memory collections (persist_directory=None)")
+        self._check_columns(int(n), None, metadata_columns)
         with self._lock:
             self._ensure_index(self._dim or _native.DIM_PAD)
             start = len(self._ids)

@@ -6,7 +6,9 @@ its CUDA library is missing instead of falling back to anything here.
 
 PARITY UNPINNED for the vector arithmetic: the reference delegates it to un-vendored, un-pinned
 langchain-chroma / chromadb / chroma-hnswlib (README.md:630-639) and has no tests or golden vectors, so
-the referee is the exact brute-force definition BASELINE.json's north_star prescribes (see canonical.c).
+the referee is the exact brute-force definition BASELINE.json's north_star prescribes (see canonical.c);
+hnswlib_restated.c restates the published arithmetic of that dependency (chroma-hnswlib's distance functions
+and exhaustive search, from upstream knowledge) as a second, independently ordered checker.
 The text splitter (src/ingest_medical.py:11-87) IS pinned: tests/golden/ holds outputs produced by
 importing the reference's own parse_custom_format (oracle/gen_golden.py).
 """
@@ -17,6 +19,7 @@ from .oracle import (  # noqa: F401
     distances_from_rank_scores,
     eval_where,
     f64_scores,
+    hnswlib_topk,
     lib,
     mask_from_bool,
     merge_topk,

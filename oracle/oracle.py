@@ -35,7 +35,8 @@ def lib() -> ctypes.CDLL:
         return _LIB
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "canonical.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "hnswlib_restated.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(src2)):
         subprocess.run(["make", "-s", "-B", "-C", _HERE, "liboracle.so"], check=True)
     L = ctypes.CDLL(so)
     i64, i32, vp, u64 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64
@@ -53,6 +54,10 @@ def lib() -> ctypes.CDLL:
     L.orc_norms_f32.restype = None
     L.orc_synth_rows.argtypes = [u64, i64, i64, i32, vp]
     L.orc_synth_rows.restype = None
+    L.hnsw_distances.argtypes = [i32, i32, vp, i64, i64, vp, vp]
+    L.hnsw_distances.restype = None
+    L.hnsw_bruteforce_knn.argtypes = [vp, i64, vp, i32, vp, vp]
+    L.hnsw_bruteforce_knn.restype = None
     _LIB = L
     return L
 
@@ -253,6 +258,29 @@ def _select(scores: np.ndarray, k: int, allowed: np.ndarray | None):
 def referee_topk_f64(qn, stored, k: int, allowed: np.ndarray | None = None):
     """float64 referee computed from the STORED values (bf16 rows are upcast)."""
     return _select(f64_scores(qn, stored), k, None if allowed is None else np.asarray(allowed, bool))
+
+
+def hnswlib_topk(space: str, rows_raw: np.ndarray, q_raw: np.ndarray, k: int, order: str = "simd16",
+                 allowed: np.ndarray | None = None):
+    """chroma-hnswlib's published arithmetic (oracle/hnswlib_restated.c): its distance functions for `space` ("l2" | "ip" |
+    "cosine", the last with normalize_vector on rows and queries) over RAW fp32 vectors, in the scalar or the 16-lane SIMD
+    summation order, and bruteforce.h's exhaustive top-k.  -> (distance [B, k] ascending, ids [B, k]); -1 / inf padded."""
+    L = lib()
+    rows = np.ascontiguousarray(rows_raw, np.float32)
+    q = np.ascontiguousarray(q_raw, np.float32).reshape(-1, rows.shape[1])
+    n, dim = rows.shape
+    code = {"l2": 0, "ip": 1, "cosine": 2}[space]
+    allow = None if allowed is None else mask_from_bool(np.asarray(allowed, bool))
+    out_d = np.empty((q.shape[0], k), np.float32)
+    out_i = np.empty((q.shape[0], k), np.int64)
+
+    def one(b):
+        d = np.empty(n, np.float32)
+        L.hnsw_distances(code, 1 if order == "simd16" else 0, _p(rows), n, dim, _p(q[b]), _p(d))
+        L.hnsw_bruteforce_knn(_p(d), n, None if allow is None else _p(allow), k, _p(out_d[b]), _p(out_i[b]))
+
+    _pmap(one, range(q.shape[0]))
+    return out_d, out_i
 
 
 def sgemm_topk(qn: np.ndarray, rows_f32: np.ndarray, k: int, allowed: np.ndarray | None = None):

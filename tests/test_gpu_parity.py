@@ -1582,3 +1582,35 @@ def test_kernels_against_the_independent_float64_referee_at_one_million_rows(gpu
     assert idx.stats()["last_pipeline"] == 2
     assert_within_north_star("cosine", sb, ib, qb, ref_d, ref_i)
     idx.close()
+
+
+@pytest.mark.parametrize("order", ["scalar", "simd16"])
+def test_kernels_against_the_published_arithmetic_of_chroma_hnswlib(gpu, order):
+    """The CUDA results against what the reference's own dependency computes (oracle/hnswlib_restated.c: chroma-hnswlib's
+    distance functions over the RAW fp32 vectors in its sequential / 16-lane summation order, its exhaustive search): an
+    fp32 collection, all three spaces, SIMT scan (B = 1), single-launch tensor pipeline over the bf16 scoring shadow
+    (cosine) and over the fp32 rows (l2 / ip), segmented pipeline -- ids identical apart from near ties, distances within
+    north_star's 1e-5 relative."""
+    from referee import assert_within_north_star
+    n, B, k = 300_000, 8, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x *= np.linspace(0.03, 0.09, n, dtype=np.float32)[:, None]
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    q = (q * np.float32(1.3)).astype(np.float32)
+    idx = native().Index(768, "fp32", capacity_rows=n)
+    idx.set_metric("l2")
+    idx.add(x)
+    for space in ("cosine", "l2", "ip"):
+        idx.set_metric(space)
+        ref_d, ref_i = O.hnswlib_topk(space, x, q, k, order=order)
+        ref_d = ref_d.astype(np.float64)
+        for path, want in ((0, None), (2, 1), (4, 1), (1, 0)):
+            idx.set_path(path)
+            s, i = idx.search(q, k)
+            if want is not None:
+                assert idx.stats()["last_path"] == want
+            assert_within_north_star(space, s, i, q, ref_d, ref_i)
+        idx.set_path(0)
+        s1, i1 = idx.search(q[:1], k)
+        assert_within_north_star(space, s1, i1, q[:1], ref_d[:1], ref_i[:1])
+    idx.close()

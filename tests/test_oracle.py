@@ -147,3 +147,48 @@ def test_oracle_against_an_independent_float64_referee_at_one_million_rows(dtype
         s, i = O.brute_force_topk(qn, st, k, **kw)
         ref_d, ref_i = f64_topk(q, st, norms, k, space)
         assert_within_north_star(space, s, i, q, ref_d, ref_i)
+
+
+@pytest.mark.parametrize("order", ["scalar", "simd16"])
+def test_oracle_against_the_published_arithmetic_of_chroma_hnswlib(order):
+    """What the reference actually runs is chroma-hnswlib (un-vendored; oracle/hnswlib_restated.c restates its distance
+    functions -- sequential and 16-lane SIMD summation order, `1 - ip` / squared L2 over the RAW vectors, normalize_vector
+    for the cosine space -- and its exhaustive search).  The canonical oracle must agree with it under north_star's
+    tolerance in all three spaces: ids identical apart from near ties, distances within 1e-5 relative."""
+    from referee import assert_within_north_star
+    n, B, k = 200_000, 6, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x *= np.linspace(0.03, 0.09, n, dtype=np.float32)[:, None]       # raw norms 0.5 .. 1.5
+    q, _ = O.planted_queries(0x0BADC0DE, B, SEED, n, 768)
+    q = (q * np.float32(1.3)).astype(np.float32)
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    norms = O.row_norms(x, 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    for space in ("cosine", "l2", "ip"):
+        kw = {} if space == "cosine" else dict(metric=space, norms=norms, q_norms=O.row_norms(q, 768))
+        s, i = O.brute_force_topk(qn, st, k, **kw)
+        ref_d, ref_i = O.hnswlib_topk(space, x, q, k, order=order)
+        assert_within_north_star(space, s, i, q, ref_d.astype(np.float64), ref_i)
+
+
+def test_hnswlib_restatement_known_answers():
+    """The restated exhaustive search on hand-made distances: ties keep the LOWER label in the result (the heap's worst is
+    the larger label), a filter removes rows before selection, short stores are padded."""
+    L = O.lib()
+    import ctypes
+    d = np.array([0.5, 0.1, 0.5, 0.3, 0.1, 0.9], np.float32)
+    out_d, out_i = np.empty(3, np.float32), np.empty(3, np.int64)
+    L.hnsw_bruteforce_knn(ctypes.c_void_p(d.ctypes.data), 6, None, 3, ctypes.c_void_p(out_d.ctypes.data), ctypes.c_void_p(out_i.ctypes.data))
+    assert out_i.tolist() == [1, 4, 3] and out_d.tolist() == [np.float32(0.1), np.float32(0.1), np.float32(0.3)]
+    allow = O.mask_from_bool(np.array([1, 0, 1, 0, 0, 1], bool))
+    L.hnsw_bruteforce_knn(ctypes.c_void_p(d.ctypes.data), 6, ctypes.c_void_p(allow.ctypes.data), 3, ctypes.c_void_p(out_d.ctypes.data), ctypes.c_void_p(out_i.ctypes.data))
+    assert out_i.tolist() == [0, 2, 5]
+    L.hnsw_bruteforce_knn(ctypes.c_void_p(d.ctypes.data), 2, None, 3, ctypes.c_void_p(out_d.ctypes.data), ctypes.c_void_p(out_i.ctypes.data))
+    assert out_i.tolist() == [1, 0, -1] and np.isinf(out_d[2])
+    # unit basis vectors: ip distance exactly 0 / 1, squared l2 exactly 0 / 2, in either summation order
+    e = np.eye(4, 768, dtype=np.float32)
+    for order in ("scalar", "simd16"):
+        dd, ii = O.hnswlib_topk("ip", e, e[2:3], 4, order=order)
+        assert ii[0, 0] == 2 and dd[0].tolist() == [0.0, 1.0, 1.0, 1.0]
+        dd, ii = O.hnswlib_topk("l2", e, e[2:3], 4, order=order)
+        assert ii[0].tolist() == [2, 0, 1, 3] and dd[0].tolist() == [0.0, 2.0, 2.0, 2.0]

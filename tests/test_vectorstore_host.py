@@ -341,3 +341,20 @@ def test_bulk_rows_with_implicit_ids_and_tombstone_compaction(tmp_path, embedder
     assert vs.get(ids=["z"])["documents"] == ["t2"] and vs.get(ids=["row-0"])["ids"] == []
     sc, rid = vs.search_batch(q, 3, filter={"g": 1})
     assert all(vs._cols.row(int(r))["g"] == 1 for r in rid.ravel())
+
+
+def test_a_bad_metadata_column_is_refused_before_any_row_reaches_the_index():
+    """Rows and host tables move together: a column of the wrong length must fail BEFORE the device add, or every later add
+    would find the document table and the device rows out of step."""
+    vs = MediQueryVectorStore(index_factory=OracleIndex, dim=768, collection_metadata={"hnsw:space": "cosine"})
+    x = O.synth_rows(7, 0, 10, 768)
+    with pytest.raises(ValueError):
+        vs.add_embeddings((None, x), metadata_columns={"g": np.arange(9)})
+    with pytest.raises(ValueError):
+        vs.add_embeddings((None, x), metadatas=[{}] * 10, metadata_columns={"g": np.arange(10)})
+    with pytest.raises(ValueError):
+        vs.add_synthetic(1, 10, metadata_columns={"g": np.arange(11)})
+    assert len(vs) == 0 and (vs._index is None or len(vs._index) == 0)
+    ids = vs.add_embeddings((None, x), metadata_columns={"g": np.arange(10)})
+    assert len(ids) == 10 and len(vs) == 10
+    assert vs.similarity_search_by_vector(x[3], k=1, filter={"g": 3})[0].id == ids[3]
