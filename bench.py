@@ -498,6 +498,20 @@ def main():
             res, out, (q_np, planted) = H.point(sh, name, b, w["k"], steps, 3, mask)
             if rank == 0:
                 res["check"] = check_results(name, q_np, planted, out[0].cpu().numpy(), out[1].cpu().numpy(), w["k"], None, mask_fn)
+            if world == 1 and mask is None:
+                # the same batch as a blocking call with HOST buffers (pinned queries in, host results out), wall clock
+                q_host = torch.from_numpy(q_np).pin_memory().numpy()
+                for _ in range(3):
+                    got = sh.index.search(q_host, w["k"])
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    got = sh.index.search(q_host, w["k"])
+                dt = time.perf_counter() - t0
+                assert np.array_equal(got[1], out[1].cpu().numpy()) and \
+                    np.array_equal(got[0].view(np.uint32), out[0].cpu().numpy().view(np.uint32)), "e2e results differ from the device-resident path"
+                res["e2e"] = {"value": b * steps / dt, "unit": "queries/s", "ms_per_step": 1e3 * dt / steps,
+                              "h2d_bytes_per_step": b * 768 * 4, "d2h_bytes_per_step": b * w["k"] * 12,
+                              "through": "mqvs_search (blocking): pinned host queries -> host results"}
             block["points"].append(res)
         sh.index.close()
         del sh

@@ -58,7 +58,8 @@ typedef struct mqvs_stats {
     uint64_t scan_launches;      /* of those, corpus-scan (K2) launches */
     uint64_t scan_bytes;         /* algorithmic corpus bytes streamed by the scans: rows * 768 * sizeof(elem) per pass */
     double   scan_ms;            /* device time of the scan launches (CUDA events on the launch stream) */
-    double   last_search_ms;     /* device time of the last search, first kernel to last */
+    double   last_search_ms;     /* device time of the last search: its scan launches (= last_scan_ms), or first kernel to last when the
+                                    process runs with MQVS_TIMING=1 (two more CUDA events per search) */
     double   last_scan_ms;       /* device time of the last search's scan launches */
     uint32_t last_scan_passes;   /* corpus passes the last search needed */
     uint32_t last_path;          /* 0 = SIMT fp32 scan, 1 = tensor-core shortlist + fp32 rescoring */

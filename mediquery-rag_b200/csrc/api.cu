@@ -83,10 +83,12 @@ int grow(mqvs_store* s, uint64_t need_rows) {
 static void settle_slot(mqvs_store* s, int slot) {
     auto& ev = s->evr[slot];
     if (!ev.pending) return;
-    if (cudaEventSynchronize(ev.e[3]) == cudaSuccess) {
+    const bool scan_only = s->timing_level == 2;
+    if (cudaEventSynchronize(ev.e[scan_only ? 2 : 3]) == cudaSuccess) {
         float total = 0.f, scan = 0.f;
-        cudaEventElapsedTime(&total, ev.e[0], ev.e[3]);
         cudaEventElapsedTime(&scan, ev.e[1], ev.e[2]);
+        if (scan_only) total = scan;
+        else cudaEventElapsedTime(&total, ev.e[0], ev.e[3]);
         s->stats.last_search_ms = total;
         s->stats.last_scan_ms = scan;
         s->stats.scan_ms += scan;
@@ -244,7 +246,7 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     cudaEvent_t* ev = s->evr[slot].e;
 // (the shards of a multi-device handle skip the four timing events per search: at eight devices driven by one host thread
 // every API call is on the critical path of the last device's start)
-#define MQVS_EV(i_) do { if (s->timing) CU(cudaEventRecord(ev[i_], st)); } while (0)
+#define MQVS_EV(i_) do { if (s->timing && (s->timing_level != 2 || (i_) == 1 || (i_) == 2)) CU(cudaEventRecord(ev[i_], st)); } while (0)
     const bool tensor = use_tensor_path(s, B, k);
     const bool fused = !tensor && s->path != 3 && s->metric == MQVS_METRIC_COSINE && scan_fused_ok(B, k);
     s->last_fused = fused;
@@ -367,6 +369,9 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     auto enqueue_repair = [&]() {
         // nobody can look at the flags here: one band round per 128 queries of the batch, at most two, then as many exact-scan
         // rounds as it takes to cover all B queries -- the asynchronous search is exact on its own, whatever gets flagged
+        // (measured and rejected in round 2: the chain as ONE conditional-graph launch -- a gate kernel reading the flag count
+        // + an IF body -- for searches that repeat: 281.4 vs 282.6 us per step at 1M rows, B = 64, and 10 us SLOWER at B = 1;
+        // idle launches pipeline behind the running kernel and cost next to nothing, a graph launch does not)
         if (!defer_repair)
             enqueue_tensor_repair(s, B, k, mask_dev, id_base, out_scores_dev, out_ids_dev, st, B > 128 ? 2 : 1,
                                   (B + s->max_device_fix - 1) / s->max_device_fix);
@@ -505,6 +510,10 @@ int create_single(int dev, int dim, int store_dtype, uint64_t capacity_rows, mqv
     s->shadow_on = store_dtype == MQVS_F32 && getenv("MQVS_NO_SHADOW") == nullptr;
     s->sm_count = prop.multiProcessorCount;
     s->coop_ok = prop.cooperativeLaunch != 0;
+    // MQVS_TIMING=1: four CUDA events per search instead of the two around the scan (stats.last_search_ms then covers the
+    // first kernel to the last); MQVS_TIMING=0: none (stats.scan_ms / last_search_ms stay 0)
+    if (const char* t = getenv("MQVS_TIMING")) s->timing_level = atoi(t) == 1 ? 1 : (atoi(t) == 0 ? 0 : 2);
+    s->timing = s->timing_level != 0;
     auto bail = [&](int rc) {
         destroy_single(s);
         return rc;

@@ -155,6 +155,10 @@ struct mqvs_store {
         bool pending = false;
     } evr[kEvRing];
     int ev_cursor = 0;
+    // CUDA events per search: 2 = the two that bracket the scan launches (default: stats.scan_ms, what bench.py's roofline
+    // divides by), 1 = four (also first kernel to last: stats.last_search_ms), 0 = none.  A timed event costs ~3 us of stream
+    // time: four of them were 11 us of a 282 us search at 1M rows (measured, round 2), two are 6.
+    int timing_level = 2;
     bool timing = true;  // record the CUDA events behind stats.scan_ms / last_search_ms (off for the shards of a multi-device handle)
     mqvs::DevBuf qraw, qn, qnorm, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
     mqvs::DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch

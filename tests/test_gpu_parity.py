@@ -1614,3 +1614,57 @@ def test_kernels_against_the_published_arithmetic_of_chroma_hnswlib(gpu, order):
         s1, i1 = idx.search(q[:1], k)
         assert_within_north_star(space, s1, i1, q[:1], ref_d[:1], ref_i[:1])
     idx.close()
+
+
+@pytest.mark.parametrize("path,dups,clusters", [(2, 1500, False), (4, 300, False), (2, 0, True), (2, 0, False)])
+def test_repeated_async_searches_with_alternating_buffers_and_a_growing_store_stay_exact(gpu, path, dups, clusters):
+    """A steady stream of identical asynchronous searches (a serving loop, bench.py's `value`) whose device-side repair
+    chain runs every time: same bits as the oracle whether it has work (duplicates defeat the shortlist -> exact-scan rounds;
+    dense clusters -> band pass) or not (random rows), with one or two alternating output buffers (callers that allocate
+    their outputs per call), and after rows were added."""
+    import torch
+    n, B, k = 20000, 40, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    if dups:
+        x[5000:5000 + dups] = x[123]
+    if clusters:  # 100-member clusters at cosine ~0.98: the margin fails, the band pass repairs
+        centres = x[:200].copy()
+        x = (centres[np.arange(n) % 200] + 0.012 * x).astype(np.float32)
+    noise = O.synth_rows(77, 0, B, 768)
+    q = (x[123][None, :] + 0.01 * noise).astype(np.float32)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    idx = native().Index(768, "bf16")
+    idx.add(x)
+    idx.set_path(path)
+    stream = torch.cuda.current_stream().cuda_stream
+    qd = torch.from_numpy(q).cuda()
+    bufs = [(torch.empty((B, k), dtype=torch.float32, device="cuda"), torch.empty((B, k), dtype=torch.int64, device="cuda"))
+            for _ in range(2)]
+    for rep in range(7):
+        out_s, out_i = bufs[rep % 2 if rep >= 3 else 0]
+        out_s.fill_(7.0)
+        out_i.fill_(-7)
+        idx.search_device(qd, k, out_s, out_i, stream=stream)
+        torch.cuda.synchronize()
+        assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    stt = idx.stats()
+    assert stt["unrepaired"] == 0 and stt["last_path"] == 1
+    if dups:
+        assert stt["exact_fallbacks"] >= 7 * B
+    if clusters:
+        assert stt["band_repairs"] + stt["exact_fallbacks"] >= 7
+    # the store changes: the captured chains describe the old corpus and must not run
+    extra = O.synth_rows(SEED + 9, 0, 3000, 768)
+    extra[17] = x[123] * 1.0000001
+    idx.add(extra)
+    st2, _ = O.normalize_rows(np.concatenate([x, extra]), "bf16", 768)
+    es2, ei2 = O.brute_force_topk(qn, st2, k)
+    for rep in range(3):
+        out_s, out_i = bufs[0]
+        idx.search_device(qd, k, out_s, out_i, stream=stream)
+        torch.cuda.synchronize()
+        assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es2, ei2)
+    assert idx.stats()["unrepaired"] == 0
+    idx.close()
