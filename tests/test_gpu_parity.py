@@ -1668,3 +1668,33 @@ def test_repeated_async_searches_with_alternating_buffers_and_a_growing_store_st
         assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es2, ei2)
     assert idx.stats()["unrepaired"] == 0
     idx.close()
+
+
+def test_timing_levels_of_the_search_events(gpu, monkeypatch):
+    """stats.scan_ms (what bench.py's roofline divides by) comes from two timed CUDA events around the scan launches;
+    MQVS_TIMING=1 adds the first-kernel-to-last bracket, MQVS_TIMING=0 records nothing.  Read when a handle is created;
+    results do not depend on it."""
+    n, B, k = 70_000, 8, 10
+    q, _ = O.planted_queries(QSEED, B, SEED, n, 768)
+    seen = {}
+    for level in (None, "1", "0"):
+        if level is None:
+            monkeypatch.delenv("MQVS_TIMING", raising=False)
+        else:
+            monkeypatch.setenv("MQVS_TIMING", level)
+        idx = native().Index(768, "bf16", capacity_rows=n)
+        idx.add_synthetic(SEED, 0, n)
+        for B_ in (B, 1):  # tensor pipeline, latency kernel
+            s, i = idx.search(q[:B_], k)
+            st = idx.stats()
+            seen[(level, B_)] = (s.copy(), i.copy())
+            if level == "0":
+                assert st["scan_ms"] == 0.0 and st["last_search_ms"] == 0.0
+            elif level == "1":
+                assert st["last_search_ms"] >= st["last_scan_ms"] > 0.0
+            else:
+                assert st["last_search_ms"] == st["last_scan_ms"] > 0.0
+        idx.close()
+    for B_ in (B, 1):
+        for level in ("1", "0"):
+            assert_bit_equal(*seen[(level, B_)], *seen[(None, B_)])

@@ -192,3 +192,23 @@ def test_hnswlib_restatement_known_answers():
         assert ii[0, 0] == 2 and dd[0].tolist() == [0.0, 1.0, 1.0, 1.0]
         dd, ii = O.hnswlib_topk("l2", e, e[2:3], 4, order=order)
         assert ii[0].tolist() == [2, 0, 1, 3] and dd[0].tolist() == [0.0, 2.0, 2.0, 2.0]
+
+
+def test_hnswlib_restatement_with_a_filter_agrees_with_the_masked_oracle():
+    """hnswlib's exhaustive search takes a filter functor (chromadb hands it the ids a `where` allows): same rows as the
+    canonical oracle under the same allow-bitmask, k clamped to the allowed rows."""
+    from referee import assert_within_north_star
+    n, B, k = 30_000, 4, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    q, _ = O.planted_queries(0x0BADC0DE, B, SEED, n, 768)
+    allowed = (np.arange(n) % 7) == 3
+    st, _ = O.normalize_rows(x, "fp32", 768)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    s, i = O.brute_force_topk(qn, st, k, O.mask_from_bool(allowed))
+    ref_d, ref_i = O.hnswlib_topk("cosine", x, q, k, allowed=allowed)
+    assert allowed[ref_i].all()
+    assert_within_north_star("cosine", s, i, q, ref_d.astype(np.float64), ref_i)
+    few = np.zeros(n, bool)
+    few[[5, 77, 4000]] = True
+    d3, i3 = O.hnswlib_topk("l2", x, q, k, allowed=few)
+    assert (np.sort(i3[:, :3], axis=1) == np.array([5, 77, 4000])).all() and (i3[:, 3:] == -1).all() and np.isinf(d3[:, 3:]).all()
