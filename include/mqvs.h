@@ -217,7 +217,9 @@ MQVS_API int mqvs_load(mqvs_t* s, const char* path);
 /* Tombstone compaction (collection.delete / upsert leave dead rows that every scan still streams): keep only the rows whose
  * bit is set in keep_words_host (bit r & 31 of word r >> 5, ceil(rows / 32) words), gathered bit-for-bit on the device in
  * ascending order, so surviving row r becomes row popcount(keep[0 .. r)).  Stored norms follow; device-resident metadata
- * columns are dropped.  Single-device handles only (rows of a multi-device handle would have to change devices). */
+ * columns are dropped.  On a multi-device handle the survivors keep their GLOBAL order and therefore change device where the
+ * block-cyclic placement says so: they travel through a pinned host buffer, chunk by chunk (same bits, same result as
+ * compacting a single-device handle that holds the same rows). */
 MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out);
 
 /* collection_metadata={"hnsw:space": ...} -- the space rows are RANKED in when the raw vectors given to mqvs_add are not

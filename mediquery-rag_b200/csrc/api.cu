@@ -1209,9 +1209,7 @@ MQVS_API int mqvs_column_set_text(mqvs_t* s, int col_id, const uint64_t* offsets
 MQVS_API int mqvs_compact(mqvs_t* s, const uint32_t* keep_words_host, uint64_t* new_count_out) {
     MQVS_RANGE("mqvs_compact");
     if (!s || !keep_words_host || !new_count_out) return fail(MQVS_E_INVALID, "NULL argument");
-    if (s->multi)
-        return fail(MQVS_E_INVALID, "compaction of a multi-device handle is not implemented (rows would have to move between "
-                                    "devices): rebuild the collection");
+    if (s->multi) return multi_compact(s, keep_words_host, new_count_out);
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->dev));
     CU(cudaStreamSynchronize(s->st));

@@ -414,6 +414,150 @@ int multi_get_rows(mqvs_store* P, const int64_t* row_ids, uint64_t n, float* out
     return MQVS_OK;
 }
 
+// ---- tombstone compaction over several devices.  The survivors keep their global order, so surviving row r becomes global
+// row r' = popcount(keep[0 .. r)) <= r and, the placement being block-cyclic in the global row, may change device.  Chunk by
+// chunk in ascending r': every part gathers the chunk's source rows it holds (gather_raw_rows_kernel, bit for bit) and hands
+// them to a pinned bounce buffer, the host puts them in chunk order, and the chunk is written to the (part, local row)
+// coordinates of the new rows [a, a + c).  Those coordinates are the old rows [a, a + c): every live one among them has a new
+// index below a + c and was consumed by this chunk or an earlier one, and no later source lies below a + c -- the same
+// argument as the single-device compaction's.  Rows cross PCIe twice; compaction is rare and runs at a few GB/s.
+int multi_compact(mqvs_store* P, const uint32_t* keep_words_host, uint64_t* new_count_out) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard guard;
+    Multi* M = P->multi;
+    const int W = M->W;
+    for (int p = 0; p < W; ++p) {
+        MQVS_CU(cudaSetDevice(M->devs[p]));
+        MQVS_CU(cudaStreamSynchronize(M->parts[p]->st));
+    }
+    std::vector<uint64_t> keep;
+    keep.reserve((size_t)M->n);
+    for (uint64_t r = 0; r < M->n; ++r)
+        if ((keep_words_host[r >> 5] >> (r & 31)) & 1u) keep.push_back(r);
+    const uint64_t m = keep.size(), n_old = M->n;
+    if (m == n_old) {
+        *new_count_out = m;
+        return MQVS_OK;
+    }
+    const size_t rb = P->row_bytes();
+    const uint64_t chunk = 8192;
+    PinBuf bounce;
+    std::vector<PinBuf> part_host(W);
+    std::vector<DevBuf> ids(W), tmp(W);
+    auto release = [&]() {
+        bounce.release();
+        for (int p = 0; p < W; ++p) {
+            cudaSetDevice(M->devs[p]);
+            part_host[p].release();
+            ids[p].release();
+            tmp[p].release();
+        }
+    };
+    auto broken = [&](cudaError_t e) {
+        release();
+        cudaGetLastError();
+        return mqvs_fail(MQVS_E_CUDA, "compaction failed: %s (the store is in an undefined state)", cudaGetErrorString(e));
+    };
+    int rc = bounce.ensure(std::min(chunk, m ? m : 1) * rb);
+    // stored norms follow their rows: small enough (4 bytes per row) to do on the host in one go, before any row moves
+    const bool norms = M->parts[0]->keep_norms;
+    std::vector<std::vector<float>> old_norms(W), new_norms(W);
+    if (rc == MQVS_OK && norms) {
+        for (int p = 0; p < W; ++p) {
+            const uint64_t cnt = M->map.count(p, n_old);
+            old_norms[p].resize((size_t)cnt);
+            new_norms[p].resize((size_t)M->map.count(p, m));
+            cudaSetDevice(M->devs[p]);
+            if (cnt) {
+                cudaError_t e = cudaMemcpy(old_norms[p].data(), M->parts[p]->norms, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) return broken(e);
+            }
+        }
+        for (uint64_t r = 0; r < m; ++r)
+            new_norms[M->map.part_of(r)][M->map.local_of(r)] = old_norms[M->map.part_of(keep[r])][M->map.local_of(keep[r])];
+    }
+    if (rc != MQVS_OK) {
+        release();
+        return rc;
+    }
+    uint64_t launches = 0;
+    std::vector<std::vector<uint32_t>> loc(W), pos(W);
+    for (uint64_t a = 0; a < m; a += chunk) {
+        const uint64_t c = std::min(chunk, m - a);
+        if (keep[a + c - 1] == a + c - 1) continue;  // nothing dead up to here: these rows are already in place
+        // 1. every part gathers the chunk's source rows it holds
+        for (int p = 0; p < W; ++p) {
+            loc[p].clear();
+            pos[p].clear();
+        }
+        for (uint64_t j = 0; j < c; ++j) {
+            const int p = (int)M->map.part_of(keep[a + j]);
+            loc[p].push_back((uint32_t)M->map.local_of(keep[a + j]));
+            pos[p].push_back((uint32_t)j);
+        }
+        for (int p = 0; p < W; ++p) {
+            if (loc[p].empty()) continue;
+            mqvs_store* part = M->parts[p];
+            cudaSetDevice(M->devs[p]);
+            const size_t np = loc[p].size();
+            if ((rc = ids[p].ensure(chunk * sizeof(uint32_t))) != MQVS_OK || (rc = tmp[p].ensure(chunk * rb)) != MQVS_OK ||
+                (rc = part_host[p].ensure(chunk * rb)) != MQVS_OK) {
+                release();
+                return rc;
+            }
+            cudaError_t e = cudaMemcpyAsync(ids[p].p, loc[p].data(), np * sizeof(uint32_t), cudaMemcpyHostToDevice, part->st);
+            if (e != cudaSuccess) return broken(e);
+            launch_gather_raw_rows(part->rows, rb, (const uint32_t*)ids[p].p, np, tmp[p].p, part->st);
+            e = cudaMemcpyAsync(part_host[p].p, tmp[p].p, np * rb, cudaMemcpyDeviceToHost, part->st);
+            if (e != cudaSuccess) return broken(e);
+            ++launches;
+        }
+        for (int p = 0; p < W; ++p) {
+            if (loc[p].empty()) continue;
+            cudaSetDevice(M->devs[p]);
+            cudaError_t e = cudaStreamSynchronize(M->parts[p]->st);
+            if (e != cudaSuccess) return broken(e);
+            for (size_t i = 0; i < pos[p].size(); ++i)
+                memcpy((char*)bounce.p + (size_t)pos[p][i] * rb, (const char*)part_host[p].p + i * rb, rb);
+        }
+        // 2. the chunk, in order, to the coordinates of the new rows [a, a + c)
+        cudaError_t werr = cudaSuccess;
+        for_block_runs(M->map, a, c, [&](int p, uint64_t local, uint64_t cnt, uint64_t off) {
+            if (werr != cudaSuccess) return;
+            cudaSetDevice(M->devs[p]);
+            werr = cudaMemcpyAsync((char*)M->parts[p]->rows + local * rb, (const char*)bounce.p + off * rb, cnt * rb,
+                                   cudaMemcpyHostToDevice, M->parts[p]->st);
+        });
+        if (werr != cudaSuccess) return broken(werr);
+        for (int p = 0; p < W; ++p) {  // the bounce buffer is reused by the next chunk
+            cudaSetDevice(M->devs[p]);
+            cudaError_t e = cudaStreamSynchronize(M->parts[p]->st);
+            if (e != cudaSuccess) return broken(e);
+        }
+    }
+    for (int p = 0; p < W; ++p) {
+        mqvs_store* part = M->parts[p];
+        cudaSetDevice(M->devs[p]);
+        const uint64_t cnt = M->map.count(p, m);
+        if (norms && cnt) {
+            cudaError_t e = cudaMemcpy(part->norms, new_norms[p].data(), cnt * sizeof(float), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return broken(e);
+        }
+        part->n = cnt;
+        part->stats.rows = cnt;
+        part->bounds_rows = 0;
+        part->shadow_rows = 0;  // rows moved: the scoring shadow is rebuilt before the next tensor search
+        for (auto& col : part->columns) col.used = false;  // row numbers changed under them
+        part->f_table_dirty = true;
+    }
+    M->parts[0]->stats.kernel_launches += launches;
+    M->n = m;
+    M->has_token = false;
+    release();
+    *new_count_out = m;
+    return MQVS_OK;
+}
+
 // ---- persistence: the same file as a single-device handle writes (rows in GLOBAL order), so a directory written on eight
 // GPUs opens on one and the other way round
 namespace {

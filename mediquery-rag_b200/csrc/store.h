@@ -268,6 +268,7 @@ int multi_search(mqvs_store* s, const float* q, int q_is_device, int B, int k, c
                  int64_t id_base, float* out_scores, int64_t* out_ids, int out_is_device, cudaStream_t caller_stream,
                  bool blocking);
 int multi_get_rows(mqvs_store* s, const int64_t* row_ids, uint64_t n, float* out_host);
+int multi_compact(mqvs_store* s, const uint32_t* keep_words_host, uint64_t* new_count_out);
 int multi_save(mqvs_store* s, const char* path, uint64_t first_row);
 int multi_load(mqvs_store* s, const char* path);
 int multi_column_set(mqvs_store* s, int col_id, int col_type, const void* values_host, const uint8_t* present_host, uint64_t n);

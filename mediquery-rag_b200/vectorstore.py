@@ -771,8 +771,6 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         dead = int((~self._live).sum())
         if dead == 0 or self._index is None or not hasattr(self._index, "compact"):
             return 0
-        if len(getattr(self._index, "devices", [0])) > 1:
-            return 0  # rows of a multi-device handle would have to move between GPUs: rebuild such a collection instead
         from .filters import pack_mask
         keep = np.flatnonzero(self._live)
         new_n = self._index.compact(pack_mask(self._live))

@@ -1698,3 +1698,62 @@ def test_timing_levels_of_the_search_events(gpu, monkeypatch):
     for B_ in (B, 1):
         for level in ("1", "0"):
             assert_bit_equal(*seen[(level, B_)], *seen[(None, B_)])
+
+
+@pytest.mark.parametrize("W,dtype", [(3, "fp32"), (4, "bf16"), (2, "fp32")])
+def test_tombstone_compaction_of_a_multi_device_handle_equals_the_single_device_one(gpu, W, dtype, tmp_path):
+    """mqvs_compact on a handle over W row shards: survivors keep their GLOBAL order and therefore change shard (block-cyclic
+    placement of the new row numbers).  Rows, stored norms and search results must be the same bits as after compacting a
+    single-device handle over the same rows -- prefix kept in place, deletions inside and across 4096-row blocks, a second
+    compaction, appends afterwards (the parts must still be balanced and contiguous)."""
+    from mediquery_rag_b200 import MediQueryVectorStore
+    M = native()
+    n = 50_000 + 17
+    x = O.synth_rows(0x5EED000C, 0, n, 768) * np.float32(1.7)
+    multi, single = M.Index(768, dtype, device=[0] * W), M.Index(768, dtype)
+    for idx in (multi, single):
+        idx.set_metric("l2")
+        idx.add(x)
+    rng = np.random.default_rng(5)
+    keep = rng.random(n) < 0.45
+    keep[:9000] = True                 # a prefix of more than two blocks that stays where it is
+    keep[20_000:29_000] = False        # whole blocks disappear
+    live = np.flatnonzero(keep)
+    for idx in (multi, single):
+        assert idx.compact(O.mask_from_bool(keep)) == live.size == len(idx)
+    every = np.arange(live.size)
+    assert np.array_equal(multi.get_rows(every).view(np.uint32), single.get_rows(every).view(np.uint32))
+    assert np.array_equal(multi.get_norms(), single.get_norms())
+    xs = x[keep]
+    q = xs[[7, 9000, live.size - 1]] + np.float32(0.01) * O.synth_rows(3, 0, 3, 768)
+    for B_ in (3, 1):
+        s, i = multi.search(q[:B_], 5)
+        s1, i1 = single.search(q[:B_], 5)
+        assert_bit_equal(s, i, s1, i1)
+        es, ei = O.brute_force_topk(O.normalize_rows(q[:B_], "fp32", 768)[0], O.normalize_rows(xs, dtype, 768)[0], 5, metric="l2",
+                                    norms=O.row_norms(xs, 768), q_norms=O.row_norms(q[:B_], 768))
+        assert_bit_equal(s, i, es, ei)
+    # again (now nothing but a tail goes), then appends land behind the survivors on every part
+    keep2 = np.ones(live.size, bool)
+    keep2[-3000:] = rng.random(3000) < 0.5
+    extra = O.synth_rows(0x5EED000D, 0, 6000, 768)
+    for idx in (multi, single):
+        assert idx.compact(O.mask_from_bool(keep2)) == int(keep2.sum())
+        assert idx.add(extra) == int(keep2.sum())
+    every = np.arange(len(single))
+    assert len(multi) == len(single)
+    assert np.array_equal(multi.get_rows(every).view(np.uint32), single.get_rows(every).view(np.uint32))
+    qq = np.concatenate([extra[[5, 5999]], xs[keep2][[100]]])
+    assert_bit_equal(*multi.search(qq, 4), *single.search(qq, 4))
+    multi.close()
+    single.close()
+    # through the store: a collection over several shards compacts by itself once most rows are dead, persists, reopens on one device
+    vs = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"},
+                              devices=[0] * W, store_dtype=dtype)
+    ids = vs.add_embeddings(([f"c{r}" for r in range(12_000)], x[:12_000]), metadatas=[{"g": r % 5} for r in range(12_000)])
+    vs.delete(ids[:9000])
+    assert len(vs._ids) == 3000 and len(vs) == 3000 and len(vs._index) == 3000
+    hit = vs.similarity_search_by_vector(x[11_000], k=1, filter={"g": 11_000 % 5})[0]
+    assert hit.page_content == "c11000"
+    re = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"}, store_dtype=dtype)
+    assert len(re) == 3000 and re.similarity_search_by_vector(x[11_999], k=1)[0].id == ids[11_999]
