@@ -623,13 +623,17 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             if isinstance(ids, str):
                 ids = [ids]
             rows = [r for r in (self._row_of(str(i)) for i in ids) if r is not None and self._live[r]]
-            if where:
-                from .filters import evaluate
-                ok = evaluate(where, self._cols)
+            if where or where_document:
+                from .filters import evaluate, evaluate_document
+                ok = evaluate(where, self._cols) if where else np.ones(len(self._ids), bool)
+                if where_document:
+                    ok = ok & evaluate_document(where_document, self._texts)
                 rows = [r for r in rows if ok[r]]
         else:
-            from .filters import evaluate
+            from .filters import evaluate, evaluate_document
             ok = self._live if not where else (evaluate(where, self._cols) & self._live)
+            if where_document:  # collection.get(where_document={"$contains": ...}), as in chromadb
+                ok = ok & evaluate_document(where_document, self._texts)
             rows = np.flatnonzero(ok).tolist()
         rows = rows[(offset or 0):]
         if limit is not None:
@@ -655,10 +659,15 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                 for i, t, m in zip(got["ids"], got["documents"], got["metadatas"])]
 
     def delete(self, ids: Optional[List[str]] = None, **kwargs: Any) -> Optional[bool]:
-        """Rows are tombstoned (cleared from the live bitmap that is AND-ed into every search mask)."""
-        if ids is None:
+        """Rows are tombstoned (cleared from the live bitmap that is AND-ed into every search mask).  `where=` /
+        `where_document=` keyword arguments select rows the way chromadb's collection.delete does (langchain_chroma passes
+        them through); with `ids` as well, only those of the ids that match go."""
+        where, where_document = kwargs.get("where"), kwargs.get("where_document")
+        if ids is None and not where and not where_document:
             return False
         with self._lock:
+            if where or where_document:
+                ids = self.get(ids=ids, where=where, where_document=where_document, include=[])["ids"]
             for i in ids:
                 r = self._id2row.pop(str(i), None)
                 if r is None:

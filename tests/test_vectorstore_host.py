@@ -358,3 +358,42 @@ def test_a_bad_metadata_column_is_refused_before_any_row_reaches_the_index():
     ids = vs.add_embeddings((None, x), metadata_columns={"g": np.arange(10)})
     assert len(ids) == 10 and len(vs) == 10
     assert vs.similarity_search_by_vector(x[3], k=1, filter={"g": 3})[0].id == ids[3]
+
+
+def test_get_honours_where_document(medical_docs, embedder):
+    """collection.get(where=..., where_document={"$contains": ...}) as chromadb offers it: both conditions, live rows only."""
+    docs = make_docs(medical_docs, 60)
+    vs = MediQueryVectorStore.from_documents(docs, embedder, index_factory=OracleIndex)
+    needle = "血压"
+    want = [d.page_content for d in docs if needle in d.page_content]
+    assert 0 < len(want) < 60
+    got = vs.get(where_document={"$contains": needle})
+    assert got["documents"] == want
+    assert vs.get(where_document={"$not_contains": needle})["documents"] == [d.page_content for d in docs if needle not in d.page_content]
+    title = docs[[needle in d.page_content for d in docs].index(True)].metadata["title"]
+    both = vs.get(where={"title": title}, where_document={"$contains": needle})
+    assert both["documents"] and all(needle in t for t in both["documents"]) and all(m["title"] == title for m in both["metadatas"])
+    some_ids = vs.get()["ids"][:10]
+    by_id = vs.get(ids=some_ids, where_document={"$contains": needle})
+    assert by_id["documents"] == [d.page_content for d in docs[:10] if needle in d.page_content]
+    vs.delete(got["ids"][:1])
+    assert vs.get(where_document={"$contains": needle})["documents"] == want[1:]
+
+
+def test_delete_by_where_and_where_document(medical_docs, embedder):
+    docs = make_docs(medical_docs, 60)
+    vs = MediQueryVectorStore.from_documents(docs, embedder, index_factory=OracleIndex)
+    needle = "血压"
+    n_hit = sum(needle in d.page_content for d in docs)
+    assert vs.delete(where_document={"$contains": needle}) is True and len(vs) == 60 - n_hit
+    assert all(needle not in d.page_content for d in vs.similarity_search(needle, k=10))
+    ids = vs.get()["ids"]
+    source = vs.get()["metadatas"][0]["source"]                       # every chunk carries the same source (ingest_medical.py:78)
+    before = len(vs)
+    assert vs.delete(ids=ids[5:8], where={"source": source}) is True  # ids AND where: only those three go
+    assert len(vs) == before - 3 and vs.get(ids=ids[5:8])["ids"] == [] and vs.get(ids=ids[:1])["ids"] == ids[:1]
+    assert vs.delete(ids=ids[:2], where={"source": "nothing has this"}) is True and len(vs) == before - 3
+    title = vs.get()["metadatas"][0]["title"]
+    vs.delete(where={"title": title})
+    assert vs.get(where={"title": title})["ids"] == [] and len(vs) < before - 3
+    assert vs.delete() is False
