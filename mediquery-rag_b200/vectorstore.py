@@ -141,6 +141,71 @@ class _RowColumn:
         return None
 
 
+class _CollectionView:
+    """`vectorstore._collection`: the part of chromadb's Collection that code written against langchain_chroma reaches for
+    (`_collection.count()`, `.query(query_embeddings=..., n_results=...)`, `.get`, `.delete`, `.name`, `.metadata`).  A view
+    over the store: nothing is copied, every call lands on the same kernels."""
+
+    def __init__(self, store: "MediQueryVectorStore") -> None:
+        self._store = store
+
+    @property
+    def name(self) -> str:
+        return self._store._collection_name
+
+    @property
+    def metadata(self) -> Dict[str, Any]:
+        return dict(self._store._collection_metadata)
+
+    def count(self) -> int:
+        return len(self._store)
+
+    def get(self, ids=None, where=None, limit=None, offset=None, where_document=None, include=None) -> Dict[str, Any]:
+        return self._store.get(ids=ids, where=where, limit=limit, offset=offset, where_document=where_document, include=include)
+
+    def delete(self, ids=None, where=None, where_document=None) -> None:
+        self._store.delete(ids=ids, where=where, where_document=where_document)
+
+    def query(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None, where_document=None,
+              include: Optional[List[str]] = None) -> Dict[str, Any]:
+        """chromadb's collection.query: one result list PER query (the batch goes through one search), distances in the
+        collection's hnsw:space, best first."""
+        st = self._store
+        if query_embeddings is None:
+            if query_texts is None:
+                raise ValueError("query needs query_embeddings or query_texts")
+            texts = [query_texts] if isinstance(query_texts, str) else list(query_texts)
+            if st._embedding_function is None:
+                raise ValueError("this store was built without an embedding_function; pass query_embeddings")
+            query_embeddings = st._embedding_function.embed_documents(texts)
+        q = np.ascontiguousarray(query_embeddings, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        include = list(include) if include is not None else ["metadatas", "documents", "distances"]
+        with st._lock:
+            scores, rows = st.search_batch(q, n_results, where, where_document)
+            ranked = st.rank_space()
+            if ranked == "cosine":
+                dist = np.where(rows >= 0, (2.0 - 2.0 * scores) if st._space == "l2" else (1.0 - scores), np.inf)
+            else:
+                qn = np.linalg.norm(q.astype(np.float64), axis=1)[:, None]
+                t = scores.astype(np.float64)
+                dist = np.where(rows >= 0, qn * qn - 2.0 * np.maximum(qn, 1e-12) * t if ranked == "l2"
+                                else 1.0 - np.maximum(qn, 1e-12) * t, np.inf)
+            per_query = [[int(r) for r in row if r >= 0] for row in rows]
+            out: Dict[str, Any] = {"ids": [[st._ids[r] for r in rr] for rr in per_query], "distances": None, "metadatas": None,
+                                   "documents": None, "embeddings": None, "included": include}
+            if "distances" in include:
+                out["distances"] = [[float(d) for d in dd[:len(rr)]] for dd, rr in zip(dist, per_query)]
+            if "metadatas" in include:
+                out["metadatas"] = [[st._cols.row(r) for r in rr] for rr in per_query]
+            if "documents" in include:
+                out["documents"] = [[st._texts[r] for r in rr] for rr in per_query]
+            if "embeddings" in include:
+                out["embeddings"] = [st.get(ids=[st._ids[r] for r in rr], include=["embeddings"])["embeddings"] for rr in per_query]
+        return out
+
+
 class MediQueryRetriever:
     """What `as_retriever()` returns when langchain_core is absent: `.invoke(query) -> list[Document]`."""
 
@@ -253,6 +318,11 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
     @property
     def embeddings(self) -> Optional[Embeddings]:
         return self._embedding_function
+
+    @property
+    def _collection(self) -> _CollectionView:
+        """What `langchain_chroma.Chroma._collection` is used for in the wild: `.count()`, `.query(...)`, `.get`, `.delete`."""
+        return _CollectionView(self)
 
     def __len__(self) -> int:
         return int(self._live.sum())

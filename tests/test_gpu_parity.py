@@ -1757,3 +1757,23 @@ def test_tombstone_compaction_of_a_multi_device_handle_equals_the_single_device_
     assert hit.page_content == "c11000"
     re = MediQueryVectorStore(persist_directory=str(tmp_path / "db"), collection_metadata={"hnsw:space": "cosine"}, store_dtype=dtype)
     assert len(re) == 3000 and re.similarity_search_by_vector(x[11_999], k=1)[0].id == ids[11_999]
+
+
+def test_collection_query_batches_through_the_cuda_path(gpu, medical_docs, embedder):
+    """`vectorstore._collection.query(query_embeddings=[...])` -- chromadb's batch call, which langchain_chroma itself uses --
+    over the reference's 154 chunks: the CUDA path and the oracle double return the same ids, documents and distances for
+    all 154 queries at once, with and without a where / where_document filter."""
+    from conftest import OracleIndex
+    from mediquery_rag_b200 import Document, MediQueryVectorStore
+    docs = [Document(page_content=d["page_content"], metadata=d["metadata"]) for d in medical_docs["docs"]]
+    ids = [f"chunk-{j}" for j in range(len(docs))]
+    emb = np.asarray(embedder.embed_documents([d.page_content for d in docs]), np.float32)
+    stores = [MediQueryVectorStore(embedding_function=embedder, **kw) for kw in ({}, {"index_factory": OracleIndex})]
+    for vs in stores:
+        vs.add_documents(docs, ids=ids)
+    for kw in ({}, {"where_document": {"$contains": "血压"}}, {"where": {"tags": {"$contains": docs[0].metadata["tags"].replace("，", ",").split(",")[0].strip()}}}):
+        got, want = (vs._collection.query(query_embeddings=emb, n_results=5, **kw) for vs in stores)
+        assert got["ids"] == want["ids"] and got["documents"] == want["documents"] and got["metadatas"] == want["metadatas"]
+        assert np.array_equal(np.asarray(got["distances"], np.float64), np.asarray(want["distances"], np.float64))
+    assert [r[0] for r in stores[0]._collection.query(query_embeddings=emb, n_results=1)["ids"]] == ids
+    assert stores[0]._collection.count() == 154

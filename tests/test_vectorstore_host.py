@@ -397,3 +397,26 @@ def test_delete_by_where_and_where_document(medical_docs, embedder):
     vs.delete(where={"title": title})
     assert vs.get(where={"title": title})["ids"] == [] and len(vs) < before - 3
     assert vs.delete() is False
+
+
+def test_collection_view_counts_and_queries_like_chromadb(medical_docs, embedder):
+    docs = make_docs(medical_docs, 80)
+    vs = MediQueryVectorStore.from_documents(docs, embedder, index_factory=OracleIndex)
+    col = vs._collection
+    assert col.count() == 80 and col.name == "langchain" and col.metadata == {}
+    qs = [docs[3].page_content, docs[50].page_content]
+    res = col.query(query_texts=qs, n_results=4)
+    assert [len(x) for x in res["ids"]] == [4, 4] and res["documents"][0][0] == qs[0] and res["documents"][1][0] == qs[1]
+    for j, qtext in enumerate(qs):  # same rows and distances as the LangChain call, query by query
+        ref = vs.similarity_search_with_score(qtext, k=4)
+        assert res["documents"][j] == [d.page_content for d, _ in ref]
+        assert np.allclose(res["distances"][j], [dist for _, dist in ref], atol=1e-6)
+        assert res["metadatas"][j] == [d.metadata for d, _ in ref]
+    emb = np.asarray(embedder.embed_documents(qs), np.float32)
+    by_vec = col.query(query_embeddings=emb, n_results=4, include=["distances"])
+    assert by_vec["ids"] == res["ids"] and by_vec["documents"] is None
+    needle = "血压"
+    filt = col.query(query_embeddings=emb[0], n_results=100, where_document={"$contains": needle})
+    assert len(filt["ids"]) == 1 and 0 < len(filt["ids"][0]) == sum(needle in d.page_content for d in docs)
+    col.delete(ids=res["ids"][0][:1])
+    assert col.count() == 79 and col.get(ids=res["ids"][0][:1])["ids"] == []
