@@ -1775,5 +1775,8 @@ def test_collection_query_batches_through_the_cuda_path(gpu, medical_docs, embed
         got, want = (vs._collection.query(query_embeddings=emb, n_results=5, **kw) for vs in stores)
         assert got["ids"] == want["ids"] and got["documents"] == want["documents"] and got["metadatas"] == want["metadatas"]
         assert np.array_equal(np.asarray(got["distances"], np.float64), np.asarray(want["distances"], np.float64))
-    assert [r[0] for r in stores[0]._collection.query(query_embeddings=emb, n_results=1)["ids"]] == ids
+    top1 = stores[0]._collection.query(query_embeddings=emb, n_results=1)
+    # every chunk finds itself (or an identical chunk with a lower row number: the knowledge base repeats a few)
+    assert [t[0] for t in top1["documents"]] == [d.page_content for d in docs]
+    assert all(ids.index(r[0]) <= j for j, r in enumerate(top1["ids"]))
     assert stores[0]._collection.count() == 154
