@@ -302,6 +302,38 @@ __device__ __forceinline__ void apply_space(uint32_t (&v)[32], const TileSpace& 
     }
 }
 
+// The same transform with the tile's 256 norms already in registers (TileNorms below): lane l holds the norms of rows
+// l * 8 .. l * 8 + 7 of the tile, so row j of chunk ch lives in register j & 7 of lane 4 ch + (j >> 3).
+struct TileNorms {
+    float a[8];   // norms of tile rows lane * 8 + i
+    float2 b;     // lanes 0 .. 7: (largest, smallest) norm of chunk `lane`
+};
+// Issued once per tile, before its first chunk is read from TMEM: the per-chunk loads they replace (one dependent global load
+// for the bounds, one for the norms, per chunk and warp, nothing to overlap them with) made the l2 / ip epilogue
+// latency-bound once the CTA-pair kernel had halved the MMA time per tile (config 3, ip: main segment 40.4 vs 36.7 ms).
+__device__ __forceinline__ void load_tile_norms(TileNorms& tn, const TileSpace& sp, uint32_t tile_row0, uint32_t n_rows, int lane) {
+    const uint32_t r0 = tile_row0 + (uint32_t)lane * 8u;
+    if (tile_row0 + (uint32_t)BN <= n_rows) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(sp.norms + r0));
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(sp.norms + r0) + 1);
+        tn.a[0] = lo.x; tn.a[1] = lo.y; tn.a[2] = lo.z; tn.a[3] = lo.w;
+        tn.a[4] = hi.x; tn.a[5] = hi.y; tn.a[6] = hi.z; tn.a[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tn.a[i] = __ldg(sp.norms + min(r0 + (uint32_t)i, n_rows - 1u));
+    }
+    const uint32_t crow = tile_row0 + (uint32_t)(lane & 7) * 32u;
+    tn.b = crow < n_rows ? __ldg(sp.bounds + (crow >> 5)) : make_float2(0.0f, 0.0f);
+}
+__device__ __forceinline__ void apply_space_tile(uint32_t (&v)[32], const TileNorms& tn, float h, int ch) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float a = __shfl_sync(0xffffffffu, tn.a[j & 7], 4 * ch + (j >> 3));
+        const float t = __fmaf_rn(a, __uint_as_float(v[j]), -__fmul_rn(__fmul_rn(a, a), h));
+        v[j] = v[j] == 0xff800000u ? v[j] : __float_as_uint(t);  // masked / out-of-range rows stay -inf (a may be 0)
+    }
+}
+
 struct ChunkTop {
     uint32_t v[8];
     uint32_t mn;     // min of v
@@ -315,6 +347,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
                                               float& tau, uint32_t& cnt, uint64_t* lst, ChunkTop* trk = nullptr,
                                               const TileSpace sp = TileSpace()) {
     constexpr int KPL = CAP / 32;
+    TileNorms tn;
+    if (sp.norms != nullptr) load_tile_norms(tn, sp, tile_row0, n_rows, lane);  // uniform: l2 / ip spaces
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
         const uint32_t row0 = tile_row0 + ch * 32;
@@ -339,8 +373,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
         if (sp.norms != nullptr) {  // uniform: l2 / ip spaces
             // most chunks hold nothing near the threshold: reject them with a bound on their ranking scores (two floats
             // per chunk) before paying for the transform of all 32 x 32 scores
-            if (__ballot_sync(0xffffffffu, chunk_score_bound(mx, __ldg(sp.bounds + (row0 >> 5)), sp.h) >= tau) == 0u) continue;
-            apply_space(v, sp, row0, n_rows, lane);
+            const float2 cb = make_float2(__shfl_sync(0xffffffffu, tn.b.x, ch), __shfl_sync(0xffffffffu, tn.b.y, ch));
+            if (__ballot_sync(0xffffffffu, chunk_score_bound(mx, cb, sp.h) >= tau) == 0u) continue;
+            apply_space_tile(v, tn, sp.h, ch);
             mx = max32(v, grp);
         }
         const unsigned hit = __ballot_sync(0xffffffffu, mx >= tau);
