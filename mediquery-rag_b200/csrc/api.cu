@@ -225,9 +225,9 @@ static void enqueue_tensor_repair(mqvs_store* s, int B, int k, const uint32_t* m
     for (int r = 0; r < fix_rounds; ++r) {
         launch_scan_fix(s->rows, s->dtype, (uint32_t)s->n, (const float*)s->qn.p, b.flags, B, s->max_device_fix, fix_list, fix_n,
                         s->fix_counters, mask_dev, k, (uint64_t*)s->tc_fixcand.p, s->sm_count, st, s->last_space.metric,
-                        s->last_space.norms, s->last_space.qnorm, /*count_leftover=*/r + 1 == fix_rounds);
+                        s->last_space.norms, s->last_space.qnorm, /*count_leftover=*/r + 1 == fix_rounds, b.flag_count);
         launch_merge_fix((const uint64_t*)s->tc_fixcand.p, s->max_device_fix, scan_fix_grid(s->sm_count) * k, k, id_base,
-                         fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st);
+                         fix_list, fix_n, b.flags, out_scores_dev, out_ids_dev, st, b.flag_count);
         s->stats.kernel_launches += 2;
     }
 }

@@ -269,19 +269,35 @@ scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __rest
                 const uint32_t* __restrict__ flags, int B, int max_fix, uint32_t* __restrict__ fix_list,
                 uint32_t* __restrict__ fix_n, unsigned long long* __restrict__ counters,
                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ cand, int cand_stride, int metric,
-                const float* __restrict__ row_norms, const float* __restrict__ q_norms_all, int count_leftover) {
+                const float* __restrict__ row_norms, const float* __restrict__ q_norms_all, int count_leftover,
+                const uint32_t* __restrict__ flag_count) {
     extern __shared__ __align__(16) uint64_t smem_keys[];
     __shared__ uint32_t list_s[256];
     __shared__ uint32_t n_s, total_s;
     const int lane = threadIdx.x & 31;
+    // Nothing flagged (the common case of the rounds an asynchronous search enqueues blind): one word says so.  Walking the
+    // B flags instead cost every CTA of every idle round B / 32 dependent loads -- 104 us per round at B = 16384, 64 rounds
+    // per search: a quarter of config 5's step (profiles/r02_ncu_launches_c5shard_*.csv).  flag_count >= the flags that are
+    // set (every setter adds, the repairs subtract), so zero is safe to trust; any other value only costs the walk.
+    if (__ldcg(flag_count) == 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *fix_n = 0u;
+        return;
+    }
     if (threadIdx.x < 32) {
         uint32_t base = 0;
-        for (int c = 0; c < B; c += 32) {
-            const bool f = c + lane < B && flags[c + lane] != 0u;
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-            if (f && pos < (uint32_t)max_fix) list_s[pos] = (uint32_t)(c + lane);
-            base += __popc(m);
+        for (int c0 = 0; c0 < B; c0 += 256) {  // eight independent loads in flight per lane
+            uint32_t fl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) fl[u] = c0 + u * 32 + lane < B ? __ldcg(flags + c0 + u * 32 + lane) : 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32;
+                const bool f = fl[u] != 0u;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                if (f && pos < (uint32_t)max_fix) list_s[pos] = (uint32_t)(c + lane);
+                base += __popc(m);
+            }
         }
         if (lane == 0) {
             total_s = base;
@@ -420,7 +436,7 @@ int scan_fix_grid(int sm_count) { return sm_count * 2; }
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
                      int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all,
-                     bool count_leftover) {
+                     bool count_leftover, const uint32_t* flag_count) {
     const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
@@ -435,11 +451,11 @@ void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* 
         if (metric != MQVS_METRIC_COSINE)                                                                                          \
             scan_fix_kernel<T_, KPL_, U_, true><<<grid, kScanThreads, smem, st>>>(                                                 \
                 (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, metric,      \
-                row_norms, q_norms_all, leftover);                                                                                 \
+                row_norms, q_norms_all, leftover, flag_count);                                                                     \
         else                                                                                                                       \
             scan_fix_kernel<T_, KPL_, U_, false><<<grid, kScanThreads, smem, st>>>(                                                \
                 (const T_*)rows, n_rows, qn_all, flags, B, max_fix, fix_list, fix_n, counters, mask, k, cand, stride, 0, nullptr,  \
-                nullptr, leftover);                                                                                                \
+                nullptr, leftover, flag_count);                                                                                    \
     } while (0)
     if (dtype == MQVS_F32) {
         if (kpl == 1) MQVS_FIX(float, 1, 2); else if (kpl == 4) MQVS_FIX(float, 4, 2); else MQVS_FIX(float, 32, 2);

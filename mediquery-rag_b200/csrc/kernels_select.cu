@@ -48,7 +48,7 @@ merge_keys_small_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int6
 __global__ void __launch_bounds__(kSelThreads)
 merge_fix_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, int buf_n, int64_t id_base,
                  const uint32_t* __restrict__ fix_list, const uint32_t* __restrict__ fix_n, uint32_t* __restrict__ flags,
-                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids, uint32_t* __restrict__ flag_count) {
     extern __shared__ __align__(16) uint64_t buf[];
     if (blockIdx.x >= *fix_n) return;
     const uint32_t q = fix_list[blockIdx.x];
@@ -66,7 +66,10 @@ merge_fix_kernel(const uint64_t* __restrict__ keys_in, int m, int k, int kp, int
         out_scores[o] = key ? key_score(key) : -INFINITY;
         out_ids[o] = key ? (int64_t)key_id(key) + id_base : -1;
     }
-    if (threadIdx.x == 0) flags[q] = 0u;
+    if (threadIdx.x == 0) {
+        flags[q] = 0u;
+        atomicSub(flag_count, 1u);  // (keeps the count exact, so the rounds after the last repair exit on one word)
+    }
 }
 
 // Cross-shard merge with 64-bit ids: entries are (order-preserving score bits, id); sorted by score desc, id asc.
@@ -147,12 +150,13 @@ void launch_merge_keys(const uint64_t* keys_in, int B, int m, int k, int64_t id_
 }
 
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
-                      const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+                      const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                      uint32_t* flag_count) {
     int kp = next_pow2(k);
     int buf_n = kp * 2 > 2048 ? kp * 2 : 2048;
     size_t smem = (size_t)buf_n * sizeof(uint64_t);
     merge_fix_kernel<<<max_fix, kSelThreads, smem, st>>>(keys_in, m, k, kp, buf_n, id_base, fix_list, fix_n, flags,
-                                                         out_scores, out_ids);
+                                                         out_scores, out_ids, flag_count);
 }
 
 void launch_merge_candidates(const float* scores, const int64_t* ids, int W, int B, int k, float* out_scores,

@@ -92,10 +92,18 @@ __global__ void __launch_bounds__(128)
 prep_band_kernel(const float* __restrict__ qn, const uint32_t* __restrict__ flags, int B, uint32_t* __restrict__ band_list,
                  uint32_t* __restrict__ band_n, const uint32_t* __restrict__ band, T* __restrict__ q_op,
                  uint32_t* __restrict__ tau, unsigned int* __restrict__ gbar, const float* __restrict__ hq,
-                 float* __restrict__ h_op) {
+                 float* __restrict__ h_op, const uint32_t* __restrict__ flag_count) {
     __shared__ uint32_t list_s[BM];
     __shared__ uint32_t n_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 4 + warp;
+    // nothing flagged: one word says so (walking B flags with one warp is 0.2 ms at B = 16384; see scan_fix_kernel)
+    if (__ldcg(flag_count) == 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            gbar[0] = gbar[1] = gbar[2] = 0u;
+            *band_n = 0u;
+        }
+        return;
+    }
     if (warp == 0) {
         uint32_t base = 0;
         for (int c = 0; c < B && base < (uint32_t)BM; c += 32) {
@@ -238,10 +246,10 @@ const char* search_band(const Buffers& b, const Plan& p, const void* rows, int d
     if (!make_map(&mx, rows, (uint64_t)n_rows, dtype, BN)) return "cuTensorMapEncodeTiled failed for the corpus";
     if (dtype == MQVS_F32)
         prep_band_kernel<float><<<BM / 4, 128, 0, st>>>(qn, b.flags, B, b.band_list, b.band_n, b.band, (float*)b.q_op, b.tau, b.gbar,
-                                                        hq, b.h_op);
+                                                        hq, b.h_op, b.flag_count);
     else
         prep_band_kernel<__nv_bfloat16><<<BM / 4, 128, 0, st>>>(qn, b.flags, B, b.band_list, b.band_n, b.band, (__nv_bfloat16*)b.q_op,
-                                                                 b.tau, b.gbar, hq, b.h_op);
+                                                                 b.tau, b.gbar, hq, b.h_op, b.flag_count);
     FusedArgs a{};
     a.n_rows = n_rows;
     a.n_queries = 0;  // read from band_n on the device

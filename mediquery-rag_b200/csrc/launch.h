@@ -53,10 +53,11 @@ void launch_scan_simt_metric(const void* rows, int dtype, uint32_t n_rows, const
 int scan_fix_grid(int sm_count);  // CTAs (= candidate stride per listed query) of the repair scan
 void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* qn_all, const uint32_t* flags, int B, int max_fix,
                      uint32_t* fix_list, uint32_t* fix_n, unsigned long long* counters, const uint32_t* mask, int k, uint64_t* cand,
-                     int sm_count, cudaStream_t st, int metric = 0, const float* row_norms = nullptr,
-                     const float* q_norms_all = nullptr, bool count_leftover = true);
+                     int sm_count, cudaStream_t st, int metric, const float* row_norms, const float* q_norms_all,
+                     bool count_leftover, const uint32_t* flag_count);
 void launch_merge_fix(const uint64_t* keys_in, int max_fix, int m, int k, int64_t id_base, const uint32_t* fix_list,
-                      const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st);
+                      const uint32_t* fix_n, uint32_t* flags, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                      uint32_t* flag_count);
 
 // Latency path: the whole search (query normalisation, scan, top-k, final merge) in ONE launch, for B <= 4, k <= 16.
 // cand: scratch of B * scan_fused_max_grid * k keys (no memset needed); ticket: device uint32, zero between calls;

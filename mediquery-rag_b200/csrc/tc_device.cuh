@@ -349,6 +349,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
     constexpr int KPL = CAP / 32;
     TileNorms tn;
     if (sp.norms != nullptr) load_tile_norms(tn, sp, tile_row0, n_rows, lane);  // uniform: l2 / ip spaces
+    // the tile's 8 allow-mask words in ONE load per warp (lane ch holds the word of chunk ch), before the first chunk is read:
+    // a load per chunk sits in front of a branch and of the masking of all 32 scores, with nothing to overlap it with
+    uint32_t mw_l = 0xffffffffu;
+    if (mask != nullptr) {
+        const uint32_t crow = tile_row0 + (uint32_t)(lane & 7) * 32u;
+        mw_l = crow < n_rows ? __ldg(mask + (crow >> 5)) : 0u;
+    }
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
         const uint32_t row0 = tile_row0 + ch * 32;
@@ -357,7 +364,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tile_row0
         // fast-reject test: thresholds are learnt on allowed rows only, so at 10 % selectivity unmasked scores would send
         // ten times as many chunks through the hit path only to be dropped there (measured: +17 % on config 5); chunks
         // without any allowed row are not even read from TMEM.
-        uint32_t mw = mask ? __ldg(mask + (row0 >> 5)) : 0xffffffffu;
+        uint32_t mw = __shfl_sync(0xffffffffu, mw_l, ch);
         if (n_rows - row0 < 32) mw &= (1u << (n_rows - row0)) - 1u;
         if (mw == 0u) continue;
         uint32_t v[32];

@@ -16,9 +16,14 @@ run() {  # run <name> <bench args...>
         done
     done
 }
-run c4n1 --steps 10 --warmup 3 --points 1
-run c4shard --rows 12500000 --steps 20 --warmup 5 --points 1,16
-run c2 --workload c2 --steps 20 --warmup 5 --points 1
+if [ -n "$AB_RUNS" ]; then  # AB_RUNS="name1:bench args;name2:bench args"
+    IFS=';' read -ra SPECS <<< "$AB_RUNS"
+    for spec in "${SPECS[@]}"; do run "${spec%%:*}" ${spec#*:}; done
+else
+    run c4n1 --steps 10 --warmup 3 --points 1
+    run c4shard --rows 12500000 --steps 20 --warmup 5 --points 1,16
+    run c2 --workload c2 --steps 20 --warmup 5 --points 1
+fi
 cp /tmp/libmqvs_after.so $LIB
 python - <<'P'
 import glob, json
