@@ -33,7 +33,7 @@ using mqvs::elem_size;
 namespace mqvs {
 namespace api {
 
-constexpr int kMaxFixRound = 256;
+constexpr int kMaxFixRound = 1024;  // flagged queries one exact-scan repair round can take (scan_fix_kernel's list)
 constexpr int kWideChunk = 256;    // queries per pass of a k > 128 search (the single-launch tensor pipeline's two query tiles)  // capacity of the device-side repair list (flagged queries per exact-scan round)
 
 int grow(mqvs_store* s, uint64_t need_rows) {
@@ -298,7 +298,9 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
         if ((rc = s->tc_lists.ensure(tc::lists_bytes(plan))) != MQVS_OK) return rc;
         if ((rc = s->tc_keys.ensure((size_t)plan.b_pad * plan.kprime * sizeof(uint64_t) * 2)) != MQVS_OK) return rc;
         // exact-scan repair rounds: 64 flagged queries each for small batches, up to 256 for large ones (fewer idle rounds)
-        s->max_device_fix = B <= 64 ? 64 : (B <= 1024 ? 128 : kMaxFixRound);
+        // (very large batches with small k: 1024 per round -- a blind asynchronous search enqueues ceil(B / m) rounds, and even an
+        // idle round is two launches: 128 of them per 16384-query batch were 0.45 ms of config 5's 24 ms step)
+        s->max_device_fix = B <= 64 ? 64 : (B <= 1024 ? 128 : (B <= 4096 || k > 32 ? 256 : kMaxFixRound));
         if ((rc = s->tc_fixcand.ensure((size_t)s->max_device_fix * scan_fix_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
         if (report_to_host && ((size_t)B + 4) * sizeof(uint32_t) > s->flags_map.bytes) {
             if ((rc = s->flags_map.ensure(((size_t)B + 4) * sizeof(uint32_t) * 2)) != MQVS_OK) return rc;

@@ -272,7 +272,7 @@ scan_fix_kernel(const T* __restrict__ rows, uint32_t n_rows, const float* __rest
                 const float* __restrict__ row_norms, const float* __restrict__ q_norms_all, int count_leftover,
                 const uint32_t* __restrict__ flag_count) {
     extern __shared__ __align__(16) uint64_t smem_keys[];
-    __shared__ uint32_t list_s[256];
+    __shared__ uint32_t list_s[1024];
     __shared__ uint32_t n_s, total_s;
     const int lane = threadIdx.x & 31;
     // Nothing flagged (the common case of the rounds an asynchronous search enqueues blind): one word says so.  Walking the
@@ -440,7 +440,7 @@ void launch_scan_fix(const void* rows, int dtype, uint32_t n_rows, const float* 
     const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * sizeof(uint64_t);
     const int grid = scan_fix_grid(sm_count), stride = grid;  // every slot of a listed query is written: no memset
-    if (max_fix > 256) max_fix = 256;
+    if (max_fix > 1024) max_fix = 1024;  // list_s
     const int leftover = count_leftover ? 1 : 0;
 #define MQVS_FIX(T_, KPL_, U_)                                                                                                     \
     do {                                                                                                                           \

@@ -1780,3 +1780,31 @@ def test_collection_query_batches_through_the_cuda_path(gpu, medical_docs, embed
     assert [t[0] for t in top1["documents"]] == [d.page_content for d in docs]
     assert all(ids.index(r[0]) <= j for j, r in enumerate(top1["ids"]))
     assert stores[0]._collection.count() == 154
+
+
+def test_very_large_async_batch_with_every_query_flagged_is_repaired_in_rounds_of_1024(gpu):
+    """B > 4096 (k <= 32): the blind asynchronous search enqueues ceil(B / 1024) exact-scan rounds.  5000 queries all aimed at
+    a row with 300 exact copies defeat the segmented pipeline's shortlist, so every round has a full list to work through."""
+    import torch
+    n, B, k = 20000, 5000, 10
+    x = O.synth_rows(SEED, 0, n, 768)
+    x[5000:5300] = x[123]
+    q = (x[123][None, :] + 0.01 * O.synth_rows(78, 0, B, 768)).astype(np.float32)
+    qn, _ = O.normalize_rows(q, "fp32", 768)
+    st, _ = O.normalize_rows(x, "bf16", 768)
+    es, ei = O.brute_force_topk(qn, st, k)
+    idx = native().Index(768, "bf16")
+    idx.add(x)
+    idx.set_path(4)
+    qd = torch.from_numpy(q).cuda()
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    before = idx.stats()["exact_fallbacks"]
+    idx.search_device(qd, k, out_s, out_i, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_bit_equal(out_s.cpu().numpy(), out_i.cpu().numpy(), es, ei)
+    stt = idx.stats()
+    assert stt["unrepaired"] == 0 and stt["exact_fallbacks"] - before >= B // 2
+    s, i = idx.search(q, k)  # the blocking call over the same batch
+    assert_bit_equal(s, i, es, ei)
+    idx.close()
