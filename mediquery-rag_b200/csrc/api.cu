@@ -126,7 +126,15 @@ static bool use_tensor_path(const mqvs_store* s, int B, int k) {
     // (l2 / ip spaces: the transform makes the tensor epilogue ~4 % slower than the SIMT scan for the 1-2 queries that scan
     // holds the roofline for -- 0.508 vs 0.489 ms at 1M x 768 fp32, B=1 -- so those stay on the SIMT scan at every size)
     if (s->n >= 1000000ull && (s->metric == MQVS_METRIC_COSINE || B > simt_max)) return true;
-    return B > simt_max && s->n >= 65536;
+    if (B > simt_max && s->n >= 65536) return true;
+    // Everything else from 4096 rows up (round 2, profiles/r02_small_store_crossover.json: blocking host-buffer calls on one
+    // B200, every space, both row types): the single-launch tensor pipeline beats both SIMT forms for EVERY batch of two or
+    // more queries -- 8192 bf16 rows: B = 2 64 vs 78 us, B = 64 83 vs 504 us, B = 1024 0.40 vs 7.1 ms (the SIMT scan takes at
+    // most four queries per pass); fp32 pairs below 1M rows, l2 space, 131072 rows: 100 vs 132 us.  Without cooperative
+    // launches the segmented pipeline's fixed launches pay from 16 queries on.  Single queries stay on the latency kernel
+    // (52.9 vs 61.1 us at 4096 rows, a tie from 8192).
+    const bool one_launch = s->coop_ok && B <= 256 && mqvs::tc::fused_ok(B, k, s->sm_count);
+    return B >= 2 && k <= 128 && (one_launch || B >= 16);
 }
 
 // Brings the bf16 scoring shadow of an fp32 store up to date (store.h).  -> true when the tensor pipelines may stream it.

@@ -868,7 +868,6 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
     assert idx.norm_deviation() == float(np.abs(nr - np.float32(1.0)).max())
     st, _ = O.normalize_rows(x, dtype, 768)
     rng = np.random.default_rng(2)
-    simt_max = 2 if dtype == "fp32" else 1  # api.cu:use_tensor_path below 1M rows
     for B, k, frac in ((1, 10, None), (3, 5, None), (9, 10, 0.3), (2, 40, None), (1, 200, 0.5), (200, 100, 0.5), (300, 10, None),
                        (64, 10, None)):
         q = (_raw_rows(B, seed=QSEED) * np.float32(3.0) + 0.5 * x[rng.integers(0, n, B)]).astype(np.float32)
@@ -878,7 +877,7 @@ def test_l2_and_ip_spaces_over_raw_vectors_are_bit_exact(gpu, space, dtype, tmp_
         es, ei = O.brute_force_topk(qn, st, k, mask, metric=space, norms=nr, q_norms=O.row_norms(q, 768))
         assert_bit_equal(s, i, es, ei)
         stats = idx.stats()
-        tensor = B > simt_max and k <= 128
+        tensor = B >= 2 and k <= 128  # api.cu:use_tensor_path below 1M rows: every batch of two or more queries
         assert stats["last_path"] == int(tensor) and stats["last_pipeline"] == ((3 if B <= 256 else 2) if tensor else 0), stats
         assert stats["exact_fallbacks"] == 0
     assert not np.array_equal(O.brute_force_topk(qn, st, k)[1], ei)  # the space matters on these rows
