@@ -57,7 +57,10 @@ typedef struct mqvs_stats {
     uint64_t kernel_launches;    /* kernels launched by this handle since creation */
     uint64_t scan_launches;      /* of those, corpus-scan (K2) launches */
     uint64_t scan_bytes;         /* algorithmic corpus bytes streamed by the scans: rows * 768 * sizeof(elem) per pass */
-    double   scan_ms;            /* device time of the scan launches (CUDA events on the launch stream) */
+    double   scan_ms;            /* device time of the scan launches (CUDA events on the launch stream).  One exception: a blocking
+                                    mqvs_search with host outputs on the single-launch latency path (B <= 4, k <= 16, small stores)
+                                    records no events -- they cost 6 us of a 33 us call -- and adds the host-observed time from the
+                                    launch call to the kernel's completion word instead; MQVS_TIMING=1 or 2 restores the events */
     double   last_search_ms;     /* device time of the last search: its scan launches (= last_scan_ms), or first kernel to last when the
                                     process runs with MQVS_TIMING=1 (two more CUDA events per search) */
     double   last_scan_ms;       /* device time of the last search's scan launches */

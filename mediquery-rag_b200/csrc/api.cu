@@ -3,6 +3,8 @@
 #include <fcntl.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <chrono>
 #include <thread>
 
 #include "store.h"
@@ -263,16 +265,24 @@ int enqueue_search(mqvs_store* s, const float* q_raw_dev, int B, int k, const ui
     if (fused) {
         // latency path: normalisation, scan, top-k and the final merge in one launch
         if ((rc = s->cand.ensure((size_t)B * scan_fused_max_grid(s->sm_count) * k * sizeof(uint64_t))) != MQVS_OK) return rc;
-        MQVS_EV(0);
-        MQVS_EV(1);
+        // A blocking host-buffer call (host_status: the caller watches the kernel's completion word) is timed by that caller on
+        // the host clock: two timed events cost ~6 us of stream time around a kernel that takes 17 us on the reference's 154
+        // chunks (profiles/r02_latency_ab.log: 38.6 -> 32.6 us per call).  MQVS_TIMING=1 / 2 brings the events back.
+        const bool events = s->timing && (host_status == nullptr || s->timing_from_env);
+        if (events) {
+            MQVS_EV(0);
+            MQVS_EV(1);
+        }
         // (q_raw_host: a host caller's queries ride in the kernel's parameter block -- no copy of their own)
         launch_scan_fused(s->rows, s->dtype, (uint32_t)s->n, q_raw_dev, s->dim, B, mask_dev, k, (uint64_t*)s->cand.p,
                           out_scores_dev, out_ids_dev, id_base, s->ticket_dev, (unsigned int*)(s->bad_dev + 1), ++s->epoch,
                           s->sm_count, st, host_status, q_raw_host);
-        MQVS_EV(2);
-        MQVS_EV(3);
+        if (events) {
+            MQVS_EV(2);
+            MQVS_EV(3);
+        }
         CU(cudaGetLastError());
-        s->evr[slot].pending = s->timing;
+        s->evr[slot].pending = events;
         s->stats.kernel_launches += 1;
         s->stats.scan_launches += 1;
         s->stats.scan_bytes += s->n * s->row_bytes();
@@ -522,7 +532,10 @@ int create_single(int dev, int dim, int store_dtype, uint64_t capacity_rows, mqv
     s->coop_ok = prop.cooperativeLaunch != 0;
     // MQVS_TIMING=1: four CUDA events per search instead of the two around the scan (stats.last_search_ms then covers the
     // first kernel to the last); MQVS_TIMING=0: none (stats.scan_ms / last_search_ms stay 0)
-    if (const char* t = getenv("MQVS_TIMING")) s->timing_level = atoi(t) == 1 ? 1 : (atoi(t) == 0 ? 0 : 2);
+    if (const char* t = getenv("MQVS_TIMING")) {
+        s->timing_level = atoi(t) == 1 ? 1 : (atoi(t) == 0 ? 0 : 2);
+        s->timing_from_env = true;
+    }
     s->timing = s->timing_level != 0;
     auto bail = [&](int rc) {
         destroy_single(s);
@@ -902,10 +915,32 @@ static int search_locked(mqvs_t* s, const float* q, int q_is_device, int B, int 
         status[0] = 0;
     }
     if (zero_copy) {
+        const bool host_timed = s->timing && !s->timing_from_env;  // (enqueue_search records no events for this call then)
+        const auto t_launch = std::chrono::steady_clock::now();
         if ((rc = enqueue_search(s, q_dev, B, k, mask_dev, 0, os, oi, s->st, status, false, false, inline_q ? q : nullptr)) != MQVS_OK)
             return rc;
-        CU(cudaStreamSynchronize(s->st));
-        if (status[0] != s->epoch) return fail(MQVS_E_CUDA, "latency path: the kernel did not report completion");
+        // The kernel's last store is the completion word in mapped host memory (after a system-wide fence behind the results):
+        // watching that word returns as soon as it lands, without the driver's stream-sync round trip behind the kernel and
+        // the timing event that follows it.  Bounded: a scan that takes longer (or a failed launch) falls through to the sync.
+        static const bool no_spin = getenv("MQVS_NO_SPIN_WAIT") != nullptr;  // developer knob: measure what it buys
+        if (!no_spin) {
+            volatile unsigned int* done = status;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 1; done[0] != s->epoch; ++spins) {
+                if ((spins & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (((volatile unsigned int*)status)[0] != s->epoch) CU(cudaStreamSynchronize(s->st));
+        if (((volatile unsigned int*)status)[0] != s->epoch) return fail(MQVS_E_CUDA, "latency path: the kernel did not report completion");
+        if (host_timed) {  // launch call -> completion word seen: what the caller waited for the device
+            const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_launch).count();
+            s->stats.last_search_ms = s->stats.last_scan_ms = ms;
+            s->stats.scan_ms += ms;
+        }
         memcpy(out_scores, os, n_out * sizeof(float));
         memcpy(out_ids, oi, n_out * sizeof(int64_t));
         if (status[1]) return fail(MQVS_E_INVALID, "queries with a non-finite norm in a batch of %d", B);

@@ -159,6 +159,7 @@ struct mqvs_store {
     // divides by), 1 = four (also first kernel to last: stats.last_search_ms), 0 = none.  A timed event costs ~3 us of stream
     // time: four of them were 11 us of a 282 us search at 1M rows (measured, round 2), two are 6.
     int timing_level = 2;
+    bool timing_from_env = false;  // MQVS_TIMING was set: every path records its CUDA events, the latency path included
     bool timing = true;  // record the CUDA events behind stats.scan_ms / last_search_ms (off for the shards of a multi-device handle)
     mqvs::DevBuf qraw, qn, qnorm, cand, out_s, out_i, maskbuf, idbuf, gatherbuf;
     mqvs::DevBuf tc_qop, tc_small, tc_cnt, tc_lists, tc_keys, tc_fixcand, tc_cmax;  // tensor-core path scratch
