@@ -402,6 +402,8 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
             raise ValueError(f"expected {n} embeddings of one width, got shape {tuple(vectors.shape)}")
         if metadatas is not None and len(metadatas) != n:
             raise ValueError(f"{len(metadatas)} metadatas for {n} texts")
+        if metadatas is not None and not all(md is None or isinstance(md, Mapping) for md in metadatas):
+            raise TypeError("every metadata must be a mapping or None")
         if ids is None:
             ids = [str(uuid.uuid4()) for _ in range(n)]
         ids = [str(i) for i in ids]
@@ -554,12 +556,14 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                  where_document: Optional[Mapping[str, Any]] = None) -> List[Tuple[Document, float]]:
         """(Document, distance in the collection's hnsw:space) pairs, best (smallest distance) first."""
         q = np.asarray(vector, dtype=np.float32)
-        scores, rows = self.search_batch(q[None, :], k, filter, where_document)
-        ranked = self.rank_space()
+        with self._lock:  # row numbers -> documents under the same lock as the search: a compaction in between renumbers rows
+            scores, rows = self.search_batch(q[None, :], k, filter, where_document)
+            ranked = self.rank_space()
+            hits = self._docs(scores[0], rows[0])
         if ranked == "cosine":
-            return [(d, _distance(self._space, s)) for d, s in self._docs(scores[0], rows[0])]
+            return [(d, _distance(self._space, s)) for d, s in hits]
         q_norm = float(np.linalg.norm(q.astype(np.float64)))
-        return [(d, _raw_distance(ranked, t, q_norm)) for d, t in self._docs(scores[0], rows[0])]
+        return [(d, _raw_distance(ranked, t, q_norm)) for d, t in hits]
 
     def similarity_search(self, query: str, k: int = DEFAULT_K, filter: Optional[Dict[str, Any]] = None,
                           **kwargs: Any) -> List[Document]:
@@ -586,10 +590,12 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                                        ) -> List[Tuple[Document, np.ndarray]]:
         """langchain_chroma's (Document, stored embedding) pairs, best first: the vectors as the collection returns them for
         `get(include=["embeddings"])` (raw vectors in an l2 / ip collection, unit rows otherwise)."""
-        hits = self._similar(self._embed_query(query), k, filter, where_document)
-        if not hits:
-            return []
-        emb = self.get(ids=[d.id for d, _ in hits], include=["embeddings"])
+        q = self._embed_query(query)
+        with self._lock:
+            hits = self._similar(q, k, filter, where_document)
+            if not hits:
+                return []
+            emb = self.get(ids=[d.id for d, _ in hits], include=["embeddings"])
         by_id = dict(zip(emb["ids"], emb["embeddings"]))
         return [(d, np.asarray(by_id[d.id])) for d, _ in hits]
 
@@ -617,6 +623,10 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
                                                 **kwargs: Any) -> List[Document]:
         """Shortlist fetch_k rows on the GPU, then the usual greedy MMR over those (host, fetch_k is tiny)."""
         q = np.asarray(embedding, dtype=np.float32)
+        with self._lock:
+            return self._mmr_locked(q, k, fetch_k, lambda_mult, filter)
+
+    def _mmr_locked(self, q: np.ndarray, k: int, fetch_k: int, lambda_mult: float, filter) -> List[Document]:
         scores, rows = self.search_batch(q[None, :], fetch_k, filter)
         rows = rows[0][rows[0] >= 0]
         if rows.shape[0] == 0:
@@ -645,10 +655,11 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
         self.update_documents([document_id], [document])
 
     def update_documents(self, ids: List[str], documents: List[Document]) -> None:
-        missing = [i for i in ids if self._row_of(str(i)) is None]
-        if missing:
-            raise ValueError(f"unknown document ids: {missing[:3]}")
-        self.add_texts([d.page_content for d in documents], [d.metadata for d in documents], ids=[str(i) for i in ids])
+        with self._lock:
+            missing = [i for i in ids if self._row_of(str(i)) is None]
+            if missing:
+                raise ValueError(f"unknown document ids: {missing[:3]}")
+            self.add_texts([d.page_content for d in documents], [d.metadata for d in documents], ids=[str(i) for i in ids])
 
     # LangChain's VectorStore exposes a-prefixed coroutines that run the blocking call in a worker thread; the handle is
     # safe to use from any thread (tests/test_gpu_parity.py::test_one_handle_from_several_host_threads...).  With
@@ -688,6 +699,10 @@ class MediQueryVectorStore(_Base):  # type: ignore[misc]
     def get(self, ids: Optional[Sequence[str]] = None, where: Optional[Mapping[str, Any]] = None,
             limit: Optional[int] = None, offset: Optional[int] = None, where_document: Any = None,
             include: Optional[List[str]] = None) -> Dict[str, Any]:
+        with self._lock:  # the tables and the row numbering must not move (add / delete / compaction) while rows are collected
+            return self._get_locked(ids, where, limit, offset, where_document, include)
+
+    def _get_locked(self, ids, where, limit, offset, where_document, include) -> Dict[str, Any]:
         include = list(include) if include is not None else ["metadatas", "documents"]
         if ids is not None:
             if isinstance(ids, str):

@@ -420,3 +420,39 @@ def test_collection_view_counts_and_queries_like_chromadb(medical_docs, embedder
     assert len(filt["ids"]) == 1 and 0 < len(filt["ids"][0]) == sum(needle in d.page_content for d in docs)
     col.delete(ids=res["ids"][0][:1])
     assert col.count() == 79 and col.get(ids=res["ids"][0][:1])["ids"] == []
+
+
+def test_a_metadata_that_is_not_a_mapping_is_refused_before_any_row_reaches_the_index(embedder):
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex)
+    with pytest.raises(TypeError):
+        vs.add_texts(["a", "b"], metadatas=[{"g": 1}, "not a dict"])
+    assert len(vs) == 0 and (vs._index is None or len(vs._index) == 0)
+    assert vs.add_texts(["a", "b"], metadatas=[{"g": 1}, None], ids=["x", "y"]) == ["x", "y"]
+    assert vs.get(ids=["x"])["metadatas"] == [{"g": 1}]
+
+
+def test_a_compaction_cannot_slip_between_a_search_and_its_documents(embedder):
+    """A compaction renumbers rows; a search maps its row numbers to documents under the same lock as the scan.  Here another
+    thread deletes + compacts right after the scan returned its rows: it has to wait until the documents are collected."""
+    import threading
+    texts = [f"chunk {i} " + "x" * (i % 7) for i in range(1500)]
+    vs = MediQueryVectorStore(embedding_function=embedder, index_factory=OracleIndex, compact_dead_fraction=0.0)
+    ids = vs.add_texts(texts, ids=[f"id-{i}" for i in range(len(texts))])
+    real, started = vs.search_batch, []
+
+    def search_then_compaction_elsewhere(*a, **kw):
+        out = real(*a, **kw)
+        if not started:
+            t = threading.Thread(target=lambda: (vs.delete(ids[:1000]), vs.compact()))
+            started.append(t)
+            t.start()
+            t.join(0.3)  # finishes here if nothing holds it back -> the rows in `out` would then name other documents
+        return out
+
+    vs.search_batch = search_then_compaction_elsewhere
+    got = vs.similarity_search(texts[1200], k=1)
+    started[0].join()
+    assert got[0].page_content == texts[1200] and got[0].id == "id-1200"
+    assert len(vs) == 500 and vs.similarity_search(texts[1200], k=1)[0].page_content == texts[1200]
+    vs.search_batch, started[:] = real, []
+    assert vs.get(ids=["id-1200"])["documents"] == [texts[1200]]
